@@ -1,0 +1,136 @@
+/* spx_b200.h -- C ABI of the B200-native superpixel engine (libspx_b200.so).
+ *
+ * Drop-in boundary for the ONE hot path of AbsurdePhoton/superpixels-segmentation-gui-opencv:
+ * MainWindow::on_button_compute_clicked (mainwindow.cpp:2062-2151), i.e. cv::cvtColor(BGR2Lab|BGR2HSV)
+ * followed by cv::ximgproc::SuperpixelSLIC / SuperpixelLSC / SuperpixelSEEDS.
+ * Each entry point names the reference interface it replaces.  The cv::ximgproc-shaped C++ adapter
+ * over this ABI is include/spx_ximgproc.hpp; the binding a maintainer adds is in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; strides are in BYTES; images are 8-bit interleaved (CV_8UC<n>),
+ *     label maps are int32 (CV_32SC1), masks are uint8 {0,255} (CV_8UC1).
+ *   - every function returns an int status: 0 = ok, negative = error (OpenCV-style codes below);
+ *     nothing throws or aborts across the boundary; spx_last_error() gives the message (thread-local).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     SPX_ERR_GPU.
+ *   - "_dev" variants take/return DEVICE pointers and enqueue on the object's stream without
+ *     synchronising (used by the batch path, where frames are resident in HBM).
+ *   - an object is bound to one device and one stream; calls on one object must be serialised by
+ *     the caller (same contract as the reference: single GUI thread, create -> iterate ->
+ *     [enforceLabelConnectivity] -> getters).
+ */
+#ifndef SPX_B200_H
+#define SPX_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPX_OK            0
+#define SPX_ERR_BADARG   (-5)    /* cv::Error::StsBadArg   */
+#define SPX_ERR_ASSERT   (-215)  /* cv::Error::StsAssert   */
+#define SPX_ERR_NOMEM    (-4)    /* cv::Error::StsNoMem    */
+#define SPX_ERR_GPU      (-217)  /* cv::Error::GpuApiCallError */
+#define SPX_ERR_INTERNAL (-3)    /* cv::Error::StsInternal */
+
+/* cv::ximgproc::SLICType (slic.hpp), passed by the GUI as algorithm+SLIC (mainwindow.cpp:2105) */
+#define SPX_SLIC   100
+#define SPX_SLICO  101
+#define SPX_MSLIC  102
+
+int         spx_version(void);
+const char* spx_last_error(void);
+int         spx_device_count(int* count);
+
+/* ---- cv::cvtColor(converted, converted, COLOR_BGR2Lab / COLOR_BGR2HSV), mainwindow.cpp:2096-2097 ----
+ * 8UC3 -> 8UC3, bit-exact with OpenCV's 8-bit integer pipelines.  In-place (src == dst) is allowed. */
+int spx_bgr2lab8(const uint8_t* src, size_t src_stride, uint8_t* dst, size_t dst_stride, int width, int height, int device);
+int spx_bgr2hsv8(const uint8_t* src, size_t src_stride, uint8_t* dst, size_t dst_stride, int width, int height, int device);
+int spx_bgr2lab8_dev(const void* d_src, size_t src_stride, void* d_dst, size_t dst_stride, int width, int height, void* cuda_stream);
+int spx_bgr2hsv8_dev(const void* d_src, size_t src_stride, void* d_dst, size_t dst_stride, int width, int height, void* cuda_stream);
+
+/* ---- cv::ximgproc::SuperpixelSLIC (mainwindow.h:170, mainwindow.cpp:2105-2111) ---- */
+typedef struct spx_slic spx_slic_t;
+
+/* createSuperpixelSLIC(image, algorithm, region_size, ruler) -- mainwindow.cpp:2105.
+ * `image` is the already colour-converted 8-bit image (1..4 channels; the GUI passes 3). */
+int spx_slic_create(const uint8_t* image, size_t stride, int width, int height, int channels,
+                    int algorithm, int region_size, float ruler, int device, spx_slic_t** out);
+/* same, image already resident on the current CUDA device; work is enqueued on `cuda_stream`
+ * (NULL = a private stream owned by the object). */
+int spx_slic_create_dev(const void* d_image, size_t stride, int width, int height, int channels,
+                        int algorithm, int region_size, float ruler, void* cuda_stream, spx_slic_t** out);
+/* re-run the constructor on a new frame of identical geometry/parameters, reusing all device
+ * allocations (what `slic = createSuperpixelSLIC(...)` does on every COMPUTE click, minus malloc). */
+int spx_slic_reset(spx_slic_t*, const uint8_t* image, size_t stride);
+int spx_slic_reset_dev(spx_slic_t*, const void* d_image, size_t stride);
+/* SuperpixelSLIC::iterate(num_iterations) -- mainwindow.cpp:2106 */
+int spx_slic_iterate(spx_slic_t*, int num_iterations);
+/* SuperpixelSLIC::enforceLabelConnectivity(min_element_size) -- mainwindow.cpp:2108 (0 = no-op) */
+int spx_slic_enforce_label_connectivity(spx_slic_t*, int min_element_size);
+/* SuperpixelSLIC::getNumberOfSuperpixels() -- mainwindow.cpp:2109 (synchronises) */
+int spx_slic_get_number_of_superpixels(spx_slic_t*, int* out);
+/* SuperpixelSLIC::getLabels(labels) -- mainwindow.cpp:2110; CV_32SC1 */
+int spx_slic_get_labels(spx_slic_t*, int32_t* dst, size_t dst_stride);
+int spx_slic_get_labels_dev(spx_slic_t*, void* d_dst, size_t dst_stride);
+/* SuperpixelSLIC::getLabelContourMask(mask, thick_line) -- mainwindow.cpp:2111; CV_8UC1 {0,255} */
+int spx_slic_get_label_contour_mask(spx_slic_t*, uint8_t* dst, size_t dst_stride, int thick_line);
+int spx_slic_get_label_contour_mask_dev(spx_slic_t*, void* d_dst, size_t dst_stride, int thick_line);
+/* test hooks: inject a label map (bit-exact checks of connectivity / contour), read the centres.
+ * centres: rows of (c0..c[channels-1], x, y) float32; `rows` = capacity of dst in rows. */
+int spx_slic_set_labels(spx_slic_t*, const int32_t* src, size_t src_stride, int numlabels);
+int spx_slic_get_centres(spx_slic_t*, float* dst, int rows);
+int spx_slic_synchronize(spx_slic_t*);
+/* number of kernels this object has launched so far (bench.py's gpu_launches) */
+int spx_slic_launch_count(spx_slic_t*, long long* out);
+/* cv::Ptr<SuperpixelSLIC> release (the GUI overwrites `slic` on every COMPUTE, mainwindow.cpp:2105) */
+int spx_slic_destroy(spx_slic_t*);
+
+/* ---- batch of independent frames on one device (BASELINE.json configs[4]) ----
+ * For every frame i: createSuperpixelSLIC(frame_i) ; iterate(num_iterations) ;
+ * [enforceLabelConnectivity(min_element_size) if > 0] ; getLabels -> d_labels[i]
+ * ; [getLabelContourMask(thick_line) -> d_masks[i] if d_masks != NULL].
+ * All pointers in the arrays are DEVICE pointers (dense: stride = width*channels, width*4, width).
+ * `n_streams` engines work concurrently.  Blocks until the batch is done. */
+int spx_slic_batch_dev(const void* const* d_frames, int n_frames, int width, int height, int channels,
+                       int algorithm, int region_size, float ruler, int num_iterations,
+                       int min_element_size, void* const* d_labels, void* const* d_masks, int thick_line,
+                       int n_streams, long long* launches_out);
+
+/* ---- stand-alone stages on a caller-supplied label map (host buffers) ----
+ * same arithmetic as the member functions above; used for bit-exact stage tests. */
+int spx_enforce_label_connectivity(int32_t* labels, size_t stride, int width, int height,
+                                   int numlabels, int min_element_size, int device, int* numlabels_out);
+/* flavour 0 = SuperpixelSLIC/LSC::getLabelContourMask, 1 = SuperpixelSEEDS::getLabelContourMask */
+int spx_label_contour_mask(const int32_t* labels, size_t stride, int width, int height, int thick_line,
+                           int flavour, uint8_t* dst, size_t dst_stride, int device);
+
+/* ---- cv::ximgproc::SuperpixelLSC (mainwindow.h:171, mainwindow.cpp:2114-2120) ---- */
+typedef struct spx_lsc spx_lsc_t;
+int spx_lsc_create(const uint8_t* image, size_t stride, int width, int height, int channels,
+                   int region_size, float ratio, int device, spx_lsc_t** out);
+int spx_lsc_iterate(spx_lsc_t*, int num_iterations);
+int spx_lsc_enforce_label_connectivity(spx_lsc_t*, int min_element_size);
+int spx_lsc_get_number_of_superpixels(spx_lsc_t*, int* out);
+int spx_lsc_get_labels(spx_lsc_t*, int32_t* dst, size_t dst_stride);
+int spx_lsc_get_label_contour_mask(spx_lsc_t*, uint8_t* dst, size_t dst_stride, int thick_line);
+int spx_lsc_set_labels(spx_lsc_t*, const int32_t* src, size_t src_stride, int numlabels);
+int spx_lsc_destroy(spx_lsc_t*);
+
+/* ---- cv::ximgproc::SuperpixelSEEDS (mainwindow.h:172, mainwindow.cpp:2123-2127) ---- */
+typedef struct spx_seeds spx_seeds_t;
+int spx_seeds_create(int width, int height, int channels, int num_superpixels, int num_levels,
+                     int prior, int histogram_bins, int double_step, int device, spx_seeds_t** out);
+/* SuperpixelSEEDS::iterate(img, num_iterations) -- mainwindow.cpp:2124 */
+int spx_seeds_iterate(spx_seeds_t*, const uint8_t* image, size_t stride, int num_iterations);
+int spx_seeds_get_number_of_superpixels(spx_seeds_t*, int* out);
+int spx_seeds_get_labels(spx_seeds_t*, int32_t* dst, size_t dst_stride);
+int spx_seeds_get_label_contour_mask(spx_seeds_t*, uint8_t* dst, size_t dst_stride, int thick_line);
+int spx_seeds_destroy(spx_seeds_t*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPX_B200_H */

@@ -75,6 +75,7 @@ struct spxo_slic {
     int w, h, C, algorithm, S;
     float ruler;
     int K;
+    int K0;                  /* seeds at creation (MSLIC growth cap = 4*K0) */
     uint8_t* ch[SPXO_MAXC];  /* planes (cv::split) */
     int32_t* labels;
     float* kc[SPXO_MAXC];    /* centre colour per channel */
@@ -199,6 +200,7 @@ spxo_slic* spxo_slic_create(const uint8_t* img, size_t stride, int w, int h, int
         }
     }
     for (int n = 0; n < s->K; n++) s->adaptk[n] = 1.0f;
+    s->K0 = s->K;
     return s;
 }
 
@@ -333,7 +335,7 @@ void spxo_slic_iterate(spxo_slic* s, int num_iterations)
     size_t N = (size_t)s->w * s->h;
     float* distvec = (float*)malloc(N * sizeof(float));
     if (s->algorithm == 101) {
-        /* PerformSLICO: dist = distchans/maxchans[n] + distxy/(S*S); maxchans/maxxy start at FLT_MIN,
+        /* PerformSLICO: dist = distchans/maxchans[n] + distxy/(S*S); maxchans/maxxy start at 100 / S*S,
            are reset to FLT_MIN after the first assignment, then track the per-label maxima of the
            distchans / distxy planes (which hold the LAST visiting cluster's value per pixel). */
         float* distchans = (float*)malloc(N * sizeof(float));
@@ -341,7 +343,8 @@ void spxo_slic_iterate(spxo_slic* s, int num_iterations)
         for (size_t i = 0; i < N; i++) { distchans[i] = FLT_MAX; distxy[i] = FLT_MAX; }
         float* maxchans = (float*)malloc(sizeof(float) * s->K);
         float* maxxy = (float*)malloc(sizeof(float) * s->K);
-        for (int k = 0; k < s->K; k++) { maxchans[k] = FLT_MIN; maxxy[k] = FLT_MIN; }
+        /* start values as in Achanta's SLICO ("just start with 10"): 10*10 and S*S [recalled, UNPINNED] */
+        for (int k = 0; k < s->K; k++) { maxchans[k] = 10.0f * 10.0f; maxxy[k] = (float)(s->S * s->S); }
         const float xywt = (float)(s->S * s->S);
         for (int itr = 0; itr < num_iterations; itr++) {
             slic_assign(s, distvec, xywt, distchans, distxy, maxchans);
@@ -372,10 +375,12 @@ void spxo_slic_iterate(spxo_slic* s, int num_iterations)
  * target=2 "from paper").  After each centre update:
  *   area(p)  = area of the unit square at p on the 2-manifold (x, y, q*c0, q*c1, q*c2), q = S/ruler,
  *              as two triangles (p,p+x,p+y) and (p+x+y,p+x,p+y); float32, Gram determinant;
- *   A[k]     = sum of area(p) over pixels of label k (row-major order), Abar = sum(A)/K;
+ *   A[k]     = sum over pixels of label k of (int64)(area(p)*256) (fixed point, so the sum is
+ *              order independent), Abar = float(sum A)/(K*256);
  *   adaptk[k]= clamp(sqrt(Abar / A[k]), 1/target, target)      (small windows where content is dense)
  *   split    : clusters with A[k] > split*Abar spawn 3 new centres at the quarter offsets of their
- *              window (K grows, appended in ascending k order); the parent moves to the 4th quarter.
+ *              window (K grows, appended in ascending k order); the parent moves to the 1st quarter.
+ *              An iteration whose splits would take K above 4*K0 performs no split at all.
  */
 static inline float tri_area5(const float* a, const float* b, const float* c)
 {
@@ -393,8 +398,8 @@ static void mslic_adapt(spxo_slic* s)
 {
     const int w = s->w, h = s->h, C = s->C, K = s->K, S = s->S;
     const float q = (float)S / s->ruler;
-    double* A = (double*)calloc(K, sizeof(double));
-    double tot = 0.0;
+    int64_t* A = (int64_t*)calloc(K, sizeof(int64_t));
+    int64_t tot = 0;
     for (int y = 0; y < h - 1; y++)
         for (int x = 0; x < w - 1; x++) {
             float P[4][5];
@@ -405,25 +410,26 @@ static void mslic_adapt(spxo_slic* s)
                     P[j][2 + c] = c < C ? q * (float)s->ch[c][(size_t)yy * w + xx] : 0.f;
             }
             float a = tri_area5(P[0], P[1], P[2]) + tri_area5(P[3], P[1], P[2]);
-            A[s->labels[(size_t)y * w + x]] += (double)a;
-            tot += (double)a;
+            int64_t fx = (int64_t)(a * 256.0f);      /* fixed point: order-independent sums */
+            A[s->labels[(size_t)y * w + x]] += fx;
+            tot += fx;
         }
     const float target = 2.0f, split = 4.0f;
-    float abar = (float)(tot / (double)K);
+    float abar = (float)tot / ((float)K * 256.0f);
     int newK = K;
     for (int k = 0; k < K; k++) {
-        float ak = (float)A[k];
+        float ak = (float)A[k] / 256.0f;
         float r = ak > 0.f ? sqrtf(abar / ak) : target;
         if (r < 1.0f / target) r = 1.0f / target;
         if (r > target) r = target;
         s->adaptk[k] = r;
         if (ak > split * abar) newK += 3;
     }
-    if (newK > K) {
+    if (newK > K && newK <= 4 * s->K0) {   /* growth cap: no splits once K would exceed 4*K0 */
         slic_reserve(s, newK);
         int n = K;
         for (int k = 0; k < K; k++) {
-            if (!((float)A[k] > split * abar)) continue;
+            if (!((float)A[k] / 256.0f > split * abar)) continue;
             float o = 0.5f * (float)S * s->adaptk[k];
             float cx = s->kx[k], cy = s->ky[k];
             const float ox[4] = { -o, o, -o, o }, oy[4] = { -o, -o, o, o };

@@ -1,0 +1,68 @@
+// common.cuh -- shared helpers of the B200 superpixel engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include "../../include/spx_b200.h"
+
+namespace spx {
+
+void set_error(const char* fmt, ...);
+
+#define SPX_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            spx::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return SPX_ERR_GPU;                                                                \
+        }                                                                                      \
+    } while (0)
+
+#define SPX_CHECK(st)                         \
+    do {                                      \
+        int s__ = (st);                       \
+        if (s__ != SPX_OK) return s__;        \
+    } while (0)
+
+#define SPX_REQUIRE(cond, code, ...)          \
+    do {                                      \
+        if (!(cond)) {                        \
+            spx::set_error(__VA_ARGS__);      \
+            return (code);                    \
+        }                                     \
+    } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// fails loudly when there is no usable CUDA device (no CPU fallback anywhere in this library)
+int require_device(int device);
+
+// ---- post-processing stages shared by SLIC / LSC / SEEDS engines (post.cu) ----
+struct PostWorkspace {
+    int w = 0, h = 0;
+    int* parent = nullptr;      // union-find parents / component roots        [N]
+    int* csize = nullptr;       // component sizes (indexed by root pixel)      [N]
+    int* newid = nullptr;       // new label per component root                [N]
+    int* link = nullptr;        // small component -> component supplying `adjlabel` [N]
+    int* blocksum = nullptr;    // scan scratch
+    int* flag = nullptr;        // device flags / counters [8]
+    unsigned char* diff = nullptr;   // contour: differing-neighbour bit masks [N]
+    unsigned char* takenA = nullptr; // contour ping-pong                      [N]
+    unsigned char* takenB = nullptr;
+    int* h_flag = nullptr;      // pinned host mirror [8]
+    long long launches = 0;
+    int alloc(int w_, int h_);
+    void release();
+};
+// labels: dense int32 with pitch `lpitch` (elements). In place. numlabels_out written to ws.h_flag[0]
+// asynchronously is NOT done: the function synchronises the stream once to read the new label count.
+int enforce_connectivity_dev(PostWorkspace& ws, int* d_labels, int lpitch, int numlabels, int min_element_size,
+                             cudaStream_t st, int* numlabels_out);
+// flavour 0: SLIC/LSC istaken rule; 1: SEEDS rule.  d_mask pitch in bytes.
+int contour_mask_dev(PostWorkspace& ws, const int* d_labels, int lpitch, int thick_line, int flavour,
+                     unsigned char* d_mask, size_t mpitch, cudaStream_t st);
+
+}  // namespace spx

@@ -1,0 +1,33 @@
+// slic.cuh -- device-side state of one SuperpixelSLIC object (SLIC / SLICO / MSLIC).
+#pragma once
+#include "common.cuh"
+
+namespace spx {
+
+#define SPX_MAXC 4
+
+// centre / accumulator arrays, all of capacity Kcap
+struct SlicArrays {
+    float* kx; float* ky;            // centre position (float32 means, as upstream)
+    float* kc;                       // centre colour, channel-major: kc[c*Kcap + k]
+    int* ikx; int* iky; int* ioff;   // (int)kx, (int)ky, window half-size (S, or int(S*adaptk) for MSLIC)
+    float* adaptk;                   // MSLIC scale
+    float* maxc; float* maxxy;       // SLICO running maxima (read by the assignment of this iteration)
+    unsigned* maxc_acc; unsigned* maxxy_acc;   // SLICO maxima being accumulated (float bits, >= 0)
+    unsigned long long* acc;         // accumulators, field-major: acc[f*Kcap + k], f = c0..cC-1, x, y, count
+    int* next;                       // per-bin linked lists of centres
+    int* head[2];                    // bin heads, double buffered by iteration parity
+    long long* area;                 // MSLIC fixed-point manifold area per cluster
+};
+
+struct SlicGeom {
+    int w, h, C, S, K, Kcap;
+    int nbx, nby;                    // bins of S x S pixels
+    int lp;                          // label pitch (elements)
+    size_t ipitch;                   // image pitch (bytes)
+    int alg;                         // 100/101/102
+    int radius;                      // bin search radius (1, or more for MSLIC)
+    float xywt;                      // SLIC/MSLIC: (S/ruler)^2 ; SLICO: S*S
+};
+
+}  // namespace spx
