@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 superpixel engine (see the contract in DESIGN.md "Measurement").
+
+Workload (BASELINE.json metric "SLIC megapixels/sec (10 iters, 4K)"; configs[4] frame shape):
+  per GPU a batch of B distinct synthetic 3840x2160 frames (already Lab, 8UC3, resident in HBM, B*24.9 MB > L2);
+  a STEP runs, for every frame of the batch, createSuperpixelSLIC(frame, SLIC, 20, 10) [seeds + perturbation],
+  iterate(10) and getLabels into a device buffer, through the C-ABI batch entry point.
+  value  = megapixels/s over all GPUs with inputs resident (device timing, max over ranks);
+  e2e    = same metric through the host-buffer C-ABI calls (pinned host frames in, labels out: H2D + D2H inside);
+  roofline = dominant kernel (slic assignment) : 7 B/px algorithmic / measured launch time vs measured HBM peak;
+  cpu_baseline = the oracle restatement on the box's host cores, bounded sample.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--frames B]
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "superpixels-segmentation-gui-opencv_b200"
+
+W4K, H4K, REGION, RULER, ITERS = 3840, 2160, 20, 10.0, 10
+METRIC = "slic_megapixels_per_sec_10iters_4k"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_frames(synth, n_distinct):
+    return [synth.synth(W4K, H4K, s)[0] for s in range(n_distinct)]
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's own CPU implementation of the path, timed on the host cores.  The reference's arithmetic
+    lives in OpenCV-contrib ximgproc, which is neither vendored nor installable here, so this arm times the
+    oracle restatement (kind "port") with every host thread; one step = one 4K frame (bounded sample)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    synth = importlib.import_module(PKG + ".synth")
+    cores = os.cpu_count() or 1
+    O.set_threads(cores)
+    bgr = make_frames(synth, 1)[0]
+    lab = O.bgr2lab8(bgr)
+
+    def step():
+        s = O.SuperpixelSLIC(lab, O.SLIC, REGION, RULER)
+        s.iterate(ITERS)
+        return s.getLabels()
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    mps = W4K * H4K / 1e6 / dt
+    out = {"impl": "reference", "metric": METRIC, "value": mps, "unit": "MP/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "SLIC region_size=20 ruler=10, 10 iterations, 3840x2160 synthetic frame "
+                                  "(createSuperpixelSLIC + iterate + getLabels), 1 frame per step"},
+           "cpu_baseline": {"value": mps, "unit": "MP/s", "cores": cores, "kind": "port",
+                            "sample": "%d x one 4K frame, oracle restatement of ximgproc SLIC with OpenMP row bands" % args.steps},
+           "e2e": {"value": mps, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    spx = importlib.import_module(PKG)
+    synth = importlib.import_module(PKG + ".synth")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available() or spx.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; this engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    L = spx.lib()
+    B = args.frames
+    npx = W4K * H4K
+
+    # ---- inputs: B distinct device-resident Lab frames (distinct buffers: B * 24.9 MB >> 126 MB L2)
+    distinct = make_frames(synth, args.distinct)
+    frames_host = []
+    frames_dev = []
+    for i in range(B):
+        bgr = distinct[(i + rank) % len(distinct)]
+        t = torch.from_numpy(bgr).to(dev)
+        rc = L.spx_bgr2lab8_dev(t.data_ptr(), W4K * 3, t.data_ptr(), W4K * 3, W4K, H4K, None)
+        assert rc == 0, L.spx_last_error()
+        frames_dev.append(t)
+    torch.cuda.synchronize()
+    n_host = min(B, args.e2e_frames)
+    for i in range(n_host):
+        frames_host.append(frames_dev[i].cpu().pin_memory())
+    labels_dev = [torch.empty((H4K, W4K), dtype=torch.int32, device=dev) for _ in range(B)]
+    fptr = [t.data_ptr() for t in frames_dev]
+    lptr = [t.data_ptr() for t in labels_dev]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches = [0]
+
+    def step():
+        launches[0] += spx.slic_batch_dev(fptr, W4K, H4K, 3, spx.SLIC, REGION, RULER, ITERS, 0, lptr, None, False,
+                                          args.streams)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches[0] = 0
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()          # blocks until the batch is done on the library's streams
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    ev_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    el = torch.tensor([max(ev_ms / 1e3, 0.0)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    elapsed = float(el.item())
+    value = world * B * args.steps * npx / 1e6 / elapsed
+
+    # ---- e2e: host buffers in, host labels out, through the reference-facing calls (H2D + D2H timed)
+    n_thr = min(args.e2e_threads, n_host)
+    host_labels = [torch.empty((H4K, W4K), dtype=torch.int32).pin_memory() for _ in range(n_thr)]
+    objs = [None] * n_thr
+
+    def e2e_worker(t, nrep):
+        torch.cuda.set_device(local)
+        for r in range(nrep):
+            for i in range(t, n_host, n_thr):
+                f = frames_host[i]
+                if objs[t] is None:
+                    h = C.c_void_p(None)
+                    rc = L.spx_slic_create(f.data_ptr(), W4K * 3, W4K, H4K, 3, spx.SLIC, REGION, RULER, local, C.byref(h))
+                    assert rc == 0, L.spx_last_error()
+                    objs[t] = h
+                else:
+                    assert L.spx_slic_reset(objs[t], f.data_ptr(), W4K * 3) == 0, L.spx_last_error()
+                assert L.spx_slic_iterate(objs[t], ITERS) == 0, L.spx_last_error()
+                assert L.spx_slic_get_labels(objs[t], host_labels[t].data_ptr(), W4K * 4) == 0, L.spx_last_error()
+
+    def e2e_pass(nrep):
+        th = [threading.Thread(target=e2e_worker, args=(t, nrep)) for t in range(n_thr)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+
+    e2e_pass(1)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_pass(args.e2e_reps)
+    torch.cuda.synchronize()
+    e2e_dt = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_dt], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_host * args.e2e_reps * npx / 1e6 / float(e2e_t.item())
+    e2e_ref_labels = host_labels[0].numpy().copy()
+    for h in objs:
+        if h is not None:
+            L.spx_slic_destroy(h)
+
+    # ---- roofline of the dominant kernel: time the steady-state iterate(10) of ONE frame on its own stream
+    roof = None
+    cpu = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        h = C.c_void_p(None)
+        st = torch.cuda.Stream(device=dev)
+        assert L.spx_slic_create_dev(fptr[0], W4K * 3, W4K, H4K, 3, spx.SLIC, REGION, RULER, C.c_void_p(st.cuda_stream), C.byref(h)) == 0
+        times = []
+        with torch.cuda.stream(st):
+            for r in range(8):
+                assert L.spx_slic_reset_dev(h, fptr[r % B], W4K * 3) == 0
+                a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+                a0.record(st)
+                assert L.spx_slic_iterate(h, ITERS) == 0
+                a1.record(st)
+                st.synchronize()
+                if r >= 3:
+                    times.append(a0.elapsed_time(a1))
+        it_ms = float(np.median(times))
+        # the dominant kernel alone: CUDA events around single launches on the object's stream (state after 10
+        # iterations = steady state), L2 flushed before every launch and, for comparison, L2-warm
+        kms = C.c_float(0); kms_warm = C.c_float(0)
+        assert L.spx_slic_time_assign(h, 20, 1, C.byref(kms)) == 0, L.spx_last_error()
+        assert L.spx_slic_time_assign(h, 20, 0, C.byref(kms_warm)) == 0, L.spx_last_error()
+        L.spx_slic_destroy(h)
+        alg_bytes = 7.0 * npx                      # per assignment launch: 3 B Lab read + 4 B label write per pixel
+        achieved = alg_bytes / (kms.value * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "slic_assign (fused assignment + centre accumulation)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "kernel_ms": kms.value, "kernel_ms_l2_warm": kms_warm.value,
+                "iterate10_ms_one_frame": it_ms, "assign_share_of_iterate": ITERS * kms_warm.value / it_ms,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "batch_frac": (7.0 * ITERS * npx) * (value * 1e6 / npx) / 1e9 / peak}
+        # ---- cpu baseline: oracle restatement, bounded sample (2 frames), all host threads
+        from oracle import oracle as O
+        cores = os.cpu_count() or 1
+        O.set_threads(cores)
+        lab0 = frames_host[0].numpy()
+        t0 = time.perf_counter()
+        nb = 2
+        for _ in range(nb):
+            s = O.SuperpixelSLIC(lab0, O.SLIC, REGION, RULER); s.iterate(ITERS); ol = s.getLabels()
+        cdt = (time.perf_counter() - t0) / nb
+        cpu = {"value": npx / 1e6 / cdt, "unit": "MP/s", "cores": cores, "kind": "port",
+               "sample": "%d x one 4K frame (create + iterate(10) + getLabels), oracle restatement, OpenMP %d threads" % (nb, cores),
+               "label_agreement_vs_gpu": float((ol == e2e_ref_labels).mean())}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic",
+               "config": {"workload": "SLIC region_size=20 ruler=10, 10 iterations, 3840x2160 synthetic frames "
+                                      "(createSuperpixelSLIC + iterate + getLabels per frame)",
+                          "frames_per_gpu_per_step": B, "streams": args.streams,
+                          "l2": "inputs larger than L2: %d distinct frame buffers = %.0f MB per GPU" % (B, B * npx * 3 / 1e6)},
+               "frames_per_sec": value * 1e6 / npx,
+               "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": n_host * npx * 3,
+                       "d2h_bytes_per_step": n_host * npx * 4, "frames": n_host, "threads": n_thr},
+               "gpu_launches": launches[0], "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+               "wall_s_timed": wall}
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=32, help="frames per GPU per step")
+    ap.add_argument("--distinct", type=int, default=4, help="distinct synthetic frames generated (cycled)")
+    ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--e2e-frames", type=int, default=8)
+    ap.add_argument("--e2e-reps", type=int, default=2)
+    ap.add_argument("--e2e-threads", type=int, default=4)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -85,6 +85,10 @@ int spx_slic_get_centres(spx_slic_t*, float* dst, int rows);
 int spx_slic_synchronize(spx_slic_t*);
 /* number of kernels this object has launched so far (bench.py's gpu_launches) */
 int spx_slic_launch_count(spx_slic_t*, long long* out);
+/* measurement hook (bench.py roofline): average device time in ms of ONE launch of the dominant kernel (the fused
+ * assignment + accumulation pass) over `reps` launches at the object's current state, timed with CUDA events on the
+ * object's stream; when flush_l2 != 0 a 256 MB buffer is overwritten before every launch.  State is left unchanged. */
+int spx_slic_time_assign(spx_slic_t*, int reps, int flush_l2, float* avg_ms);
 /* cv::Ptr<SuperpixelSLIC> release (the GUI overwrites `slic` on every COMPUTE, mainwindow.cpp:2105) */
 int spx_slic_destroy(spx_slic_t*);
 

@@ -1,0 +1,791 @@
+// slic.cu -- SuperpixelSLIC (SLIC / SLICO / MSLIC) engine and its C ABI.
+//
+// Replaces cv::ximgproc::createSuperpixelSLIC / iterate / enforceLabelConnectivity / getLabels /
+// getNumberOfSuperpixels / getLabelContourMask as called from mainwindow.cpp:2105-2111.
+//
+// Upstream's assignment is a cluster-ordered scatter ("for n in 0..K-1: for pixels in the window of
+// n: if d < dist ..."), i.e. for every pixel the arg-min over the clusters whose window contains it,
+// ties to the lowest n.  Here it is a gather: centres are binned by (int(kx)/S, int(ky)/S); a pixel
+// in bin (bx,by) only has to look at bins bx-r..bx+r x by-r..by+r (r = 1; 2 for MSLIC's enlarged
+// windows).  Same float32 operation order as upstream, no FMA contraction -> identical labels.
+//
+// This file holds the engine, the seeding / binning / centre-update kernels and the GENERIC
+// per-pixel assignment kernel (any channel count, any region size).  The tiled fast path for
+// 3-channel images lives in slic_tile.cu.
+#include "slic.cuh"
+#include <cfloat>
+#include <map>
+#include <vector>
+#include <cstdlib>
+
+namespace spx {
+
+// implemented in slic_tile.cu; returns false when the configuration is outside the fast path
+bool slic_tile_supported(const SlicGeom& g);
+int slic_tile_assign(const SlicGeom& g, const SlicArrays& a, const unsigned char* d_img, int* d_labels,
+                     const int* d_K, int parity, int* d_overflow, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int refl101(int p, int n)
+{
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) p = p < 0 ? -p : 2 * (n - 1) - p;
+    return p;
+}
+// DetectChEdges at one pixel: sum_c (I(x+1)-I(x-1))^2 + (I(y+1)-I(y-1))^2 (Sobel ksize=1, REFLECT_101).
+// All terms are integers < 2^24, so float32 evaluation order is irrelevant.
+__device__ float edge_mag(const unsigned char* __restrict__ img, size_t pitch, int w, int h, int C, int x, int y)
+{
+    int xm = refl101(x - 1, w), xp = refl101(x + 1, w), ym = refl101(y - 1, h), yp = refl101(y + 1, h);
+    int e = 0;
+    for (int c = 0; c < C; c++) {
+        int dx = (int)img[(size_t)y * pitch + (size_t)xp * C + c] - (int)img[(size_t)y * pitch + (size_t)xm * C + c];
+        int dy = (int)img[(size_t)yp * pitch + (size_t)x * C + c] - (int)img[(size_t)ym * pitch + (size_t)x * C + c];
+        e += dx * dx + dy * dy;
+    }
+    return (float)e;
+}
+
+struct SeedParams {
+    int hex;                 // 0: GetChSeedsS strip grid, 1: GetChSeedsK hexagonal grid
+    int xstrips, xerr_i, yerr_i;   // strip grid
+    int ne, no;              // hex grid: seeds per even / odd row
+};
+
+// GetChSeedsS / GetChSeedsK + PerturbSeeds, one thread per seed
+__global__ void slic_seed_kernel(SlicGeom g, SlicArrays a, const unsigned char* __restrict__ img, SeedParams sp)
+{
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= g.K) return;
+    const int S = g.S;
+    int X, Y;
+    if (!sp.hex) {
+        int gy = n / sp.xstrips, gx = n - gy * sp.xstrips;
+        X = gx * S + S / 2 + gx * sp.xerr_i;
+        Y = gy * S + S / 2 + gy * sp.yerr_i;
+        X = min(X, g.w - 1); Y = min(Y, g.h - 1);
+    } else {
+        int per2 = sp.ne + sp.no;
+        int pr = n / per2, rem = n - pr * per2;
+        int r = 2 * pr, gx = rem;
+        if (rem >= sp.ne) { r++; gx = rem - sp.ne; }
+        Y = r * S + S / 2;
+        X = gx * S + ((S / 2) << (r & 1));
+    }
+    // PerturbSeeds: strict-min edge magnitude over the 8 neighbours, move only if BOTH coordinates change
+    const int dx8[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
+    const int dy8[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+    int sx = X, sy = Y;
+    float best = edge_mag(img, g.ipitch, g.w, g.h, g.C, X, Y);
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) {
+        int nx = X + dx8[i], ny = Y + dy8[i];
+        if (nx >= 0 && nx < g.w && ny >= 0 && ny < g.h) {
+            float e = edge_mag(img, g.ipitch, g.w, g.h, g.C, nx, ny);
+            if (e < best) { best = e; sx = nx; sy = ny; }
+        }
+    }
+    if (sx != X && sy != Y) { X = sx; Y = sy; }
+    a.kx[n] = (float)X; a.ky[n] = (float)Y;
+    a.ikx[n] = X; a.iky[n] = Y; a.ioff[n] = S;
+    a.adaptk[n] = 1.0f;
+    for (int c = 0; c < g.C; c++) a.kc[(size_t)c * g.Kcap + n] = (float)img[(size_t)Y * g.ipitch + (size_t)X * g.C + c];
+}
+
+__device__ __forceinline__ void bin_insert(const SlicGeom& g, const SlicArrays& a, int* head, int n, int ix, int iy)
+{
+    int bx = min(max(ix, 0) / g.S, g.nbx - 1), by = min(max(iy, 0) / g.S, g.nby - 1);
+    a.next[n] = atomicExch(&head[by * g.nbx + bx], n);
+}
+__global__ void slic_bin_kernel(SlicGeom g, SlicArrays a, const int* __restrict__ d_K, int parity)
+{
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= *d_K) return;
+    bin_insert(g, a, a.head[parity], n, a.ikx[n], a.iky[n]);
+}
+__global__ void fill_i32_kernel(int* p, int v, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void slico_begin_kernel(SlicGeom g, SlicArrays a, float* __restrict__ dcplane, size_t nplane)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nplane) dcplane[i] = FLT_MAX;
+    if (i < (size_t)g.K) { a.maxc[i] = 10.0f * 10.0f; a.maxc_acc[i] = __float_as_uint(FLT_MIN); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GENERIC assignment + accumulation: one thread per pixel, walks the bin lists in global memory.
+// Exact for every configuration; used when the tiled kernel does not apply.
+// ------------------------------------------------------------------------------------------------
+template <int ALG>   // 100 SLIC, 101 SLICO, 102 MSLIC
+__global__ void __launch_bounds__(256) slic_assign_generic_kernel(SlicGeom g, SlicArrays a, const unsigned char* __restrict__ img,
+                                                                  int* __restrict__ labels, float* __restrict__ dcplane,
+                                                                  int parity, int tile_x0, int tile_y0, int tile_w, int tile_h)
+{
+    int x = tile_x0 + blockIdx.x * 32 + (threadIdx.x & 31);
+    int y = tile_y0 + blockIdx.y * 8 + (threadIdx.x >> 5);
+    bool inside = x < min(g.w, tile_x0 + tile_w) && y < min(g.h, tile_y0 + tile_h);
+    int label = -1;
+    int pix[SPX_MAXC] = {0, 0, 0, 0};
+    float lastdc = 0.f;
+    if (inside) {
+        const unsigned char* p = img + (size_t)y * g.ipitch + (size_t)x * g.C;
+        float fpix[SPX_MAXC];
+        for (int c = 0; c < g.C; c++) { pix[c] = p[c]; fpix[c] = (float)pix[c]; }
+        const float fx = (float)x, fy = (float)y;
+        const int* head = a.head[parity];
+        int bx = x / g.S, by = y / g.S;
+        float best = FLT_MAX;
+        int bestn = -1, lastn = -1;
+        for (int yy = max(by - g.radius, 0); yy <= min(by + g.radius, g.nby - 1); yy++)
+            for (int xx = max(bx - g.radius, 0); xx <= min(bx + g.radius, g.nbx - 1); xx++)
+                for (int n = head[yy * g.nbx + xx]; n >= 0; n = a.next[n]) {
+                    int off = a.ioff[n];
+                    int ix = a.ikx[n], iy = a.iky[n];
+                    if (x < ix - off || x >= ix + off || y < iy - off || y >= iy + off) continue;
+                    float dc = 0.f;
+                    for (int c = 0; c < g.C; c++) {
+                        float t = __fsub_rn(fpix[c], a.kc[(size_t)c * g.Kcap + n]);
+                        dc = __fadd_rn(dc, __fmul_rn(t, t));
+                    }
+                    float ex = __fsub_rn(fx, a.kx[n]), ey = __fsub_rn(fy, a.ky[n]);
+                    float dxy = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                    float d;
+                    if (ALG == 101) {
+                        d = __fadd_rn(__fdiv_rn(dc, a.maxc[n]), __fdiv_rn(dxy, g.xywt));
+                        if (n > lastn) { lastn = n; lastdc = dc; }
+                    } else {
+                        d = __fadd_rn(dc, __fdiv_rn(dxy, g.xywt));
+                        if (ALG == 102) d = __fdiv_rn(d, a.adaptk[n]);
+                    }
+                    if (d < best || (d == best && n < bestn)) { best = d; bestn = n; }
+                }
+        size_t li = (size_t)y * g.lp + x;
+        if (bestn >= 0) { labels[li] = bestn; label = bestn; }
+        else label = labels[li];                       // covered by no window: keeps its label
+        if (ALG == 101) {
+            size_t pi = (size_t)y * g.w + x;
+            if (lastn >= 0) dcplane[pi] = lastdc; else lastdc = dcplane[pi];
+        }
+    }
+    // warp-aggregated accumulation of (channels, x, y, count) and the SLICO maximum
+    int key = inside ? label : -1 - (int)(threadIdx.x & 31);
+    unsigned m = __match_any_sync(0xffffffffu, key);
+    bool leader = inside && (int)(threadIdx.x & 31) == __ffs(m) - 1;
+    for (int c = 0; c < g.C; c++) {
+        int s = __reduce_add_sync(m, pix[c]);
+        if (leader) atomicAdd(&a.acc[(size_t)c * g.Kcap + label], (unsigned long long)s);
+    }
+    int sx = __reduce_add_sync(m, inside ? x : 0), sy = __reduce_add_sync(m, inside ? y : 0);
+    if (leader) {
+        atomicAdd(&a.acc[(size_t)g.C * g.Kcap + label], (unsigned long long)sx);
+        atomicAdd(&a.acc[(size_t)(g.C + 1) * g.Kcap + label], (unsigned long long)sy);
+        atomicAdd(&a.acc[(size_t)(g.C + 2) * g.Kcap + label], (unsigned long long)__popc(m));
+    }
+    if (ALG == 101) {
+        unsigned mx = __reduce_max_sync(m, __float_as_uint(lastdc));   // dc >= 0: float order == uint order
+        if (leader) atomicMax(&a.maxc_acc[label], mx);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// centre update (SeedNormInvoker): mean = float(sum)/float(count), count<=0 -> 1; then re-bin.
+// ------------------------------------------------------------------------------------------------
+__global__ void slic_finalize_kernel(SlicGeom g, SlicArrays a, const int* __restrict__ d_K, int parity, int do_bin)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nb = g.nbx * g.nby;
+    if (t < nb) a.head[parity][t] = -1;              // the lists just consumed; reused two iterations later
+    const int K = *d_K;
+    if (t >= K) return;
+    unsigned long long cnt = a.acc[(size_t)(g.C + 2) * g.Kcap + t];
+    float m = (float)(cnt == 0 ? 1ull : cnt);
+    for (int c = 0; c < g.C; c++) {
+        a.kc[(size_t)c * g.Kcap + t] = __fdiv_rn((float)a.acc[(size_t)c * g.Kcap + t], m);
+        a.acc[(size_t)c * g.Kcap + t] = 0;
+    }
+    float kx = __fdiv_rn((float)a.acc[(size_t)g.C * g.Kcap + t], m);
+    float ky = __fdiv_rn((float)a.acc[(size_t)(g.C + 1) * g.Kcap + t], m);
+    a.acc[(size_t)g.C * g.Kcap + t] = 0;
+    a.acc[(size_t)(g.C + 1) * g.Kcap + t] = 0;
+    a.acc[(size_t)(g.C + 2) * g.Kcap + t] = 0;
+    a.kx[t] = kx; a.ky[t] = ky;
+    int ix = (int)kx, iy = (int)ky;
+    a.ikx[t] = ix; a.iky[t] = iy;
+    if (g.alg == 101) {                               // maxchans[k] <- accumulated maximum; seeds the next one
+        unsigned mb = a.maxc_acc[t];
+        a.maxc[t] = __uint_as_float(mb);
+    }
+    if (do_bin) bin_insert(g, a, a.head[parity ^ 1], t, ix, iy);
+}
+
+// ------------------------------------------------------------------------------------------------
+// MSLIC content-adaptive step (normative statement: DESIGN.md, "MSLIC restatement")
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tri_area5(const float* a, const float* b, const float* c)
+{
+    float uu = 0.f, vv = 0.f, uv = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        float u = __fsub_rn(b[i], a[i]), v = __fsub_rn(c[i], a[i]);
+        uu = __fadd_rn(uu, __fmul_rn(u, u));
+        vv = __fadd_rn(vv, __fmul_rn(v, v));
+        uv = __fadd_rn(uv, __fmul_rn(u, v));
+    }
+    float gg = __fsub_rn(__fmul_rn(uu, vv), __fmul_rn(uv, uv));
+    if (gg < 0.f) gg = 0.f;
+    return __fmul_rn(0.5f, __fsqrt_rn(gg));
+}
+__global__ void __launch_bounds__(256) mslic_area_kernel(SlicGeom g, SlicArrays a, const unsigned char* __restrict__ img,
+                                                          const int* __restrict__ labels, float q)
+{
+    int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    bool inside = x < g.w - 1 && y < g.h - 1;
+    long long fx = 0;
+    int label = -1;
+    if (inside) {
+        float P[4][5];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int xx = x + (j & 1), yy = y + (j >> 1);
+            P[j][0] = (float)xx; P[j][1] = (float)yy;
+            const unsigned char* p = img + (size_t)yy * g.ipitch + (size_t)xx * g.C;
+#pragma unroll
+            for (int c = 0; c < 3; c++) P[j][2 + c] = c < g.C ? __fmul_rn(q, (float)p[c]) : 0.f;
+        }
+        float ar = __fadd_rn(tri_area5(P[0], P[1], P[2]), tri_area5(P[3], P[1], P[2]));
+        fx = (long long)__fmul_rn(ar, 256.0f);
+        label = labels[(size_t)y * g.lp + x];
+    }
+    int key = inside ? label : -1 - (int)(threadIdx.x & 31);
+    unsigned m = __match_any_sync(0xffffffffu, key);
+    // 64-bit warp sum over the match group
+    long long s = 0;
+    for (unsigned rem = m; rem; rem &= rem - 1) s += __shfl_sync(m, fx, __ffs(rem) - 1);
+    if (inside && (int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd((unsigned long long*)&a.area[label], (unsigned long long)s);
+}
+// single CTA: mean area, adaptk, split list (ascending k), append new centres, window half-sizes
+__global__ void __launch_bounds__(1024) mslic_adapt_kernel(SlicGeom g, SlicArrays a, const unsigned char* __restrict__ img,
+                                                            int* __restrict__ d_K, int K0)
+{
+    __shared__ long long s_red[32];
+    __shared__ int s_scan[32];
+    __shared__ long long s_tot;
+    __shared__ int s_nsplit, s_carry;
+    const int K = *d_K;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    long long part = 0;
+    for (int k = tid; k < K; k += 1024) part += a.area[k];
+    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) s_red[wid] = part;
+    __syncthreads();
+    if (tid == 0) { long long t = 0; for (int i = 0; i < 32; i++) t += s_red[i]; s_tot = t; s_nsplit = 0; s_carry = 0; }
+    __syncthreads();
+    const float target = 2.0f, split = 4.0f;
+    const float abar = __fdiv_rn((float)s_tot, __fmul_rn((float)K, 256.0f));
+    int mysplits = 0;
+    for (int k = tid; k < K; k += 1024) {
+        float ak = __fdiv_rn((float)a.area[k], 256.0f);
+        float r = ak > 0.f ? __fsqrt_rn(__fdiv_rn(abar, ak)) : target;
+        r = fminf(fmaxf(r, __fdiv_rn(1.0f, target)), target);
+        a.adaptk[k] = r;
+        if (ak > __fmul_rn(split, abar)) mysplits++;
+    }
+    atomicAdd(&s_nsplit, mysplits);
+    __syncthreads();
+    const int nsplit = s_nsplit;
+    const bool do_split = nsplit > 0 && K + 3 * nsplit <= 4 * K0 && K + 3 * nsplit <= g.Kcap;
+    if (do_split) {
+        for (int base = 0; base < K; base += 1024) {
+            int k = base + tid;
+            int f = 0;
+            float ak = 0.f;
+            if (k < K) { ak = __fdiv_rn((float)a.area[k], 256.0f); f = ak > __fmul_rn(split, abar) ? 1 : 0; }
+            unsigned b = __ballot_sync(0xffffffffu, f);
+            int pre = __popc(b & ((1u << lane) - 1));
+            if (lane == 0) s_scan[wid] = __popc(b);
+            __syncthreads();
+            int off = s_carry;
+            for (int q2 = 0; q2 < wid; q2++) off += s_scan[q2];
+            if (f) {
+                int n = K + 3 * (off + pre);
+                float o = __fmul_rn(__fmul_rn(0.5f, (float)g.S), a.adaptk[k]);
+                float cx = a.kx[k], cy = a.ky[k];
+                const float ox[4] = {-o, o, -o, o}, oy[4] = {-o, -o, o, o};
+                for (int j = 0; j < 4; j++) {
+                    float nx = __fadd_rn(cx, ox[j]), ny = __fadd_rn(cy, oy[j]);
+                    nx = fminf(fmaxf(nx, 0.f), (float)(g.w - 1));
+                    ny = fminf(fmaxf(ny, 0.f), (float)(g.h - 1));
+                    int dst = j == 0 ? k : n++;
+                    a.kx[dst] = nx; a.ky[dst] = ny;
+                    a.ikx[dst] = (int)nx; a.iky[dst] = (int)ny;
+                    for (int c = 0; c < g.C; c++)
+                        a.kc[(size_t)c * g.Kcap + dst] = (float)img[(size_t)(int)ny * g.ipitch + (size_t)(int)nx * g.C + c];
+                    a.adaptk[dst] = a.adaptk[k];
+                }
+            }
+            __syncthreads();
+            if (tid == 0) { int t = 0; for (int i = 0; i < 32; i++) t += s_scan[i]; s_carry += t; }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    const int newK = do_split ? K + 3 * nsplit : K;
+    for (int k = tid; k < newK; k += 1024) {
+        a.ioff[k] = (int)__fmul_rn((float)g.S, a.adaptk[k]);
+        a.area[k] = 0;
+    }
+    if (tid == 0) *d_K = newK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// engine
+// ------------------------------------------------------------------------------------------------
+struct SlicEngine {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    bool own_stream = false;
+    SlicGeom g{};
+    SlicArrays a{};
+    float ruler = 10.f;
+    unsigned char* d_img = nullptr;
+    int* d_labels = nullptr;
+    float* d_dcplane = nullptr;      // SLICO only
+    unsigned char* d_mask = nullptr;
+    int* d_K = nullptr;
+    int* d_overflow = nullptr;
+    int* h_pinned = nullptr;         // [4]
+    int K0 = 0;
+    int numlabels = 0;
+    int parity = 0;
+    bool use_tile = false;
+    bool use_graph = true;
+    long long launches = 0;
+    PostWorkspace post;
+    std::map<long long, cudaGraphExec_t> graphs;
+    std::vector<void*> allocs;
+
+    template <typename T> int dalloc(T** p, size_t n)
+    {
+        SPX_CUDA(cudaMalloc((void**)p, n * sizeof(T) > 0 ? n * sizeof(T) : 4));
+        allocs.push_back((void*)*p);
+        return SPX_OK;
+    }
+    ~SlicEngine()
+    {
+        cudaSetDevice(device);
+        if (st) cudaStreamSynchronize(st);
+        for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+        for (void* p : allocs) cudaFree(p);
+        post.release();
+        if (h_pinned) cudaFreeHost(h_pinned);
+        if (own_stream && st) cudaStreamDestroy(st);
+    }
+
+    SeedParams seed_params(int* K_out) const
+    {
+        SeedParams sp{};
+        const int S = g.S, w = g.w, h = g.h;
+        if (g.alg == SPX_SLICO) {
+            sp.hex = 1;
+            int rows = 0;
+            while (rows * S + S / 2 <= h - 1) rows++;
+            auto cnt = [&](int off) { int c = 0; while (c * S + off <= w - 1) c++; return c; };
+            sp.ne = cnt(S / 2);
+            sp.no = cnt((S / 2) << 1);
+            *K_out = (rows / 2) * (sp.ne + sp.no) + (rows & 1) * sp.ne;
+        } else {
+            int xstrips = (int)(0.5f + (float)w / (float)S);
+            int ystrips = (int)(0.5f + (float)h / (float)S);
+            if (xstrips < 1 || ystrips < 1) { *K_out = 0; return sp; }
+            float xe = (float)(w - S * xstrips) / (float)xstrips;
+            float ye = (float)(h - S * ystrips) / (float)ystrips;
+            sp.xstrips = xstrips; sp.xerr_i = (int)xe; sp.yerr_i = (int)ye;
+            *K_out = xstrips * ystrips;
+        }
+        return sp;
+    }
+
+    int init(int w, int h, int C, int alg, int S, float ruler_)
+    {
+        SPX_REQUIRE(w > 0 && h > 0 && (long long)w * h < (1ll << 31), SPX_ERR_BADARG, "createSuperpixelSLIC: bad image size %dx%d", w, h);
+        SPX_REQUIRE(C >= 1 && C <= SPX_MAXC, SPX_ERR_BADARG, "createSuperpixelSLIC: 1..4 channels supported, got %d", C);
+        SPX_REQUIRE(alg == SPX_SLIC || alg == SPX_SLICO || alg == SPX_MSLIC, SPX_ERR_INTERNAL, "No such algorithm");
+        SPX_REQUIRE(S >= 1, SPX_ERR_BADARG, "createSuperpixelSLIC: region_size must be >= 1");
+        SPX_REQUIRE(ruler_ > 0.f || alg == SPX_SLICO, SPX_ERR_BADARG, "createSuperpixelSLIC: ruler must be > 0");
+        ruler = ruler_;
+        g.w = w; g.h = h; g.C = C; g.S = S; g.alg = alg;
+        g.ipitch = round_up((size_t)w * C, 16) + 16;
+        g.lp = (int)round_up((size_t)w, 4);
+        g.nbx = cdiv(w, S); g.nby = cdiv(h, S);
+        g.radius = alg == SPX_MSLIC ? 2 : 1;
+        if (alg == SPX_SLICO) g.xywt = (float)(S * S);
+        else { float q = (float)S / ruler; g.xywt = q * q; }
+        int K = 0;
+        seed_params(&K);
+        SPX_REQUIRE(K >= 1, SPX_ERR_BADARG, "createSuperpixelSLIC: region_size %d leaves no seed in a %dx%d image", S, w, h);
+        g.K = K; K0 = K;
+        g.Kcap = alg == SPX_MSLIC ? 4 * K : K;
+        const size_t kc = (size_t)g.Kcap;
+        SPX_CHECK(dalloc(&d_img, g.ipitch * (size_t)(h + 1)));
+        SPX_CHECK(dalloc(&d_labels, (size_t)g.lp * h));
+        SPX_CHECK(dalloc(&d_mask, (size_t)w * h));
+        SPX_CHECK(dalloc(&a.kx, kc)); SPX_CHECK(dalloc(&a.ky, kc)); SPX_CHECK(dalloc(&a.kc, kc * C));
+        SPX_CHECK(dalloc(&a.ikx, kc)); SPX_CHECK(dalloc(&a.iky, kc)); SPX_CHECK(dalloc(&a.ioff, kc));
+        SPX_CHECK(dalloc(&a.adaptk, kc));
+        SPX_CHECK(dalloc(&a.maxc, kc)); SPX_CHECK(dalloc(&a.maxxy, kc));
+        SPX_CHECK(dalloc(&a.maxc_acc, kc)); SPX_CHECK(dalloc(&a.maxxy_acc, kc));
+        SPX_CHECK(dalloc(&a.acc, kc * (C + 3)));
+        SPX_CHECK(dalloc(&a.next, kc));
+        SPX_CHECK(dalloc(&a.head[0], (size_t)g.nbx * g.nby)); SPX_CHECK(dalloc(&a.head[1], (size_t)g.nbx * g.nby));
+        SPX_CHECK(dalloc(&a.area, kc));
+        SPX_CHECK(dalloc(&d_K, 4)); SPX_CHECK(dalloc(&d_overflow, 4));
+        if (alg == SPX_SLICO) SPX_CHECK(dalloc(&d_dcplane, (size_t)w * h));
+        SPX_CUDA(cudaMallocHost(&h_pinned, 4 * sizeof(int)));
+        SPX_CUDA(cudaMemsetAsync(d_img, 0, g.ipitch * (size_t)(h + 1), st));
+        use_tile = slic_tile_supported(g) && !getenv("SPX_SLIC_GENERIC");
+        use_graph = !getenv("SPX_NO_GRAPH");
+        return SPX_OK;
+    }
+
+    // the part of the constructor that depends on the pixels: seeds, perturbation, first binning
+    int seed()
+    {
+        const size_t kc = (size_t)g.Kcap;
+        g.K = K0; numlabels = K0; parity = 0;
+        SPX_CUDA(cudaMemsetAsync(d_labels, 0, (size_t)g.lp * g.h * sizeof(int), st));
+        SPX_CUDA(cudaMemsetAsync(a.acc, 0, kc * (g.C + 3) * sizeof(unsigned long long), st));
+        SPX_CUDA(cudaMemsetAsync(a.area, 0, kc * sizeof(long long), st));
+        SPX_CUDA(cudaMemsetAsync(a.head[0], 0xFF, (size_t)g.nbx * g.nby * sizeof(int), st));
+        SPX_CUDA(cudaMemsetAsync(a.head[1], 0xFF, (size_t)g.nbx * g.nby * sizeof(int), st));
+        SPX_CUDA(cudaMemsetAsync(d_overflow, 0, 4 * sizeof(int), st));
+        h_pinned[0] = K0;
+        SPX_CUDA(cudaMemcpyAsync(d_K, h_pinned, sizeof(int), cudaMemcpyHostToDevice, st));
+        int K = 0;
+        SeedParams sp = seed_params(&K);
+        slic_seed_kernel<<<cdiv(K0, 128), 128, 0, st>>>(g, a, d_img, sp);
+        slic_bin_kernel<<<cdiv(K0, 128), 128, 0, st>>>(g, a, d_K, 0);
+        launches += 2;
+        SPX_CUDA(cudaGetLastError());
+        return SPX_OK;
+    }
+
+    int upload(const uint8_t* img, size_t stride, bool from_device)
+    {
+        SPX_REQUIRE(img && stride >= (size_t)g.w * g.C, SPX_ERR_BADARG, "createSuperpixelSLIC: bad image pointer/stride");
+        SPX_CUDA(cudaMemcpy2DAsync(d_img, g.ipitch, img, stride, (size_t)g.w * g.C, g.h,
+                                   from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        return SPX_OK;
+    }
+
+    int enqueue_iterations(int n)
+    {
+        const int threads_fin = max(g.Kcap, g.nbx * g.nby);
+        if (g.alg == SPX_SLICO) {
+            size_t np = (size_t)g.w * g.h;
+            slico_begin_kernel<<<(unsigned)((max(np, (size_t)g.K) + 255) / 256), 256, 0, st>>>(g, a, d_dcplane, np);
+            launches++;
+        }
+        for (int it = 0; it < n; it++) {
+            bool tiled = false;
+            if (use_tile) {
+                SPX_CHECK(slic_tile_assign(g, a, d_img, d_labels, d_K, parity, d_overflow, st));
+                tiled = true;
+                launches++;
+            }
+            if (!tiled) {
+                dim3 grid(cdiv(g.w, 32), cdiv(g.h, 8));
+                if (g.alg == SPX_SLIC) slic_assign_generic_kernel<100><<<grid, 256, 0, st>>>(g, a, d_img, d_labels, d_dcplane, parity, 0, 0, g.w, g.h);
+                else if (g.alg == SPX_SLICO) slic_assign_generic_kernel<101><<<grid, 256, 0, st>>>(g, a, d_img, d_labels, d_dcplane, parity, 0, 0, g.w, g.h);
+                else slic_assign_generic_kernel<102><<<grid, 256, 0, st>>>(g, a, d_img, d_labels, d_dcplane, parity, 0, 0, g.w, g.h);
+                launches++;
+            }
+            const int do_bin = g.alg == SPX_MSLIC ? 0 : 1;
+            slic_finalize_kernel<<<cdiv(threads_fin, 256), 256, 0, st>>>(g, a, d_K, parity, do_bin);
+            launches++;
+            if (g.alg == SPX_MSLIC) {
+                float q = (float)g.S / ruler;
+                mslic_area_kernel<<<dim3(cdiv(g.w, 32), cdiv(g.h, 8)), 256, 0, st>>>(g, a, d_img, d_labels, q);
+                mslic_adapt_kernel<<<1, 1024, 0, st>>>(g, a, d_img, d_K, K0);
+                slic_bin_kernel<<<cdiv(g.Kcap, 128), 128, 0, st>>>(g, a, d_K, parity ^ 1);
+                launches += 3;
+            }
+            parity ^= 1;
+        }
+        SPX_CUDA(cudaGetLastError());
+        return SPX_OK;
+    }
+
+    int enqueue_assign()
+    {
+        if (use_tile) return slic_tile_assign(g, a, d_img, d_labels, d_K, parity, d_overflow, st);
+        dim3 grid(cdiv(g.w, 32), cdiv(g.h, 8));
+        if (g.alg == SPX_SLIC) slic_assign_generic_kernel<100><<<grid, 256, 0, st>>>(g, a, d_img, d_labels, d_dcplane, parity, 0, 0, g.w, g.h);
+        else if (g.alg == SPX_SLICO) slic_assign_generic_kernel<101><<<grid, 256, 0, st>>>(g, a, d_img, d_labels, d_dcplane, parity, 0, 0, g.w, g.h);
+        else slic_assign_generic_kernel<102><<<grid, 256, 0, st>>>(g, a, d_img, d_labels, d_dcplane, parity, 0, 0, g.w, g.h);
+        SPX_CUDA(cudaGetLastError());
+        return SPX_OK;
+    }
+    int time_assign(int reps, int flush, float* avg_ms)
+    {
+        void* fl = nullptr;
+        const size_t flbytes = 256u << 20;
+        if (flush) SPX_CUDA(cudaMalloc(&fl, flbytes));
+        cudaEvent_t e0, e1;
+        SPX_CUDA(cudaEventCreate(&e0)); SPX_CUDA(cudaEventCreate(&e1));
+        double tot = 0;
+        int rc = SPX_OK;
+        for (int r = 0; r < reps + 1 && rc == SPX_OK; r++) {      // launch 0 is a warm-up
+            if (fl) cudaMemsetAsync(fl, r, flbytes, st);
+            cudaEventRecord(e0, st);
+            rc = enqueue_assign();
+            cudaEventRecord(e1, st);
+            if (cudaEventSynchronize(e1) != cudaSuccess) { set_error("time_assign: kernel failed"); rc = SPX_ERR_GPU; }
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (r > 0) tot += ms;
+            launches++;
+        }
+        // the accumulators were fed `reps+1` times: clear them (centres / labels are unchanged)
+        cudaMemsetAsync(a.acc, 0, (size_t)g.Kcap * (g.C + 3) * sizeof(unsigned long long), st);
+        cudaStreamSynchronize(st);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (fl) cudaFree(fl);
+        *avg_ms = (float)(tot / (reps > 0 ? reps : 1));
+        return rc;
+    }
+
+    int iterate(int n)
+    {
+        SPX_REQUIRE(n >= 0, SPX_ERR_BADARG, "iterate: num_iterations must be >= 0");
+        if (n == 0) return SPX_OK;
+        if (!use_graph) { SPX_CHECK(enqueue_iterations(n)); }
+        else {
+            long long key = ((long long)n << 1) | parity;
+            auto it = graphs.find(key);
+            if (it == graphs.end()) {
+                cudaGraph_t graph = nullptr;
+                long long l0 = launches;
+                int p0 = parity;
+                SPX_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                int rc = enqueue_iterations(n);
+                cudaError_t e = cudaStreamEndCapture(st, &graph);
+                if (rc != SPX_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+                SPX_CUDA(e);
+                cudaGraphExec_t exec = nullptr;
+                SPX_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+                cudaGraphDestroy(graph);
+                graphs[key] = exec;
+                graph_launches[key] = launches - l0;
+                launches = l0; parity = p0;
+                it = graphs.find(key);
+            }
+            SPX_CUDA(cudaGraphLaunch(it->second, st));
+            launches += graph_launches[key];
+            parity ^= (n & 1);
+        }
+        if (g.alg == SPX_MSLIC) {
+            SPX_CUDA(cudaMemcpyAsync(h_pinned, d_K, sizeof(int), cudaMemcpyDeviceToHost, st));
+            SPX_CUDA(cudaStreamSynchronize(st));
+            g.K = h_pinned[0];
+        }
+        numlabels = g.K;
+        return SPX_OK;
+    }
+    std::map<long long, long long> graph_launches;
+
+    int ensure_post()
+    {
+        return post.alloc(g.w, g.h);
+    }
+    int enforce(int min_element_size)
+    {
+        SPX_CHECK(ensure_post());
+        long long l0 = post.launches;
+        int k = numlabels;
+        SPX_CHECK(enforce_connectivity_dev(post, d_labels, g.lp, numlabels, min_element_size, st, &k));
+        launches += post.launches - l0;
+        numlabels = k;
+        return SPX_OK;
+    }
+    int contour(unsigned char* d_dst, size_t pitch, int thick_line)
+    {
+        SPX_CHECK(ensure_post());
+        long long l0 = post.launches;
+        SPX_CHECK(contour_mask_dev(post, d_labels, g.lp, thick_line, 0, d_dst, pitch, st));
+        launches += post.launches - l0;
+        return SPX_OK;
+    }
+};
+
+static int make_engine(int w, int h, int C, int alg, int S, float ruler, cudaStream_t user_stream, SlicEngine** out)
+{
+    SlicEngine* e = new SlicEngine();
+    cudaGetDevice(&e->device);
+    if (user_stream) { e->st = user_stream; e->own_stream = false; }
+    else {
+        cudaError_t ce = cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking);
+        if (ce != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(ce)); delete e; return SPX_ERR_GPU; }
+        e->own_stream = true;
+    }
+    int rc = e->init(w, h, C, alg, S, ruler);
+    if (rc != SPX_OK) { delete e; return rc; }
+    *out = e;
+    return SPX_OK;
+}
+
+}  // namespace spx
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+using spx::SlicEngine;
+struct spx_slic { SlicEngine* e; };
+
+#define SLIC_ENTER(h)                                                                     \
+    SPX_REQUIRE((h) && (h)->e, SPX_ERR_BADARG, "NULL SuperpixelSLIC handle");             \
+    SlicEngine* e = (h)->e;                                                               \
+    SPX_CUDA(cudaSetDevice(e->device))
+
+static int slic_create_common(const void* image, size_t stride, int w, int h, int C, int alg, int S, float ruler,
+                              cudaStream_t stream, bool from_device, spx_slic_t** out)
+{
+    using namespace spx;
+    SPX_REQUIRE(out, SPX_ERR_BADARG, "createSuperpixelSLIC: out is NULL");
+    *out = nullptr;
+    SPX_REQUIRE(image, SPX_ERR_BADARG, "createSuperpixelSLIC: image is NULL");
+    SlicEngine* e = nullptr;
+    SPX_CHECK(make_engine(w, h, C, alg, S, ruler, stream, &e));
+    int rc = e->upload((const uint8_t*)image, stride, from_device);
+    if (rc == SPX_OK) rc = e->seed();
+    if (rc != SPX_OK) { delete e; return rc; }
+    *out = new spx_slic{e};
+    return SPX_OK;
+}
+
+extern "C" int spx_slic_create(const uint8_t* image, size_t stride, int w, int h, int C, int alg, int S, float ruler,
+                               int device, spx_slic_t** out)
+{
+    SPX_CHECK(spx::require_device(device));
+    return slic_create_common(image, stride, w, h, C, alg, S, ruler, nullptr, false, out);
+}
+extern "C" int spx_slic_create_dev(const void* d_image, size_t stride, int w, int h, int C, int alg, int S, float ruler,
+                                   void* stream, spx_slic_t** out)
+{
+    int dev = 0;
+    SPX_CUDA(cudaGetDevice(&dev));
+    SPX_CHECK(spx::require_device(dev));
+    return slic_create_common(d_image, stride, w, h, C, alg, S, ruler, (cudaStream_t)stream, true, out);
+}
+extern "C" int spx_slic_reset(spx_slic_t* h, const uint8_t* image, size_t stride)
+{
+    SLIC_ENTER(h);
+    SPX_CHECK(e->upload(image, stride, false));
+    return e->seed();
+}
+extern "C" int spx_slic_reset_dev(spx_slic_t* h, const void* d_image, size_t stride)
+{
+    SLIC_ENTER(h);
+    SPX_CHECK(e->upload((const uint8_t*)d_image, stride, true));
+    return e->seed();
+}
+extern "C" int spx_slic_iterate(spx_slic_t* h, int n)
+{
+    SLIC_ENTER(h);
+    return e->iterate(n);
+}
+extern "C" int spx_slic_enforce_label_connectivity(spx_slic_t* h, int min_element_size)
+{
+    SLIC_ENTER(h);
+    return e->enforce(min_element_size);
+}
+extern "C" int spx_slic_get_number_of_superpixels(spx_slic_t* h, int* out)
+{
+    SLIC_ENTER(h);
+    SPX_REQUIRE(out, SPX_ERR_BADARG, "getNumberOfSuperpixels: out is NULL");
+    SPX_CUDA(cudaStreamSynchronize(e->st));
+    *out = e->numlabels;
+    return SPX_OK;
+}
+extern "C" int spx_slic_get_labels(spx_slic_t* h, int32_t* dst, size_t dst_stride)
+{
+    SLIC_ENTER(h);
+    SPX_REQUIRE(dst && dst_stride >= (size_t)e->g.w * 4, SPX_ERR_BADARG, "getLabels: bad destination");
+    SPX_CUDA(cudaMemcpy2DAsync(dst, dst_stride, e->d_labels, (size_t)e->g.lp * 4, (size_t)e->g.w * 4, e->g.h, cudaMemcpyDeviceToHost, e->st));
+    SPX_CUDA(cudaStreamSynchronize(e->st));
+    return SPX_OK;
+}
+extern "C" int spx_slic_get_labels_dev(spx_slic_t* h, void* d_dst, size_t dst_stride)
+{
+    SLIC_ENTER(h);
+    SPX_REQUIRE(d_dst && dst_stride >= (size_t)e->g.w * 4, SPX_ERR_BADARG, "getLabels: bad destination");
+    SPX_CUDA(cudaMemcpy2DAsync(d_dst, dst_stride, e->d_labels, (size_t)e->g.lp * 4, (size_t)e->g.w * 4, e->g.h, cudaMemcpyDeviceToDevice, e->st));
+    return SPX_OK;
+}
+extern "C" int spx_slic_get_label_contour_mask(spx_slic_t* h, uint8_t* dst, size_t dst_stride, int thick_line)
+{
+    SLIC_ENTER(h);
+    SPX_REQUIRE(dst && dst_stride >= (size_t)e->g.w, SPX_ERR_BADARG, "getLabelContourMask: bad destination");
+    SPX_CHECK(e->contour(e->d_mask, e->g.w, thick_line));
+    SPX_CUDA(cudaMemcpy2DAsync(dst, dst_stride, e->d_mask, e->g.w, e->g.w, e->g.h, cudaMemcpyDeviceToHost, e->st));
+    SPX_CUDA(cudaStreamSynchronize(e->st));
+    return SPX_OK;
+}
+extern "C" int spx_slic_get_label_contour_mask_dev(spx_slic_t* h, void* d_dst, size_t dst_stride, int thick_line)
+{
+    SLIC_ENTER(h);
+    SPX_REQUIRE(d_dst && dst_stride >= (size_t)e->g.w, SPX_ERR_BADARG, "getLabelContourMask: bad destination");
+    return e->contour((unsigned char*)d_dst, dst_stride, thick_line);
+}
+extern "C" int spx_slic_set_labels(spx_slic_t* h, const int32_t* src, size_t src_stride, int numlabels)
+{
+    SLIC_ENTER(h);
+    SPX_REQUIRE(src && src_stride >= (size_t)e->g.w * 4, SPX_ERR_BADARG, "setLabels: bad source");
+    SPX_CUDA(cudaMemcpy2DAsync(e->d_labels, (size_t)e->g.lp * 4, src, src_stride, (size_t)e->g.w * 4, e->g.h, cudaMemcpyHostToDevice, e->st));
+    SPX_CUDA(cudaStreamSynchronize(e->st));
+    if (numlabels > 0) e->numlabels = numlabels;
+    return SPX_OK;
+}
+extern "C" int spx_slic_get_centres(spx_slic_t* h, float* dst, int rows)
+{
+    SLIC_ENTER(h);
+    const int K = e->g.K, C = e->g.C, Kcap = e->g.Kcap;
+    SPX_REQUIRE(dst && rows >= K, SPX_ERR_BADARG, "getCentres: need room for %d rows", K);
+    std::vector<float> tmp((size_t)Kcap * (C + 2));
+    SPX_CUDA(cudaStreamSynchronize(e->st));
+    SPX_CUDA(cudaMemcpy(tmp.data(), e->a.kc, sizeof(float) * (size_t)Kcap * C, cudaMemcpyDeviceToHost));
+    SPX_CUDA(cudaMemcpy(tmp.data() + (size_t)Kcap * C, e->a.kx, sizeof(float) * Kcap, cudaMemcpyDeviceToHost));
+    SPX_CUDA(cudaMemcpy(tmp.data() + (size_t)Kcap * (C + 1), e->a.ky, sizeof(float) * Kcap, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < K; k++)
+        for (int f = 0; f < C + 2; f++) dst[(size_t)k * (C + 2) + f] = tmp[(size_t)f * Kcap + k];
+    return SPX_OK;
+}
+extern "C" int spx_slic_synchronize(spx_slic_t* h)
+{
+    SLIC_ENTER(h);
+    SPX_CUDA(cudaStreamSynchronize(e->st));
+    return SPX_OK;
+}
+extern "C" int spx_slic_launch_count(spx_slic_t* h, long long* out)
+{
+    SPX_REQUIRE(h && h->e && out, SPX_ERR_BADARG, "launch_count: bad argument");
+    *out = h->e->launches;
+    return SPX_OK;
+}
+extern "C" int spx_slic_time_assign(spx_slic_t* h, int reps, int flush_l2, float* avg_ms)
+{
+    SLIC_ENTER(h);
+    SPX_REQUIRE(avg_ms && reps >= 1, SPX_ERR_BADARG, "time_assign: bad argument");
+    return e->time_assign(reps, flush_l2, avg_ms);
+}
+extern "C" int spx_slic_destroy(spx_slic_t* h)
+{
+    if (!h) return SPX_OK;
+    delete h->e;
+    delete h;
+    return SPX_OK;
+}

@@ -1,0 +1,52 @@
+"""CPU-only: the C-ABI library loads, exports every symbol include/spx_b200.h declares, and fails loudly
+(no CPU fallback) when no CUDA device is present."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "spx_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(spx_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_exported(spx):
+    L = spx.lib()
+    names = _declared()
+    assert len(names) >= 40
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_version_and_error_string(spx):
+    L = spx.lib()
+    assert L.spx_version() >= 100
+    assert isinstance(L.spx_last_error(), bytes)
+
+
+def test_no_cpu_fallback_without_gpu(spx):
+    if spx.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    img = np.zeros((32, 32, 3), np.uint8)
+    with pytest.raises(spx.SpxError) as ei:
+        spx.cvtColor(img, spx.COLOR_BGR2Lab)
+    assert ei.value.code == -217
+    with pytest.raises(spx.SpxError):
+        spx.createSuperpixelSLIC(img, spx.SLIC, 8, 10.0)
+    with pytest.raises(spx.SpxError):
+        spx.label_contour_mask(np.zeros((8, 8), np.int32))
+
+
+def test_product_does_not_reference_oracle():
+    pkg = os.path.join(ROOT, "superpixels-segmentation-gui-opencv_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".inc")):
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                assert "spx_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f

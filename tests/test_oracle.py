@@ -1,0 +1,97 @@
+"""CPU-only: pins the oracle against the reference's own artefacts."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+
+def test_lab_hsv_match_cv2_sampled(O):
+    """full 2^24 exhaustive check runs in tools/gen_color_tables.py; here every 5th level per channel + noise"""
+    import cv2
+    v = np.arange(0, 256, 5, dtype=np.uint8)
+    b, g, r = np.meshgrid(v, v, v, indexing="ij")
+    img = np.stack([b, g, r], -1).reshape(52, -1, 3)
+    rng = np.random.default_rng(1)
+    img = np.concatenate([img, rng.integers(0, 256, (52, 4096, 3), dtype=np.uint8)], 1)
+    img = np.ascontiguousarray(img)
+    assert (O.bgr2lab8(img) == cv2.cvtColor(img, cv2.COLOR_BGR2Lab)).all()
+    assert (O.bgr2hsv8(img) == cv2.cvtColor(img, cv2.COLOR_BGR2HSV)).all()
+
+
+def test_color_tables_identical_for_oracle_and_product():
+    root = os.path.dirname(GOLDEN)
+    root = os.path.dirname(root)
+    a = open(os.path.join(root, "oracle", "spx_color_tables.h")).read().split("#define", 1)[1].split("\n", 1)[1]
+    b = open(os.path.join(root, "superpixels-segmentation-gui-opencv_b200", "csrc", "color_tables.inc")).read().split("#define", 1)[1].split("\n", 1)[1]
+    assert a == b
+
+
+def test_slic_fixture_known_answer(O, example_bgr, example_lab):
+    """example/*-grid.png = getLabelContourMask(SLIC S=16 ruler=30 10 it, connectivity 25, thick_line=false)
+    plus hand-drawn outlines inside x[400,1100) y[200,1000)  (SURVEY.md section 4, Appendix D)."""
+    import cv2
+    grid = cv2.imread(os.path.join(GOLDEN, "logo-absurdephoton-segmentation-grid.png"))
+    mask = cv2.imread(os.path.join(GOLDEN, "logo-absurdephoton-segmentation-mask.png"))
+    s = O.SuperpixelSLIC(example_lab, O.SLIC, 16, 30.0)
+    assert s.getNumberOfSuperpixels() == 8836
+    s.iterate(10)
+    s.enforceLabelConnectivity(25)
+    assert s.getNumberOfSuperpixels() == 8924
+    m = s.getLabelContourMask(False)
+    d = (m != 0) != (grid != 0).any(-1)
+    assert int(d.sum()) == 6308
+    box = np.zeros_like(d); box[200:1000, 400:1100] = True
+    assert int((d & ~box).sum()) == 0
+    L = s.getLabels()
+    code = (mask[..., 0].astype(np.int64) << 16) | (mask[..., 1].astype(np.int64) << 8) | mask[..., 2]
+    uc, inv = np.unique(code, return_inverse=True)
+    hist = np.zeros((L.max() + 1, len(uc)), np.int64)
+    np.add.at(hist, (L.ravel(), inv.ravel()), 1)
+    assert int((hist.sum(1) - hist.max(1)).sum()) == 6202
+
+
+def test_slic_cfg1_counts(O, example_lab):
+    """BASELINE.json configs[0]: SLIC S=20 ruler=10 10 it + connectivity on the example image"""
+    s = O.SuperpixelSLIC(example_lab, O.SLIC, 20, 10.0)
+    assert s.getNumberOfSuperpixels() == 5625
+    s.iterate(10)
+    s.enforceLabelConnectivity(25)
+    assert s.getNumberOfSuperpixels() == 5529
+
+
+def test_threads_do_not_change_results(O, example_lab):
+    sub = np.ascontiguousarray(example_lab[300:700, 400:900])
+    O.set_threads(1)
+    a = O.SuperpixelSLIC(sub, O.SLIC, 12, 15.0); a.iterate(5)
+    O.set_threads(4)
+    b = O.SuperpixelSLIC(sub, O.SLIC, 12, 15.0); b.iterate(5)
+    assert (a.getLabels() == b.getLabels()).all()
+    assert (a.getCentres() == b.getCentres()).all()
+
+
+def test_connectivity_properties(O):
+    from conftest import random_label_map
+    rng = np.random.default_rng(3)
+    lab = random_label_map(rng, 97, 131)
+    out, k = O.enforce_label_connectivity(lab, int(lab.max()) + 1, 25)
+    assert out.min() == 0 and out.max() == k - 1
+    # every label is one 4-connected component
+    import cv2
+    for l in range(k):
+        n, _ = cv2.connectedComponents((out == l).astype(np.uint8), connectivity=4)
+        assert n == 2
+
+
+def test_contour_flavours(O):
+    from conftest import random_label_map
+    lab = random_label_map(np.random.default_rng(5), 64, 80)
+    for thick in (False, True):
+        m = O.label_contour_mask(lab, thick)
+        assert set(np.unique(m)) <= {0, 255}
+    thin = O.label_contour_mask(lab, False)
+    thick = O.label_contour_mask(lab, True)
+    assert thick.sum() <= thin.sum()          # threshold 2 marks fewer pixels than threshold 1
+    # SEEDS flavour with thick_line=false is the same recurrence as SLIC's threshold 1
+    assert (O.label_contour_mask(lab, False, seeds_flavour=True) == thin).all()
