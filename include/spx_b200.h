@@ -111,6 +111,10 @@ int spx_enforce_label_connectivity(int32_t* labels, size_t stride, int width, in
 int spx_label_contour_mask(const int32_t* labels, size_t stride, int width, int height, int thick_line,
                            int flavour, uint8_t* dst, size_t dst_stride, int device);
 
+/* test hook: the tiled SLIC kernel replaces the IEEE division by the constant xywt=(S/ruler)^2 with a correctly rounded
+ * multiply/FMA sequence; this counts inputs (out of n pseudo-random ones) where it differs from the division. */
+int spx_selftest_division(float w, int n, int device, int* mismatches);
+
 /* ---- cv::ximgproc::SuperpixelLSC (mainwindow.h:171, mainwindow.cpp:2114-2120) ---- */
 typedef struct spx_lsc spx_lsc_t;
 int spx_lsc_create(const uint8_t* image, size_t stride, int width, int height, int channels,

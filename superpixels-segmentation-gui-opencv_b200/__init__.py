@@ -76,6 +76,7 @@ def lib():
         "spx_slic_batch_dev": [pp, i32, i32, i32, i32, i32, i32, f32, i32, i32, pp, pp, i32, i32, C.POINTER(C.c_longlong)],
         "spx_enforce_label_connectivity": [vp, sz, i32, i32, i32, i32, i32, pi],
         "spx_label_contour_mask": [vp, sz, i32, i32, i32, i32, vp, sz, i32],
+        "spx_selftest_division": [f32, i32, i32, pi],
         "spx_lsc_create": [vp, sz, i32, i32, i32, i32, f32, i32, pp],
         "spx_lsc_iterate": [vp, i32],
         "spx_lsc_enforce_label_connectivity": [vp, i32],
@@ -157,6 +158,13 @@ def label_contour_mask(labels, thick_line=True, seeds_flavour=False, device=0):
     out = np.empty((h, w), np.uint8)
     _ck(lib().spx_label_contour_mask(_p(lab), w * 4, w, h, int(bool(thick_line)), int(bool(seeds_flavour)), _p(out), w, device))
     return out
+
+
+def selftest_division(w, n=1 << 22, device=0):
+    """test hook: mismatches of the kernel's constant-divisor sequence against the IEEE division"""
+    bad = C.c_int(0)
+    _ck(lib().spx_selftest_division(float(w), int(n), device, C.byref(bad)))
+    return bad.value
 
 
 class _Superpixel:

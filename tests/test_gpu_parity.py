@@ -179,6 +179,22 @@ def test_slic_properties_4k(spx, synthmod):
     assert abs(br - 0.9982) < 1e-3 and abs(ue - 0.01543) < 1e-3, (br, ue)
 
 
+@pytest.mark.parametrize("S,ruler", [(16, 30.0), (20, 10.0), (25, 7.0), (30, 30.0), (17, 3.0), (200, 1.0), (14, 100.0)])
+def test_constant_division_is_ieee_exact(spx, S, ruler):
+    q = np.float32(S) / np.float32(ruler)
+    assert spx.selftest_division(float(q * q)) == 0
+
+
+def test_slic_4k_equals_oracle(spx, O, synthmod):
+    """BASELINE.json metric config at full size: labels and centres identical to the oracle"""
+    img, _ = synthmod.synth(3840, 2160, 1)
+    lab = spx.cvtColor(img, spx.COLOR_BGR2Lab)
+    a, b = _run_pair(spx, O, lab, spx.SLIC, 20, 10.0, 10)
+    la, lb = a.getLabels(), b.getLabels()
+    assert float((la == lb).mean()) == 1.0
+    assert (a.getCentres() == b.getCentres()).all()
+
+
 # ---------------------------------------------------------------- error behaviour (cv::Exception analogue)
 def test_errors(spx):
     img = np.zeros((16, 16, 3), np.uint8)
