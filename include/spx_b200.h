@@ -103,6 +103,9 @@ int spx_slic_batch_dev(const void* const* d_frames, int n_frames, int width, int
                        int min_element_size, void* const* d_labels, void* const* d_masks, int thick_line,
                        int n_streams, long long* launches_out);
 
+/* frees the engines (device buffers, captured graphs) spx_slic_batch_dev keeps pooled between calls */
+int spx_slic_batch_release(void);
+
 /* ---- stand-alone stages on a caller-supplied label map (host buffers) ----
  * same arithmetic as the member functions above; used for bit-exact stage tests. */
 int spx_enforce_label_connectivity(int32_t* labels, size_t stride, int width, int height,

@@ -74,6 +74,7 @@ def lib():
         "spx_slic_time_assign": [vp, i32, i32, C.POINTER(C.c_float)],
         "spx_slic_destroy": [vp],
         "spx_slic_batch_dev": [pp, i32, i32, i32, i32, i32, i32, f32, i32, i32, pp, pp, i32, i32, C.POINTER(C.c_longlong)],
+        "spx_slic_batch_release": [],
         "spx_enforce_label_connectivity": [vp, sz, i32, i32, i32, i32, i32, pi],
         "spx_label_contour_mask": [vp, sz, i32, i32, i32, i32, vp, sz, i32],
         "spx_selftest_division": [f32, i32, i32, pi],

@@ -104,7 +104,7 @@ __global__ void slic_bin_kernel(SlicGeom g, SlicArrays a, const int* __restrict_
 {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= *d_K) return;
-    bin_insert(g, a, a.head[parity], n, a.ikx[n], a.iky[n]);
+    bin_insert(g, a, parity ? a.head[1] : a.head[0], n, a.ikx[n], a.iky[n]);
 }
 __global__ void fill_i32_kernel(int* p, int v, size_t n)
 {
@@ -140,7 +140,7 @@ __global__ void slic_finalize_kernel(SlicGeom g, SlicArrays a, const int* __rest
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int nb = g.nbx * g.nby;
-    if (t < nb) a.head[parity][t] = -1;              // the lists just consumed; reused two iterations later
+    if (t < nb) (parity ? a.head[1] : a.head[0])[t] = -1;              // the lists just consumed; reused two iterations later
     const int K = *d_K;
     if (t >= K) return;
     unsigned long long cnt = a.acc[(size_t)(g.C + 2) * g.Kcap + t];
@@ -161,7 +161,7 @@ __global__ void slic_finalize_kernel(SlicGeom g, SlicArrays a, const int* __rest
         unsigned mb = a.maxc_acc[t];
         a.maxc[t] = __uint_as_float(mb);
     }
-    if (do_bin) bin_insert(g, a, a.head[parity ^ 1], t, ix, iy);
+    if (do_bin) bin_insert(g, a, parity ? a.head[0] : a.head[1], t, ix, iy);
 }
 
 // ------------------------------------------------------------------------------------------------

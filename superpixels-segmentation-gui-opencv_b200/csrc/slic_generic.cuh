@@ -21,7 +21,7 @@ __device__ __forceinline__ void slic_pixel_generic(const SlicGeom& g, const Slic
         float fpix[SPX_MAXC];
         for (int c = 0; c < g.C; c++) { pix[c] = p[c]; fpix[c] = (float)pix[c]; }
         const float fx = (float)x, fy = (float)y;
-        const int* head = a.head[parity];
+        const int* head = parity ? a.head[1] : a.head[0];
         int bx = x / g.S, by = y / g.S;
         float best = FLT_MAX;
         int bestn = -1, lastn = -1;

@@ -6,9 +6,8 @@
 //           strict '<', so ascending order reproduces its tie-breaking), stages their centres in shared
 //           memory and tabulates the separable spatial terms ex2[c][x], ey2[c][y] (+inf outside the
 //           window, so that an out-of-window candidate can never win).
-//   main  : a warp handles an 8x8 patch, 2 horizontally adjacent pixels per thread, and visits only the
-//           candidates whose window meets the patch (5.8 per pixel on average at S=20; 4.0 is the
-//           minimum).  The distance arithmetic is upstream's float32 sequence, evaluated with the sm_100
+//   main  : a warp handles a 16x8 patch, 2x2 pixels per thread, and visits only the candidates whose
+//           window meets the patch (6.7 per pixel on average at S=20; 4.0 is the minimum).  The distance arithmetic is upstream's float32 sequence, evaluated with the sm_100
 //           packed f32x2 instructions (FADD2/FMUL2/FFMA2: same rounding per element, half the issue
 //           slots), never contracted:   d = ((t0*t0 + t1*t1) + t2*t2) + (ex2+ey2)/xywt.
 //           The IEEE division by the constant xywt is a multiply when xywt is a power of two, otherwise
@@ -69,63 +68,118 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
     return r;
 }
 
+// ---- shared memory layout -----------------------------------------------------------------------
+// One 544-byte record per candidate, so that a single (uniform) record offset addresses everything:
+//   +0   (-kc0,-kc0) (-kc1,-kc1)      16 B      +16  (-kc2,-kc2)  8 B   (+24 pad)
+//   +32  ex2[64]  float               256 B     (x-kx)^2 [pre-divided by xywt when it is a power of two], +inf outside
+//   +288 ey2[32]  float2 (v,v)        256 B     (y-ky)^2 likewise, duplicated so a row's term is a ready f32x2 operand
+constexpr int REC = 544;
+constexpr int REC_EX = 32;
+constexpr int REC_EY = 288;
 struct TileSmem {
-    u64 cenA[CAP][2];          // (-kc0,-kc0), (-kc1,-kc1)
-    u64 cenB[CAP];             // (-kc2,-kc2)
-    float ex[CAP][TW];         // (x-kx)^2 [scaled by 1/xywt when it is a power of two], +inf outside the window
-    u64 ey[CAP][TH];           // ((y-ky)^2, same) duplicated into both halves
+    __align__(16) unsigned char rec[CAP * REC];
     int4 win[CAP];             // window: x_lo, x_hi, y_lo, y_hi (half open)
-    unsigned acc[CAP][8];      // L, a, count... see FIELD order below
+    unsigned acc[CAP][8];      // 0 c0, 1 c1, 2 c2, 3 count, 4 x (tile relative), 5 y (tile relative)
     int n[CAP];                // cluster index per slot, ascending
     int list[CAP];
     int cnt;
 };
-// shared accumulator fields: 0 c0, 1 c1, 2 c2, 3 count, 4 x (tile relative), 5 y (tile relative)
 
-// all 32 lanes call; slot < 0 = nothing to add.  wA = c0 | c1<<16, wB = c2 | count<<16, wC = xrel | yrel<<16
-__device__ __forceinline__ void warp_accumulate(unsigned (*acc)[8], int slot, unsigned wA, unsigned wB, unsigned wC, int lane)
+struct TileArgs {
+    const int* head; const int* next; const int* ikx; const int* iky;
+    const float* kx; const float* ky; const float* kc;
+    unsigned long long* acc;
+    int w, h, S, Kcap, nbx, nby, lp;
+    size_t ipitch;
+    float xywt, rcp_xywt;
+};
+
+// per-label sums of one warp step.  Every thread contributes up to four pixels (slot s[j], words wA/wB/wC[j]:
+// wA = c0 | c1<<16, wB = c2 | count<<16, wC = xrel | yrel<<16).  Labels are visited in ascending slot order:
+// REDUX.MIN picks the next one (result lands in a uniform register), REDUX.SUM adds its three words over the
+// warp, and lanes 0..5 add one field each to the CTA's shared accumulators.
+__device__ __forceinline__ void warp_accumulate4(unsigned (*acc)[8], const int (&s)[4], const unsigned (&wA)[4],
+                                                 const unsigned (&wB)[4], const unsigned (&wC)[4], int lane)
 {
-    unsigned rem = __ballot_sync(0xffffffffu, slot >= 0);
-    while (rem) {
-        const int leader = __ffs(rem) - 1;
-        const int cur = __shfl_sync(0xffffffffu, slot, leader);
-        const bool eq = slot == cur;
-        const unsigned m = __ballot_sync(0xffffffffu, eq);
-        const unsigned A = __reduce_add_sync(0xffffffffu, eq ? wA : 0u);
-        const unsigned B = __reduce_add_sync(0xffffffffu, eq ? wB : 0u);
-        const unsigned Cc = __reduce_add_sync(0xffffffffu, eq ? wC : 0u);
+    // thread-local merge: everything equal to the first pixel's slot is summed up front (the common case)
+    unsigned pA = wA[0], pB = wB[0], pC = wC[0];
+    unsigned key0 = (unsigned)s[0];               // -1 -> 0xffffffff = nothing
+    unsigned kj[3];
+    bool left = false;
+#pragma unroll
+    for (int j = 1; j < 4; j++) {
+        const bool e = s[j] == s[0];
+        pA += e ? wA[j] : 0u; pB += e ? wB[j] : 0u; pC += e ? wC[j] : 0u;
+        kj[j - 1] = e ? 0xffffffffu : (unsigned)s[j];
+        left |= !e && s[j] >= 0;
+    }
+    // primary pass
+    for (;;) {
+        const unsigned cur = __reduce_min_sync(0xffffffffu, key0);
+        if (cur == 0xffffffffu) break;
+        const bool e = key0 == cur;
+        const unsigned A = __reduce_add_sync(0xffffffffu, e ? pA : 0u);
+        const unsigned B = __reduce_add_sync(0xffffffffu, e ? pB : 0u);
+        const unsigned Cc = __reduce_add_sync(0xffffffffu, e ? pC : 0u);
+        key0 = e ? 0xffffffffu : key0;
         if (lane < 6) {
             const unsigned wsel = lane < 2 ? A : lane < 4 ? B : Cc;
-            const unsigned v = (lane & 1) ? (wsel >> 16) : (wsel & 0xffffu);
-            atomicAdd(&acc[cur][lane], v);
+            atomicAdd(&acc[cur][lane], (lane & 1) ? (wsel >> 16) : (wsel & 0xffffu));
         }
-        rem &= ~m;
+    }
+    // leftovers: pixels whose slot differs from the thread's first pixel
+    if (__any_sync(0xffffffffu, left)) {
+        for (;;) {
+            const unsigned mine = min(kj[0], min(kj[1], kj[2]));
+            const unsigned cur = __reduce_min_sync(0xffffffffu, mine);
+            if (cur == 0xffffffffu) break;
+            unsigned cA = 0, cB = 0, cC = 0;
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const bool e = kj[j] == cur;
+                cA += e ? wA[j + 1] : 0u; cB += e ? wB[j + 1] : 0u; cC += e ? wC[j + 1] : 0u;
+                kj[j] = e ? 0xffffffffu : kj[j];
+            }
+            const unsigned A = __reduce_add_sync(0xffffffffu, cA);
+            const unsigned B = __reduce_add_sync(0xffffffffu, cB);
+            const unsigned Cc = __reduce_add_sync(0xffffffffu, cC);
+            if (lane < 6) {
+                const unsigned wsel = lane < 2 ? A : lane < 4 ? B : Cc;
+                atomicAdd(&acc[cur][lane], (lane & 1) ? (wsel >> 16) : (wsel & 0xffffu));
+            }
+        }
     }
 }
 
+__device__ __forceinline__ void acc_global_pixel(const TileArgs& t, int n, int c0, int c1, int c2, int x, int y)
+{
+    atomicAdd(&t.acc[n], (u64)c0); atomicAdd(&t.acc[(size_t)t.Kcap + n], (u64)c1);
+    atomicAdd(&t.acc[2 * (size_t)t.Kcap + n], (u64)c2); atomicAdd(&t.acc[3 * (size_t)t.Kcap + n], (u64)x);
+    atomicAdd(&t.acc[4 * (size_t)t.Kcap + n], (u64)y); atomicAdd(&t.acc[5 * (size_t)t.Kcap + n], 1ull);
+}
+
 template <bool POW2>
-__global__ void __launch_bounds__(256, 3) slic_tile_kernel(SlicGeom g, SlicArrays a, const unsigned char* __restrict__ img,
-                                                            int* __restrict__ labels, int parity, float rcp_xywt,
-                                                            int* __restrict__ d_overflow)
+__global__ void __launch_bounds__(256, 3) slic_tile_kernel(const TileArgs t, SlicGeom g, SlicArrays a,
+                                                            const unsigned char* __restrict__ img, int* __restrict__ labels,
+                                                            int parity, int* __restrict__ d_overflow)
 {
     __shared__ TileSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int S = g.S;
+    const int S = t.S;
     const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
-    const int tx1 = min(tx0 + TW, g.w), ty1 = min(ty0 + TH, g.h);
+    const int tx1 = min(tx0 + TW, t.w), ty1 = min(ty0 + TH, t.h);
     if (tid == 0) sm.cnt = 0;
     __syncthreads();
 
     // ---- candidates: clusters with int(kx) in (tx0-S, tx1+S) and int(ky) in (ty0-S, ty1+S)
     {
-        const int bx0 = max(tx0 - S + 1, 0) / S, bx1 = min((tx1 + S - 1) / S, g.nbx - 1);
-        const int by0 = max(ty0 - S + 1, 0) / S, by1 = min((ty1 + S - 1) / S, g.nby - 1);
+        const int bx0 = max(tx0 - S + 1, 0) / S, bx1 = min((tx1 + S - 1) / S, t.nbx - 1);
+        const int by0 = max(ty0 - S + 1, 0) / S, by1 = min((ty1 + S - 1) / S, t.nby - 1);
         const int nbw = bx1 - bx0 + 1, nbins = nbw * (by1 - by0 + 1);
-        const int* head = a.head[parity];
         for (int b = tid; b < nbins; b += 256) {
             const int by = by0 + b / nbw, bx = bx0 + b % nbw;
-            for (int n = head[by * g.nbx + bx]; n >= 0; n = a.next[n]) {
-                const int ix = a.ikx[n], iy = a.iky[n];
+            for (int n = t.head[by * t.nbx + bx]; n >= 0; n = t.next[n]) {
+                const int ix = t.ikx[n], iy = t.iky[n];
                 if (ix - S < tx1 && ix + S > tx0 && iy - S < ty1 && iy + S > ty0) {
                     const int i = atomicAdd(&sm.cnt, 1);
                     if (i < CAP) sm.list[i] = n;
@@ -141,7 +195,7 @@ __global__ void __launch_bounds__(256, 3) slic_tile_kernel(SlicGeom g, SlicArray
         for (int r = warp; r < TH; r += 8)
             for (int c0 = 0; c0 < TW; c0 += 32) {
                 const int x = tx0 + c0 + lane, y = ty0 + r;
-                slic_pixel_generic<100>(g, a, img, labels, nullptr, parity, x, y, x < g.w && y < g.h);
+                slic_pixel_generic<100>(g, a, img, labels, nullptr, parity, x, y, x < t.w && y < t.h);
             }
         return;
     }
@@ -151,11 +205,10 @@ __global__ void __launch_bounds__(256, 3) slic_tile_kernel(SlicGeom g, SlicArray
         int rank = 0;
         for (int j = 0; j < cnt; j++) rank += sm.list[j] < n ? 1 : 0;
         sm.n[rank] = n;
-        const float k0 = -a.kc[n], k1 = -a.kc[(size_t)g.Kcap + n], k2 = -a.kc[2 * (size_t)g.Kcap + n];
-        sm.cenA[rank][0] = pack2(k0, k0);
-        sm.cenA[rank][1] = pack2(k1, k1);
-        sm.cenB[rank] = pack2(k2, k2);
-        const int ix = a.ikx[n], iy = a.iky[n];
+        const float k0 = -t.kc[n], k1 = -t.kc[(size_t)t.Kcap + n], k2 = -t.kc[2 * (size_t)t.Kcap + n];
+        u64* r64 = reinterpret_cast<u64*>(sm.rec + rank * REC);
+        r64[0] = pack2(k0, k0); r64[1] = pack2(k1, k1); r64[2] = pack2(k2, k2);
+        const int ix = t.ikx[n], iy = t.iky[n];
         sm.win[rank] = make_int4(ix - S, ix + S, iy - S, iy + S);
     }
     for (int i = tid; i < cnt * 8; i += 256) (&sm.acc[0][0])[i] = 0u;
@@ -166,110 +219,138 @@ __global__ void __launch_bounds__(256, 3) slic_tile_kernel(SlicGeom g, SlicArray
         const int c = i >> 6, xx = i & (TW - 1);
         const int x = tx0 + xx;
         const int4 wn = sm.win[c];
-        const float e = __fsub_rn((float)x, a.kx[sm.n[c]]);
+        const float e = __fsub_rn((float)x, t.kx[sm.n[c]]);
         float v = __fmul_rn(e, e);
-        if (POW2) v = __fmul_rn(v, rcp_xywt);
-        sm.ex[c][xx] = (x >= wn.x && x < wn.y) ? v : inf;
+        if (POW2) v = __fmul_rn(v, t.rcp_xywt);
+        reinterpret_cast<float*>(sm.rec + c * REC + REC_EX)[xx] = (x >= wn.x && x < wn.y) ? v : inf;
     }
     for (int i = tid; i < cnt * TH; i += 256) {
         const int c = i >> 5, yy = i & (TH - 1);
         const int y = ty0 + yy;
         const int4 wn = sm.win[c];
-        const float e = __fsub_rn((float)y, a.ky[sm.n[c]]);
+        const float e = __fsub_rn((float)y, t.ky[sm.n[c]]);
         float v = __fmul_rn(e, e);
-        if (POW2) v = __fmul_rn(v, rcp_xywt);
+        if (POW2) v = __fmul_rn(v, t.rcp_xywt);
         v = (y >= wn.z && y < wn.w) ? v : inf;
-        sm.ey[c][yy] = pack2(v, v);
+        reinterpret_cast<u64*>(sm.rec + c * REC + REC_EY)[yy] = pack2(v, v);
     }
     __syncthreads();
 
-    // ---- main: warp = 8 px x 8 rows per step, 2 px per thread
-    const int lx = lane & 3, ly = lane >> 2;
-    const int xo = 8 * warp + 2 * lx;          // tile-relative x of the thread's first pixel
+    // ---- main: a warp owns a 16x8 patch per step (lanes 8 x 4, 2x2 pixels per thread); the CTA's 8 warps cover
+    //      64x16, two steps cover the tile
+    const int lx = lane & 7, ly = lane >> 3;
+    const int wx = warp & 3, wy = warp >> 2;
+    const int xo = 16 * wx + 2 * lx;           // tile-relative x of the thread's left pixels
     const int x = tx0 + xo;
-    const u64 R2 = pack2(rcp_xywt, rcp_xywt);
-    const float nw = -g.xywt;
+    const u64 R2 = pack2(t.rcp_xywt, t.rcp_xywt);
+    const float nw = -t.xywt;
     const u64 NW2 = pack2(nw, nw);
-    const int X0 = tx0 + 8 * warp, X1 = X0 + 8;
-#pragma unroll 1
-    for (int step = 0; step < TH / 8; step++) {
-        const int yo = 8 * step + ly;
-        const int y = ty0 + yo;
-        const bool in0 = x < g.w && y < g.h, in1 = x + 1 < g.w && y < g.h;
-        unsigned b01 = 0, b23 = 0, b45 = 0;
-        if (y < g.h) {
-            const unsigned short* p = reinterpret_cast<const unsigned short*>(img + (size_t)y * g.ipitch + (size_t)x * 3);
-            b01 = p[0]; b23 = p[1]; b45 = p[2];
+    const int X0 = tx0 + 16 * wx, X1 = X0 + 16;
+    const unsigned char* thr_ex = sm.rec + REC_EX + xo * 4;
+    // first step's pixels
+    unsigned raw[2][3];
+    auto load_rows = [&](int yy, unsigned (&dst)[2][3]) {
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            dst[r][0] = dst[r][1] = dst[r][2] = 0;
+            if (yy + r < t.h) {
+                const unsigned short* p = reinterpret_cast<const unsigned short*>(img + (size_t)(yy + r) * t.ipitch + (size_t)x * 3);
+                dst[r][0] = __ldg(p); dst[r][1] = __ldg(p + 1); dst[r][2] = __ldg(p + 2);
+            }
         }
-        const int c00 = b01 & 255, c01 = b01 >> 8, c02 = b23 & 255, c10 = b23 >> 8, c11 = b45 & 255, c12 = b45 >> 8;
-        const u64 P0 = pack2((float)c00, (float)c10), P1 = pack2((float)c01, (float)c11), P2 = pack2((float)c02, (float)c12);
-        // candidates whose window meets this warp's patch
-        const int Y0 = ty0 + 8 * step, Y1 = Y0 + 8;
+    };
+    load_rows(ty0 + 8 * wy + 2 * ly, raw);
+#pragma unroll 1
+    for (int step = 0; step < TH / 16; step++) {
+        const int yo = 16 * step + 8 * wy + 2 * ly;
+        const int y = ty0 + yo;
+        unsigned cur[2][3];
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) cur[r][k] = raw[r][k];
+        if (step + 1 < TH / 16) load_rows(y + 16, raw);      // prefetch the next step's pixels
+        // unpack: pixel (r, 0) = bytes 0..2, pixel (r, 1) = bytes 3..5
+        int cc[2][2][3];
+        u64 P[2][3];
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            cc[r][0][0] = cur[r][0] & 255; cc[r][0][1] = cur[r][0] >> 8; cc[r][0][2] = cur[r][1] & 255;
+            cc[r][1][0] = cur[r][1] >> 8;  cc[r][1][1] = cur[r][2] & 255; cc[r][1][2] = cur[r][2] >> 8;
+#pragma unroll
+            for (int k = 0; k < 3; k++) P[r][k] = pack2((float)cc[r][0][k], (float)cc[r][1][k]);
+        }
+        // candidates whose window meets this warp's patch; REDUX.OR makes the mask a uniform-register value
+        const int Y0 = ty0 + 16 * step + 8 * wy, Y1 = Y0 + 8;
         unsigned m0, m1 = 0;
         {
             int4 wn = sm.win[lane];
             m0 = __ballot_sync(0xffffffffu, lane < cnt && wn.x < X1 && wn.y > X0 && wn.z < Y1 && wn.w > Y0);
+            m0 = __reduce_or_sync(0xffffffffu, m0);
             if (cnt > 32) {
                 wn = sm.win[lane + 32];
                 m1 = __ballot_sync(0xffffffffu, lane + 32 < cnt && wn.x < X1 && wn.y > X0 && wn.z < Y1 && wn.w > Y0);
+                m1 = __reduce_or_sync(0xffffffffu, m1);
             }
         }
-        float best0 = FLT_MAX, best1 = FLT_MAX;
-        int slot0 = -1, slot1 = -1;
+        float best[2][2] = {{FLT_MAX, FLT_MAX}, {FLT_MAX, FLT_MAX}};
+        int slot[2][2] = {{-1, -1}, {-1, -1}};
+        const unsigned char* thr_ey = sm.rec + REC_EY + yo * 8;
 #pragma unroll 1
         for (int half = 0; half < 2; half++) {
             unsigned m = half ? m1 : m0;
             while (m) {
                 const int c = (__ffs(m) - 1) + 32 * half;
                 m &= m - 1;
-                const ulonglong2 ca = *reinterpret_cast<const ulonglong2*>(&sm.cenA[c][0]);
-                const u64 cb = sm.cenB[c];
-                const u64 exv = *reinterpret_cast<const u64*>(&sm.ex[c][xo]);
-                const u64 eyv = sm.ey[c][yo];
-                const u64 t0 = add2(P0, ca.x), t1 = add2(P1, ca.y), t2 = add2(P2, cb);
-                u64 d = add2_products(mul2(t0, t0), mul2(t1, t1));
-                d = add2_products(d, mul2(t2, t2));
-                u64 s = add2(exv, eyv);
-                if (!POW2) {
-                    const u64 q0 = mul2(s, R2);
-                    const u64 e = fma2(q0, NW2, s);
-                    s = fma2(e, R2, q0);
+                const int ro = c * REC;
+                const ulonglong2 ca = *reinterpret_cast<const ulonglong2*>(sm.rec + ro);
+                const u64 cb = *reinterpret_cast<const u64*>(sm.rec + ro + 16);
+                const u64 exv = *reinterpret_cast<const u64*>(thr_ex + ro);
+                const ulonglong2 eyv = *reinterpret_cast<const ulonglong2*>(thr_ey + ro);
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const u64 t0 = add2(P[r][0], ca.x), t1 = add2(P[r][1], ca.y), t2 = add2(P[r][2], cb);
+                    u64 d = add2_products(mul2(t0, t0), mul2(t1, t1));
+                    d = add2_products(d, mul2(t2, t2));
+                    u64 s = add2(exv, r ? eyv.y : eyv.x);
+                    if (!POW2) {
+                        const u64 q0 = mul2(s, R2);
+                        const u64 e = fma2(q0, NW2, s);
+                        s = fma2(e, R2, q0);
+                    }
+                    d = add2(d, s);
+                    float d0, d1;
+                    unpack2(d, d0, d1);
+                    if (d0 < best[r][0]) { best[r][0] = d0; slot[r][0] = c; }
+                    if (d1 < best[r][1]) { best[r][1] = d1; slot[r][1] = c; }
                 }
-                d = add2(d, s);
-                float d0, d1;
-                unpack2(d, d0, d1);
-                if (d0 < best0) { best0 = d0; slot0 = c; }
-                if (d1 < best1) { best1 = d1; slot1 = c; }
             }
         }
-        // ---- labels (a pixel no window covers keeps its label)
-        int n0 = -1, n1 = -1;
-        int* lrow = labels + (size_t)y * g.lp + x;
-        if (in0) n0 = slot0 >= 0 ? sm.n[slot0] : lrow[0];
-        if (in1) n1 = slot1 >= 0 ? sm.n[slot1] : lrow[1];
-        if (in1) *reinterpret_cast<int2*>(lrow) = make_int2(n0, n1);
-        else if (in0) lrow[0] = n0;
-        // ---- accumulate (channels, count, x, y) per label
-        {
-            const int s0 = in0 ? slot0 : -1, s1 = in1 ? slot1 : -1;
-            const bool same = s0 == s1;
-            const unsigned a0 = (unsigned)c00 | ((unsigned)c01 << 16), b0 = (unsigned)c02 | (1u << 16), w0 = (unsigned)xo | ((unsigned)yo << 16);
-            const unsigned a1 = (unsigned)c10 | ((unsigned)c11 << 16), b1 = (unsigned)c12 | (1u << 16), w1 = (unsigned)(xo + 1) | ((unsigned)yo << 16);
-            warp_accumulate(sm.acc, s0, same ? a0 + a1 : a0, same ? b0 + b1 : b0, same ? w0 + w1 : w0, lane);
-            const int sec = same ? -1 : s1;
-            if (__any_sync(0xffffffffu, sec >= 0)) warp_accumulate(sm.acc, sec, a1, b1, w1, lane);
-            // uncovered pixels (rare): straight to the global accumulators of the label they keep
-            if (in0 && slot0 < 0) {
-                atomicAdd(&a.acc[n0], (u64)c00); atomicAdd(&a.acc[(size_t)g.Kcap + n0], (u64)c01);
-                atomicAdd(&a.acc[2 * (size_t)g.Kcap + n0], (u64)c02); atomicAdd(&a.acc[3 * (size_t)g.Kcap + n0], (u64)x);
-                atomicAdd(&a.acc[4 * (size_t)g.Kcap + n0], (u64)y); atomicAdd(&a.acc[5 * (size_t)g.Kcap + n0], 1ull);
-            }
-            if (in1 && slot1 < 0) {
-                atomicAdd(&a.acc[n1], (u64)c10); atomicAdd(&a.acc[(size_t)g.Kcap + n1], (u64)c11);
-                atomicAdd(&a.acc[2 * (size_t)g.Kcap + n1], (u64)c12); atomicAdd(&a.acc[3 * (size_t)g.Kcap + n1], (u64)(x + 1));
-                atomicAdd(&a.acc[4 * (size_t)g.Kcap + n1], (u64)y); atomicAdd(&a.acc[5 * (size_t)g.Kcap + n1], 1ull);
+        // ---- labels (a pixel no window covers keeps its label) and accumulation words
+        int sj[4];
+        unsigned wA[4], wB[4], wC[4];
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const int yy = y + r;
+            int* lrow = labels + (size_t)yy * t.lp + x;
+            const bool in0 = x < t.w && yy < t.h, in1 = x + 1 < t.w && yy < t.h;
+            int n0 = -1, n1 = -1;
+            if (in0) n0 = slot[r][0] >= 0 ? sm.n[slot[r][0]] : lrow[0];
+            if (in1) n1 = slot[r][1] >= 0 ? sm.n[slot[r][1]] : lrow[1];
+            if (in1) *reinterpret_cast<int2*>(lrow) = make_int2(n0, n1);
+            else if (in0) lrow[0] = n0;
+            if (in0 && slot[r][0] < 0) acc_global_pixel(t, n0, cc[r][0][0], cc[r][0][1], cc[r][0][2], x, yy);
+            if (in1 && slot[r][1] < 0) acc_global_pixel(t, n1, cc[r][1][0], cc[r][1][1], cc[r][1][2], x + 1, yy);
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int j = 2 * r + q;
+                sj[j] = (q ? in1 : in0) ? slot[r][q] : -1;
+                wA[j] = (unsigned)cc[r][q][0] | ((unsigned)cc[r][q][1] << 16);
+                wB[j] = (unsigned)cc[r][q][2] | (1u << 16);
+                wC[j] = (unsigned)(xo + q) | ((unsigned)(yo + r) << 16);
             }
         }
+        warp_accumulate4(sm.acc, sj, wA, wB, wC, lane);
     }
     __syncthreads();
     // ---- flush: one global atomic per field per candidate that received pixels
@@ -283,7 +364,7 @@ __global__ void __launch_bounds__(256, 3) slic_tile_kernel(SlicGeom g, SlicArray
         if (f == 3) field = 5;
         else if (f == 4) { field = 3; v += (u64)count * (u64)tx0; }
         else if (f == 5) { field = 4; v += (u64)count * (u64)ty0; }
-        atomicAdd(&a.acc[(size_t)field * g.Kcap + n], v);
+        atomicAdd(&t.acc[(size_t)field * t.Kcap + n], v);
     }
 }
 
@@ -312,9 +393,13 @@ int slic_tile_assign(const SlicGeom& g, const SlicArrays& a, const unsigned char
 {
     (void)d_K;
     dim3 grid(cdiv(g.w, TW), cdiv(g.h, TH));
-    const float r = 1.0f / g.xywt;
-    if (is_pow2(g.xywt)) slic_tile_kernel<true><<<grid, 256, 0, st>>>(g, a, d_img, d_labels, parity, r, d_overflow);
-    else slic_tile_kernel<false><<<grid, 256, 0, st>>>(g, a, d_img, d_labels, parity, r, d_overflow);
+    TileArgs t;
+    t.head = a.head[parity]; t.next = a.next; t.ikx = a.ikx; t.iky = a.iky;
+    t.kx = a.kx; t.ky = a.ky; t.kc = a.kc; t.acc = a.acc;
+    t.w = g.w; t.h = g.h; t.S = g.S; t.Kcap = g.Kcap; t.nbx = g.nbx; t.nby = g.nby; t.lp = g.lp;
+    t.ipitch = g.ipitch; t.xywt = g.xywt; t.rcp_xywt = 1.0f / g.xywt;
+    if (is_pow2(g.xywt)) slic_tile_kernel<true><<<grid, 256, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);
+    else slic_tile_kernel<false><<<grid, 256, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);
     SPX_CUDA(cudaGetLastError());
     return SPX_OK;
 }
