@@ -95,16 +95,40 @@ __global__ void slic_seed_kernel(SlicGeom g, SlicArrays a, const unsigned char* 
     for (int c = 0; c < g.C; c++) a.kc[(size_t)c * g.Kcap + n] = (float)img[(size_t)Y * g.ipitch + (size_t)X * g.C + c];
 }
 
-__device__ __forceinline__ void bin_insert(const SlicGeom& g, const SlicArrays& a, int* head, int n, int ix, int iy)
+// insert centre n into its S x S bin (linked list) and, for the tiled path, append its record to the list of every
+// tile its window [ix-off, ix+off) x [iy-off, iy+off) touches
+__device__ __forceinline__ void bin_insert(const SlicGeom& g, const SlicArrays& a, int par, int n, int ix, int iy)
 {
+    int* head = par ? a.head[1] : a.head[0];
     int bx = min(max(ix, 0) / g.S, g.nbx - 1), by = min(max(iy, 0) / g.S, g.nby - 1);
     a.next[n] = atomicExch(&head[by * g.nbx + bx], n);
+    if (g.tile_on) {
+        int* cnt = par ? a.tl_count[1] : a.tl_count[0];
+        TileRec* recs = par ? a.tl_rec[1] : a.tl_rec[0];
+        const int off = a.ioff[n];
+        const int tx0 = max(ix - off, 0) / TILE_W, tx1 = min(ix + off - 1, g.w - 1) / TILE_W;
+        const int ty0 = max(iy - off, 0) / TILE_H, ty1 = min(iy + off - 1, g.h - 1) / TILE_H;
+        TileRec r;
+        r.kx = a.kx[n]; r.ky = a.ky[n];
+        r.k0 = a.kc[n]; r.k1 = a.kc[(size_t)g.Kcap + n]; r.k2 = a.kc[2 * (size_t)g.Kcap + n];
+        r.n = n; r.ix = ix; r.iy = iy;
+        for (int ty = ty0; ty <= ty1; ty++)
+            for (int tx = tx0; tx <= tx1; tx++) {
+                const int tile = ty * g.tiles_x + tx;
+                const int slot = atomicAdd(&cnt[tile], 1);
+                if (slot < TILE_CAP) {
+                    float4* dst = reinterpret_cast<float4*>(&recs[(size_t)tile * TILE_CAP + slot]);
+                    dst[0] = make_float4(r.kx, r.ky, r.k0, r.k1);
+                    dst[1] = make_float4(r.k2, __int_as_float(r.n), __int_as_float(r.ix), __int_as_float(r.iy));
+                }
+            }
+    }
 }
 __global__ void slic_bin_kernel(SlicGeom g, SlicArrays a, const int* __restrict__ d_K, int parity)
 {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= *d_K) return;
-    bin_insert(g, a, parity ? a.head[1] : a.head[0], n, a.ikx[n], a.iky[n]);
+    bin_insert(g, a, parity, n, a.ikx[n], a.iky[n]);
 }
 __global__ void fill_i32_kernel(int* p, int v, size_t n)
 {
@@ -140,7 +164,9 @@ __global__ void slic_finalize_kernel(SlicGeom g, SlicArrays a, const int* __rest
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int nb = g.nbx * g.nby;
-    if (t < nb) (parity ? a.head[1] : a.head[0])[t] = -1;              // the lists just consumed; reused two iterations later
+    if (t < nb) (parity ? a.head[1] : a.head[0])[t] = -1;
+    if (g.tile_on && t < g.tiles_x * g.tiles_y) (parity ? a.tl_count[1] : a.tl_count[0])[t] = 0;
+    //              // the lists just consumed; reused two iterations later
     const int K = *d_K;
     if (t >= K) return;
     unsigned long long cnt = a.acc[(size_t)(g.C + 2) * g.Kcap + t];
@@ -161,7 +187,7 @@ __global__ void slic_finalize_kernel(SlicGeom g, SlicArrays a, const int* __rest
         unsigned mb = a.maxc_acc[t];
         a.maxc[t] = __uint_as_float(mb);
     }
-    if (do_bin) bin_insert(g, a, parity ? a.head[0] : a.head[1], t, ix, iy);
+    if (do_bin) bin_insert(g, a, parity ^ 1, t, ix, iy);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -388,7 +414,16 @@ struct SlicEngine {
         if (alg == SPX_SLICO) SPX_CHECK(dalloc(&d_dcplane, (size_t)w * h));
         SPX_CUDA(cudaMallocHost(&h_pinned, 4 * sizeof(int)));
         SPX_CUDA(cudaMemsetAsync(d_img, 0, g.ipitch * (size_t)(h + 1), st));
+        g.tiles_x = cdiv(w, TILE_W); g.tiles_y = cdiv(h, TILE_H);
         use_tile = slic_tile_supported(g) && !getenv("SPX_SLIC_GENERIC");
+        g.tile_on = use_tile ? 1 : 0;
+        if (use_tile) {
+            const size_t nt = (size_t)g.tiles_x * g.tiles_y;
+            for (int p = 0; p < 2; p++) {
+                SPX_CHECK(dalloc(&a.tl_count[p], nt));
+                SPX_CHECK(dalloc(&a.tl_rec[p], nt * TILE_CAP));
+            }
+        }
         use_graph = !getenv("SPX_NO_GRAPH");
         return SPX_OK;
     }
@@ -404,6 +439,8 @@ struct SlicEngine {
         SPX_CUDA(cudaMemsetAsync(a.head[0], 0xFF, (size_t)g.nbx * g.nby * sizeof(int), st));
         SPX_CUDA(cudaMemsetAsync(a.head[1], 0xFF, (size_t)g.nbx * g.nby * sizeof(int), st));
         SPX_CUDA(cudaMemsetAsync(d_overflow, 0, 4 * sizeof(int), st));
+        if (use_tile)
+            for (int p = 0; p < 2; p++) SPX_CUDA(cudaMemsetAsync(a.tl_count[p], 0, (size_t)g.tiles_x * g.tiles_y * sizeof(int), st));
         h_pinned[0] = K0;
         SPX_CUDA(cudaMemcpyAsync(d_K, h_pinned, sizeof(int), cudaMemcpyHostToDevice, st));
         int K = 0;
@@ -425,7 +462,7 @@ struct SlicEngine {
 
     int enqueue_iterations(int n)
     {
-        const int threads_fin = max(g.Kcap, g.nbx * g.nby);
+        const int threads_fin = max(max(g.Kcap, g.nbx * g.nby), g.tiles_x * g.tiles_y);
         if (g.alg == SPX_SLICO) {
             size_t np = (size_t)g.w * g.h;
             slico_begin_kernel<<<(unsigned)((max(np, (size_t)g.K) + 255) / 256), 256, 0, st>>>(g, a, d_dcplane, np);

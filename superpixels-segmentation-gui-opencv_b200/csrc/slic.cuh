@@ -18,7 +18,15 @@ struct SlicArrays {
     int* next;                       // per-bin linked lists of centres
     int* head[2];                    // bin heads, double buffered by iteration parity
     long long* area;                 // MSLIC fixed-point manifold area per cluster
+    int* tl_count[2];                // tiled path: candidates per 32x32 tile, double buffered like head[]
+    struct TileRec* tl_rec[2];       // tiled path: candidate records, TILE_CAP per tile
 };
+
+// one candidate of a tile: everything the tiled assignment kernel needs about a cluster (32 bytes)
+struct TileRec { float kx, ky, k0, k1, k2; int n, ix, iy; };
+constexpr int TILE_W = 32;           // tile of the tiled assignment kernel
+constexpr int TILE_H = 32;
+constexpr int TILE_CAP = 48;         // candidate capacity per tile (more -> exact per-pixel fallback for that tile)
 
 struct SlicGeom {
     int w, h, C, S, K, Kcap;
@@ -28,6 +36,8 @@ struct SlicGeom {
     int alg;                         // 100/101/102
     int radius;                      // bin search radius (1, or more for MSLIC)
     float xywt;                      // SLIC/MSLIC: (S/ruler)^2 ; SLICO: S*S
+    int tiles_x, tiles_y;            // grid of TILE_W x TILE_H tiles
+    int tile_on;                     // the tiled path is in use: centres are also scattered into the tile lists
 };
 
 }  // namespace spx

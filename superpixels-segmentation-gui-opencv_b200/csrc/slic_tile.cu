@@ -1,8 +1,9 @@
 // slic_tile.cu -- tiled fast path of the SLIC assignment + centre accumulation (3-channel, SLIC=100).
 //
-// One CTA owns a 64x32 pixel tile.
-//   setup : the CTA collects the clusters whose window [int(k)-S, int(k)+S) meets the tile from the
-//           centre bins, sorts them by cluster index (upstream visits clusters in ascending n with a
+// One CTA (128 threads) owns a 32x32 pixel tile.
+//   setup : the centre-update kernel has appended to the tile's list every cluster whose window
+//           [int(k)-S, int(k)+S) meets the tile; the CTA reads that list (one coalesced 32-byte record per
+//           cluster), sorts it by cluster index (upstream visits clusters in ascending n with a
 //           strict '<', so ascending order reproduces its tie-breaking), stages their centres in shared
 //           memory and tabulates the separable spatial terms ex2[c][x], ey2[c][y] (+inf outside the
 //           window, so that an out-of-window candidate can never win).
@@ -22,10 +23,11 @@
 
 namespace spx {
 
-constexpr int TW = 64;      // tile width  (8 warps x 8 px)
-constexpr int TH = 32;      // tile height (4 steps x 8 rows)
-constexpr int CAP = 64;     // candidate capacity per tile
-constexpr int MIN_S = 14;   // below this the candidate lists outgrow CAP: generic kernel instead
+constexpr int TW = TILE_W;   // 32: two warps side by side, 16 px each
+constexpr int TH = TILE_H;   // 32: two warp rows x 8 rows x two steps
+constexpr int CAP = TILE_CAP;
+constexpr int NT = 128;      // threads per CTA
+constexpr int MIN_S = 14;    // below this the candidate lists outgrow CAP too often: generic kernel instead
 
 typedef unsigned long long u64;
 
@@ -69,27 +71,26 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
 }
 
 // ---- shared memory layout -----------------------------------------------------------------------
-// One 544-byte record per candidate, so that a single (uniform) record offset addresses everything:
+// One 416-byte record per candidate, so that a single record offset addresses everything:
 //   +0   (-kc0,-kc0) (-kc1,-kc1)      16 B      +16  (-kc2,-kc2)  8 B   (+24 pad)
-//   +32  ex2[64]  float               256 B     (x-kx)^2 [pre-divided by xywt when it is a power of two], +inf outside
-//   +288 ey2[32]  float2 (v,v)        256 B     (y-ky)^2 likewise, duplicated so a row's term is a ready f32x2 operand
-constexpr int REC = 544;
+//   +32  ex2[32]  float               128 B     (x-kx)^2 [pre-divided by xywt when it is a power of two], +inf outside
+//   +160 ey2[32]  float2 (v,v)        256 B     (y-ky)^2 likewise, duplicated so a row's term is a ready f32x2 operand
+constexpr int REC = 416;
 constexpr int REC_EX = 32;
-constexpr int REC_EY = 288;
+constexpr int REC_EY = 160;
 struct TileSmem {
     __align__(16) unsigned char rec[CAP * REC];
     int4 win[CAP];             // window: x_lo, x_hi, y_lo, y_hi (half open)
     unsigned acc[CAP][8];      // 0 c0, 1 c1, 2 c2, 3 count, 4 x (tile relative), 5 y (tile relative)
+    float kxy[CAP][2];         // centre position per slot
     int n[CAP];                // cluster index per slot, ascending
     int list[CAP];
-    int cnt;
 };
 
 struct TileArgs {
-    const int* head; const int* next; const int* ikx; const int* iky;
-    const float* kx; const float* ky; const float* kc;
+    const int* tl_count; const TileRec* tl_rec;
     unsigned long long* acc;
-    int w, h, S, Kcap, nbx, nby, lp;
+    int w, h, S, Kcap, tiles_x, lp;
     size_t ipitch;
     float xywt, rcp_xywt;
 };
@@ -158,96 +159,32 @@ __device__ __forceinline__ void acc_global_pixel(const TileArgs& t, int n, int c
     atomicAdd(&t.acc[4 * (size_t)t.Kcap + n], (u64)y); atomicAdd(&t.acc[5 * (size_t)t.Kcap + n], 1ull);
 }
 
+// exact per-pixel path for a tile whose candidate list overflowed (kept out of line: it is cold)
+__device__ __noinline__ void tile_fallback(const SlicGeom& g, const SlicArrays& a, const unsigned char* img, int* labels,
+                                           int parity, int tx0, int ty0, int warp, int lane)
+{
+    for (int r = warp; r < TH; r += NT / 32) {
+        const int x = tx0 + lane, y = ty0 + r;
+        slic_pixel_generic<100>(g, a, img, labels, nullptr, parity, x, y, x < g.w && y < g.h);
+    }
+}
+
 template <bool POW2>
-__global__ void __launch_bounds__(256, 3) slic_tile_kernel(const TileArgs t, SlicGeom g, SlicArrays a,
-                                                            const unsigned char* __restrict__ img, int* __restrict__ labels,
-                                                            int parity, int* __restrict__ d_overflow)
+__global__ void __launch_bounds__(NT, 5) slic_tile_kernel(const __grid_constant__ TileArgs t, const __grid_constant__ SlicGeom g, const __grid_constant__ SlicArrays a,
+                                                           const unsigned char* __restrict__ img, int* __restrict__ labels,
+                                                           int parity, int* __restrict__ d_overflow)
 {
     __shared__ TileSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int S = t.S;
+    const int tile = blockIdx.y * t.tiles_x + blockIdx.x;
     const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
-    const int tx1 = min(tx0 + TW, t.w), ty1 = min(ty0 + TH, t.h);
-    if (tid == 0) sm.cnt = 0;
-    __syncthreads();
 
-    // ---- candidates: clusters with int(kx) in (tx0-S, tx1+S) and int(ky) in (ty0-S, ty1+S)
-    {
-        const int bx0 = max(tx0 - S + 1, 0) / S, bx1 = min((tx1 + S - 1) / S, t.nbx - 1);
-        const int by0 = max(ty0 - S + 1, 0) / S, by1 = min((ty1 + S - 1) / S, t.nby - 1);
-        const int nbw = bx1 - bx0 + 1, nbins = nbw * (by1 - by0 + 1);
-        for (int b = tid; b < nbins; b += 256) {
-            const int by = by0 + b / nbw, bx = bx0 + b % nbw;
-            for (int n = t.head[by * t.nbx + bx]; n >= 0; n = t.next[n]) {
-                const int ix = t.ikx[n], iy = t.iky[n];
-                if (ix - S < tx1 && ix + S > tx0 && iy - S < ty1 && iy + S > ty0) {
-                    const int i = atomicAdd(&sm.cnt, 1);
-                    if (i < CAP) sm.list[i] = n;
-                }
-            }
-        }
-    }
-    __syncthreads();
-    const int cnt = sm.cnt;
-    if (cnt > CAP) {
-        // too many candidates for the shared-memory tables: exact per-pixel path for this tile
-        if (tid == 0) atomicAdd(d_overflow, 1);
-        for (int r = warp; r < TH; r += 8)
-            for (int c0 = 0; c0 < TW; c0 += 32) {
-                const int x = tx0 + c0 + lane, y = ty0 + r;
-                slic_pixel_generic<100>(g, a, img, labels, nullptr, parity, x, y, x < t.w && y < t.h);
-            }
-        return;
-    }
-    // ---- sort by cluster index, stage centres
-    if (tid < cnt) {
-        const int n = sm.list[tid];
-        int rank = 0;
-        for (int j = 0; j < cnt; j++) rank += sm.list[j] < n ? 1 : 0;
-        sm.n[rank] = n;
-        const float k0 = -t.kc[n], k1 = -t.kc[(size_t)t.Kcap + n], k2 = -t.kc[2 * (size_t)t.Kcap + n];
-        u64* r64 = reinterpret_cast<u64*>(sm.rec + rank * REC);
-        r64[0] = pack2(k0, k0); r64[1] = pack2(k1, k1); r64[2] = pack2(k2, k2);
-        const int ix = t.ikx[n], iy = t.iky[n];
-        sm.win[rank] = make_int4(ix - S, ix + S, iy - S, iy + S);
-    }
-    for (int i = tid; i < cnt * 8; i += 256) (&sm.acc[0][0])[i] = 0u;
-    __syncthreads();
-    // ---- separable spatial tables
-    const float inf = __int_as_float(0x7f800000);
-    for (int i = tid; i < cnt * TW; i += 256) {
-        const int c = i >> 6, xx = i & (TW - 1);
-        const int x = tx0 + xx;
-        const int4 wn = sm.win[c];
-        const float e = __fsub_rn((float)x, t.kx[sm.n[c]]);
-        float v = __fmul_rn(e, e);
-        if (POW2) v = __fmul_rn(v, t.rcp_xywt);
-        reinterpret_cast<float*>(sm.rec + c * REC + REC_EX)[xx] = (x >= wn.x && x < wn.y) ? v : inf;
-    }
-    for (int i = tid; i < cnt * TH; i += 256) {
-        const int c = i >> 5, yy = i & (TH - 1);
-        const int y = ty0 + yy;
-        const int4 wn = sm.win[c];
-        const float e = __fsub_rn((float)y, t.ky[sm.n[c]]);
-        float v = __fmul_rn(e, e);
-        if (POW2) v = __fmul_rn(v, t.rcp_xywt);
-        v = (y >= wn.z && y < wn.w) ? v : inf;
-        reinterpret_cast<u64*>(sm.rec + c * REC + REC_EY)[yy] = pack2(v, v);
-    }
-    __syncthreads();
-
-    // ---- main: a warp owns a 16x8 patch per step (lanes 8 x 4, 2x2 pixels per thread); the CTA's 8 warps cover
-    //      64x16, two steps cover the tile
+    // ---- first pixels in flight before anything else (lanes 8 x 4, 2x2 pixels per thread, warps 2 x 2)
     const int lx = lane & 7, ly = lane >> 3;
-    const int wx = warp & 3, wy = warp >> 2;
+    const int wx = warp & 1, wy = warp >> 1;
     const int xo = 16 * wx + 2 * lx;           // tile-relative x of the thread's left pixels
     const int x = tx0 + xo;
-    const u64 R2 = pack2(t.rcp_xywt, t.rcp_xywt);
-    const float nw = -t.xywt;
-    const u64 NW2 = pack2(nw, nw);
-    const int X0 = tx0 + 16 * wx, X1 = X0 + 16;
-    const unsigned char* thr_ex = sm.rec + REC_EX + xo * 4;
-    // first step's pixels
     unsigned raw[2][3];
     auto load_rows = [&](int yy, unsigned (&dst)[2][3]) {
 #pragma unroll
@@ -260,6 +197,59 @@ __global__ void __launch_bounds__(256, 3) slic_tile_kernel(const TileArgs t, Sli
         }
     };
     load_rows(ty0 + 8 * wy + 2 * ly, raw);
+
+    // ---- candidates: the centre-update kernel appended every cluster whose window touches this tile
+    const int cnt = t.tl_count[tile];
+    if (cnt > CAP) {
+        if (tid == 0) atomicAdd(d_overflow, 1);
+        tile_fallback(g, a, img, labels, parity, tx0, ty0, warp, lane);
+        return;
+    }
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+    if (tid < cnt) {
+        const float4* src = reinterpret_cast<const float4*>(&t.tl_rec[(size_t)tile * CAP + tid]);
+        r0 = src[0]; r1 = src[1];
+        sm.list[tid] = __float_as_int(r1.y);
+    }
+    __syncthreads();
+    // ---- sort by cluster index (upstream's visiting order), stage centres
+    if (tid < cnt) {
+        const int n = __float_as_int(r1.y);
+        int rank = 0;
+        for (int j = 0; j < cnt; j++) rank += sm.list[j] < n ? 1 : 0;
+        sm.n[rank] = n;
+        u64* r64 = reinterpret_cast<u64*>(sm.rec + rank * REC);
+        r64[0] = pack2(-r0.z, -r0.z); r64[1] = pack2(-r0.w, -r0.w); r64[2] = pack2(-r1.x, -r1.x);
+        const int ix = __float_as_int(r1.z), iy = __float_as_int(r1.w);
+        sm.win[rank] = make_int4(ix - S, ix + S, iy - S, iy + S);
+        sm.kxy[rank][0] = r0.x; sm.kxy[rank][1] = r0.y;
+    }
+    for (int i = tid; i < cnt * 8; i += NT) (&sm.acc[0][0])[i] = 0u;
+    __syncthreads();
+    // ---- separable spatial tables: thread (c, j) fills ex2[c][j] and ey2[c][j]
+    {
+        const float inf = __int_as_float(0x7f800000);
+        for (int i = tid; i < cnt * 32; i += NT) {
+            const int c = i >> 5, j = i & 31;
+            const int4 wn = sm.win[c];
+            const int px = tx0 + j, py = ty0 + j;
+            const float ex = __fsub_rn((float)px, sm.kxy[c][0]), ey = __fsub_rn((float)py, sm.kxy[c][1]);
+            float vx = __fmul_rn(ex, ex), vy = __fmul_rn(ey, ey);
+            if (POW2) { vx = __fmul_rn(vx, t.rcp_xywt); vy = __fmul_rn(vy, t.rcp_xywt); }
+            vx = (px >= wn.x && px < wn.y) ? vx : inf;
+            vy = (py >= wn.z && py < wn.w) ? vy : inf;
+            reinterpret_cast<float*>(sm.rec + c * REC + REC_EX)[j] = vx;
+            reinterpret_cast<u64*>(sm.rec + c * REC + REC_EY)[j] = pack2(vy, vy);
+        }
+    }
+    __syncthreads();
+
+    // ---- main: a warp owns a 16x8 patch per step; the CTA's 4 warps cover 32x16, two steps cover the tile
+    const u64 R2 = pack2(t.rcp_xywt, t.rcp_xywt);
+    const float nw = -t.xywt;
+    const u64 NW2 = pack2(nw, nw);
+    const int X0 = tx0 + 16 * wx, X1 = X0 + 16;
+    const unsigned char* thr_ex = sm.rec + REC_EX + xo * 4;
 #pragma unroll 1
     for (int step = 0; step < TH / 16; step++) {
         const int yo = 16 * step + 8 * wy + 2 * ly;
@@ -280,17 +270,15 @@ __global__ void __launch_bounds__(256, 3) slic_tile_kernel(const TileArgs t, Sli
 #pragma unroll
             for (int k = 0; k < 3; k++) P[r][k] = pack2((float)cc[r][0][k], (float)cc[r][1][k]);
         }
-        // candidates whose window meets this warp's patch; REDUX.OR makes the mask a uniform-register value
+        // candidates whose window meets this warp's patch (CAP <= 64: two ballots)
         const int Y0 = ty0 + 16 * step + 8 * wy, Y1 = Y0 + 8;
         unsigned m0, m1 = 0;
         {
             int4 wn = sm.win[lane];
             m0 = __ballot_sync(0xffffffffu, lane < cnt && wn.x < X1 && wn.y > X0 && wn.z < Y1 && wn.w > Y0);
-            m0 = __reduce_or_sync(0xffffffffu, m0);
             if (cnt > 32) {
-                wn = sm.win[lane + 32];
+                wn = sm.win[min(lane + 32, CAP - 1)];
                 m1 = __ballot_sync(0xffffffffu, lane + 32 < cnt && wn.x < X1 && wn.y > X0 && wn.z < Y1 && wn.w > Y0);
-                m1 = __reduce_or_sync(0xffffffffu, m1);
             }
         }
         float best[2][2] = {{FLT_MAX, FLT_MAX}, {FLT_MAX, FLT_MAX}};
@@ -312,13 +300,13 @@ __global__ void __launch_bounds__(256, 3) slic_tile_kernel(const TileArgs t, Sli
                     const u64 t0 = add2(P[r][0], ca.x), t1 = add2(P[r][1], ca.y), t2 = add2(P[r][2], cb);
                     u64 d = add2_products(mul2(t0, t0), mul2(t1, t1));
                     d = add2_products(d, mul2(t2, t2));
-                    u64 s = add2(exv, r ? eyv.y : eyv.x);
+                    u64 sxy = add2(exv, r ? eyv.y : eyv.x);
                     if (!POW2) {
-                        const u64 q0 = mul2(s, R2);
-                        const u64 e = fma2(q0, NW2, s);
-                        s = fma2(e, R2, q0);
+                        const u64 q0 = mul2(sxy, R2);
+                        const u64 e = fma2(q0, NW2, sxy);
+                        sxy = fma2(e, R2, q0);
                     }
-                    d = add2(d, s);
+                    d = add2(d, sxy);
                     float d0, d1;
                     unpack2(d, d0, d1);
                     if (d0 < best[r][0]) { best[r][0] = d0; slot[r][0] = c; }
@@ -354,7 +342,7 @@ __global__ void __launch_bounds__(256, 3) slic_tile_kernel(const TileArgs t, Sli
     }
     __syncthreads();
     // ---- flush: one global atomic per field per candidate that received pixels
-    for (int i = tid; i < cnt * 6; i += 256) {
+    for (int i = tid; i < cnt * 6; i += NT) {
         const int c = i / 6, f = i - 6 * c;
         const unsigned count = sm.acc[c][3];
         if (count == 0) continue;
@@ -392,14 +380,13 @@ int slic_tile_assign(const SlicGeom& g, const SlicArrays& a, const unsigned char
                      int parity, int* d_overflow, cudaStream_t st)
 {
     (void)d_K;
-    dim3 grid(cdiv(g.w, TW), cdiv(g.h, TH));
+    dim3 grid(g.tiles_x, g.tiles_y);
     TileArgs t;
-    t.head = a.head[parity]; t.next = a.next; t.ikx = a.ikx; t.iky = a.iky;
-    t.kx = a.kx; t.ky = a.ky; t.kc = a.kc; t.acc = a.acc;
-    t.w = g.w; t.h = g.h; t.S = g.S; t.Kcap = g.Kcap; t.nbx = g.nbx; t.nby = g.nby; t.lp = g.lp;
+    t.tl_count = a.tl_count[parity]; t.tl_rec = a.tl_rec[parity]; t.acc = a.acc;
+    t.w = g.w; t.h = g.h; t.S = g.S; t.Kcap = g.Kcap; t.tiles_x = g.tiles_x; t.lp = g.lp;
     t.ipitch = g.ipitch; t.xywt = g.xywt; t.rcp_xywt = 1.0f / g.xywt;
-    if (is_pow2(g.xywt)) slic_tile_kernel<true><<<grid, 256, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);
-    else slic_tile_kernel<false><<<grid, 256, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);
+    if (is_pow2(g.xywt)) slic_tile_kernel<true><<<grid, NT, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);
+    else slic_tile_kernel<false><<<grid, NT, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);
     SPX_CUDA(cudaGetLastError());
     return SPX_OK;
 }
