@@ -128,25 +128,16 @@ __device__ __forceinline__ void warp_accumulate4(unsigned (*acc)[8], const int (
             atomicAdd(&acc[cur][lane], (lane & 1) ? (wsel >> 16) : (wsel & 0xffffu));
         }
     }
-    // leftovers: pixels whose slot differs from the thread's first pixel
+    // leftovers: pixels whose slot differs from the thread's first pixel (threads on a label boundary): few lanes,
+    // so plain shared-memory atomics are cheaper than another round of warp reductions
     if (__any_sync(0xffffffffu, left)) {
-        for (;;) {
-            const unsigned mine = min(kj[0], min(kj[1], kj[2]));
-            const unsigned cur = __reduce_min_sync(0xffffffffu, mine);
-            if (cur == 0xffffffffu) break;
-            unsigned cA = 0, cB = 0, cC = 0;
 #pragma unroll
-            for (int j = 0; j < 3; j++) {
-                const bool e = kj[j] == cur;
-                cA += e ? wA[j + 1] : 0u; cB += e ? wB[j + 1] : 0u; cC += e ? wC[j + 1] : 0u;
-                kj[j] = e ? 0xffffffffu : kj[j];
-            }
-            const unsigned A = __reduce_add_sync(0xffffffffu, cA);
-            const unsigned B = __reduce_add_sync(0xffffffffu, cB);
-            const unsigned Cc = __reduce_add_sync(0xffffffffu, cC);
-            if (lane < 6) {
-                const unsigned wsel = lane < 2 ? A : lane < 4 ? B : Cc;
-                atomicAdd(&acc[cur][lane], (lane & 1) ? (wsel >> 16) : (wsel & 0xffffu));
+        for (int j = 0; j < 3; j++) {
+            if (kj[j] != 0xffffffffu) {
+                unsigned* dst = acc[kj[j]];
+                atomicAdd(dst + 0, wA[j + 1] & 0xffffu); atomicAdd(dst + 1, wA[j + 1] >> 16);
+                atomicAdd(dst + 2, wB[j + 1] & 0xffffu); atomicAdd(dst + 3, 1u);
+                atomicAdd(dst + 4, wC[j + 1] & 0xffffu); atomicAdd(dst + 5, wC[j + 1] >> 16);
             }
         }
     }
@@ -260,15 +251,22 @@ __global__ void __launch_bounds__(NT, 5) slic_tile_kernel(const __grid_constant_
 #pragma unroll
             for (int k = 0; k < 3; k++) cur[r][k] = raw[r][k];
         if (step + 1 < TH / 16) load_rows(y + 16, raw);      // prefetch the next step's pixels
-        // unpack: pixel (r, 0) = bytes 0..2, pixel (r, 1) = bytes 3..5
-        int cc[2][2][3];
+        // unpack without the (quarter-rate) I2F unit: byte -> float as (0x4B0000bb as float) - 2^23, built with PRMT.
+        // w01 = [c00 c01 c02 c10], w2 = [c11 c12 0 0]   (pixel (r,0) = bytes 0..2, pixel (r,1) = bytes 3..5)
         u64 P[2][3];
+        unsigned w01[2], w2[2];
+        {
+            const unsigned MAGIC = 0x4B000100u;          // bytes: 00 01 00 4B
+            const u64 M2 = pack2(-8388608.0f, -8388608.0f);
 #pragma unroll
-        for (int r = 0; r < 2; r++) {
-            cc[r][0][0] = cur[r][0] & 255; cc[r][0][1] = cur[r][0] >> 8; cc[r][0][2] = cur[r][1] & 255;
-            cc[r][1][0] = cur[r][1] >> 8;  cc[r][1][1] = cur[r][2] & 255; cc[r][1][2] = cur[r][2] >> 8;
-#pragma unroll
-            for (int k = 0; k < 3; k++) P[r][k] = pack2((float)cc[r][0][k], (float)cc[r][1][k]);
+            for (int r = 0; r < 2; r++) {
+                w01[r] = cur[r][0] | (cur[r][1] << 16);
+                w2[r] = cur[r][2];
+                const float a0 = __uint_as_float(__byte_perm(w01[r], MAGIC, 0x7640)), b0 = __uint_as_float(__byte_perm(w01[r], MAGIC, 0x7643));
+                const float a1 = __uint_as_float(__byte_perm(w01[r], MAGIC, 0x7641)), b1 = __uint_as_float(__byte_perm(w2[r], MAGIC, 0x7640));
+                const float a2 = __uint_as_float(__byte_perm(w01[r], MAGIC, 0x7642)), b2 = __uint_as_float(__byte_perm(w2[r], MAGIC, 0x7641));
+                P[r][0] = add2(pack2(a0, b0), M2); P[r][1] = add2(pack2(a1, b1), M2); P[r][2] = add2(pack2(a2, b2), M2);
+            }
         }
         // candidates whose window meets this warp's patch (CAP <= 64: two ballots)
         const int Y0 = ty0 + 16 * step + 8 * wy, Y1 = Y0 + 8;
@@ -327,16 +325,17 @@ __global__ void __launch_bounds__(NT, 5) slic_tile_kernel(const __grid_constant_
             if (in1) n1 = slot[r][1] >= 0 ? sm.n[slot[r][1]] : lrow[1];
             if (in1) *reinterpret_cast<int2*>(lrow) = make_int2(n0, n1);
             else if (in0) lrow[0] = n0;
-            if (in0 && slot[r][0] < 0) acc_global_pixel(t, n0, cc[r][0][0], cc[r][0][1], cc[r][0][2], x, yy);
-            if (in1 && slot[r][1] < 0) acc_global_pixel(t, n1, cc[r][1][0], cc[r][1][1], cc[r][1][2], x + 1, yy);
-#pragma unroll
-            for (int q = 0; q < 2; q++) {
-                const int j = 2 * r + q;
-                sj[j] = (q ? in1 : in0) ? slot[r][q] : -1;
-                wA[j] = (unsigned)cc[r][q][0] | ((unsigned)cc[r][q][1] << 16);
-                wB[j] = (unsigned)cc[r][q][2] | (1u << 16);
-                wC[j] = (unsigned)(xo + q) | ((unsigned)(yo + r) << 16);
-            }
+            const unsigned MAGIC = 0x4B000100u;
+            wA[2 * r] = __byte_perm(w01[r], MAGIC, 0x4140);          // c00 | c01 << 16
+            wB[2 * r] = __byte_perm(w01[r], MAGIC, 0x4542);          // c02 | 1 << 16
+            wA[2 * r + 1] = __byte_perm(w01[r], w2[r], 0x6463);      // c10 | c11 << 16
+            wB[2 * r + 1] = __byte_perm(w2[r], MAGIC, 0x4541);       // c12 | 1 << 16
+            wC[2 * r] = (unsigned)xo | ((unsigned)(yo + r) << 16);
+            wC[2 * r + 1] = wC[2 * r] + 1u;
+            sj[2 * r] = in0 ? slot[r][0] : -1;
+            sj[2 * r + 1] = in1 ? slot[r][1] : -1;
+            if (in0 && slot[r][0] < 0) acc_global_pixel(t, n0, wA[2 * r] & 0xffff, wA[2 * r] >> 16, wB[2 * r] & 0xffff, x, yy);
+            if (in1 && slot[r][1] < 0) acc_global_pixel(t, n1, wA[2 * r + 1] & 0xffff, wA[2 * r + 1] >> 16, wB[2 * r + 1] & 0xffff, x + 1, yy);
         }
         warp_accumulate4(sm.acc, sj, wA, wB, wC, lane);
     }
