@@ -58,6 +58,8 @@ def lib():
             L.spxo_lsc_get_number_of_superpixels.argtypes = [vp]
             L.spxo_lsc_get_number_of_superpixels.restype = i32
             L.spxo_lsc_get_labels.argtypes = [vp, vp]
+            L.spxo_lsc_set_labels.argtypes = [vp, vp, i32]
+            L.spxo_lsc_get_centres.argtypes = [vp, vp]
             L.spxo_lsc_get_label_contour_mask.argtypes = [vp, vp, i32]
         if hasattr(L, "spxo_seeds_create"):
             L.spxo_seeds_create.restype = vp
@@ -182,6 +184,16 @@ class SuperpixelLSC(_Base):
 
     def enforceLabelConnectivity(self, min_element_size=25):
         lib().spxo_lsc_enforce_label_connectivity(self._h, int(min_element_size))
+
+    def setLabels(self, labels, numlabels=0):
+        lab = np.ascontiguousarray(labels, dtype=np.int32)
+        lib().spxo_lsc_set_labels(self._h, _p(lab), int(numlabels))
+
+    def getCentres(self):
+        """K rows of (2C+4 feature means, seed x, seed y)"""
+        out = np.empty((self.getNumberOfSuperpixels(), 2 * self.c + 6), np.float32)
+        lib().spxo_lsc_get_centres(self._h, _p(out))
+        return out
 
 
 class SuperpixelSEEDS(_Base):

@@ -61,6 +61,9 @@ void spxo_lsc_iterate(spxo_lsc*, int num_iterations);
 void spxo_lsc_enforce_label_connectivity(spxo_lsc*, int min_element_size);
 int  spxo_lsc_get_number_of_superpixels(const spxo_lsc*);
 void spxo_lsc_get_labels(const spxo_lsc*, int32_t* dst);
+void spxo_lsc_set_labels(spxo_lsc*, const int32_t* src, int numlabels);
+/* centres: K rows of (2C+4 feature means, seed x, seed y) float32 */
+void spxo_lsc_get_centres(const spxo_lsc*, float* dst);
 void spxo_lsc_get_label_contour_mask(const spxo_lsc*, uint8_t* dst, int thick_line);
 
 /* ---- SuperpixelSEEDS, mainwindow.cpp:2123-2127 (PARITY UNPINNED; sizing pinned by screenshot) ---- */

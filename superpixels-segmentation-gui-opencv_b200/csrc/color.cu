@@ -8,10 +8,12 @@
 
 namespace spx {
 
-__constant__ unsigned short c_gamma[256];
-__constant__ unsigned short c_cbrt[2048];
-__constant__ int c_sdiv[256];
-__constant__ int c_hdiv[256];
+// the tables live in ordinary global memory: every lane of a warp stages a DIFFERENT entry into shared memory, which
+// the constant cache would serialise 32-fold
+__device__ unsigned short c_gamma[256];
+__device__ unsigned short c_cbrt[2048];
+__device__ int c_sdiv[256];
+__device__ int c_hdiv[256];
 static bool g_tables_loaded[64] = {false};
 
 static int load_tables()
@@ -121,7 +123,7 @@ int cvt8_dev(int mode, const void* d_src, size_t sstride, void* d_dst, size_t ds
     bool vec = ((uintptr_t)d_src % 4 == 0) && ((uintptr_t)d_dst % 4 == 0) && sstride % 4 == 0 && dstride % 4 == 0;
     long long total = (long long)((w + 3) / 4) * h;
     int blocks = (int)((total + 255) / 256);
-    int maxb = 148 * 8 * 4;
+    int maxb = 148 * 8;      // grid-stride: one wave of 8 CTAs per SM, the tables are staged once per CTA
     if (blocks > maxb) blocks = maxb;
     const unsigned char* s = (const unsigned char*)d_src;
     unsigned char* d = (unsigned char*)d_dst;

@@ -23,7 +23,8 @@ namespace spx {
 
 // implemented in slic_tile.cu; returns false when the configuration is outside the fast path
 bool slic_tile_supported(const SlicGeom& g);
-int slic_tile_assign(const SlicGeom& g, const SlicArrays& a, const unsigned char* d_img, int* d_labels,
+int slic_tile_prepare(const SlicGeom& g, const unsigned char* d_img, unsigned* d_img4, cudaStream_t st);
+int slic_tile_assign(const SlicGeom& g, const SlicArrays& a, const unsigned char* d_img, const unsigned* d_img4, int* d_labels,
                      const int* d_K, int parity, int* d_overflow, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------
@@ -95,40 +96,65 @@ __global__ void slic_seed_kernel(SlicGeom g, SlicArrays a, const unsigned char* 
     for (int c = 0; c < g.C; c++) a.kc[(size_t)c * g.Kcap + n] = (float)img[(size_t)Y * g.ipitch + (size_t)X * g.C + c];
 }
 
-// insert centre n into its S x S bin (linked list) and, for the tiled path, append its record to the list of every
-// tile its window [ix-off, ix+off) x [iy-off, iy+off) touches
-__device__ __forceinline__ void bin_insert(const SlicGeom& g, const SlicArrays& a, int par, int n, int ix, int iy)
+// ---- binning: centre n goes into its S x S bin (linked list, used by the generic kernel and the tile fallback) and,
+// for the tiled path, its record is appended to the list of every tile its window [ix-off, ix+off) x [iy-off, iy+off)
+// touches.  The scatter is done by the whole CTA over (centre, tile) pairs, so the global atomics of one centre do not
+// queue behind each other.
+constexpr int BIN_CTA = 128;
+struct BinStage {                       // what the scatter needs about the CTA's centres
+    float4 a[BIN_CTA];                  // kx, ky, k0, k1
+    float4 b[BIN_CTA];                  // k2, n, ix, iy (ints as bits)
+    int4 span[BIN_CTA];                 // tx0, ty0, tiles across, tiles down  (across = 0: nothing to scatter)
+};
+__device__ __forceinline__ void bin_stage(const SlicGeom& g, const SlicArrays& a, int par, BinStage& sh, int slot, int n, bool valid)
 {
-    int* head = par ? a.head[1] : a.head[0];
-    int bx = min(max(ix, 0) / g.S, g.nbx - 1), by = min(max(iy, 0) / g.S, g.nby - 1);
-    a.next[n] = atomicExch(&head[by * g.nbx + bx], n);
-    if (g.tile_on) {
-        int* cnt = par ? a.tl_count[1] : a.tl_count[0];
-        TileRec* recs = par ? a.tl_rec[1] : a.tl_rec[0];
-        const int off = a.ioff[n];
-        const int tx0 = max(ix - off, 0) / TILE_W, tx1 = min(ix + off - 1, g.w - 1) / TILE_W;
-        const int ty0 = max(iy - off, 0) / TILE_H, ty1 = min(iy + off - 1, g.h - 1) / TILE_H;
-        TileRec r;
-        r.kx = a.kx[n]; r.ky = a.ky[n];
-        r.k0 = a.kc[n]; r.k1 = a.kc[(size_t)g.Kcap + n]; r.k2 = a.kc[2 * (size_t)g.Kcap + n];
-        r.n = n; r.ix = ix; r.iy = iy;
-        for (int ty = ty0; ty <= ty1; ty++)
-            for (int tx = tx0; tx <= tx1; tx++) {
-                const int tile = ty * g.tiles_x + tx;
-                const int slot = atomicAdd(&cnt[tile], 1);
-                if (slot < TILE_CAP) {
-                    float4* dst = reinterpret_cast<float4*>(&recs[(size_t)tile * TILE_CAP + slot]);
-                    dst[0] = make_float4(r.kx, r.ky, r.k0, r.k1);
-                    dst[1] = make_float4(r.k2, __int_as_float(r.n), __int_as_float(r.ix), __int_as_float(r.iy));
+    int4 span = make_int4(0, 0, 0, 0);
+    if (valid) {
+        const int ix = a.ikx[n], iy = a.iky[n];
+        int* head = par ? a.head[1] : a.head[0];
+        int bx = min(max(ix, 0) / g.S, g.nbx - 1), by = min(max(iy, 0) / g.S, g.nby - 1);
+        a.next[n] = atomicExch(&head[by * g.nbx + bx], n);
+        if (g.tile_on) {
+            const int off = a.ioff[n];
+            const int tx0 = max(ix - off, 0) / TILE_W, tx1 = min(ix + off - 1, g.w - 1) / TILE_W;
+            const int ty0 = max(iy - off, 0) / TILE_H, ty1 = min(iy + off - 1, g.h - 1) / TILE_H;
+            if (tx1 >= tx0 && ty1 >= ty0) span = make_int4(tx0, ty0, tx1 - tx0 + 1, ty1 - ty0 + 1);
+            sh.a[slot] = make_float4(a.kx[n], a.ky[n], a.kc[n], a.kc[(size_t)g.Kcap + n]);
+            sh.b[slot] = make_float4(a.kc[2 * (size_t)g.Kcap + n], __int_as_float(n), __int_as_float(ix), __int_as_float(iy));
+        }
+    }
+    sh.span[slot] = span;
+}
+// all threads of the CTA; call after __syncthreads()
+__device__ __forceinline__ void bin_scatter(const SlicGeom& g, const SlicArrays& a, int par, const BinStage& sh)
+{
+    if (!g.tile_on) return;
+    int* cnt = par ? a.tl_count[1] : a.tl_count[0];
+    TileRec* recs = par ? a.tl_rec[1] : a.tl_rec[0];
+    // work item = (centre slot, j) with j in 0..15 walking the span in a 4x4 pattern (bigger spans: strided repeats)
+#pragma unroll 4
+    for (int i = threadIdx.x; i < BIN_CTA * 16; i += BIN_CTA) {
+        const int slot = i >> 4, j = i & 15;
+        const int4 sp = sh.span[slot];
+        for (int ty = j >> 2; ty < sp.w; ty += 4)
+            for (int tx = j & 3; tx < sp.z; tx += 4) {
+                const int tile = (sp.y + ty) * g.tiles_x + sp.x + tx;
+                const int pos = atomicAdd(&cnt[tile], 1);
+                if (pos < TILE_CAP) {
+                    float4* dst = reinterpret_cast<float4*>(&recs[(size_t)tile * TILE_CAP + pos]);
+                    dst[0] = sh.a[slot];
+                    dst[1] = sh.b[slot];
                 }
             }
     }
 }
-__global__ void slic_bin_kernel(SlicGeom g, SlicArrays a, const int* __restrict__ d_K, int parity)
+__global__ void __launch_bounds__(BIN_CTA) slic_bin_kernel(SlicGeom g, SlicArrays a, const int* __restrict__ d_K, int parity)
 {
-    int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= *d_K) return;
-    bin_insert(g, a, parity, n, a.ikx[n], a.iky[n]);
+    __shared__ BinStage sh;
+    const int n = blockIdx.x * BIN_CTA + threadIdx.x;
+    bin_stage(g, a, parity, sh, threadIdx.x, n, n < *d_K);
+    __syncthreads();
+    bin_scatter(g, a, parity, sh);
 }
 __global__ void fill_i32_kernel(int* p, int v, size_t n)
 {
@@ -160,34 +186,38 @@ __global__ void __launch_bounds__(256) slic_assign_generic_kernel(SlicGeom g, Sl
 // ------------------------------------------------------------------------------------------------
 // centre update (SeedNormInvoker): mean = float(sum)/float(count), count<=0 -> 1; then re-bin.
 // ------------------------------------------------------------------------------------------------
-__global__ void slic_finalize_kernel(SlicGeom g, SlicArrays a, const int* __restrict__ d_K, int parity, int do_bin)
+__global__ void __launch_bounds__(BIN_CTA) slic_finalize_kernel(SlicGeom g, SlicArrays a, const int* __restrict__ d_K, int parity, int do_bin)
 {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ BinStage sh;
+    int t = blockIdx.x * BIN_CTA + threadIdx.x;
     const int nb = g.nbx * g.nby;
     if (t < nb) (parity ? a.head[1] : a.head[0])[t] = -1;
     if (g.tile_on && t < g.tiles_x * g.tiles_y) (parity ? a.tl_count[1] : a.tl_count[0])[t] = 0;
     //              // the lists just consumed; reused two iterations later
     const int K = *d_K;
-    if (t >= K) return;
-    unsigned long long cnt = a.acc[(size_t)(g.C + 2) * g.Kcap + t];
-    float m = (float)(cnt == 0 ? 1ull : cnt);
-    for (int c = 0; c < g.C; c++) {
-        a.kc[(size_t)c * g.Kcap + t] = __fdiv_rn((float)a.acc[(size_t)c * g.Kcap + t], m);
-        a.acc[(size_t)c * g.Kcap + t] = 0;
+    if (t < K) {
+        unsigned long long cnt = a.acc[(size_t)(g.C + 2) * g.Kcap + t];
+        float m = (float)(cnt == 0 ? 1ull : cnt);
+        for (int c = 0; c < g.C; c++) {
+            a.kc[(size_t)c * g.Kcap + t] = __fdiv_rn((float)a.acc[(size_t)c * g.Kcap + t], m);
+            a.acc[(size_t)c * g.Kcap + t] = 0;
+        }
+        float kx = __fdiv_rn((float)a.acc[(size_t)g.C * g.Kcap + t], m);
+        float ky = __fdiv_rn((float)a.acc[(size_t)(g.C + 1) * g.Kcap + t], m);
+        a.acc[(size_t)g.C * g.Kcap + t] = 0;
+        a.acc[(size_t)(g.C + 1) * g.Kcap + t] = 0;
+        a.acc[(size_t)(g.C + 2) * g.Kcap + t] = 0;
+        a.kx[t] = kx; a.ky[t] = ky;
+        a.ikx[t] = (int)kx; a.iky[t] = (int)ky;
+        if (g.alg == 101) {                               // maxchans[k] <- accumulated maximum; seeds the next one
+            unsigned mb = a.maxc_acc[t];
+            a.maxc[t] = __uint_as_float(mb);
+        }
     }
-    float kx = __fdiv_rn((float)a.acc[(size_t)g.C * g.Kcap + t], m);
-    float ky = __fdiv_rn((float)a.acc[(size_t)(g.C + 1) * g.Kcap + t], m);
-    a.acc[(size_t)g.C * g.Kcap + t] = 0;
-    a.acc[(size_t)(g.C + 1) * g.Kcap + t] = 0;
-    a.acc[(size_t)(g.C + 2) * g.Kcap + t] = 0;
-    a.kx[t] = kx; a.ky[t] = ky;
-    int ix = (int)kx, iy = (int)ky;
-    a.ikx[t] = ix; a.iky[t] = iy;
-    if (g.alg == 101) {                               // maxchans[k] <- accumulated maximum; seeds the next one
-        unsigned mb = a.maxc_acc[t];
-        a.maxc[t] = __uint_as_float(mb);
-    }
-    if (do_bin) bin_insert(g, a, parity ^ 1, t, ix, iy);
+    if (!do_bin) return;                                  // uniform
+    bin_stage(g, a, parity ^ 1, sh, threadIdx.x, t, t < K);
+    __syncthreads();
+    bin_scatter(g, a, parity ^ 1, sh);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -320,6 +350,7 @@ struct SlicEngine {
     SlicArrays a{};
     float ruler = 10.f;
     unsigned char* d_img = nullptr;
+    unsigned* d_img4 = nullptr;      // tiled path: padded Lab1 words (c0,c1,c2,1)
     int* d_labels = nullptr;
     float* d_dcplane = nullptr;      // SLICO only
     unsigned char* d_mask = nullptr;
@@ -387,7 +418,9 @@ struct SlicEngine {
         ruler = ruler_;
         g.w = w; g.h = h; g.C = C; g.S = S; g.alg = alg;
         g.ipitch = round_up((size_t)w * C, 16) + 16;
-        g.lp = (int)round_up((size_t)w, 4);
+        g.tiles_x = cdiv(w, TILE_W); g.tiles_y = cdiv(h, TILE_H);
+        g.lp = g.tiles_x * TILE_W;
+        g.p4 = g.tiles_x * TILE_W;
         g.nbx = cdiv(w, S); g.nby = cdiv(h, S);
         g.radius = alg == SPX_MSLIC ? 2 : 1;
         if (alg == SPX_SLICO) g.xywt = (float)(S * S);
@@ -399,7 +432,7 @@ struct SlicEngine {
         g.Kcap = alg == SPX_MSLIC ? 4 * K : K;
         const size_t kc = (size_t)g.Kcap;
         SPX_CHECK(dalloc(&d_img, g.ipitch * (size_t)(h + 1)));
-        SPX_CHECK(dalloc(&d_labels, (size_t)g.lp * h));
+        SPX_CHECK(dalloc(&d_labels, (size_t)g.lp * g.tiles_y * TILE_H));
         SPX_CHECK(dalloc(&d_mask, (size_t)w * h));
         SPX_CHECK(dalloc(&a.kx, kc)); SPX_CHECK(dalloc(&a.ky, kc)); SPX_CHECK(dalloc(&a.kc, kc * C));
         SPX_CHECK(dalloc(&a.ikx, kc)); SPX_CHECK(dalloc(&a.iky, kc)); SPX_CHECK(dalloc(&a.ioff, kc));
@@ -414,11 +447,13 @@ struct SlicEngine {
         if (alg == SPX_SLICO) SPX_CHECK(dalloc(&d_dcplane, (size_t)w * h));
         SPX_CUDA(cudaMallocHost(&h_pinned, 4 * sizeof(int)));
         SPX_CUDA(cudaMemsetAsync(d_img, 0, g.ipitch * (size_t)(h + 1), st));
-        g.tiles_x = cdiv(w, TILE_W); g.tiles_y = cdiv(h, TILE_H);
         use_tile = slic_tile_supported(g) && !getenv("SPX_SLIC_GENERIC");
         g.tile_on = use_tile ? 1 : 0;
         if (use_tile) {
             const size_t nt = (size_t)g.tiles_x * g.tiles_y;
+            const size_t n4 = (size_t)g.p4 * g.tiles_y * TILE_H;
+            SPX_CHECK(dalloc(&d_img4, n4));
+            SPX_CUDA(cudaMemsetAsync(d_img4, 0, n4 * sizeof(unsigned), st));
             for (int p = 0; p < 2; p++) {
                 SPX_CHECK(dalloc(&a.tl_count[p], nt));
                 SPX_CHECK(dalloc(&a.tl_rec[p], nt * TILE_CAP));
@@ -433,7 +468,7 @@ struct SlicEngine {
     {
         const size_t kc = (size_t)g.Kcap;
         g.K = K0; numlabels = K0; parity = 0;
-        SPX_CUDA(cudaMemsetAsync(d_labels, 0, (size_t)g.lp * g.h * sizeof(int), st));
+        SPX_CUDA(cudaMemsetAsync(d_labels, 0, (size_t)g.lp * g.tiles_y * TILE_H * sizeof(int), st));
         SPX_CUDA(cudaMemsetAsync(a.acc, 0, kc * (g.C + 3) * sizeof(unsigned long long), st));
         SPX_CUDA(cudaMemsetAsync(a.area, 0, kc * sizeof(long long), st));
         SPX_CUDA(cudaMemsetAsync(a.head[0], 0xFF, (size_t)g.nbx * g.nby * sizeof(int), st));
@@ -445,8 +480,9 @@ struct SlicEngine {
         SPX_CUDA(cudaMemcpyAsync(d_K, h_pinned, sizeof(int), cudaMemcpyHostToDevice, st));
         int K = 0;
         SeedParams sp = seed_params(&K);
+        if (use_tile) { SPX_CHECK(slic_tile_prepare(g, d_img, d_img4, st)); launches++; }
         slic_seed_kernel<<<cdiv(K0, 128), 128, 0, st>>>(g, a, d_img, sp);
-        slic_bin_kernel<<<cdiv(K0, 128), 128, 0, st>>>(g, a, d_K, 0);
+        slic_bin_kernel<<<cdiv(K0, BIN_CTA), BIN_CTA, 0, st>>>(g, a, d_K, 0);
         launches += 2;
         SPX_CUDA(cudaGetLastError());
         return SPX_OK;
@@ -471,7 +507,7 @@ struct SlicEngine {
         for (int it = 0; it < n; it++) {
             bool tiled = false;
             if (use_tile) {
-                SPX_CHECK(slic_tile_assign(g, a, d_img, d_labels, d_K, parity, d_overflow, st));
+                SPX_CHECK(slic_tile_assign(g, a, d_img, d_img4, d_labels, d_K, parity, d_overflow, st));
                 tiled = true;
                 launches++;
             }
@@ -483,13 +519,13 @@ struct SlicEngine {
                 launches++;
             }
             const int do_bin = g.alg == SPX_MSLIC ? 0 : 1;
-            slic_finalize_kernel<<<cdiv(threads_fin, 256), 256, 0, st>>>(g, a, d_K, parity, do_bin);
+            slic_finalize_kernel<<<cdiv(threads_fin, BIN_CTA), BIN_CTA, 0, st>>>(g, a, d_K, parity, do_bin);
             launches++;
             if (g.alg == SPX_MSLIC) {
                 float q = (float)g.S / ruler;
                 mslic_area_kernel<<<dim3(cdiv(g.w, 32), cdiv(g.h, 8)), 256, 0, st>>>(g, a, d_img, d_labels, q);
                 mslic_adapt_kernel<<<1, 1024, 0, st>>>(g, a, d_img, d_K, K0);
-                slic_bin_kernel<<<cdiv(g.Kcap, 128), 128, 0, st>>>(g, a, d_K, parity ^ 1);
+                slic_bin_kernel<<<cdiv(g.Kcap, BIN_CTA), BIN_CTA, 0, st>>>(g, a, d_K, parity ^ 1);
                 launches += 3;
             }
             parity ^= 1;
@@ -500,7 +536,7 @@ struct SlicEngine {
 
     int enqueue_assign()
     {
-        if (use_tile) return slic_tile_assign(g, a, d_img, d_labels, d_K, parity, d_overflow, st);
+        if (use_tile) return slic_tile_assign(g, a, d_img, d_img4, d_labels, d_K, parity, d_overflow, st);
         dim3 grid(cdiv(g.w, 32), cdiv(g.h, 8));
         if (g.alg == SPX_SLIC) slic_assign_generic_kernel<100><<<grid, 256, 0, st>>>(g, a, d_img, d_labels, d_dcplane, parity, 0, 0, g.w, g.h);
         else if (g.alg == SPX_SLICO) slic_assign_generic_kernel<101><<<grid, 256, 0, st>>>(g, a, d_img, d_labels, d_dcplane, parity, 0, 0, g.w, g.h);

@@ -31,7 +31,8 @@ constexpr int TILE_CAP = 48;         // candidate capacity per tile (more -> exa
 struct SlicGeom {
     int w, h, C, S, K, Kcap;
     int nbx, nby;                    // bins of S x S pixels
-    int lp;                          // label pitch (elements)
+    int lp;                          // label pitch (elements), a multiple of TILE_W; rows are padded to the tile grid
+    int p4;                          // pitch (pixels) of the padded Lab1 word image of the tiled path
     size_t ipitch;                   // image pitch (bytes)
     int alg;                         // 100/101/102
     int radius;                      // bin search radius (1, or more for MSLIC)

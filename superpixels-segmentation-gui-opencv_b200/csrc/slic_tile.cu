@@ -1,21 +1,25 @@
-// slic_tile.cu -- tiled fast path of the SLIC assignment + centre accumulation (3-channel, SLIC=100).
+// slic_tile.cu -- tiled fast path of the SLIC assignment + centre accumulation (3-channel, SLIC=100).   [v5]
 //
-// One CTA (128 threads) owns a 32x32 pixel tile.
-//   setup : the centre-update kernel has appended to the tile's list every cluster whose window
-//           [int(k)-S, int(k)+S) meets the tile; the CTA reads that list (one coalesced 32-byte record per
-//           cluster), sorts it by cluster index (upstream visits clusters in ascending n with a
-//           strict '<', so ascending order reproduces its tie-breaking), stages their centres in shared
-//           memory and tabulates the separable spatial terms ex2[c][x], ey2[c][y] (+inf outside the
-//           window, so that an out-of-window candidate can never win).
-//   main  : a warp handles a 16x8 patch, 2x2 pixels per thread, and visits only the candidates whose
-//           window meets the patch (6.7 per pixel on average at S=20; 4.0 is the minimum).  The distance arithmetic is upstream's float32 sequence, evaluated with the sm_100
-//           packed f32x2 instructions (FADD2/FMUL2/FFMA2: same rounding per element, half the issue
-//           slots), never contracted:   d = ((t0*t0 + t1*t1) + t2*t2) + (ex2+ey2)/xywt.
-//           The IEEE division by the constant xywt is a multiply when xywt is a power of two, otherwise
-//           Markstein's correctly rounded q = a*r; q += fma(-q, w, a)*r with r = RN(1/w).
-//   accum : per-warp REDUX sums of (L,a,b,x,y,1) per label, shared-memory accumulators per candidate,
-//           one 64-bit global atomic per field per candidate per CTA.
-// Algorithmic traffic: 3 B/px read + 4 B/px written per iteration.
+// One CTA (128 threads) owns a 32x32 pixel tile of the "Lab1" image (one 32-bit word per pixel: c0,c1,c2,1; rows and
+// columns padded to the tile grid with zero words, so no load or store in the hot loop needs a bounds check).
+//   setup   : the centre update appended to the tile's list every cluster whose window [int(k)-S, int(k)+S) meets the
+//             tile.  The CTA reads the list (one 32-byte record per cluster), ranks it by cluster index (upstream visits
+//             clusters in ascending n with a strict '<', so ascending order reproduces its tie-breaking), stages
+//             (-k0,-k1,-k2,n) per candidate and tabulates the separable spatial terms ex2[c][x], ey2[c][y] with packed
+//             f32x2 arithmetic (+inf outside the window: an out-of-window candidate can never win).
+//   phase 1 : a warp handles a 16x8 patch per step, 2x2 pixels per thread, and visits only the candidates whose window
+//             meets the patch (6.4 per patch at S=20; 4.0 per pixel is the minimum).  Upstream's float32 sequence
+//                 d = ((t0*t0 + t1*t1) + t2*t2) + (ex2+ey2)/xywt
+//             is evaluated with the sm_100 packed instructions FADD2/FMUL2 (same rounding per element, half the issue
+//             slots; scalar operands are broadcast by the instruction), never contracted.  The IEEE division by the
+//             constant xywt is a multiply when xywt is a power of two (folded into the tables), otherwise Markstein's
+//             correctly rounded q = a*r; q += fma(-q, w, a)*r with r = RN(1/w).  Labels go out as 8-byte stores, the
+//             winning candidate slot of every pixel into a 1 KB shared-memory map.
+//   phase 2 : accumulation over the slot map with a scattered thread->pixel mapping (the 32 lanes of a warp sit in
+//             different clusters, so their shared-memory atomics rarely collide): a thread sums 4 consecutive pixels
+//             split by at most two slots with byte-SIMD masks and adds (c0,c1,c2,count,x,y) to the CTA's per-candidate
+//             accumulators; then one 64-bit global atomic per field per candidate that received pixels.
+// Algorithmic traffic: 3 B/px read + 4 B/px written per iteration (the padded word layout moves 4 + 4).
 #include "slic.cuh"
 #include "slic_generic.cuh"
 #include <cfloat>
@@ -27,6 +31,7 @@ constexpr int TW = TILE_W;   // 32: two warps side by side, 16 px each
 constexpr int TH = TILE_H;   // 32: two warp rows x 8 rows x two steps
 constexpr int CAP = TILE_CAP;
 constexpr int NT = 128;      // threads per CTA
+constexpr int NCOPY = 8;
 constexpr int MIN_S = 14;    // below this the candidate lists outgrow CAP too often: generic kernel instead
 
 typedef unsigned long long u64;
@@ -69,84 +74,39 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
     return r;
 }
+__device__ __forceinline__ u64 bcast2(float v) { return pack2(v, v); }   // ptxas folds this into a scalar operand
 
 // ---- shared memory layout -----------------------------------------------------------------------
-// One 416-byte record per candidate, so that a single record offset addresses everything:
-//   +0   (-kc0,-kc0) (-kc1,-kc1)      16 B      +16  (-kc2,-kc2)  8 B   (+24 pad)
-//   +32  ex2[32]  float               128 B     (x-kx)^2 [pre-divided by xywt when it is a power of two], +inf outside
-//   +160 ey2[32]  float2 (v,v)        256 B     (y-ky)^2 likewise, duplicated so a row's term is a ready f32x2 operand
-constexpr int REC = 416;
-constexpr int REC_EX = 32;
-constexpr int REC_EY = 160;
-struct TileSmem {
-    __align__(16) unsigned char rec[CAP * REC];
-    int4 win[CAP];             // window: x_lo, x_hi, y_lo, y_hi (half open)
-    unsigned acc[CAP][8];      // 0 c0, 1 c1, 2 c2, 3 count, 4 x (tile relative), 5 y (tile relative)
-    float kxy[CAP][2];         // centre position per slot
-    int n[CAP];                // cluster index per slot, ascending
+// one record per candidate, so that a single multiply addresses everything the inner loop reads
+struct __align__(16) CandRec {
+    float4 k;                    // (-k0, -k1, -k2, n as int bits)
+    float ex2[TW];               // (x-kx)^2 [times 1/xywt when it is a power of two], +inf outside the window
+    float ey2[TH];               // (y-ky)^2 likewise
+};
+struct __align__(16) TileSmem {
+    CandRec rec[CAP];            // ascending n
+    int4 win[CAP];               // window: x_lo, x_hi, y_lo, y_hi (half open)
+    // accumulators: NCOPY privatised copies (a lane uses copy lane&7, so lanes that sit in the same cluster rarely hit
+    // the same address); per candidate 4 packed words: c0 | count<<18, c1, c2, x | y<<16 (tile-relative; a tile has
+    // 1024 pixels, so c <= 261120 < 2^18, count <= 2^10, x,y sums <= 31744 < 2^16)
+    __align__(16) unsigned acc[NCOPY][CAP * 4 + 4];
+    float kxy[CAP][2];           // centre position per slot
     int list[CAP];
+    unsigned char slot[TH][TW];  // winning candidate slot per pixel (0xFF: none / handled on the spot)
 };
 
 struct TileArgs {
     const int* tl_count; const TileRec* tl_rec;
     unsigned long long* acc;
-    int w, h, S, Kcap, tiles_x, lp;
-    size_t ipitch;
+    const unsigned* img4;        // Lab1 words, pitch p4 (pixels)
+    int w, h, S, Kcap, tiles_x, lp, p4;
     float xywt, rcp_xywt;
 };
 
-// per-label sums of one warp step.  Every thread contributes up to four pixels (slot s[j], words wA/wB/wC[j]:
-// wA = c0 | c1<<16, wB = c2 | count<<16, wC = xrel | yrel<<16).  Labels are visited in ascending slot order:
-// REDUX.MIN picks the next one (result lands in a uniform register), REDUX.SUM adds its three words over the
-// warp, and lanes 0..5 add one field each to the CTA's shared accumulators.
-__device__ __forceinline__ void warp_accumulate4(unsigned (*acc)[8], const int (&s)[4], const unsigned (&wA)[4],
-                                                 const unsigned (&wB)[4], const unsigned (&wC)[4], int lane)
+__device__ __forceinline__ void acc_global_pixel(const TileArgs& t, int n, unsigned px, int x, int y)
 {
-    // thread-local merge: everything equal to the first pixel's slot is summed up front (the common case)
-    unsigned pA = wA[0], pB = wB[0], pC = wC[0];
-    unsigned key0 = (unsigned)s[0];               // -1 -> 0xffffffff = nothing
-    unsigned kj[3];
-    bool left = false;
-#pragma unroll
-    for (int j = 1; j < 4; j++) {
-        const bool e = s[j] == s[0];
-        pA += e ? wA[j] : 0u; pB += e ? wB[j] : 0u; pC += e ? wC[j] : 0u;
-        kj[j - 1] = e ? 0xffffffffu : (unsigned)s[j];
-        left |= !e && s[j] >= 0;
-    }
-    // primary pass
-    for (;;) {
-        const unsigned cur = __reduce_min_sync(0xffffffffu, key0);
-        if (cur == 0xffffffffu) break;
-        const bool e = key0 == cur;
-        const unsigned A = __reduce_add_sync(0xffffffffu, e ? pA : 0u);
-        const unsigned B = __reduce_add_sync(0xffffffffu, e ? pB : 0u);
-        const unsigned Cc = __reduce_add_sync(0xffffffffu, e ? pC : 0u);
-        key0 = e ? 0xffffffffu : key0;
-        if (lane < 6) {
-            const unsigned wsel = lane < 2 ? A : lane < 4 ? B : Cc;
-            atomicAdd(&acc[cur][lane], (lane & 1) ? (wsel >> 16) : (wsel & 0xffffu));
-        }
-    }
-    // leftovers: pixels whose slot differs from the thread's first pixel (threads on a label boundary): few lanes,
-    // so plain shared-memory atomics are cheaper than another round of warp reductions
-    if (__any_sync(0xffffffffu, left)) {
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            if (kj[j] != 0xffffffffu) {
-                unsigned* dst = acc[kj[j]];
-                atomicAdd(dst + 0, wA[j + 1] & 0xffffu); atomicAdd(dst + 1, wA[j + 1] >> 16);
-                atomicAdd(dst + 2, wB[j + 1] & 0xffffu); atomicAdd(dst + 3, 1u);
-                atomicAdd(dst + 4, wC[j + 1] & 0xffffu); atomicAdd(dst + 5, wC[j + 1] >> 16);
-            }
-        }
-    }
-}
-
-__device__ __forceinline__ void acc_global_pixel(const TileArgs& t, int n, int c0, int c1, int c2, int x, int y)
-{
-    atomicAdd(&t.acc[n], (u64)c0); atomicAdd(&t.acc[(size_t)t.Kcap + n], (u64)c1);
-    atomicAdd(&t.acc[2 * (size_t)t.Kcap + n], (u64)c2); atomicAdd(&t.acc[3 * (size_t)t.Kcap + n], (u64)x);
+    atomicAdd(&t.acc[n], (u64)(px & 0xffu)); atomicAdd(&t.acc[(size_t)t.Kcap + n], (u64)((px >> 8) & 0xffu));
+    atomicAdd(&t.acc[2 * (size_t)t.Kcap + n], (u64)((px >> 16) & 0xffu)); atomicAdd(&t.acc[3 * (size_t)t.Kcap + n], (u64)x);
     atomicAdd(&t.acc[4 * (size_t)t.Kcap + n], (u64)y); atomicAdd(&t.acc[5 * (size_t)t.Kcap + n], 1ull);
 }
 
@@ -160,10 +120,31 @@ __device__ __noinline__ void tile_fallback(const SlicGeom& g, const SlicArrays& 
     }
 }
 
+// phase-1 cold path: some pixel of the warp's patch is covered by no window (or lies outside the image).
+// Everything is passed by value so that the hot loop's state never has to live in local memory.
+__device__ __noinline__ void step_slow(const TileArgs& t, TileSmem& sm, int* labels, unsigned slots4, unsigned p00, unsigned p01,
+                                       unsigned p10, unsigned p11, int x, int y, int xo, int yo)
+{
+    const unsigned px[4] = {p00, p01, p10, p11};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int r = i >> 1, k = i & 1;
+        const int xx = x + k, yy = y + r;
+        const unsigned s = (slots4 >> (8 * i)) & 0xffu;         // 0xFF: no candidate
+        unsigned char sb = 0xFF;
+        if (xx < t.w && yy < t.h) {
+            int* lp = labels + (size_t)yy * t.lp + xx;
+            if (s != 0xffu) { *lp = __float_as_int(sm.rec[s].k.w); sb = (unsigned char)s; }
+            else acc_global_pixel(t, *lp, px[i], xx, yy);       // keeps its label; sums go straight to global
+        }
+        sm.slot[yo + r][xo + k] = sb;
+    }
+}
+
 template <bool POW2>
-__global__ void __launch_bounds__(NT, 5) slic_tile_kernel(const __grid_constant__ TileArgs t, const __grid_constant__ SlicGeom g, const __grid_constant__ SlicArrays a,
-                                                           const unsigned char* __restrict__ img, int* __restrict__ labels,
-                                                           int parity, int* __restrict__ d_overflow)
+__global__ void __launch_bounds__(NT, 8) slic_tile_kernel(const __grid_constant__ TileArgs t, const __grid_constant__ SlicGeom g,
+                                                           const __grid_constant__ SlicArrays a, const unsigned char* __restrict__ img,
+                                                           int* __restrict__ labels, int parity, int* __restrict__ d_overflow)
 {
     __shared__ TileSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -176,95 +157,90 @@ __global__ void __launch_bounds__(NT, 5) slic_tile_kernel(const __grid_constant_
     const int wx = warp & 1, wy = warp >> 1;
     const int xo = 16 * wx + 2 * lx;           // tile-relative x of the thread's left pixels
     const int x = tx0 + xo;
-    unsigned raw[2][3];
-    auto load_rows = [&](int yy, unsigned (&dst)[2][3]) {
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-            dst[r][0] = dst[r][1] = dst[r][2] = 0;
-            if (yy + r < t.h) {
-                const unsigned short* p = reinterpret_cast<const unsigned short*>(img + (size_t)(yy + r) * t.ipitch + (size_t)x * 3);
-                dst[r][0] = __ldg(p); dst[r][1] = __ldg(p + 1); dst[r][2] = __ldg(p + 2);
-            }
-        }
-    };
-    load_rows(ty0 + 8 * wy + 2 * ly, raw);
+    const unsigned* pimg = t.img4 + (size_t)(ty0 + 8 * wy + 2 * ly) * t.p4 + x;    // this thread's first pixel pair
+    uint2 nxt0 = __ldg(reinterpret_cast<const uint2*>(pimg));
+    uint2 nxt1 = __ldg(reinterpret_cast<const uint2*>(pimg + t.p4));
+    const int p4_16 = 16 * t.p4, p4_17 = 17 * t.p4;
 
     // ---- candidates: the centre-update kernel appended every cluster whose window touches this tile
-    const int cnt = t.tl_count[tile];
+    // (the record loads do not wait for the count: slots beyond it hold stale records that are never used)
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+    if (tid < CAP) {
+        const float4* src = reinterpret_cast<const float4*>(&t.tl_rec[(size_t)tile * CAP + tid]);
+        r0 = __ldg(src); r1 = __ldg(src + 1);
+    }
+    const int cnt = __ldg(&t.tl_count[tile]);
     if (cnt > CAP) {
         if (tid == 0) atomicAdd(d_overflow, 1);
         tile_fallback(g, a, img, labels, parity, tx0, ty0, warp, lane);
         return;
     }
-    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-    if (tid < cnt) {
-        const float4* src = reinterpret_cast<const float4*>(&t.tl_rec[(size_t)tile * CAP + tid]);
-        r0 = src[0]; r1 = src[1];
-        sm.list[tid] = __float_as_int(r1.y);
-    }
+    if (tid < cnt) sm.list[tid] = __float_as_int(r1.y);
     __syncthreads();
-    // ---- sort by cluster index (upstream's visiting order), stage centres
+    // ---- rank by cluster index (upstream's visiting order), stage centres
     if (tid < cnt) {
         const int n = __float_as_int(r1.y);
         int rank = 0;
         for (int j = 0; j < cnt; j++) rank += sm.list[j] < n ? 1 : 0;
-        sm.n[rank] = n;
-        u64* r64 = reinterpret_cast<u64*>(sm.rec + rank * REC);
-        r64[0] = pack2(-r0.z, -r0.z); r64[1] = pack2(-r0.w, -r0.w); r64[2] = pack2(-r1.x, -r1.x);
+        sm.rec[rank].k = make_float4(-r0.z, -r0.w, -r1.x, r1.y);
         const int ix = __float_as_int(r1.z), iy = __float_as_int(r1.w);
         sm.win[rank] = make_int4(ix - S, ix + S, iy - S, iy + S);
         sm.kxy[rank][0] = r0.x; sm.kxy[rank][1] = r0.y;
     }
-    for (int i = tid; i < cnt * 8; i += NT) (&sm.acc[0][0])[i] = 0u;
+    {   // zero the accumulators of the candidates in use: copy tid>>4, candidates (tid&15), +16, ... as 16-byte stores
+        unsigned* cp = sm.acc[tid >> 4];
+        for (int c = tid & 15; c < cnt; c += 16) *reinterpret_cast<uint4*>(cp + 4 * c) = make_uint4(0u, 0u, 0u, 0u);
+    }
     __syncthreads();
-    // ---- separable spatial tables: thread (c, j) fills ex2[c][j] and ey2[c][j]
+    // ---- separable spatial tables, two entries per job: job (c, r): r < 16 -> ex2[c][2r..2r+1], else ey2[c][2(r-16)..]
     {
         const float inf = __int_as_float(0x7f800000);
         for (int i = tid; i < cnt * 32; i += NT) {
-            const int c = i >> 5, j = i & 31;
+            const int c = i >> 5, r = i & 31;
+            const bool isx = r < 16;
+            const int j = 2 * (r & 15);
             const int4 wn = sm.win[c];
-            const int px = tx0 + j, py = ty0 + j;
-            const float ex = __fsub_rn((float)px, sm.kxy[c][0]), ey = __fsub_rn((float)py, sm.kxy[c][1]);
-            float vx = __fmul_rn(ex, ex), vy = __fmul_rn(ey, ey);
-            if (POW2) { vx = __fmul_rn(vx, t.rcp_xywt); vy = __fmul_rn(vy, t.rcp_xywt); }
-            vx = (px >= wn.x && px < wn.y) ? vx : inf;
-            vy = (py >= wn.z && py < wn.w) ? vy : inf;
-            reinterpret_cast<float*>(sm.rec + c * REC + REC_EX)[j] = vx;
-            reinterpret_cast<u64*>(sm.rec + c * REC + REC_EY)[j] = pack2(vy, vy);
+            const int p = (isx ? tx0 : ty0) + j;
+            const int lo = isx ? wn.x : wn.z, hi = isx ? wn.y : wn.w;
+            const float k = sm.kxy[c][isx ? 0 : 1];
+            // int -> float without the conversion unit: (2^23 + p) - 2^23, exact for p < 2^23
+            const float f0 = __fsub_rn(__int_as_float(0x4B000000 | p), 8388608.0f);
+            const u64 e = add2(pack2(f0, __fadd_rn(f0, 1.0f)), bcast2(-k));
+            u64 v = mul2(e, e);
+            if (POW2) v = mul2(v, bcast2(t.rcp_xywt));
+            float v0, v1;
+            unpack2(v, v0, v1);
+            v0 = (p >= lo && p < hi) ? v0 : inf;
+            v1 = (p + 1 >= lo && p + 1 < hi) ? v1 : inf;
+            float* dst = isx ? &sm.rec[c].ex2[j] : &sm.rec[c].ey2[j];
+            *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
         }
     }
     __syncthreads();
 
-    // ---- main: a warp owns a 16x8 patch per step; the CTA's 4 warps cover 32x16, two steps cover the tile
-    const u64 R2 = pack2(t.rcp_xywt, t.rcp_xywt);
-    const float nw = -t.xywt;
-    const u64 NW2 = pack2(nw, nw);
+    // ---- phase 1: a warp owns a 16x8 patch per step; the CTA's 4 warps cover 32x16, two steps cover the tile
     const int X0 = tx0 + 16 * wx, X1 = X0 + 16;
-    const unsigned char* thr_ex = sm.rec + REC_EX + xo * 4;
+    int* lrow = labels + (size_t)(ty0 + 8 * wy + 2 * ly) * t.lp + x;
+    const bool interior = tx0 + TW <= t.w && ty0 + TH <= t.h;
 #pragma unroll 1
     for (int step = 0; step < TH / 16; step++) {
         const int yo = 16 * step + 8 * wy + 2 * ly;
         const int y = ty0 + yo;
-        unsigned cur[2][3];
-#pragma unroll
-        for (int r = 0; r < 2; r++)
-#pragma unroll
-            for (int k = 0; k < 3; k++) cur[r][k] = raw[r][k];
-        if (step + 1 < TH / 16) load_rows(y + 16, raw);      // prefetch the next step's pixels
-        // unpack without the (quarter-rate) I2F unit: byte -> float as (0x4B0000bb as float) - 2^23, built with PRMT.
-        // w01 = [c00 c01 c02 c10], w2 = [c11 c12 0 0]   (pixel (r,0) = bytes 0..2, pixel (r,1) = bytes 3..5)
+        unsigned px[2][2] = {{nxt0.x, nxt0.y}, {nxt1.x, nxt1.y}};
+        if (step + 1 < TH / 16) {                                 // prefetch the next step's pixels
+            nxt0 = __ldg(reinterpret_cast<const uint2*>(pimg + p4_16));
+            nxt1 = __ldg(reinterpret_cast<const uint2*>(pimg + p4_17));
+        }
+        // unpack without the conversion unit: byte -> float as (0x4B0000bb as float) - 2^23, built with PRMT
         u64 P[2][3];
-        unsigned w01[2], w2[2];
         {
-            const unsigned MAGIC = 0x4B000100u;          // bytes: 00 01 00 4B
-            const u64 M2 = pack2(-8388608.0f, -8388608.0f);
+            const unsigned MAGIC = 0x4B000000u;
+            const u64 M2 = bcast2(-8388608.0f);
 #pragma unroll
             for (int r = 0; r < 2; r++) {
-                w01[r] = cur[r][0] | (cur[r][1] << 16);
-                w2[r] = cur[r][2];
-                const float a0 = __uint_as_float(__byte_perm(w01[r], MAGIC, 0x7640)), b0 = __uint_as_float(__byte_perm(w01[r], MAGIC, 0x7643));
-                const float a1 = __uint_as_float(__byte_perm(w01[r], MAGIC, 0x7641)), b1 = __uint_as_float(__byte_perm(w2[r], MAGIC, 0x7640));
-                const float a2 = __uint_as_float(__byte_perm(w01[r], MAGIC, 0x7642)), b2 = __uint_as_float(__byte_perm(w2[r], MAGIC, 0x7641));
+                const float a0 = __uint_as_float(__byte_perm(px[r][0], MAGIC, 0x7440)), b0 = __uint_as_float(__byte_perm(px[r][1], MAGIC, 0x7440));
+                const float a1 = __uint_as_float(__byte_perm(px[r][0], MAGIC, 0x7441)), b1 = __uint_as_float(__byte_perm(px[r][1], MAGIC, 0x7441));
+                const float a2 = __uint_as_float(__byte_perm(px[r][0], MAGIC, 0x7442)), b2 = __uint_as_float(__byte_perm(px[r][1], MAGIC, 0x7442));
                 P[r][0] = add2(pack2(a0, b0), M2); P[r][1] = add2(pack2(a1, b1), M2); P[r][2] = add2(pack2(a2, b2), M2);
             }
         }
@@ -281,28 +257,29 @@ __global__ void __launch_bounds__(NT, 5) slic_tile_kernel(const __grid_constant_
         }
         float best[2][2] = {{FLT_MAX, FLT_MAX}, {FLT_MAX, FLT_MAX}};
         int slot[2][2] = {{-1, -1}, {-1, -1}};
-        const unsigned char* thr_ey = sm.rec + REC_EY + yo * 8;
+        const unsigned char* rec0 = reinterpret_cast<const unsigned char*>(&sm.rec[0]);
+        const unsigned char* thr_ex = reinterpret_cast<const unsigned char*>(&sm.rec[0].ex2[xo]);
+        const unsigned char* thr_ey = reinterpret_cast<const unsigned char*>(&sm.rec[0].ey2[yo]);
 #pragma unroll 1
         for (int half = 0; half < 2; half++) {
             unsigned m = half ? m1 : m0;
             while (m) {
                 const int c = (__ffs(m) - 1) + 32 * half;
                 m &= m - 1;
-                const int ro = c * REC;
-                const ulonglong2 ca = *reinterpret_cast<const ulonglong2*>(sm.rec + ro);
-                const u64 cb = *reinterpret_cast<const u64*>(sm.rec + ro + 16);
+                const int ro = c * (int)sizeof(CandRec);
+                const float4 kc = *reinterpret_cast<const float4*>(rec0 + ro);
                 const u64 exv = *reinterpret_cast<const u64*>(thr_ex + ro);
-                const ulonglong2 eyv = *reinterpret_cast<const ulonglong2*>(thr_ey + ro);
+                const float2 eyv = *reinterpret_cast<const float2*>(thr_ey + ro);
 #pragma unroll
                 for (int r = 0; r < 2; r++) {
-                    const u64 t0 = add2(P[r][0], ca.x), t1 = add2(P[r][1], ca.y), t2 = add2(P[r][2], cb);
+                    const u64 t0 = add2(P[r][0], bcast2(kc.x)), t1 = add2(P[r][1], bcast2(kc.y)), t2 = add2(P[r][2], bcast2(kc.z));
                     u64 d = add2_products(mul2(t0, t0), mul2(t1, t1));
                     d = add2_products(d, mul2(t2, t2));
-                    u64 sxy = add2(exv, r ? eyv.y : eyv.x);
+                    u64 sxy = add2(exv, bcast2(r ? eyv.y : eyv.x));
                     if (!POW2) {
-                        const u64 q0 = mul2(sxy, R2);
-                        const u64 e = fma2(q0, NW2, sxy);
-                        sxy = fma2(e, R2, q0);
+                        const u64 q0 = mul2(sxy, bcast2(t.rcp_xywt));
+                        const u64 e = fma2(q0, bcast2(-t.xywt), sxy);
+                        sxy = fma2(e, bcast2(t.rcp_xywt), q0);
                     }
                     d = add2(d, sxy);
                     float d0, d1;
@@ -312,46 +289,109 @@ __global__ void __launch_bounds__(NT, 5) slic_tile_kernel(const __grid_constant_
                 }
             }
         }
-        // ---- labels (a pixel no window covers keeps its label) and accumulation words
-        int sj[4];
-        unsigned wA[4], wB[4], wC[4];
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-            const int yy = y + r;
-            int* lrow = labels + (size_t)yy * t.lp + x;
-            const bool in0 = x < t.w && yy < t.h, in1 = x + 1 < t.w && yy < t.h;
-            int n0 = -1, n1 = -1;
-            if (in0) n0 = slot[r][0] >= 0 ? sm.n[slot[r][0]] : lrow[0];
-            if (in1) n1 = slot[r][1] >= 0 ? sm.n[slot[r][1]] : lrow[1];
-            if (in1) *reinterpret_cast<int2*>(lrow) = make_int2(n0, n1);
-            else if (in0) lrow[0] = n0;
-            const unsigned MAGIC = 0x4B000100u;
-            wA[2 * r] = __byte_perm(w01[r], MAGIC, 0x4140);          // c00 | c01 << 16
-            wB[2 * r] = __byte_perm(w01[r], MAGIC, 0x4542);          // c02 | 1 << 16
-            wA[2 * r + 1] = __byte_perm(w01[r], w2[r], 0x6463);      // c10 | c11 << 16
-            wB[2 * r + 1] = __byte_perm(w2[r], MAGIC, 0x4541);       // c12 | 1 << 16
-            wC[2 * r] = (unsigned)xo | ((unsigned)(yo + r) << 16);
-            wC[2 * r + 1] = wC[2 * r] + 1u;
-            sj[2 * r] = in0 ? slot[r][0] : -1;
-            sj[2 * r + 1] = in1 ? slot[r][1] : -1;
-            if (in0 && slot[r][0] < 0) acc_global_pixel(t, n0, wA[2 * r] & 0xffff, wA[2 * r] >> 16, wB[2 * r] & 0xffff, x, yy);
-            if (in1 && slot[r][1] < 0) acc_global_pixel(t, n1, wA[2 * r + 1] & 0xffff, wA[2 * r + 1] >> 16, wB[2 * r + 1] & 0xffff, x + 1, yy);
+        // ---- labels + slot map.  Fast path: every pixel of the patch found a candidate and the tile is interior.
+        const int any_neg = slot[0][0] | slot[0][1] | slot[1][0] | slot[1][1];
+        if (interior && !__any_sync(0xffffffffu, any_neg < 0)) {
+            const int n00 = __float_as_int(sm.rec[slot[0][0]].k.w), n01 = __float_as_int(sm.rec[slot[0][1]].k.w);
+            const int n10 = __float_as_int(sm.rec[slot[1][0]].k.w), n11 = __float_as_int(sm.rec[slot[1][1]].k.w);
+            *reinterpret_cast<int2*>(lrow) = make_int2(n00, n01);
+            *reinterpret_cast<int2*>(lrow + t.lp) = make_int2(n10, n11);
+            *reinterpret_cast<unsigned short*>(&sm.slot[yo][xo]) = (unsigned short)(slot[0][0] | (slot[0][1] << 8));
+            *reinterpret_cast<unsigned short*>(&sm.slot[yo + 1][xo]) = (unsigned short)(slot[1][0] | (slot[1][1] << 8));
+        } else {
+            const unsigned s4 = (unsigned)(slot[0][0] & 0xff) | ((unsigned)(slot[0][1] & 0xff) << 8) |
+                                ((unsigned)(slot[1][0] & 0xff) << 16) | ((unsigned)(slot[1][1] & 0xff) << 24);
+            step_slow(t, sm, labels, s4, px[0][0], px[0][1], px[1][0], px[1][1], x, y, xo, yo);
         }
-        warp_accumulate4(sm.acc, sj, wA, wB, wC, lane);
+        pimg += p4_16;
+        lrow += 16 * t.lp;
+    }
+    // phase 2's pixels (L1 hits) are requested before the barrier
+    uint4 pv2[2];
+#pragma unroll
+    for (int it = 0; it < 2; it++)
+        pv2[it] = __ldg(reinterpret_cast<const uint4*>(t.img4 + (size_t)(ty0 + (lane >> 3) * 8 + warp * 2 + it) * t.p4 + tx0 + 4 * (lane & 7)));
+    __syncthreads();
+
+    // ---- phase 2: accumulate over the slot map.  Thread -> two 4-pixel row segments; the lanes of a warp are spread
+    // over the whole tile (8 column groups x 4 rows 8 apart), so concurrent shared-memory atomics mostly hit
+    // different candidates.
+#pragma unroll
+    for (int it = 0; it < 2; it++) {
+        const int q = lane & 7;                                        // column group: pixels 4q .. 4q+3
+        const int row = (lane >> 3) * 8 + warp * 2 + it;               // rows r, r+8, r+16, r+24 within a warp
+        const unsigned sl = *reinterpret_cast<const unsigned*>(&sm.slot[row][4 * q]);
+        const uint4 pv = pv2[it];
+        // the segment's pixels belong to at most two candidates A (the first pixel's) and B (the first one that differs)
+        const unsigned s0 = sl & 0xffu, s1 = (sl >> 8) & 0xffu, s2 = (sl >> 16) & 0xffu, s3 = sl >> 24;
+        const unsigned A = s0;
+        const bool e1 = s1 == A, e2 = s2 == A, e3 = s3 == A;
+        const unsigned B = !e1 ? s1 : (!e2 ? s2 : s3);
+        const bool two = (e1 || s1 == B) && (e2 || s2 == B) && (e3 || s3 == B);
+        if (two && A != 0xffu && B != 0xffu) {
+            // even bytes (c0,c2) and odd bytes (c1,1) of every pixel, as two 16-bit lanes each
+            const unsigned E0 = pv.x & 0x00ff00ffu, E1 = pv.y & 0x00ff00ffu, E2 = pv.z & 0x00ff00ffu, E3 = pv.w & 0x00ff00ffu;
+            const unsigned O0 = (pv.x >> 8) & 0x00ff00ffu, O1 = (pv.y >> 8) & 0x00ff00ffu, O2 = (pv.z >> 8) & 0x00ff00ffu,
+                           O3 = (pv.w >> 8) & 0x00ff00ffu;
+            const unsigned m1 = e1 ? 0xffffffffu : 0u, m2 = e2 ? 0xffffffffu : 0u, m3 = e3 ? 0xffffffffu : 0u;
+            const unsigned TE = E0 + E1 + E2 + E3, TO = O0 + O1 + O2 + O3;
+            const unsigned AE = E0 + (E1 & m1) + (E2 & m2) + (E3 & m3);
+            const unsigned AO = O0 + (O1 & m1) + (O2 & m2) + (O3 & m3);
+            const unsigned cntA = AO >> 16;
+            const unsigned jA = (m1 & 1u) + (m2 & 2u) + (m3 & 3u);       // sum of the in-segment offsets of A's pixels
+            unsigned* da = &sm.acc[lane & (NCOPY - 1)][4 * A];
+            atomicAdd(da + 0, (AE & 0xffffu) | (cntA << 18)); atomicAdd(da + 1, AO & 0xffffu); atomicAdd(da + 2, AE >> 16);
+            atomicAdd(da + 3, (cntA * (4 * q) + jA) | ((cntA * row) << 16));
+            if (A != B) {
+                const unsigned BE = TE - AE, BO = TO - AO;
+                const unsigned cntB = BO >> 16, jB = 6u - jA;
+                unsigned* db = &sm.acc[lane & (NCOPY - 1)][4 * B];
+                atomicAdd(db + 0, (BE & 0xffffu) | (cntB << 18)); atomicAdd(db + 1, BO & 0xffffu); atomicAdd(db + 2, BE >> 16);
+                atomicAdd(db + 3, (cntB * (4 * q) + jB) | ((cntB * row) << 16));
+            }
+        } else {
+            // three slots in four pixels, or pixels handled on the spot in phase 1 (0xFF): one by one
+            const unsigned pw[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const unsigned s = (sl >> (8 * j)) & 0xffu;
+                if (s != 0xffu) {
+                    unsigned* d = &sm.acc[lane & (NCOPY - 1)][4 * s];
+                    atomicAdd(d + 0, (pw[j] & 0xffu) | (1u << 18)); atomicAdd(d + 1, (pw[j] >> 8) & 0xffu);
+                    atomicAdd(d + 2, (pw[j] >> 16) & 0xffu); atomicAdd(d + 3, (unsigned)(4 * q + j) | ((unsigned)row << 16));
+                }
+            }
+        }
     }
     __syncthreads();
-    // ---- flush: one global atomic per field per candidate that received pixels
-    for (int i = tid; i < cnt * 6; i += NT) {
-        const int c = i / 6, f = i - 6 * c;
-        const unsigned count = sm.acc[c][3];
-        if (count == 0) continue;
-        const int n = sm.n[c];
-        u64 v = sm.acc[c][f];
-        int field = f;                               // global order: c0, c1, c2, x, y, count
-        if (f == 3) field = 5;
-        else if (f == 4) { field = 3; v += (u64)count * (u64)tx0; }
-        else if (f == 5) { field = 4; v += (u64)count * (u64)ty0; }
-        atomicAdd(&t.acc[(size_t)field * t.Kcap + n], v);
+    // ---- flush: fold the copies, then one global atomic per field per candidate that received pixels
+    for (int i = tid; i < cnt * 4; i += NT) {
+        unsigned v = 0;
+#pragma unroll
+        for (int p = 0; p < NCOPY; p++) v += sm.acc[p][i];
+        const int c = i >> 2, f = i & 3;
+        const int n = __float_as_int(sm.rec[c].k.w);
+        if (f == 0) {
+            const unsigned count = v >> 18;
+            if (count) {
+                atomicAdd(&t.acc[n], (u64)(v & 0x3ffffu));
+                atomicAdd(&t.acc[(size_t)5 * t.Kcap + n], (u64)count);
+                sm.list[c] = (int)count;
+            } else sm.list[c] = 0;
+        } else if (f < 3) {
+            if (v) atomicAdd(&t.acc[(size_t)f * t.Kcap + n], (u64)v);
+        }
+    }
+    __syncthreads();
+    for (int c = tid; c < cnt; c += NT) {
+        const unsigned count = (unsigned)sm.list[c];
+        if (!count) continue;
+        unsigned v = 0;
+#pragma unroll
+        for (int p = 0; p < NCOPY; p++) v += sm.acc[p][4 * c + 3];
+        const int n = __float_as_int(sm.rec[c].k.w);
+        atomicAdd(&t.acc[(size_t)3 * t.Kcap + n], (u64)(v & 0xffffu) + (u64)count * (u64)tx0);
+        atomicAdd(&t.acc[(size_t)4 * t.Kcap + n], (u64)(v >> 16) + (u64)count * (u64)ty0);
     }
 }
 
@@ -375,15 +415,44 @@ bool slic_tile_supported(const SlicGeom& g)
     return g.alg == SPX_SLIC && g.C == 3 && g.S >= MIN_S && (is_pow2(g.xywt) || markstein_ok(g.xywt));
 }
 
-int slic_tile_assign(const SlicGeom& g, const SlicArrays& a, const unsigned char* d_img, int* d_labels, const int* d_K,
-                     int parity, int* d_overflow, cudaStream_t st)
+// 8UC3 rows -> Lab1 words (c0 | c1<<8 | c2<<16 | 1<<24); the padding of the tile grid stays zero
+__global__ void __launch_bounds__(256) slic_expand_lab1_kernel(const unsigned char* __restrict__ img, size_t ipitch,
+                                                                unsigned* __restrict__ img4, int p4, int w, int h)
+{
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int x = gx * 4;
+    if (x >= w || y >= h) return;
+    const unsigned* src = reinterpret_cast<const unsigned*>(img + (size_t)y * ipitch + (size_t)x * 3);   // 12-byte groups, 4-aligned
+    const unsigned a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);    // the image buffer is padded by 16 bytes per row
+    uint4 o;
+    o.x = (a & 0x00ffffffu) | 0x01000000u;
+    o.y = (__byte_perm(a, b, 0x0543) & 0x00ffffffu) | 0x01000000u;
+    o.z = (__byte_perm(b, c, 0x0432) & 0x00ffffffu) | 0x01000000u;
+    o.w = (c >> 8) | 0x01000000u;
+    if (x + 1 >= w) o.y = 0;
+    if (x + 2 >= w) o.z = 0;
+    if (x + 3 >= w) o.w = 0;
+    *reinterpret_cast<uint4*>(img4 + (size_t)y * p4 + x) = o;
+}
+
+int slic_tile_prepare(const SlicGeom& g, const unsigned char* d_img, unsigned* d_img4, cudaStream_t st)
+{
+    dim3 grid(cdiv(cdiv(g.w, 4), 256), g.h);
+    slic_expand_lab1_kernel<<<grid, 256, 0, st>>>(d_img, g.ipitch, d_img4, g.p4, g.w, g.h);
+    SPX_CUDA(cudaGetLastError());
+    return SPX_OK;
+}
+
+int slic_tile_assign(const SlicGeom& g, const SlicArrays& a, const unsigned char* d_img, const unsigned* d_img4, int* d_labels,
+                     const int* d_K, int parity, int* d_overflow, cudaStream_t st)
 {
     (void)d_K;
     dim3 grid(g.tiles_x, g.tiles_y);
     TileArgs t;
     t.tl_count = a.tl_count[parity]; t.tl_rec = a.tl_rec[parity]; t.acc = a.acc;
-    t.w = g.w; t.h = g.h; t.S = g.S; t.Kcap = g.Kcap; t.tiles_x = g.tiles_x; t.lp = g.lp;
-    t.ipitch = g.ipitch; t.xywt = g.xywt; t.rcp_xywt = 1.0f / g.xywt;
+    t.img4 = d_img4;
+    t.w = g.w; t.h = g.h; t.S = g.S; t.Kcap = g.Kcap; t.tiles_x = g.tiles_x; t.lp = g.lp; t.p4 = g.p4;
+    t.xywt = g.xywt; t.rcp_xywt = 1.0f / g.xywt;
     if (is_pow2(g.xywt)) slic_tile_kernel<true><<<grid, NT, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);
     else slic_tile_kernel<false><<<grid, NT, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);
     SPX_CUDA(cudaGetLastError());
