@@ -128,6 +128,9 @@ int spx_lsc_get_number_of_superpixels(spx_lsc_t*, int* out);
 int spx_lsc_get_labels(spx_lsc_t*, int32_t* dst, size_t dst_stride);
 int spx_lsc_get_label_contour_mask(spx_lsc_t*, uint8_t* dst, size_t dst_stride, int thick_line);
 int spx_lsc_set_labels(spx_lsc_t*, const int32_t* src, size_t src_stride, int numlabels);
+/* test hooks: centres = rows of (2*channels+4 feature means, seed x, seed y) float32; kernel launch count */
+int spx_lsc_get_centres(spx_lsc_t*, float* dst, int rows);
+int spx_lsc_launch_count(spx_lsc_t*, long long* out);
 int spx_lsc_destroy(spx_lsc_t*);
 
 /* ---- cv::ximgproc::SuperpixelSEEDS (mainwindow.h:172, mainwindow.cpp:2123-2127) ---- */

@@ -85,6 +85,8 @@ def lib():
         "spx_lsc_get_labels": [vp, vp, sz],
         "spx_lsc_get_label_contour_mask": [vp, vp, sz, i32],
         "spx_lsc_set_labels": [vp, vp, sz, i32],
+        "spx_lsc_get_centres": [vp, vp, i32],
+        "spx_lsc_launch_count": [vp, C.POINTER(C.c_longlong)],
         "spx_lsc_destroy": [vp],
         "spx_seeds_create": [i32, i32, i32, i32, i32, i32, i32, i32, i32, pp],
         "spx_seeds_iterate": [vp, vp, sz, i32],
@@ -263,6 +265,18 @@ class SuperpixelLSC(_Superpixel):
     def setLabels(self, labels, numlabels=0):
         lab = np.ascontiguousarray(labels, dtype=np.int32)
         _ck(lib().spx_lsc_set_labels(self._h, _p(lab), self.w * 4, int(numlabels)))
+
+    def getCentres(self):
+        """test hook: rows of (2*channels+4 feature means, seed x, seed y); valid before enforceLabelConnectivity"""
+        k = self.getNumberOfSuperpixels()
+        out = np.empty((k, 2 * self.c + 6), np.float32)
+        _ck(lib().spx_lsc_get_centres(self._h, _p(out), k))
+        return out
+
+    def launchCount(self):
+        n = C.c_longlong(0)
+        _ck(lib().spx_lsc_launch_count(self._h, C.byref(n)))
+        return n.value
 
 
 class SuperpixelSEEDS(_Superpixel):

@@ -1,0 +1,850 @@
+// lsc.cu -- SuperpixelLSC engine and its C ABI (replaces createSuperpixelLSC / iterate / enforceLabelConnectivity /
+// getLabels / getNumberOfSuperpixels / getLabelContourMask as called from mainwindow.cpp:2114-2120).
+//
+// PARITY UNPINNED (no lsc.cpp, no ximgproc binary, no fixture): implements, operation for operation, the restatement
+// of Li & Chen's Linear Spectral Clustering that oracle/spx_oracle_lsc.c documents.  Design:
+//   * the 2C+4 sin/cos features are never materialised (44 B/px upstream): every kernel recomputes them in registers
+//     from the 8-bit pixel and its coordinates through small tables (256 entries per channel, W and H entries for x/y)
+//     that the host builds once per image in double precision;
+//   * feature means come from exact per-channel histograms (GPU) weighted by the tables (host, 3*256 + W + H terms);
+//   * the assignment is a gather over the 3x3 bins of current seeds (a seed's window is +-step, inclusive), arg-min
+//     in (distance, seed index) order = upstream's ascending scan with strict '<';
+//   * every sum over pixels is an exact fixed-point int64 (order free): warp-level segmented reduction over runs of
+//     equal labels, one 64-bit global atomic per run and field;
+//   * connectivity: pre-pass = 8-connected components (union-find, root = first pixel in raster order) + the authors'
+//     `adj` rule resolved by relaxation over component roots; post-pass = 4-connected regions, region statistics and
+//     pixel lists in parallel, then the inherently sequential nearest-neighbour merge of small regions on the region
+//     graph by a single CTA (one step per small region), then a scan for the final ids.
+#include "common.cuh"
+#include <cub/device/device_scan.cuh>
+#include <cfloat>
+#include <cmath>
+#include <vector>
+
+namespace spx {
+
+constexpr int LSC_MAXC = 4;
+constexpr int LSC_MAXD = 2 * LSC_MAXC + 4;
+constexpr int LSC_UNK = -2;
+
+struct LscDev {
+    int w, h, C, D, K, stepx, stepy, nbx, nby;
+    size_t ipitch;
+    const unsigned char* img;
+    const float *colcos, *colsin, *wcol;          // [C][256]
+    const float *xcos, *xsin, *wx, *ycos, *ysin, *wy;
+    int *sx, *sy;                                 // seeds
+    float* cen;                                   // K x D
+    long long* sums;                              // K x (D+4): D features, W, x, y, count
+    int *head, *next;                             // bins of stepx x stepy pixels
+};
+
+template <int C>
+__device__ __forceinline__ float lsc_features(const LscDev& L, int x, int y, float (&f)[2 * C + 4])
+{
+    const unsigned char* p = L.img + (size_t)y * L.ipitch + (size_t)x * C;
+    int v[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) v[c] = p[c];
+    float wc = L.wcol[v[0]];
+#pragma unroll
+    for (int c = 1; c < C; c++) wc = __fadd_rn(wc, L.wcol[c * 256 + v[c]]);
+    const float Wt = __fadd_rn(wc, __fadd_rn(L.wx[x], L.wy[y]));
+    const float inv = __fdiv_rn(1.0f, Wt);
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        f[2 * c] = __fmul_rn(L.colcos[c * 256 + v[c]], inv);
+        f[2 * c + 1] = __fmul_rn(L.colsin[c * 256 + v[c]], inv);
+    }
+    f[2 * C] = __fmul_rn(L.xcos[x], inv); f[2 * C + 1] = __fmul_rn(L.xsin[x], inv);
+    f[2 * C + 2] = __fmul_rn(L.ycos[y], inv); f[2 * C + 3] = __fmul_rn(L.ysin[y], inv);
+    return Wt;
+}
+
+// ---- warp-level segmented sums over runs of equal keys in consecutive lanes; the last lane of a run adds to global
+struct RunInfo { int start; bool tail; };
+__device__ __forceinline__ RunInfo run_info(int key, int lane)
+{
+    const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != key);
+    RunInfo r;
+    r.start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+    r.tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+    return r;
+}
+__device__ __forceinline__ long long run_sum(long long v, const RunInfo& r, int lane)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const long long u = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane - d >= r.start) v += u;
+    }
+    return v;
+}
+
+// ---- histograms per channel (exact feature means) ------------------------------------------------------------
+__global__ void __launch_bounds__(256) lsc_hist_kernel(const unsigned char* __restrict__ img, size_t ipitch, int w, int h, int C,
+                                                        unsigned long long* __restrict__ hist)
+{
+    __shared__ unsigned sh[LSC_MAXC * 256];
+    for (int i = threadIdx.x; i < C * 256; i += 256) sh[i] = 0;
+    __syncthreads();
+    const int y = blockIdx.y;
+    for (int x = blockIdx.x * 256 + threadIdx.x; x < w; x += gridDim.x * 256)
+        for (int c = 0; c < C; c++) atomicAdd(&sh[c * 256 + img[(size_t)y * ipitch + (size_t)x * C + c]], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * 256; i += 256)
+        if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+}
+
+// ---- initial centres: plain mean of the normalised features over +-step/4, one warp per seed ----------------------
+template <int C>
+__global__ void __launch_bounds__(128) lsc_init_centres_kernel(LscDev L)
+{
+    constexpr int D = 2 * C + 4;
+    const int k = (blockIdx.x * 128 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (k >= L.K) return;
+    const int sx = L.sx[k], sy = L.sy[k];
+    const int x0 = max(sx - L.stepx / 4, 0), x1 = min(sx + L.stepx / 4, L.w - 1);
+    const int y0 = max(sy - L.stepy / 4, 0), y1 = min(sy + L.stepy / 4, L.h - 1);
+    const int ww = x1 - x0 + 1, n = ww * (y1 - y0 + 1);
+    long long s[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) s[i] = 0;
+    float f[D];
+    for (int e = lane; e < n; e += 32) {
+        lsc_features<C>(L, x0 + e % ww, y0 + e / ww, f);
+#pragma unroll
+        for (int i = 0; i < D; i++) s[i] += __float2ll_rz(__fmul_rn(f[i], 1099511627776.0f));
+    }
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+        long long v = s[i];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) L.cen[(size_t)k * D + i] = (float)__ddiv_rn(__ddiv_rn((double)v, (double)n), 1099511627776.0);
+    }
+}
+
+__global__ void lsc_bin_kernel(LscDev L)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= L.K) return;
+    const int bx = min(max(L.sx[k], 0) / L.stepx, L.nbx - 1), by = min(max(L.sy[k], 0) / L.stepy, L.nby - 1);
+    L.next[k] = atomicExch(&L.head[by * L.nbx + bx], k);
+}
+
+// ---- assignment + exact accumulation -----------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) lsc_assign_kernel(LscDev L, int* __restrict__ labels, int do_assign)
+{
+    constexpr int D = 2 * C + 4;
+    const int lane = threadIdx.x & 31;
+    const int x = blockIdx.x * 32 + lane, y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const bool inside = x < L.w && y < L.h;
+    float f[D];
+    float Wt = 0.f;
+    int label = -1 - lane;
+    if (inside) {
+        Wt = lsc_features<C>(L, x, y, f);
+        const size_t li = (size_t)y * L.w + x;
+        if (do_assign) {
+            float best = FLT_MAX;
+            int bestk = -1;
+            const int bx = x / L.stepx, by = y / L.stepy;
+            for (int yy = max(by - 1, 0); yy <= min(by + 1, L.nby - 1); yy++)
+                for (int xx = max(bx - 1, 0); xx <= min(bx + 1, L.nbx - 1); xx++)
+                    for (int k = L.head[yy * L.nbx + xx]; k >= 0; k = L.next[k]) {
+                        if (abs(x - L.sx[k]) > L.stepx || abs(y - L.sy[k]) > L.stepy) continue;
+                        const float* c = L.cen + (size_t)k * D;
+                        float d = 0.f;
+#pragma unroll
+                        for (int i = 0; i < D; i++) { const float t = __fsub_rn(f[i], c[i]); d = __fadd_rn(d, __fmul_rn(t, t)); }
+                        if (d < best || (d == best && k < bestk)) { best = d; bestk = k; }
+                    }
+            if (bestk >= 0) { labels[li] = bestk; label = bestk; }
+            else label = labels[li];                       // covered by no window: keeps its label
+        } else label = labels[li];
+    }
+    const RunInfo r = run_info(label, lane);
+    long long* dst = L.sums + (size_t)(label >= 0 ? label : 0) * (D + 4);
+    const bool emit = inside && r.tail;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+        const long long q = inside ? __float2ll_rz(__fmul_rn(__fmul_rn(Wt, f[i]), 4294967296.0f)) : 0ll;
+        const long long s = run_sum(q, r, lane);
+        if (emit) atomicAdd((unsigned long long*)&dst[i], (unsigned long long)s);
+    }
+    {
+        long long s = run_sum(inside ? __float2ll_rz(__fmul_rn(Wt, 16777216.0f)) : 0ll, r, lane);
+        if (emit) atomicAdd((unsigned long long*)&dst[D], (unsigned long long)s);
+        s = run_sum(inside ? (long long)x : 0ll, r, lane);
+        if (emit) atomicAdd((unsigned long long*)&dst[D + 1], (unsigned long long)s);
+        if (emit) {
+            const long long cnt = lane - r.start + 1;
+            atomicAdd((unsigned long long*)&dst[D + 2], (unsigned long long)(cnt * y));
+            atomicAdd((unsigned long long*)&dst[D + 3], (unsigned long long)cnt);
+        }
+    }
+}
+
+// centres = W-weighted means, seeds = integer mean position; sums cleared; seeds re-binned
+__global__ void lsc_finalize_kernel(LscDev L)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= L.K) return;
+    long long* a = L.sums + (size_t)k * (L.D + 4);
+    const long long sw = a[L.D], cnt = a[L.D + 3];
+    for (int i = 0; i < L.D; i++) {
+        L.cen[(size_t)k * L.D + i] = (cnt > 0 && sw != 0) ? (float)__ddiv_rn(__ddiv_rn((double)a[i], (double)sw), 256.0) : 0.f;
+        a[i] = 0;
+    }
+    const int sx = cnt > 0 ? (int)(a[L.D + 1] / cnt) : 0, sy = cnt > 0 ? (int)(a[L.D + 2] / cnt) : 0;
+    a[L.D] = 0; a[L.D + 1] = 0; a[L.D + 2] = 0; a[L.D + 3] = 0;
+    L.sx[k] = sx; L.sy[k] = sy;
+    const int bx = min(sx / L.stepx, L.nbx - 1), by = min(sy / L.stepy, L.nby - 1);
+    L.next[k] = atomicExch(&L.head[by * L.nbx + bx], k);
+}
+
+// ---- connected components (union-find, root = smallest raster index) ----------------------------------------------
+__device__ __forceinline__ int lsc_find(const int* P, int a)
+{
+    int p = P[a];
+    while (p != a) { a = p; p = P[a]; }
+    return a;
+}
+__device__ __forceinline__ void lsc_unite(int* P, int a, int b)
+{
+    bool done;
+    do {
+        a = lsc_find(P, a); b = lsc_find(P, b);
+        if (a < b) { int old = atomicMin(&P[b], a); done = (old == b); b = old; }
+        else if (b < a) { int old = atomicMin(&P[a], b); done = (old == a); a = old; }
+        else done = true;
+    } while (!done);
+}
+__global__ void lsc_ccl_init_kernel(const int* __restrict__ lab, int w, int h, int* __restrict__ P)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const int i = y * w + x;
+    P[i] = (x > 0 && lab[i - 1] == lab[i]) ? i - 1 : i;
+}
+template <int CONN>
+__global__ void lsc_ccl_merge_kernel(const int* __restrict__ lab, int w, int h, int* __restrict__ P)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y + 1;
+    if (x >= w || y >= h) return;
+    const int i = y * w + x, me = lab[i];
+    if (lab[i - w] == me) lsc_unite(P, i, i - w);
+    if (CONN == 8) {
+        if (x > 0 && lab[i - w - 1] == me) lsc_unite(P, i, i - w - 1);
+        if (x < w - 1 && lab[i - w + 1] == me) lsc_unite(P, i, i - w + 1);
+    }
+}
+// flatten; rootidx = own index for roots, -1 otherwise; flag = 1 for roots
+__global__ void lsc_ccl_flatten_kernel(int* __restrict__ P, int* __restrict__ csize, int* __restrict__ rootidx, int* __restrict__ flag, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r = lsc_find(P, i);
+    P[i] = r;
+    csize[i] = 0;
+    rootidx[i] = r == i ? i : -1;
+    flag[i] = r == i ? 1 : 0;
+}
+__global__ void lsc_ccl_size_kernel(const int* __restrict__ P, int* __restrict__ csize, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int key = i < n ? P[i] : -1 - lane;
+    const RunInfo r = run_info(key, lane);
+    if (i < n && r.tail) atomicAdd(&csize[key], lane - r.start + 1);
+}
+
+// ---- pre-pass: the authors' `adj` rule on the component roots (see oracle/spx_oracle_lsc.c: lsc_pre_enforce) --------
+__global__ void lsc_pre_init_kernel(const int* __restrict__ P, const int* __restrict__ lab, const int* __restrict__ csize,
+                                    int* __restrict__ FL, int* __restrict__ ADJ, int n, int bound)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || P[i] != i) return;
+    FL[i] = csize[i] <= bound ? LSC_UNK : lab[i];
+    ADJ[i] = LSC_UNK;
+}
+// adj_k = (final label of the component left of / above the root differs from L_k) ? that label : adj_{k-1}
+__global__ void lsc_pre_relax_kernel(const int* __restrict__ P, const int* __restrict__ lab, const int* __restrict__ csize,
+                                     const int* __restrict__ prevroot, volatile int* FL, volatile int* ADJ, int w, int n,
+                                     int bound, int* __restrict__ pending)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || P[i] != i || ADJ[i] != LSC_UNK) return;
+    const int x = i % w;
+    const int nb = x > 0 ? i - 1 : (i >= w ? i - w : -1);
+    int adj;
+    if (nb < 0) adj = 0;                           // pixel 0: nothing is visited yet, adj keeps its initial value
+    else {
+        const int fl = FL[P[nb]];
+        if (fl == LSC_UNK) { *pending = 1; return; }
+        if (fl != lab[i]) adj = fl;
+        else {
+            const int pr = prevroot[i];
+            if (pr < 0) adj = 0;
+            else {
+                const int a = ADJ[pr];
+                if (a == LSC_UNK) { *pending = 1; return; }
+                adj = a;
+            }
+        }
+    }
+    if (csize[i] <= bound) FL[i] = adj;
+    __threadfence();
+    ADJ[i] = adj;
+}
+__global__ void lsc_pre_relabel_kernel(const int* __restrict__ P, const int* __restrict__ FL, int* __restrict__ lab, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) lab[i] = FL[P[i]];
+}
+
+// ---- post-pass ---------------------------------------------------------------------------------------------------
+// reg[px] = region id (raster order of the roots); region size; pixel lists
+__global__ void lsc_post_region_kernel(const int* __restrict__ P, const int* __restrict__ rid, const int* __restrict__ csize,
+                                       int* __restrict__ reg, int* __restrict__ size, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int root = P[i], r = rid[root];
+    reg[i] = r;
+    if (root == i) size[r] = csize[i];
+}
+__global__ void lsc_post_fill_kernel(const int* __restrict__ reg, const int* __restrict__ off, int* __restrict__ cursor,
+                                     int* __restrict__ pxlist, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r = reg[i];
+    pxlist[off[r] + atomicAdd(&cursor[r], 1)] = i;
+}
+template <int C>
+__global__ void __launch_bounds__(256) lsc_post_sums_kernel(LscDev L, const int* __restrict__ reg, long long* __restrict__ rsum)
+{
+    constexpr int D = 2 * C + 4;
+    const int lane = threadIdx.x & 31;
+    const int x = blockIdx.x * 32 + lane, y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const bool inside = x < L.w && y < L.h;
+    float f[D];
+    float Wt = 0.f;
+    int key = -1 - lane;
+    if (inside) { Wt = lsc_features<C>(L, x, y, f); key = reg[(size_t)y * L.w + x]; }
+    const RunInfo r = run_info(key, lane);
+    long long* dst = rsum + (size_t)(key >= 0 ? key : 0) * (D + 1);
+    const bool emit = inside && r.tail;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+        const long long s = run_sum(inside ? __float2ll_rz(__fmul_rn(__fmul_rn(Wt, f[i]), 4294967296.0f)) : 0ll, r, lane);
+        if (emit) atomicAdd((unsigned long long*)&dst[i], (unsigned long long)s);
+    }
+    const long long s = run_sum(inside ? __float2ll_rz(__fmul_rn(Wt, 16777216.0f)) : 0ll, r, lane);
+    if (emit) atomicAdd((unsigned long long*)&dst[D], (unsigned long long)s);
+}
+__global__ void lsc_post_stats_kernel(const long long* __restrict__ rsum, const int* __restrict__ size, int D, int R, int threshold,
+                                      float* __restrict__ cen, float* __restrict__ Wr, int* __restrict__ cur, int* __restrict__ next,
+                                      int* __restrict__ tail, int* __restrict__ alive, int* __restrict__ smallflag)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const long long* a = rsum + (size_t)r * (D + 1);
+    const long long sw = a[D];
+    for (int j = 0; j < D; j++) cen[(size_t)r * D + j] = sw != 0 ? (float)__ddiv_rn(__ddiv_rn((double)a[j], (double)sw), 256.0) : 0.f;
+    Wr[r] = (float)__ddiv_rn((double)sw, 16777216.0);
+    cur[r] = r; next[r] = -1; tail[r] = r; alive[r] = 1;
+    smallflag[r] = size[r] < threshold ? 1 : 0;
+}
+__global__ void lsc_post_compact_kernel(const int* __restrict__ flag, const int* __restrict__ pos, int* __restrict__ out, int R)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < R && flag[r]) out[pos[r]] = r;
+}
+// the sequential part: small regions, in region order, merge into the adjacent region with the nearest centre
+// (ties -> smaller id); centres / weights / sizes / member lists updated after every merge.  One CTA.
+__global__ void __launch_bounds__(256) lsc_post_merge_kernel(const int* __restrict__ small, const int* __restrict__ nsmall_p, int threshold,
+                                                              int D, int w, int h, const int* __restrict__ reg, const int* __restrict__ off,
+                                                              const int* __restrict__ pxlist, volatile float* cen, volatile float* Wr,
+                                                              volatile int* size, volatile int* cur, volatile int* next, volatile int* tail,
+                                                              volatile int* alive)
+{
+    __shared__ float ci[LSC_MAXD];
+    __shared__ unsigned long long red[8];
+    __shared__ int s_go;
+    __shared__ unsigned long long s_best;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int ns = *nsmall_p;
+    for (int t = 0; t < ns; t++) {
+        const int i = small[t];
+        if (tid == 0) s_go = size[i] < threshold ? 1 : 0;
+        if (tid < D) ci[tid] = cen[(size_t)i * D + tid];
+        __syncthreads();
+        if (s_go) {
+            unsigned long long best = ~0ull;
+            for (int m = i; m >= 0; m = next[m]) {
+                const int a = off[m], b = off[m + 1];
+                for (int e = 4 * a + tid; e < 4 * b; e += 256) {
+                    const int p = pxlist[e >> 2], k = e & 3;
+                    const int x = p % w, y = p / w;
+                    const int nx = x + (k == 0 ? -1 : k == 2 ? 1 : 0), ny = y + (k == 1 ? -1 : k == 3 ? 1 : 0);
+                    if (nx < 0 || nx >= w || ny < 0 || ny >= h) continue;
+                    const int r = cur[reg[ny * w + nx]];
+                    if (r == i) continue;
+                    float d = 0.f;
+                    for (int j = 0; j < D; j++) { const float u = __fsub_rn(ci[j], cen[(size_t)r * D + j]); d = __fadd_rn(d, __fmul_rn(u, u)); }
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)r;
+                    best = key < best ? key : best;
+                }
+            }
+            for (int o = 16; o; o >>= 1) { const unsigned long long u = __shfl_xor_sync(0xffffffffu, best, o); best = u < best ? u : best; }
+            if (lane == 0) red[wid] = best;
+            __syncthreads();
+            if (tid == 0) {
+                unsigned long long b = red[0];
+                for (int q = 1; q < 8; q++) b = red[q] < b ? red[q] : b;
+                s_best = b;
+            }
+            __syncthreads();
+            if (s_best != ~0ull) {
+                const int nb = (int)(unsigned)(s_best & 0xffffffffull);
+                const float wn = Wr[nb], wi = Wr[i];
+                if (tid < D) {
+                    const float a = __fmul_rn(cen[(size_t)nb * D + tid], wn), b = __fmul_rn(ci[tid], wi);
+                    cen[(size_t)nb * D + tid] = __fdiv_rn(__fadd_rn(a, b), __fadd_rn(wn, wi));
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    Wr[nb] = __fadd_rn(wn, wi);
+                    size[nb] = size[nb] + size[i];
+                    for (int m = i; m >= 0; m = next[m]) cur[m] = nb;
+                    next[tail[nb]] = i; tail[nb] = tail[i];
+                    alive[i] = 0;
+                }
+            }
+        }
+        __threadfence_block();
+        __syncthreads();
+    }
+}
+__global__ void lsc_post_relabel_kernel(const int* __restrict__ reg, const int* __restrict__ cur, const int* __restrict__ newid,
+                                        int* __restrict__ lab, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) lab[i] = newid[cur[reg[i]]];
+}
+
+struct MaxOp { __device__ __forceinline__ int operator()(int a, int b) const { return a > b ? a : b; } };
+
+// ---- engine ----------------------------------------------------------------------------------------------------
+struct LscEngine {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    LscDev L{};
+    int S = 0;
+    float ratio = 0.f;
+    int numlabels = 0;
+    unsigned char* d_img = nullptr;
+    int* d_labels = nullptr;
+    unsigned char* d_mask = nullptr;
+    float* d_tab = nullptr;                 // all float tables in one allocation
+    unsigned long long* d_hist = nullptr;
+    void* d_scan_tmp = nullptr;
+    size_t scan_tmp_bytes = 0;
+    int* d_flag = nullptr;
+    int* h_pinned = nullptr;
+    long long launches = 0;
+    PostWorkspace post;
+    std::vector<void*> allocs;
+
+    template <typename T> int dalloc(T** p, size_t n)
+    {
+        SPX_CUDA(cudaMalloc((void**)p, n * sizeof(T) > 0 ? n * sizeof(T) : 4));
+        allocs.push_back((void*)*p);
+        return SPX_OK;
+    }
+    ~LscEngine()
+    {
+        cudaSetDevice(device);
+        if (st) cudaStreamSynchronize(st);
+        for (void* p : allocs) cudaFree(p);
+        if (d_scan_tmp) cudaFree(d_scan_tmp);
+        post.release();
+        if (h_pinned) cudaFreeHost(h_pinned);
+        if (st) cudaStreamDestroy(st);
+    }
+    int scan_tmp(size_t bytes)
+    {
+        if (bytes <= scan_tmp_bytes) return SPX_OK;
+        if (d_scan_tmp) cudaFree(d_scan_tmp);
+        d_scan_tmp = nullptr; scan_tmp_bytes = 0;
+        SPX_CUDA(cudaMalloc(&d_scan_tmp, bytes));
+        scan_tmp_bytes = bytes;
+        return SPX_OK;
+    }
+    int exclusive_sum(const int* in, int* out, int n)
+    {
+        size_t bytes = 0;
+        SPX_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, st));
+        SPX_CHECK(scan_tmp(bytes));
+        SPX_CUDA(cub::DeviceScan::ExclusiveSum(d_scan_tmp, bytes, in, out, n, st));
+        launches += 2;
+        return SPX_OK;
+    }
+    int exclusive_max(const int* in, int* out, int n)
+    {
+        size_t bytes = 0;
+        SPX_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, bytes, in, out, MaxOp(), -1, n, st));
+        SPX_CHECK(scan_tmp(bytes));
+        SPX_CUDA(cub::DeviceScan::ExclusiveScan(d_scan_tmp, bytes, in, out, MaxOp(), -1, n, st));
+        launches += 2;
+        return SPX_OK;
+    }
+
+    int create(const uint8_t* image, size_t stride, int w, int h, int C, int S_, float ratio_)
+    {
+        SPX_REQUIRE(image && w > 0 && h > 0 && (long long)w * h < (1ll << 30) && stride >= (size_t)w * C, SPX_ERR_BADARG,
+                    "createSuperpixelLSC: bad image");
+        SPX_REQUIRE(C >= 1 && C <= LSC_MAXC, SPX_ERR_BADARG, "createSuperpixelLSC: 1..4 channels supported, got %d", C);
+        SPX_REQUIRE(S_ >= 1, SPX_ERR_BADARG, "createSuperpixelLSC: region_size must be >= 1");
+        S = S_; ratio = ratio_;
+        const int K0 = (int)((float)(w * h) / (float)(S * S));
+        const int ColNum = (int)std::sqrt((double)K0 * w / h);
+        SPX_REQUIRE(ColNum >= 1 && K0 / ColNum >= 1, SPX_ERR_BADARG, "createSuperpixelLSC: region_size %d leaves no seed in a %dx%d image", S, w, h);
+        const int RowNum = K0 / ColNum;
+        L.w = w; L.h = h; L.C = C; L.D = 2 * C + 4; L.K = ColNum * RowNum;
+        L.stepx = w / ColNum; L.stepy = h / RowNum;
+        L.nbx = cdiv(w, L.stepx); L.nby = cdiv(h, L.stepy);
+        L.ipitch = round_up((size_t)w * C, 16);
+        numlabels = L.K;
+        const size_t N = (size_t)w * h;
+        SPX_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        SPX_CHECK(dalloc(&d_img, L.ipitch * h));
+        SPX_CHECK(dalloc(&d_labels, N));
+        SPX_CHECK(dalloc(&d_mask, N));
+        const size_t ntab = (size_t)3 * C * 256 + 3 * (size_t)w + 3 * (size_t)h;
+        SPX_CHECK(dalloc(&d_tab, ntab));
+        SPX_CHECK(dalloc(&d_hist, (size_t)C * 256));
+        SPX_CHECK(dalloc(&L.sx, (size_t)L.K)); SPX_CHECK(dalloc(&L.sy, (size_t)L.K));
+        SPX_CHECK(dalloc(&L.cen, (size_t)L.K * L.D));
+        SPX_CHECK(dalloc(&L.sums, (size_t)L.K * (L.D + 4)));
+        SPX_CHECK(dalloc(&L.head, (size_t)L.nbx * L.nby)); SPX_CHECK(dalloc(&L.next, (size_t)L.K));
+        SPX_CHECK(dalloc(&d_flag, 8));
+        SPX_CUDA(cudaMallocHost(&h_pinned, 8 * sizeof(int)));
+        L.img = d_img;
+        SPX_CUDA(cudaMemcpy2DAsync(d_img, L.ipitch, image, stride, (size_t)w * C, h, cudaMemcpyHostToDevice, st));
+        SPX_CUDA(cudaMemsetAsync(d_labels, 0, N * sizeof(int), st));
+        SPX_CUDA(cudaMemsetAsync(L.sums, 0, (size_t)L.K * (L.D + 4) * sizeof(long long), st));
+        SPX_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)C * 256 * sizeof(unsigned long long), st));
+        SPX_CUDA(cudaMemsetAsync(L.head, 0xFF, (size_t)L.nbx * L.nby * sizeof(int), st));
+        lsc_hist_kernel<<<dim3(min(cdiv(w, 256), 8), h), 256, 0, st>>>(d_img, L.ipitch, w, h, C, d_hist);
+        launches++;
+        std::vector<unsigned long long> hist((size_t)C * 256);
+        SPX_CUDA(cudaMemcpyAsync(hist.data(), d_hist, hist.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        SPX_CUDA(cudaStreamSynchronize(st));
+
+        // ---- tables (double trigonometry, rounded once) and seeds: O(256 C + W + H + K) host work
+        std::vector<float> tab(ntab);
+        float* colcos = tab.data(); float* colsin = colcos + C * 256; float* wcol = colsin + C * 256;
+        float* xcos = wcol + C * 256; float* xsin = xcos + w; float* wx = xsin + w;
+        float* ycos = wx + w; float* ysin = ycos + h; float* wy = ysin + h;
+        const double PI = 3.1415926, color = 20.0;
+        const float dist_coeff = 20.0f * ratio;
+        const double dist = (double)dist_coeff;
+        for (int c = 0; c < C; c++) {
+            const double scale = c == 0 ? 1.0 : 2.55;
+            for (int v = 0; v < 256; v++) {
+                const double th = ((double)v / 255.0) * PI / 2.0;
+                colcos[c * 256 + v] = (float)(color * std::cos(th) * scale);
+                colsin[c * 256 + v] = (float)(color * std::sin(th) * scale);
+            }
+        }
+        for (int x = 0; x < w; x++) {
+            const double th = ((double)x / (double)L.stepx) * PI / 2.0;
+            xcos[x] = (float)(dist * std::cos(th)); xsin[x] = (float)(dist * std::sin(th));
+        }
+        for (int y = 0; y < h; y++) {
+            const double th = ((double)y / (double)L.stepy) * PI / 2.0;
+            ycos[y] = (float)(dist * std::cos(th)); ysin[y] = (float)(dist * std::sin(th));
+        }
+        for (int c = 0; c < C; c++) {
+            double a = 0.0, b = 0.0;
+            for (int v = 0; v < 256; v++) { a += (double)hist[c * 256 + v] * (double)colcos[c * 256 + v]; b += (double)hist[c * 256 + v] * (double)colsin[c * 256 + v]; }
+            const float sc = (float)(a / (double)N), ss = (float)(b / (double)N);
+            for (int v = 0; v < 256; v++) wcol[c * 256 + v] = colcos[c * 256 + v] * sc + colsin[c * 256 + v] * ss;
+        }
+        {
+            double a = 0.0, b = 0.0;
+            for (int x = 0; x < w; x++) { a += (double)xcos[x]; b += (double)xsin[x]; }
+            float sc = (float)(a * (double)h / (double)N), ss = (float)(b * (double)h / (double)N);
+            for (int x = 0; x < w; x++) wx[x] = xcos[x] * sc + xsin[x] * ss;
+            a = 0.0; b = 0.0;
+            for (int y = 0; y < h; y++) { a += (double)ycos[y]; b += (double)ysin[y]; }
+            sc = (float)(a * (double)w / (double)N); ss = (float)(b * (double)w / (double)N);
+            for (int y = 0; y < h; y++) wy[y] = ycos[y] * sc + ysin[y] * ss;
+        }
+        std::vector<int> seeds((size_t)2 * L.K);
+        {
+            const int row_remain = h - L.stepy * RowNum, col_remain = w - L.stepx * ColNum;
+            int t1 = 1, n = 0;
+            for (int i = 0; i < RowNum; i++) {
+                int t2 = 1;
+                int cy = (int)(i * L.stepy + 0.5 * L.stepy + t1);
+                if (cy >= h - 1) cy = h - 1;
+                if (t1 < row_remain) t1++;
+                for (int j = 0; j < ColNum; j++) {
+                    int cx = (int)(j * L.stepx + 0.5 * L.stepx + t2);
+                    if (t2 < col_remain) t2++;
+                    if (cx >= w - 1) cx = w - 1;
+                    seeds[n] = cx; seeds[L.K + n] = cy; n++;
+                }
+            }
+        }
+        SPX_CUDA(cudaMemcpyAsync(d_tab, tab.data(), ntab * sizeof(float), cudaMemcpyHostToDevice, st));
+        SPX_CUDA(cudaMemcpyAsync(L.sx, seeds.data(), (size_t)L.K * sizeof(int), cudaMemcpyHostToDevice, st));
+        SPX_CUDA(cudaMemcpyAsync(L.sy, seeds.data() + L.K, (size_t)L.K * sizeof(int), cudaMemcpyHostToDevice, st));
+        L.colcos = d_tab; L.colsin = L.colcos + C * 256; L.wcol = L.colsin + C * 256;
+        L.xcos = L.wcol + C * 256; L.xsin = L.xcos + w; L.wx = L.xsin + w;
+        L.ycos = L.wx + w; L.ysin = L.ycos + h; L.wy = L.ysin + h;
+        const int nb = cdiv(L.K * 32, 128);
+        switch (C) {
+            case 1: lsc_init_centres_kernel<1><<<nb, 128, 0, st>>>(L); break;
+            case 2: lsc_init_centres_kernel<2><<<nb, 128, 0, st>>>(L); break;
+            case 3: lsc_init_centres_kernel<3><<<nb, 128, 0, st>>>(L); break;
+            default: lsc_init_centres_kernel<4><<<nb, 128, 0, st>>>(L); break;
+        }
+        lsc_bin_kernel<<<cdiv(L.K, 256), 256, 0, st>>>(L);
+        launches += 2;
+        SPX_CUDA(cudaGetLastError());
+        SPX_CUDA(cudaStreamSynchronize(st));       // the host vectors above go out of scope
+        return SPX_OK;
+    }
+
+    int iterate(int n)
+    {
+        SPX_REQUIRE(n >= 0, SPX_ERR_BADARG, "iterate: num_iterations must be >= 0");
+        const dim3 grid(cdiv(L.w, 32), cdiv(L.h, 8));
+        for (int it = 0; it < n; it++) {
+            switch (L.C) {
+                case 1: lsc_assign_kernel<1><<<grid, 256, 0, st>>>(L, d_labels, 1); break;
+                case 2: lsc_assign_kernel<2><<<grid, 256, 0, st>>>(L, d_labels, 1); break;
+                case 3: lsc_assign_kernel<3><<<grid, 256, 0, st>>>(L, d_labels, 1); break;
+                default: lsc_assign_kernel<4><<<grid, 256, 0, st>>>(L, d_labels, 1); break;
+            }
+            SPX_CUDA(cudaMemsetAsync(L.head, 0xFF, (size_t)L.nbx * L.nby * sizeof(int), st));
+            lsc_finalize_kernel<<<cdiv(L.K, 256), 256, 0, st>>>(L);
+            launches += 2;
+        }
+        SPX_CUDA(cudaGetLastError());
+        return SPX_OK;
+    }
+
+    int enforce(int min_element_size)
+    {
+        SPX_REQUIRE(min_element_size >= 0 && min_element_size <= 100, SPX_ERR_ASSERT,
+                    "enforceLabelConnectivity: min_element_size >= 0 && min_element_size <= 100");
+        if (min_element_size == 0) return SPX_OK;
+        const int w = L.w, h = L.h, n = w * h, D = L.D;
+        const int threshold = n / (numlabels * 4);
+        const int g1 = cdiv(n, 256);
+        const dim3 g2(cdiv(w, 256), h), g2m(cdiv(w, 256), max(h - 1, 1));
+        int *P, *csize, *rootidx, *flag, *A, *B, *Cc;
+        std::vector<void*> tmp;
+        auto talloc = [&](int** p, size_t cnt) -> int {
+            SPX_CUDA(cudaMalloc((void**)p, (cnt > 0 ? cnt : 1) * sizeof(int)));
+            tmp.push_back(*p);
+            return SPX_OK;
+        };
+        auto tfree = [&]() { for (void* p : tmp) cudaFree(p); tmp.clear(); };
+        int rc = SPX_OK;
+#define LSC_TRY(expr) do { rc = (expr); if (rc != SPX_OK) { tfree(); return rc; } } while (0)
+#define LSC_TRYCUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { set_error("%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); tfree(); return SPX_ERR_GPU; } } while (0)
+        LSC_TRY(talloc(&P, n)); LSC_TRY(talloc(&csize, n)); LSC_TRY(talloc(&rootidx, n)); LSC_TRY(talloc(&flag, n));
+        LSC_TRY(talloc(&A, n)); LSC_TRY(talloc(&B, n)); LSC_TRY(talloc(&Cc, n));
+
+        // ---- pre-pass: 8-connected components, `adj` rule
+        lsc_ccl_init_kernel<<<g2, 256, 0, st>>>(d_labels, w, h, P);
+        if (h > 1) lsc_ccl_merge_kernel<8><<<g2m, 256, 0, st>>>(d_labels, w, h, P);
+        lsc_ccl_flatten_kernel<<<g1, 256, 0, st>>>(P, csize, rootidx, flag, n);
+        lsc_ccl_size_kernel<<<g1, 256, 0, st>>>(P, csize, n);
+        launches += 4;
+        int* prevroot = Cc;
+        LSC_TRY(exclusive_max(rootidx, prevroot, n));
+        int* FL = A; int* ADJ = B;
+        lsc_pre_init_kernel<<<g1, 256, 0, st>>>(P, d_labels, csize, FL, ADJ, n, min_element_size);
+        launches++;
+        for (int round = 0; round < 1000000; round++) {
+            LSC_TRYCUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+            for (int k = 0; k < 4; k++) lsc_pre_relax_kernel<<<g1, 256, 0, st>>>(P, d_labels, csize, prevroot, FL, ADJ, w, n, min_element_size, d_flag);
+            launches += 4;
+            LSC_TRYCUDA(cudaMemcpyAsync(h_pinned, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+            LSC_TRYCUDA(cudaStreamSynchronize(st));
+            if (!h_pinned[0]) break;
+        }
+        lsc_pre_relabel_kernel<<<g1, 256, 0, st>>>(P, FL, d_labels, n);
+        launches++;
+
+        // ---- post-pass: 4-connected regions, statistics, pixel lists
+        lsc_ccl_init_kernel<<<g2, 256, 0, st>>>(d_labels, w, h, P);
+        if (h > 1) lsc_ccl_merge_kernel<4><<<g2m, 256, 0, st>>>(d_labels, w, h, P);
+        lsc_ccl_flatten_kernel<<<g1, 256, 0, st>>>(P, csize, rootidx, flag, n);
+        lsc_ccl_size_kernel<<<g1, 256, 0, st>>>(P, csize, n);
+        launches += 4;
+        int* rid = A;
+        LSC_TRY(exclusive_sum(flag, rid, n));
+        LSC_TRYCUDA(cudaMemcpyAsync(h_pinned, rid + n - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        LSC_TRYCUDA(cudaMemcpyAsync(h_pinned + 1, flag + n - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        LSC_TRYCUDA(cudaStreamSynchronize(st));
+        const int R = h_pinned[0] + h_pinned[1];
+        int *reg = B, *size, *off, *cursor, *pxlist = rootidx, *cur, *next, *tail, *alive, *smallflag, *smallpos, *small, *newid;
+        float *cen, *Wr;
+        long long* rsum;
+        LSC_TRY(talloc(&size, R + 1)); LSC_TRY(talloc(&off, R + 1)); LSC_TRY(talloc(&cursor, R));
+        LSC_TRY(talloc(&cur, R)); LSC_TRY(talloc(&next, R)); LSC_TRY(talloc(&tail, R)); LSC_TRY(talloc(&alive, R + 1));
+        LSC_TRY(talloc(&smallflag, R + 1)); LSC_TRY(talloc(&smallpos, R + 1)); LSC_TRY(talloc(&small, R)); LSC_TRY(talloc(&newid, R + 1));
+        LSC_TRY(talloc((int**)&cen, (size_t)R * D)); LSC_TRY(talloc((int**)&Wr, R));
+        LSC_TRY(talloc((int**)&rsum, (size_t)R * (D + 1) * 2));
+        LSC_TRYCUDA(cudaMemsetAsync(size, 0, (size_t)(R + 1) * sizeof(int), st));
+        LSC_TRYCUDA(cudaMemsetAsync(cursor, 0, (size_t)R * sizeof(int), st));
+        LSC_TRYCUDA(cudaMemsetAsync(rsum, 0, (size_t)R * (D + 1) * sizeof(long long), st));
+        LSC_TRYCUDA(cudaMemsetAsync(smallflag, 0, (size_t)(R + 1) * sizeof(int), st));
+        LSC_TRYCUDA(cudaMemsetAsync(alive, 0, (size_t)(R + 1) * sizeof(int), st));
+        lsc_post_region_kernel<<<g1, 256, 0, st>>>(P, rid, csize, reg, size, n);
+        launches++;
+        LSC_TRY(exclusive_sum(size, off, R + 1));
+        lsc_post_fill_kernel<<<g1, 256, 0, st>>>(reg, off, cursor, pxlist, n);
+        const dim3 gp(cdiv(w, 32), cdiv(h, 8));
+        switch (L.C) {
+            case 1: lsc_post_sums_kernel<1><<<gp, 256, 0, st>>>(L, reg, rsum); break;
+            case 2: lsc_post_sums_kernel<2><<<gp, 256, 0, st>>>(L, reg, rsum); break;
+            case 3: lsc_post_sums_kernel<3><<<gp, 256, 0, st>>>(L, reg, rsum); break;
+            default: lsc_post_sums_kernel<4><<<gp, 256, 0, st>>>(L, reg, rsum); break;
+        }
+        lsc_post_stats_kernel<<<cdiv(R, 256), 256, 0, st>>>(rsum, size, D, R, threshold, cen, Wr, cur, next, tail, alive, smallflag);
+        launches += 3;
+        LSC_TRY(exclusive_sum(smallflag, smallpos, R + 1));
+        lsc_post_compact_kernel<<<cdiv(R, 256), 256, 0, st>>>(smallflag, smallpos, small, R);
+        // ---- the sequential merge (single CTA), then final ids
+        lsc_post_merge_kernel<<<1, 256, 0, st>>>(small, smallpos + R, threshold, D, w, h, reg, off, pxlist, cen, Wr, size, cur, next, tail, alive);
+        launches += 2;
+        LSC_TRY(exclusive_sum(alive, newid, R + 1));
+        lsc_post_relabel_kernel<<<g1, 256, 0, st>>>(reg, cur, newid, d_labels, n);
+        launches++;
+        LSC_TRYCUDA(cudaMemcpyAsync(h_pinned, newid + R, sizeof(int), cudaMemcpyDeviceToHost, st));
+        LSC_TRYCUDA(cudaStreamSynchronize(st));
+        LSC_TRYCUDA(cudaGetLastError());
+        numlabels = h_pinned[0];
+        tfree();
+#undef LSC_TRY
+#undef LSC_TRYCUDA
+        return SPX_OK;
+    }
+};
+
+}  // namespace spx
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+using spx::LscEngine;
+struct spx_lsc { LscEngine* e; };
+
+#define LSC_ENTER(h)                                                                      \
+    SPX_REQUIRE((h) && (h)->e, SPX_ERR_BADARG, "NULL SuperpixelLSC handle");              \
+    LscEngine* e = (h)->e;                                                                \
+    SPX_CUDA(cudaSetDevice(e->device))
+
+extern "C" int spx_lsc_create(const uint8_t* image, size_t stride, int w, int h, int C, int S, float ratio, int device, spx_lsc_t** out)
+{
+    using namespace spx;
+    SPX_REQUIRE(out, SPX_ERR_BADARG, "createSuperpixelLSC: out is NULL");
+    *out = nullptr;
+    SPX_CHECK(require_device(device));
+    LscEngine* e = new LscEngine();
+    e->device = device;
+    int rc = e->create(image, stride, w, h, C, S, ratio);
+    if (rc != SPX_OK) { delete e; return rc; }
+    *out = new spx_lsc{e};
+    return SPX_OK;
+}
+extern "C" int spx_lsc_iterate(spx_lsc_t* h, int n)
+{
+    LSC_ENTER(h);
+    return e->iterate(n);
+}
+extern "C" int spx_lsc_enforce_label_connectivity(spx_lsc_t* h, int min_element_size)
+{
+    LSC_ENTER(h);
+    return e->enforce(min_element_size);
+}
+extern "C" int spx_lsc_get_number_of_superpixels(spx_lsc_t* h, int* out)
+{
+    LSC_ENTER(h);
+    SPX_REQUIRE(out, SPX_ERR_BADARG, "getNumberOfSuperpixels: out is NULL");
+    SPX_CUDA(cudaStreamSynchronize(e->st));
+    *out = e->numlabels;
+    return SPX_OK;
+}
+extern "C" int spx_lsc_get_labels(spx_lsc_t* h, int32_t* dst, size_t dst_stride)
+{
+    LSC_ENTER(h);
+    SPX_REQUIRE(dst && dst_stride >= (size_t)e->L.w * 4, SPX_ERR_BADARG, "getLabels: bad destination");
+    SPX_CUDA(cudaMemcpy2DAsync(dst, dst_stride, e->d_labels, (size_t)e->L.w * 4, (size_t)e->L.w * 4, e->L.h, cudaMemcpyDeviceToHost, e->st));
+    SPX_CUDA(cudaStreamSynchronize(e->st));
+    return SPX_OK;
+}
+extern "C" int spx_lsc_get_label_contour_mask(spx_lsc_t* h, uint8_t* dst, size_t dst_stride, int thick_line)
+{
+    LSC_ENTER(h);
+    SPX_REQUIRE(dst && dst_stride >= (size_t)e->L.w, SPX_ERR_BADARG, "getLabelContourMask: bad destination");
+    SPX_CHECK(e->post.alloc(e->L.w, e->L.h));
+    long long l0 = e->post.launches;
+    SPX_CHECK(spx::contour_mask_dev(e->post, e->d_labels, e->L.w, thick_line, 0, e->d_mask, e->L.w, e->st));
+    e->launches += e->post.launches - l0;
+    SPX_CUDA(cudaMemcpy2DAsync(dst, dst_stride, e->d_mask, e->L.w, e->L.w, e->L.h, cudaMemcpyDeviceToHost, e->st));
+    SPX_CUDA(cudaStreamSynchronize(e->st));
+    return SPX_OK;
+}
+extern "C" int spx_lsc_set_labels(spx_lsc_t* h, const int32_t* src, size_t src_stride, int numlabels)
+{
+    LSC_ENTER(h);
+    SPX_REQUIRE(src && src_stride >= (size_t)e->L.w * 4, SPX_ERR_BADARG, "setLabels: bad source");
+    SPX_CUDA(cudaMemcpy2DAsync(e->d_labels, (size_t)e->L.w * 4, src, src_stride, (size_t)e->L.w * 4, e->L.h, cudaMemcpyHostToDevice, e->st));
+    SPX_CUDA(cudaStreamSynchronize(e->st));
+    if (numlabels > 0) e->numlabels = numlabels;
+    return SPX_OK;
+}
+extern "C" int spx_lsc_get_centres(spx_lsc_t* h, float* dst, int rows)
+{
+    LSC_ENTER(h);
+    const int K = e->L.K, D = e->L.D;
+    SPX_REQUIRE(dst && rows >= K, SPX_ERR_BADARG, "getCentres: need room for %d rows", K);
+    std::vector<float> cen((size_t)K * D);
+    std::vector<int> sx(K), sy(K);
+    SPX_CUDA(cudaStreamSynchronize(e->st));
+    SPX_CUDA(cudaMemcpy(cen.data(), e->L.cen, cen.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    SPX_CUDA(cudaMemcpy(sx.data(), e->L.sx, (size_t)K * sizeof(int), cudaMemcpyDeviceToHost));
+    SPX_CUDA(cudaMemcpy(sy.data(), e->L.sy, (size_t)K * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < K; k++) {
+        for (int i = 0; i < D; i++) dst[(size_t)k * (D + 2) + i] = cen[(size_t)k * D + i];
+        dst[(size_t)k * (D + 2) + D] = (float)sx[k];
+        dst[(size_t)k * (D + 2) + D + 1] = (float)sy[k];
+    }
+    return SPX_OK;
+}
+extern "C" int spx_lsc_launch_count(spx_lsc_t* h, long long* out)
+{
+    SPX_REQUIRE(h && h->e && out, SPX_ERR_BADARG, "launch_count: bad argument");
+    *out = h->e->launches;
+    return SPX_OK;
+}
+extern "C" int spx_lsc_destroy(spx_lsc_t* h)
+{
+    if (!h) return SPX_OK;
+    delete h->e;
+    delete h;
+    return SPX_OK;
+}

@@ -209,3 +209,72 @@ def test_errors(spx):
         s.enforceLabelConnectivity(101)
     s.enforceLabelConnectivity(0)        # no-op, as upstream
     assert s.getNumberOfSuperpixels() == 4
+
+
+# ---------------------------------------------------------------- LSC vs oracle (PARITY UNPINNED upstream; exact vs our restatement)
+def _lsc_pair(spx, O, img, S, ratio):
+    a = O.SuperpixelLSC(img, S, ratio)
+    b = spx.createSuperpixelLSC(img, S, ratio)
+    assert a.getNumberOfSuperpixels() == b.getNumberOfSuperpixels()
+    assert (a.getCentres() == b.getCentres()).all(), "seeds / initial centres differ"
+    return a, b
+
+
+@pytest.mark.parametrize("w,h,S,ratio,iters", [(320, 240, 16, 0.075, 6), (203, 157, 10, 0.2, 4), (640, 480, 30, 0.075, 10)])
+def test_lsc_labels_and_centres_exact(spx, O, synthmod, w, h, S, ratio, iters):
+    bgr, _ = synthmod.synth(w, h, 5)
+    lab = O.bgr2lab8(bgr)
+    a, b = _lsc_pair(spx, O, lab, S, ratio)
+    a.iterate(iters); b.iterate(iters)
+    la, lb = a.getLabels(), b.getLabels()
+    agree = float((la == lb).mean())
+    assert agree >= 0.999, agree            # north-star tolerance
+    assert agree == 1.0, agree              # the restatement is order-free, so the match is exact
+    ca, cb = a.getCentres(), b.getCentres()
+    assert np.abs(ca - cb).max() <= 1e-3
+    assert (ca == cb).all()
+
+
+@pytest.mark.parametrize("p", [25, 5, 60])
+def test_lsc_full_pipeline_exact(spx, O, example_lab, p):
+    img = np.ascontiguousarray(example_lab[300:780, 420:1060])
+    a, b = _lsc_pair(spx, O, img, 20, 0.075)
+    a.iterate(8); b.iterate(8)
+    assert (a.getLabels() == b.getLabels()).all()
+    a.enforceLabelConnectivity(p); b.enforceLabelConnectivity(p)
+    assert a.getNumberOfSuperpixels() == b.getNumberOfSuperpixels()
+    assert (a.getLabels() == b.getLabels()).all()
+    for thick in (False, True):
+        assert (a.getLabelContourMask(thick) == b.getLabelContourMask(thick)).all()
+
+
+@pytest.mark.parametrize("channels", [1, 2, 4])
+def test_lsc_other_channel_counts(spx, O, channels):
+    rng = np.random.default_rng(channels + 10)
+    base = np.kron(rng.integers(0, 256, (8, 10, channels)), np.ones((12, 12, 1))).astype(np.int64)
+    img = np.clip(base + rng.integers(-6, 7, base.shape), 0, 255).astype(np.uint8)
+    a, b = _lsc_pair(spx, O, img, 10, 0.1)
+    a.iterate(4); b.iterate(4)
+    assert (a.getLabels() == b.getLabels()).all()
+    assert (a.getCentres() == b.getCentres()).all()
+
+
+@pytest.mark.parametrize("w,h,cell,noise,p,S", [(131, 97, 12, 0.05, 25, 8), (64, 64, 5, 0.2, 50, 8), (257, 129, 20, 0.02, 10, 8),
+                                                 (50, 3, 4, 0.1, 25, 2), (1, 40, 3, 0.2, 25, 1)])
+def test_lsc_connectivity_on_injected_labels(spx, O, synthmod, w, h, cell, noise, p, S):
+    """enforceLabelConnectivity given the same label map: bit-exact (pre-pass adj rule + sequential post-pass merge)"""
+    img, _ = synthmod.synth(w, h, 11)
+    lab = random_label_map(np.random.default_rng(w + h + p), h, w, cell, noise)
+    k0 = int(lab.max()) + 1
+    a = O.SuperpixelLSC(img, S, 0.075); b = spx.createSuperpixelLSC(img, S, 0.075)
+    a.setLabels(lab, k0); b.setLabels(lab, k0)
+    a.enforceLabelConnectivity(p); b.enforceLabelConnectivity(p)
+    assert a.getNumberOfSuperpixels() == b.getNumberOfSuperpixels()
+    assert (a.getLabels() == b.getLabels()).all()
+
+
+def test_lsc_errors(spx):
+    with pytest.raises(spx.SpxError):
+        spx.createSuperpixelLSC(np.zeros((8, 8, 3), np.uint8), 50, 0.075)     # no seed fits
+    with pytest.raises(spx.SpxError):
+        spx.createSuperpixelLSC(np.zeros((16, 16, 5), np.uint8), 4, 0.075)

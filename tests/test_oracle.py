@@ -95,3 +95,29 @@ def test_contour_flavours(O):
     assert thick.sum() <= thin.sum()          # threshold 2 marks fewer pixels than threshold 1
     # SEEDS flavour with thick_line=false is the same recurrence as SLIC's threshold 1
     assert (O.label_contour_mask(lab, False, seeds_flavour=True) == thin).all()
+
+
+def test_lsc_oracle_properties(O, synthmod):
+    """LSC restatement (PARITY UNPINNED upstream): seed grid, label range, connectivity after enforcement,
+    independence from the thread count"""
+    import cv2
+    bgr, gt = synthmod.synth(320, 240, 2)
+    lab = O.bgr2lab8(bgr)
+    s = O.SuperpixelLSC(lab, 16, 0.075)
+    k0 = s.getNumberOfSuperpixels()
+    assert k0 == 20 * 15                      # ColNum = int(sqrt(300*320/240)) = 20, RowNum = 300/20
+    s.iterate(6)
+    L = s.getLabels()
+    assert L.min() >= 0 and L.max() < k0
+    O.set_threads(1)
+    s1 = O.SuperpixelLSC(lab, 16, 0.075); s1.iterate(6)
+    O.set_threads(4)
+    assert (s1.getLabels() == L).all() and (s1.getCentres() == s.getCentres()).all()
+    s.enforceLabelConnectivity(25)
+    k = s.getNumberOfSuperpixels()
+    L2 = s.getLabels()
+    assert L2.min() == 0 and L2.max() == k - 1
+    for l in range(0, k, 7):
+        n, _ = cv2.connectedComponents((L2 == l).astype(np.uint8), connectivity=4)
+        assert n == 2
+    assert synthmod.boundary_recall(L2, gt) > 0.95
