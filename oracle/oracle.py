@@ -70,6 +70,9 @@ def lib():
             L.spxo_seeds_get_number_of_superpixels.restype = i32
             L.spxo_seeds_get_labels.argtypes = [vp, vp]
             L.spxo_seeds_get_label_contour_mask.argtypes = [vp, vp, i32]
+            L.spxo_seeds_set_order.argtypes = [vp, i32]
+            L.spxo_seeds_energy.argtypes = [vp, vp]
+            L.spxo_seeds_energy.restype = C.c_double
         _LIB = L
     return _LIB
 
@@ -212,3 +215,11 @@ class SuperpixelSEEDS(_Base):
         img = _img(img)
         assert img.shape == (self.h, self.w, self.c)
         lib().spxo_seeds_iterate(self._h, _p(img), self.w * self.c, int(num_iterations))
+
+    def setOrder(self, order):
+        """0 = upstream's sequential raster order, 1 = the phase-parallel order of the CUDA path"""
+        lib().spxo_seeds_set_order(self._h, int(order))
+
+    def energy(self, labels):
+        lab = np.ascontiguousarray(labels, dtype=np.int32)
+        return lib().spxo_seeds_energy(self._h, _p(lab))

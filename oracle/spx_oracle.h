@@ -71,6 +71,10 @@ typedef struct spxo_seeds spxo_seeds;
 spxo_seeds* spxo_seeds_create(int w, int h, int channels, int num_superpixels, int num_levels,
                               int prior, int histogram_bins, int double_step);
 void spxo_seeds_destroy(spxo_seeds*);
+/* visiting order: 0 = upstream's sequential raster order, 1 = the phase-parallel order of the CUDA path */
+void spxo_seeds_set_order(spxo_seeds*, int order);
+/* colour-homogeneity energy of a labelling of the image last given to iterate() (higher is better) */
+double spxo_seeds_energy(const spxo_seeds*, const int32_t* labels);
 void spxo_seeds_iterate(spxo_seeds*, const uint8_t* img, size_t stride, int num_iterations);
 int  spxo_seeds_get_number_of_superpixels(const spxo_seeds*);
 void spxo_seeds_get_labels(const spxo_seeds*, int32_t* dst);
