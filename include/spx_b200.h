@@ -142,6 +142,8 @@ int spx_seeds_iterate(spx_seeds_t*, const uint8_t* image, size_t stride, int num
 int spx_seeds_get_number_of_superpixels(spx_seeds_t*, int* out);
 int spx_seeds_get_labels(spx_seeds_t*, int32_t* dst, size_t dst_stride);
 int spx_seeds_get_label_contour_mask(spx_seeds_t*, uint8_t* dst, size_t dst_stride, int thick_line);
+/* number of kernels launched so far (test / bench hook) */
+int spx_seeds_launch_count(spx_seeds_t*, long long* out);
 int spx_seeds_destroy(spx_seeds_t*);
 
 #ifdef __cplusplus

@@ -93,6 +93,7 @@ def lib():
         "spx_seeds_get_number_of_superpixels": [vp, pi],
         "spx_seeds_get_labels": [vp, vp, sz],
         "spx_seeds_get_label_contour_mask": [vp, vp, sz, i32],
+        "spx_seeds_launch_count": [vp, C.POINTER(C.c_longlong)],
         "spx_seeds_destroy": [vp],
     }
     for name, args in sig.items():
@@ -298,6 +299,11 @@ class SuperpixelSEEDS(_Superpixel):
 
     def getLabelContourMask(self, thick_line=False):
         return super().getLabelContourMask(thick_line)
+
+    def launchCount(self):
+        n = C.c_longlong(0)
+        _ck(lib().spx_seeds_launch_count(self._h, C.byref(n)))
+        return n.value
 
 
 def createSuperpixelSLIC(image, algorithm=SLICO, region_size=10, ruler=10.0, device=0):

@@ -2,7 +2,7 @@
 // getLabels / getNumberOfSuperpixels / getLabelContourMask as called from mainwindow.cpp:2114-2120).
 //
 // PARITY UNPINNED (no lsc.cpp, no ximgproc binary, no fixture): implements, operation for operation, the restatement
-// of Li & Chen's Linear Spectral Clustering that oracle/spx_oracle_lsc.c documents.  Design:
+// of Li & Chen's Linear Spectral Clustering that the test oracle under oracle/ (LSC section) documents.  Design:
 //   * the 2C+4 sin/cos features are never materialised (44 B/px upstream): every kernel recomputes them in registers
 //     from the 8-bit pixel and its coordinates through small tables (256 entries per channel, W and H entries for x/y)
 //     that the host builds once per image in double precision;
@@ -261,7 +261,7 @@ __global__ void lsc_ccl_size_kernel(const int* __restrict__ P, int* __restrict__
     if (i < n && r.tail) atomicAdd(&csize[key], lane - r.start + 1);
 }
 
-// ---- pre-pass: the authors' `adj` rule on the component roots (see oracle/spx_oracle_lsc.c: lsc_pre_enforce) --------
+// ---- pre-pass: the authors' `adj` rule on the component roots (see the test oracle, LSC pre-pass) --------
 __global__ void lsc_pre_init_kernel(const int* __restrict__ P, const int* __restrict__ lab, const int* __restrict__ csize,
                                     int* __restrict__ FL, int* __restrict__ ADJ, int n, int bound)
 {

@@ -278,3 +278,70 @@ def test_lsc_errors(spx):
         spx.createSuperpixelLSC(np.zeros((8, 8, 3), np.uint8), 50, 0.075)     # no seed fits
     with pytest.raises(spx.SpxError):
         spx.createSuperpixelLSC(np.zeros((16, 16, 5), np.uint8), 4, 0.075)
+
+
+# ---------------------------------------------------------------- SEEDS (PARITY UNPINNED upstream)
+# the CUDA path must equal the oracle's phase-parallel order (order 1) bit for bit; order 1 vs upstream's sequential
+# order (order 0) is a statistical comparison (tests/test_oracle.py and below)
+@pytest.mark.parametrize("w,h,num,levels,prior,bins,dstep,iters", [
+    (320, 240, 200, 3, 2, 5, False, 4), (203, 157, 150, 2, 0, 4, True, 3), (256, 256, 64, 4, 5, 3, False, 5),
+    (160, 120, 300, 1, 1, 5, False, 2), (640, 360, 400, 4, 3, 5, True, 6)])
+def test_seeds_equals_phase_parallel_oracle(spx, O, synthmod, w, h, num, levels, prior, bins, dstep, iters):
+    bgr, _ = synthmod.synth(w, h, 9)
+    lab = O.bgr2lab8(bgr)
+    a = O.SuperpixelSEEDS(w, h, 3, num, levels, prior, bins, dstep); a.setOrder(1)
+    b = spx.createSuperpixelSEEDS(w, h, 3, num, levels, prior, bins, dstep)
+    assert a.getNumberOfSuperpixels() == b.getNumberOfSuperpixels()
+    assert (a.getLabels() == b.getLabels()).all()                 # the top-level grid before iterate()
+    a.iterate(lab, iters); b.iterate(lab, iters)
+    la, lb = a.getLabels(), b.getLabels()
+    assert (la == lb).all(), float((la == lb).mean())
+    for thick in (False, True):
+        assert (a.getLabelContourMask(thick) == b.getLabelContourMask(thick)).all()
+    a.iterate(lab, 2); b.iterate(lab, 2)                          # a second COMPUTE click on the same object
+    assert (a.getLabels() == b.getLabels()).all()
+
+
+def test_seeds_cfg4_vs_sequential_order(spx, O, synthmod):
+    """BASELINE.json configs[3]: 1080p, 2000 superpixels, 4 levels, 5 bins, 10 iterations.  Quality of the GPU's
+    phase-parallel order against upstream's sequential order on the same image (statistical, not label parity)."""
+    bgr, gt = synthmod.synth(1920, 1080, 0)
+    lab = spx.cvtColor(bgr, spx.COLOR_BGR2Lab)
+    g = spx.createSuperpixelSEEDS(1920, 1080, 3, 2000, 4, 2, 5, False)
+    assert g.getNumberOfSuperpixels() == 1296
+    g.iterate(lab, 10)
+    Lg = g.getLabels()
+    s = O.SuperpixelSEEDS(1920, 1080, 3, 2000, 4, 2, 5, False); s.setOrder(0)
+    s.iterate(lab, 10)
+    Ls = s.getLabels()
+    assert Lg.min() >= 0 and Lg.max() < 1296
+    br_g, br_s = synthmod.boundary_recall(Lg, gt), synthmod.boundary_recall(Ls, gt)
+    ue_g, ue_s = synthmod.undersegmentation_error(Lg, gt), synthmod.undersegmentation_error(Ls, gt)
+    e_g, e_s = s.energy(Lg), s.energy(Ls)
+    # the parallel order must not be worse than the sequential one by more than a small margin
+    assert br_g >= br_s - 0.02 and ue_g <= ue_s + 0.02 and e_g >= e_s - 0.01, (br_g, br_s, ue_g, ue_s, e_g, e_s)
+    assert g.launchCount() > 0
+
+
+def test_seeds_screenshot_sizing(spx):
+    """the reference's screenshot: 3888x5184, 1000 requested, 4 levels -> 972 (LCD shows nb_cells+1 = 973)"""
+    assert spx.createSuperpixelSEEDS(3888, 5184, 3, 1000, 4).getNumberOfSuperpixels() == 972
+
+
+def test_seeds_errors(spx):
+    with pytest.raises(spx.SpxError):
+        spx.createSuperpixelSEEDS(64, 64, 3, 100, 4, 2, 50, False)       # 50^3 bins: over the engine's limit
+    s = spx.createSuperpixelSEEDS(64, 48, 3, 20, 2)
+    with pytest.raises(spx.SpxError):
+        s.iterate(np.zeros((48, 60, 3), np.uint8), 2)
+
+
+def test_cpp_adapter_compute_click():
+    """the reference's COMPUTE click compiled against include/spx_ximgproc.hpp: all five algorithms + the HSV branch"""
+    import subprocess
+    from conftest import ROOT
+    cpp = os.path.join(ROOT, "tests", "cpp")
+    subprocess.check_call(["make", "-C", cpp, "-s"])
+    r = subprocess.run([os.path.join(cpp, "compute_click")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("nb_cells") == 6

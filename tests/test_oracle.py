@@ -121,3 +121,31 @@ def test_lsc_oracle_properties(O, synthmod):
         n, _ = cv2.connectedComponents((L2 == l).astype(np.uint8), connectivity=4)
         assert n == 2
     assert synthmod.boundary_recall(L2, gt) > 0.95
+
+
+def test_seeds_sizing_pinned_by_screenshot(O):
+    """screenshots/screenshot-segmentation.jpg: 3888x5184, Superpixels 1000, Levels 4 -> LCD 973 = nb_cells+1"""
+    assert O.SuperpixelSEEDS(3888, 5184, 3, 1000, 4).getNumberOfSuperpixels() == 972
+    assert O.SuperpixelSEEDS(1920, 1080, 3, 2000, 4).getNumberOfSuperpixels() == 1296
+
+
+def test_seeds_orders_agree_statistically(O, synthmod):
+    """the phase-parallel visiting order (what the GPU runs) vs upstream's sequential order: same decision rules,
+    comparable quality; both keep every superpixel 4-connected"""
+    import cv2
+    bgr, gt = synthmod.synth(640, 360, 4)
+    lab = O.bgr2lab8(bgr)
+    res = []
+    for order in (0, 1):
+        s = O.SuperpixelSEEDS(640, 360, 3, 400, 3, 2, 5, False); s.setOrder(order)
+        k = s.getNumberOfSuperpixels()
+        e0 = s.energy(s.getLabels()) if False else None
+        s.iterate(lab, 6)
+        L = s.getLabels()
+        assert L.min() >= 0 and L.max() < k
+        for l in range(0, k, 5):
+            n, _ = cv2.connectedComponents((L == l).astype(np.uint8), connectivity=4)
+            assert n <= 2
+        res.append((synthmod.boundary_recall(L, gt), synthmod.undersegmentation_error(L, gt), s.energy(L)))
+    (br0, ue0, en0), (br1, ue1, en1) = res
+    assert abs(br0 - br1) < 0.05 and abs(ue0 - ue1) < 0.03 and abs(en0 - en1) < 0.02, res
