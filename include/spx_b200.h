@@ -131,6 +131,9 @@ int spx_lsc_set_labels(spx_lsc_t*, const int32_t* src, size_t src_stride, int nu
 /* test hooks: centres = rows of (2*channels+4 feature means, seed x, seed y) float32; kernel launch count */
 int spx_lsc_get_centres(spx_lsc_t*, float* dst, int rows);
 int spx_lsc_launch_count(spx_lsc_t*, long long* out);
+/* visiting order of the small regions in enforceLabelConnectivity's merge pass: 1 (default) = hashed region index
+ * (short dependency chains, fast on a GPU), 0 = ascending region index (the authors' order; thousands of rounds). */
+int spx_lsc_set_merge_order(spx_lsc_t*, int order);
 int spx_lsc_destroy(spx_lsc_t*);
 
 /* ---- cv::ximgproc::SuperpixelSEEDS (mainwindow.h:172, mainwindow.cpp:2123-2127) ---- */

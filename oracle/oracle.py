@@ -60,6 +60,7 @@ def lib():
             L.spxo_lsc_get_labels.argtypes = [vp, vp]
             L.spxo_lsc_set_labels.argtypes = [vp, vp, i32]
             L.spxo_lsc_get_centres.argtypes = [vp, vp]
+            L.spxo_lsc_set_merge_order.argtypes = [vp, i32]
             L.spxo_lsc_get_label_contour_mask.argtypes = [vp, vp, i32]
         if hasattr(L, "spxo_seeds_create"):
             L.spxo_seeds_create.restype = vp
@@ -191,6 +192,10 @@ class SuperpixelLSC(_Base):
     def setLabels(self, labels, numlabels=0):
         lab = np.ascontiguousarray(labels, dtype=np.int32)
         lib().spxo_lsc_set_labels(self._h, _p(lab), int(numlabels))
+
+    def setMergeOrder(self, order):
+        """0 (default) = the authors' raster order of small regions, 1 = hashed order (what the CUDA path runs by default)"""
+        lib().spxo_lsc_set_merge_order(self._h, int(order))
 
     def getCentres(self):
         """K rows of (2C+4 feature means, seed x, seed y)"""

@@ -64,6 +64,8 @@ void spxo_lsc_get_labels(const spxo_lsc*, int32_t* dst);
 void spxo_lsc_set_labels(spxo_lsc*, const int32_t* src, int numlabels);
 /* centres: K rows of (2C+4 feature means, seed x, seed y) float32 */
 void spxo_lsc_get_centres(const spxo_lsc*, float* dst);
+/* post-pass visiting order: 0 (default) = ascending region index (authors' order), 1 = hashed index (CUDA default) */
+void spxo_lsc_set_merge_order(spxo_lsc*, int order);
 void spxo_lsc_get_label_contour_mask(const spxo_lsc*, uint8_t* dst, int thick_line);
 
 /* ---- SuperpixelSEEDS, mainwindow.cpp:2123-2127 (PARITY UNPINNED; sizing pinned by screenshot) ---- */

@@ -42,6 +42,7 @@ struct spxo_lsc {
     int w, h, C, D, S;
     float ratio;
     int K, ColNum, RowNum, stepx, stepy;
+    int merge_order;         /* post-pass visiting order: 0 = ascending region index (authors), 1 = hashed index (CUDA default) */
     uint8_t* img;            /* dense interleaved copy */
     int32_t* labels;
     int* sx; int* sy;        /* seed positions */
@@ -287,6 +288,20 @@ static void lsc_pre_enforce(spxo_lsc* s, int bound)
     free(mask); free(qx); free(qy);
 }
 
+static unsigned lsc_prio(int r)
+{
+    unsigned x = (unsigned)r;
+    x *= 2654435761u; x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+    return x;
+}
+static int g_prio_order = 0;
+static int cmp_prio(const void* a, const void* b)
+{
+    const unsigned pa = lsc_prio(*(const int*)a), pb = lsc_prio(*(const int*)b);
+    return pa < pb ? -1 : (pa > pb ? 1 : 0);
+}
+void spxo_lsc_set_merge_order(spxo_lsc* s, int order) { s->merge_order = order ? 1 : 0; }
+
 static void lsc_post_enforce(spxo_lsc* s, int threshold)
 {
     const int w = s->w, h = s->h, D = s->D;
@@ -339,10 +354,18 @@ static void lsc_post_enforce(spxo_lsc* s, int threshold)
         size[r] = (long long)(off[r + 1] - off[r]);
         cur[r] = r; next[r] = -1; tail[r] = r; alive[r] = 1;
     }
-    /* sequential merge of small regions, in region order */
+    /* sequential merge of small regions: in region order (order 0), or in the order of a bijective hash of the region
+       index (order 1: same rule, but the dependency chains between merges are short, which is what a GPU needs) */
     int* nb = (int*)malloc(sizeof(int) * 64);
     int nbcap = 64;
-    for (int i = 0; i < R; i++) {
+    int* visit = (int*)malloc(sizeof(int) * (R > 0 ? R : 1));
+    for (int r = 0; r < R; r++) visit[r] = r;
+    if (s->merge_order) {
+        g_prio_order = 1;
+        qsort(visit, R, sizeof(int), cmp_prio);
+    }
+    for (int vi = 0; vi < R; vi++) {
+        const int i = visit[vi];
         if (size[i] >= threshold) continue;
         int nnb = 0;
         for (int m = i; m >= 0; m = next[m])
@@ -384,7 +407,7 @@ static void lsc_post_enforce(spxo_lsc* s, int threshold)
     for (size_t i = 0; i < N; i++) s->labels[i] = newid[cur[reg[i]]];
     s->K = K;
     free(reg); free(qx); free(qy); free(off); free(cen); free(Wr); free(size); free(cur); free(next); free(tail);
-    free(alive); free(nb); free(newid);
+    free(alive); free(nb); free(newid); free(visit);
 }
 
 void spxo_lsc_enforce_label_connectivity(spxo_lsc* s, int min_element_size)

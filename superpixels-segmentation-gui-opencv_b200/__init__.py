@@ -87,6 +87,7 @@ def lib():
         "spx_lsc_set_labels": [vp, vp, sz, i32],
         "spx_lsc_get_centres": [vp, vp, i32],
         "spx_lsc_launch_count": [vp, C.POINTER(C.c_longlong)],
+        "spx_lsc_set_merge_order": [vp, i32],
         "spx_lsc_destroy": [vp],
         "spx_seeds_create": [i32, i32, i32, i32, i32, i32, i32, i32, i32, pp],
         "spx_seeds_iterate": [vp, vp, sz, i32],
@@ -266,6 +267,10 @@ class SuperpixelLSC(_Superpixel):
     def setLabels(self, labels, numlabels=0):
         lab = np.ascontiguousarray(labels, dtype=np.int32)
         _ck(lib().spx_lsc_set_labels(self._h, _p(lab), self.w * 4, int(numlabels)))
+
+    def setMergeOrder(self, order):
+        """1 (default) = hashed visiting order of small regions in enforceLabelConnectivity, 0 = the authors' raster order"""
+        _ck(lib().spx_lsc_set_merge_order(self._h, int(order)))
 
     def getCentres(self):
         """test hook: rows of (2*channels+4 feature means, seed x, seed y); valid before enforceLabelConnectivity"""

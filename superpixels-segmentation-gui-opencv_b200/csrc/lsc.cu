@@ -19,6 +19,7 @@
 #include <cub/device/device_scan.cuh>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace spx {
@@ -316,14 +317,6 @@ __global__ void lsc_post_region_kernel(const int* __restrict__ P, const int* __r
     reg[i] = r;
     if (root == i) size[r] = csize[i];
 }
-__global__ void lsc_post_fill_kernel(const int* __restrict__ reg, const int* __restrict__ off, int* __restrict__ cursor,
-                                     int* __restrict__ pxlist, int n)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int r = reg[i];
-    pxlist[off[r] + atomicAdd(&cursor[r], 1)] = i;
-}
 template <int C>
 __global__ void __launch_bounds__(256) lsc_post_sums_kernel(LscDev L, const int* __restrict__ reg, long long* __restrict__ rsum)
 {
@@ -347,8 +340,8 @@ __global__ void __launch_bounds__(256) lsc_post_sums_kernel(LscDev L, const int*
     if (emit) atomicAdd((unsigned long long*)&dst[D], (unsigned long long)s);
 }
 __global__ void lsc_post_stats_kernel(const long long* __restrict__ rsum, const int* __restrict__ size, int D, int R, int threshold,
-                                      float* __restrict__ cen, float* __restrict__ Wr, int* __restrict__ cur, int* __restrict__ next,
-                                      int* __restrict__ tail, int* __restrict__ alive, int* __restrict__ smallflag)
+                                      float* __restrict__ cen, float* __restrict__ Wr, int* __restrict__ alive,
+                                      int* __restrict__ smallflag, int* __restrict__ done, int* __restrict__ target)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
@@ -356,85 +349,120 @@ __global__ void lsc_post_stats_kernel(const long long* __restrict__ rsum, const 
     const long long sw = a[D];
     for (int j = 0; j < D; j++) cen[(size_t)r * D + j] = sw != 0 ? (float)__ddiv_rn(__ddiv_rn((double)a[j], (double)sw), 256.0) : 0.f;
     Wr[r] = (float)__ddiv_rn((double)sw, 16777216.0);
-    cur[r] = r; next[r] = -1; tail[r] = r; alive[r] = 1;
+    alive[r] = 1; done[r] = 0; target[r] = -1;
     smallflag[r] = size[r] < threshold ? 1 : 0;
 }
-__global__ void lsc_post_compact_kernel(const int* __restrict__ flag, const int* __restrict__ pos, int* __restrict__ out, int R)
+
+// ---- the merge of small regions -------------------------------------------------------------------------------
+// Upstream's rule is sequential: for i = 0, 1, 2, ...: if region i is (still) smaller than the threshold it merges into
+// the adjacent region with the nearest centre (ties -> smaller id) and that region's centre / weight / size are updated.
+// A merge of region j can change the decision of a later region i only if i and j are adjacent or share a neighbour
+// (the merge target).  So a pending region that is the smallest pending index within graph distance 2 takes exactly
+// the decision it would take in the sequential order, and all such regions can merge in the same round: they are
+// pairwise more than 2 apart, hence their targets are distinct and nobody reads what another one writes.
+// One round = a few passes over the pixel map (min-propagation of pending indices over region adjacencies, nearest
+// neighbour search for the safe regions, relabel); rounds repeat until nothing is pending.
+// visiting priority of a small region: order 0 = its index (upstream's raster order; the dependency chains then span the
+// image, thousands of rounds), order 1 = a bijective hash of the index (chains of O(100) rounds; the default).
+__device__ __forceinline__ unsigned lsc_prio(int r, int order)
 {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < R && flag[r]) out[pos[r]] = r;
-}
-// the sequential part: small regions, in region order, merge into the adjacent region with the nearest centre
-// (ties -> smaller id); centres / weights / sizes / member lists updated after every merge.  One CTA.
-__global__ void __launch_bounds__(256) lsc_post_merge_kernel(const int* __restrict__ small, const int* __restrict__ nsmall_p, int threshold,
-                                                              int D, int w, int h, const int* __restrict__ reg, const int* __restrict__ off,
-                                                              const int* __restrict__ pxlist, volatile float* cen, volatile float* Wr,
-                                                              volatile int* size, volatile int* cur, volatile int* next, volatile int* tail,
-                                                              volatile int* alive)
-{
-    __shared__ float ci[LSC_MAXD];
-    __shared__ unsigned long long red[8];
-    __shared__ int s_go;
-    __shared__ unsigned long long s_best;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int ns = *nsmall_p;
-    for (int t = 0; t < ns; t++) {
-        const int i = small[t];
-        if (tid == 0) s_go = size[i] < threshold ? 1 : 0;
-        if (tid < D) ci[tid] = cen[(size_t)i * D + tid];
-        __syncthreads();
-        if (s_go) {
-            unsigned long long best = ~0ull;
-            for (int m = i; m >= 0; m = next[m]) {
-                const int a = off[m], b = off[m + 1];
-                for (int e = 4 * a + tid; e < 4 * b; e += 256) {
-                    const int p = pxlist[e >> 2], k = e & 3;
-                    const int x = p % w, y = p / w;
-                    const int nx = x + (k == 0 ? -1 : k == 2 ? 1 : 0), ny = y + (k == 1 ? -1 : k == 3 ? 1 : 0);
-                    if (nx < 0 || nx >= w || ny < 0 || ny >= h) continue;
-                    const int r = cur[reg[ny * w + nx]];
-                    if (r == i) continue;
-                    float d = 0.f;
-                    for (int j = 0; j < D; j++) { const float u = __fsub_rn(ci[j], cen[(size_t)r * D + j]); d = __fadd_rn(d, __fmul_rn(u, u)); }
-                    const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)r;
-                    best = key < best ? key : best;
-                }
-            }
-            for (int o = 16; o; o >>= 1) { const unsigned long long u = __shfl_xor_sync(0xffffffffu, best, o); best = u < best ? u : best; }
-            if (lane == 0) red[wid] = best;
-            __syncthreads();
-            if (tid == 0) {
-                unsigned long long b = red[0];
-                for (int q = 1; q < 8; q++) b = red[q] < b ? red[q] : b;
-                s_best = b;
-            }
-            __syncthreads();
-            if (s_best != ~0ull) {
-                const int nb = (int)(unsigned)(s_best & 0xffffffffull);
-                const float wn = Wr[nb], wi = Wr[i];
-                if (tid < D) {
-                    const float a = __fmul_rn(cen[(size_t)nb * D + tid], wn), b = __fmul_rn(ci[tid], wi);
-                    cen[(size_t)nb * D + tid] = __fdiv_rn(__fadd_rn(a, b), __fadd_rn(wn, wi));
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    Wr[nb] = __fadd_rn(wn, wi);
-                    size[nb] = size[nb] + size[i];
-                    for (int m = i; m >= 0; m = next[m]) cur[m] = nb;
-                    next[tail[nb]] = i; tail[nb] = tail[i];
-                    alive[i] = 0;
-                }
-            }
-        }
-        __threadfence_block();
-        __syncthreads();
+    unsigned x = (unsigned)r;
+    if (order) {
+        x *= 2654435761u; x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
     }
+    return x;
 }
-__global__ void lsc_post_relabel_kernel(const int* __restrict__ reg, const int* __restrict__ cur, const int* __restrict__ newid,
-                                        int* __restrict__ lab, int n)
+__global__ void lsc_round_relabel_kernel(int* __restrict__ curlab, const int* __restrict__ target, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) lab[i] = newid[cur[reg[i]]];
+    if (i >= n) return;
+    const int t = target[curlab[i]];
+    if (t >= 0) curlab[i] = t;
+}
+__global__ void lsc_round_begin_kernel(const int* __restrict__ smallflag, const int* __restrict__ done, const int* __restrict__ size,
+                                       int threshold, int R, int order, int* __restrict__ pend, unsigned* __restrict__ key, unsigned* __restrict__ a,
+                                       unsigned long long* __restrict__ best, int* __restrict__ target, int* __restrict__ npending)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool p = r < R && smallflag[r] && !done[r] && size[r] < threshold;
+    if (r < R) { pend[r] = p ? 1 : 0; key[r] = a[r] = p ? lsc_prio(r, order) : 0xffffffffu; best[r] = ~0ull; target[r] = -1; }
+    const unsigned m = __ballot_sync(0xffffffffu, p);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(npending, __popc(m));
+}
+// a[r] = min pending index over the closed neighbourhood of r; the same kernel run on (a -> b) gives distance 2
+__global__ void lsc_round_minprop_kernel(const int* __restrict__ curlab, const unsigned* __restrict__ src, unsigned* __restrict__ dst,
+                                         int w, int h, const int* __restrict__ npending)
+{
+    if (*npending == 0) return;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const int i = y * w + x, rp = curlab[i];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        if (k == 0 ? x + 1 >= w : y + 1 >= h) continue;
+        const int rq = curlab[k == 0 ? i + 1 : i + w];
+        if (rq == rp) continue;
+        const unsigned vp = src[rp], vq = src[rq];
+        if (vq < dst[rp]) atomicMin(&dst[rp], vq);
+        if (vp < dst[rq]) atomicMin(&dst[rq], vp);
+    }
+}
+__global__ void lsc_round_copy_kernel(const unsigned* __restrict__ a, unsigned* __restrict__ b, int R, const int* __restrict__ npending)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (*npending == 0 || r >= R) return;
+    b[r] = a[r];
+}
+__device__ __forceinline__ unsigned long long lsc_pair_key(const float* __restrict__ cen, int D, int i, int r)
+{
+    float d = 0.f;
+    for (int j = 0; j < D; j++) { const float u = __fsub_rn(cen[(size_t)i * D + j], cen[(size_t)r * D + j]); d = __fadd_rn(d, __fmul_rn(u, u)); }
+    return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)r;
+}
+__global__ void lsc_round_best_kernel(const int* __restrict__ curlab, const int* __restrict__ pend, const unsigned* __restrict__ b,
+                                      const float* __restrict__ cen, int D, int order, unsigned long long* __restrict__ best, int w, int h,
+                                      const int* __restrict__ npending)
+{
+    if (*npending == 0) return;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const int i = y * w + x, rp = curlab[i];
+    const bool sp = pend[rp] && b[rp] == lsc_prio(rp, order);
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        if (k == 0 ? x + 1 >= w : y + 1 >= h) continue;
+        const int rq = curlab[k == 0 ? i + 1 : i + w];
+        if (rq == rp) continue;
+        if (sp) { const unsigned long long key = lsc_pair_key(cen, D, rp, rq); if (key < best[rp]) atomicMin(&best[rp], key); }
+        if (pend[rq] && b[rq] == lsc_prio(rq, order)) { const unsigned long long key = lsc_pair_key(cen, D, rq, rp); if (key < best[rq]) atomicMin(&best[rq], key); }
+    }
+}
+__global__ void lsc_round_merge_kernel(const int* __restrict__ pend, const unsigned* __restrict__ b, const unsigned long long* __restrict__ best,
+                                       int D, int R, int order, float* __restrict__ cen, float* __restrict__ Wr, int* __restrict__ size,
+                                       int* __restrict__ alive, int* __restrict__ done, int* __restrict__ target,
+                                       const int* __restrict__ npending)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (*npending == 0 || i >= R) return;
+    if (!pend[i] || b[i] != lsc_prio(i, order)) return;
+    done[i] = 1;
+    const unsigned long long k = best[i];
+    if (k == ~0ull) return;                                  // no neighbour at all (one region covers the image)
+    const int nb = (int)(unsigned)(k & 0xffffffffull);
+    const float wn = Wr[nb], wi = Wr[i];
+    for (int j = 0; j < D; j++) {
+        const float u = __fmul_rn(cen[(size_t)nb * D + j], wn), v = __fmul_rn(cen[(size_t)i * D + j], wi);
+        cen[(size_t)nb * D + j] = __fdiv_rn(__fadd_rn(u, v), __fadd_rn(wn, wi));
+    }
+    Wr[nb] = __fadd_rn(wn, wi);
+    size[nb] += size[i];
+    alive[i] = 0;
+    target[i] = nb;
+}
+__global__ void lsc_post_relabel_kernel(const int* __restrict__ curlab, const int* __restrict__ newid, int* __restrict__ lab, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) lab[i] = newid[curlab[i]];
 }
 
 struct MaxOp { __device__ __forceinline__ int operator()(int a, int b) const { return a > b ? a : b; } };
@@ -447,6 +475,7 @@ struct LscEngine {
     int S = 0;
     float ratio = 0.f;
     int numlabels = 0;
+    int merge_order = 1;                    // post-pass visiting order: 1 = hashed (default), 0 = upstream's raster order
     unsigned char* d_img = nullptr;
     int* d_labels = nullptr;
     unsigned char* d_mask = nullptr;
@@ -686,6 +715,7 @@ struct LscEngine {
         }
         lsc_pre_relabel_kernel<<<g1, 256, 0, st>>>(P, FL, d_labels, n);
         launches++;
+        if (getenv("SPX_LSC_DEBUG")) { cudaStreamSynchronize(st); fprintf(stderr, "[lsc] pre-pass done, launches so far %lld\n", launches); }
 
         // ---- post-pass: 4-connected regions, statistics, pixel lists
         lsc_ccl_init_kernel<<<g2, 256, 0, st>>>(d_labels, w, h, P);
@@ -699,23 +729,19 @@ struct LscEngine {
         LSC_TRYCUDA(cudaMemcpyAsync(h_pinned + 1, flag + n - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         LSC_TRYCUDA(cudaStreamSynchronize(st));
         const int R = h_pinned[0] + h_pinned[1];
-        int *reg = B, *size, *off, *cursor, *pxlist = rootidx, *cur, *next, *tail, *alive, *smallflag, *smallpos, *small, *newid;
+        int *reg = B, *size, *alive, *smallflag, *done, *target, *pend, *rk, *ra, *rb, *newid;
+        unsigned long long* best;
         float *cen, *Wr;
         long long* rsum;
-        LSC_TRY(talloc(&size, R + 1)); LSC_TRY(talloc(&off, R + 1)); LSC_TRY(talloc(&cursor, R));
-        LSC_TRY(talloc(&cur, R)); LSC_TRY(talloc(&next, R)); LSC_TRY(talloc(&tail, R)); LSC_TRY(talloc(&alive, R + 1));
-        LSC_TRY(talloc(&smallflag, R + 1)); LSC_TRY(talloc(&smallpos, R + 1)); LSC_TRY(talloc(&small, R)); LSC_TRY(talloc(&newid, R + 1));
+        LSC_TRY(talloc(&size, R + 1)); LSC_TRY(talloc(&alive, R + 1)); LSC_TRY(talloc(&smallflag, R)); LSC_TRY(talloc(&done, R));
+        LSC_TRY(talloc(&target, R)); LSC_TRY(talloc(&pend, R)); LSC_TRY(talloc(&rk, R)); LSC_TRY(talloc(&ra, R)); LSC_TRY(talloc(&rb, R));
+        LSC_TRY(talloc(&newid, R + 1)); LSC_TRY(talloc((int**)&best, (size_t)R * 2));
         LSC_TRY(talloc((int**)&cen, (size_t)R * D)); LSC_TRY(talloc((int**)&Wr, R));
         LSC_TRY(talloc((int**)&rsum, (size_t)R * (D + 1) * 2));
         LSC_TRYCUDA(cudaMemsetAsync(size, 0, (size_t)(R + 1) * sizeof(int), st));
-        LSC_TRYCUDA(cudaMemsetAsync(cursor, 0, (size_t)R * sizeof(int), st));
         LSC_TRYCUDA(cudaMemsetAsync(rsum, 0, (size_t)R * (D + 1) * sizeof(long long), st));
-        LSC_TRYCUDA(cudaMemsetAsync(smallflag, 0, (size_t)(R + 1) * sizeof(int), st));
         LSC_TRYCUDA(cudaMemsetAsync(alive, 0, (size_t)(R + 1) * sizeof(int), st));
         lsc_post_region_kernel<<<g1, 256, 0, st>>>(P, rid, csize, reg, size, n);
-        launches++;
-        LSC_TRY(exclusive_sum(size, off, R + 1));
-        lsc_post_fill_kernel<<<g1, 256, 0, st>>>(reg, off, cursor, pxlist, n);
         const dim3 gp(cdiv(w, 32), cdiv(h, 8));
         switch (L.C) {
             case 1: lsc_post_sums_kernel<1><<<gp, 256, 0, st>>>(L, reg, rsum); break;
@@ -723,15 +749,31 @@ struct LscEngine {
             case 3: lsc_post_sums_kernel<3><<<gp, 256, 0, st>>>(L, reg, rsum); break;
             default: lsc_post_sums_kernel<4><<<gp, 256, 0, st>>>(L, reg, rsum); break;
         }
-        lsc_post_stats_kernel<<<cdiv(R, 256), 256, 0, st>>>(rsum, size, D, R, threshold, cen, Wr, cur, next, tail, alive, smallflag);
+        const int gr = cdiv(R, 256);
+        lsc_post_stats_kernel<<<gr, 256, 0, st>>>(rsum, size, D, R, threshold, cen, Wr, alive, smallflag, done, target);
         launches += 3;
-        LSC_TRY(exclusive_sum(smallflag, smallpos, R + 1));
-        lsc_post_compact_kernel<<<cdiv(R, 256), 256, 0, st>>>(smallflag, smallpos, small, R);
-        // ---- the sequential merge (single CTA), then final ids
-        lsc_post_merge_kernel<<<1, 256, 0, st>>>(small, smallpos + R, threshold, D, w, h, reg, off, pxlist, cen, Wr, size, cur, next, tail, alive);
-        launches += 2;
+        // ---- merge rounds (see the comment above lsc_round_relabel_kernel); `reg` becomes the current region map
+        int rounds = 0;
+        for (;;) {
+            for (int k = 0; k < 8; k++) {
+                lsc_round_relabel_kernel<<<g1, 256, 0, st>>>(reg, target, n);
+                LSC_TRYCUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+                lsc_round_begin_kernel<<<gr, 256, 0, st>>>(smallflag, done, size, threshold, R, merge_order, pend, (unsigned*)rk, (unsigned*)ra, best, target, d_flag);
+                lsc_round_minprop_kernel<<<g2, 256, 0, st>>>(reg, (unsigned*)rk, (unsigned*)ra, w, h, d_flag);
+                lsc_round_copy_kernel<<<gr, 256, 0, st>>>((unsigned*)ra, (unsigned*)rb, R, d_flag);
+                lsc_round_minprop_kernel<<<g2, 256, 0, st>>>(reg, (unsigned*)ra, (unsigned*)rb, w, h, d_flag);
+                lsc_round_best_kernel<<<g2, 256, 0, st>>>(reg, pend, (unsigned*)rb, cen, D, merge_order, best, w, h, d_flag);
+                lsc_round_merge_kernel<<<gr, 256, 0, st>>>(pend, (unsigned*)rb, best, D, R, merge_order, cen, Wr, size, alive, done, target, d_flag);
+                launches += 7;
+                rounds++;
+            }
+            LSC_TRYCUDA(cudaMemcpyAsync(h_pinned, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+            LSC_TRYCUDA(cudaStreamSynchronize(st));
+            if (!h_pinned[0]) break;
+        }
+        if (getenv("SPX_LSC_DEBUG")) fprintf(stderr, "[lsc] post-pass: %d regions, threshold %d, %d merge rounds, launches %lld\n", R, threshold, rounds, launches);
         LSC_TRY(exclusive_sum(alive, newid, R + 1));
-        lsc_post_relabel_kernel<<<g1, 256, 0, st>>>(reg, cur, newid, d_labels, n);
+        lsc_post_relabel_kernel<<<g1, 256, 0, st>>>(reg, newid, d_labels, n);
         launches++;
         LSC_TRYCUDA(cudaMemcpyAsync(h_pinned, newid + R, sizeof(int), cudaMemcpyDeviceToHost, st));
         LSC_TRYCUDA(cudaStreamSynchronize(st));
@@ -833,6 +875,12 @@ extern "C" int spx_lsc_get_centres(spx_lsc_t* h, float* dst, int rows)
         dst[(size_t)k * (D + 2) + D] = (float)sx[k];
         dst[(size_t)k * (D + 2) + D + 1] = (float)sy[k];
     }
+    return SPX_OK;
+}
+extern "C" int spx_lsc_set_merge_order(spx_lsc_t* h, int order)
+{
+    SPX_REQUIRE(h && h->e && (order == 0 || order == 1), SPX_ERR_BADARG, "set_merge_order: bad argument");
+    h->e->merge_order = order;
     return SPX_OK;
 }
 extern "C" int spx_lsc_launch_count(spx_lsc_t* h, long long* out)

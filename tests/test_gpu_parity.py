@@ -235,10 +235,14 @@ def test_lsc_labels_and_centres_exact(spx, O, synthmod, w, h, S, ratio, iters):
     assert (ca == cb).all()
 
 
+@pytest.mark.parametrize("order", [1, 0])
 @pytest.mark.parametrize("p", [25, 5, 60])
-def test_lsc_full_pipeline_exact(spx, O, example_lab, p):
+def test_lsc_full_pipeline_exact(spx, O, example_lab, p, order):
+    """order 1 = hashed visiting order of the small regions (CUDA default), order 0 = the authors' raster order;
+    either way the CUDA path must reproduce the oracle running the same order bit for bit"""
     img = np.ascontiguousarray(example_lab[300:780, 420:1060])
     a, b = _lsc_pair(spx, O, img, 20, 0.075)
+    a.setMergeOrder(order); b.setMergeOrder(order)
     a.iterate(8); b.iterate(8)
     assert (a.getLabels() == b.getLabels()).all()
     a.enforceLabelConnectivity(p); b.enforceLabelConnectivity(p)
@@ -261,12 +265,14 @@ def test_lsc_other_channel_counts(spx, O, channels):
 
 @pytest.mark.parametrize("w,h,cell,noise,p,S", [(131, 97, 12, 0.05, 25, 8), (64, 64, 5, 0.2, 50, 8), (257, 129, 20, 0.02, 10, 8),
                                                  (50, 3, 4, 0.1, 25, 2), (1, 40, 3, 0.2, 25, 1)])
-def test_lsc_connectivity_on_injected_labels(spx, O, synthmod, w, h, cell, noise, p, S):
-    """enforceLabelConnectivity given the same label map: bit-exact (pre-pass adj rule + sequential post-pass merge)"""
+@pytest.mark.parametrize("order", [1, 0])
+def test_lsc_connectivity_on_injected_labels(spx, O, synthmod, w, h, cell, noise, p, S, order):
+    """enforceLabelConnectivity given the same label map: bit-exact (pre-pass adj rule + post-pass merge, both orders)"""
     img, _ = synthmod.synth(w, h, 11)
     lab = random_label_map(np.random.default_rng(w + h + p), h, w, cell, noise)
     k0 = int(lab.max()) + 1
     a = O.SuperpixelLSC(img, S, 0.075); b = spx.createSuperpixelLSC(img, S, 0.075)
+    a.setMergeOrder(order); b.setMergeOrder(order)
     a.setLabels(lab, k0); b.setLabels(lab, k0)
     a.enforceLabelConnectivity(p); b.enforceLabelConnectivity(p)
     assert a.getNumberOfSuperpixels() == b.getNumberOfSuperpixels()

@@ -149,3 +149,21 @@ def test_seeds_orders_agree_statistically(O, synthmod):
         res.append((synthmod.boundary_recall(L, gt), synthmod.undersegmentation_error(L, gt), s.energy(L)))
     (br0, ue0, en0), (br1, ue1, en1) = res
     assert abs(br0 - br1) < 0.05 and abs(ue0 - ue1) < 0.03 and abs(en0 - en1) < 0.02, res
+
+
+def test_lsc_merge_orders_agree_statistically(O, synthmod):
+    """post-pass merge of small regions: the hashed visiting order (CUDA default) vs the authors' raster order --
+    same rule, different order; the partitions must be close and both fully connected"""
+    bgr, gt = synthmod.synth(480, 360, 6)
+    lab = O.bgr2lab8(bgr)
+    out = []
+    for order in (0, 1):
+        s = O.SuperpixelLSC(lab, 16, 0.075); s.setMergeOrder(order)
+        s.iterate(8); s.enforceLabelConnectivity(25)
+        L = s.getLabels()
+        out.append((s.getNumberOfSuperpixels(), synthmod.boundary_recall(L, gt), synthmod.undersegmentation_error(L, gt), L))
+    (k0, br0, ue0, L0), (k1, br1, ue1, L1) = out
+    assert abs(k0 - k1) <= 0.03 * k0 and abs(br0 - br1) < 0.02 and abs(ue0 - ue1) < 0.01, (k0, k1, br0, br1, ue0, ue1)
+    # same-segment relation of horizontal neighbours agrees almost everywhere
+    same0 = L0[:, 1:] == L0[:, :-1]; same1 = L1[:, 1:] == L1[:, :-1]
+    assert float((same0 == same1).mean()) > 0.98
