@@ -25,7 +25,7 @@ namespace spx {
 bool slic_tile_supported(const SlicGeom& g);
 int slic_tile_prepare(const SlicGeom& g, const unsigned char* d_img, unsigned* d_img4, cudaStream_t st);
 int slic_tile_assign(const SlicGeom& g, const SlicArrays& a, const unsigned char* d_img, const unsigned* d_img4, int* d_labels,
-                     const int* d_K, int parity, int* d_overflow, cudaStream_t st);
+                     float* d_dcplane, const int* d_K, int parity, int* d_overflow, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------
 // device helpers
@@ -444,7 +444,7 @@ struct SlicEngine {
         SPX_CHECK(dalloc(&a.head[0], (size_t)g.nbx * g.nby)); SPX_CHECK(dalloc(&a.head[1], (size_t)g.nbx * g.nby));
         SPX_CHECK(dalloc(&a.area, kc));
         SPX_CHECK(dalloc(&d_K, 4)); SPX_CHECK(dalloc(&d_overflow, 4));
-        if (alg == SPX_SLICO) SPX_CHECK(dalloc(&d_dcplane, (size_t)w * h));
+        if (alg == SPX_SLICO) SPX_CHECK(dalloc(&d_dcplane, (size_t)g.lp * g.tiles_y * TILE_H));
         SPX_CUDA(cudaMallocHost(&h_pinned, 4 * sizeof(int)));
         SPX_CUDA(cudaMemsetAsync(d_img, 0, g.ipitch * (size_t)(h + 1), st));
         use_tile = slic_tile_supported(g) && !getenv("SPX_SLIC_GENERIC");
@@ -500,14 +500,14 @@ struct SlicEngine {
     {
         const int threads_fin = max(max(g.Kcap, g.nbx * g.nby), g.tiles_x * g.tiles_y);
         if (g.alg == SPX_SLICO) {
-            size_t np = (size_t)g.w * g.h;
+            size_t np = (size_t)g.lp * g.tiles_y * TILE_H;       // the plane has the label pitch
             slico_begin_kernel<<<(unsigned)((max(np, (size_t)g.K) + 255) / 256), 256, 0, st>>>(g, a, d_dcplane, np);
             launches++;
         }
         for (int it = 0; it < n; it++) {
             bool tiled = false;
             if (use_tile) {
-                SPX_CHECK(slic_tile_assign(g, a, d_img, d_img4, d_labels, d_K, parity, d_overflow, st));
+                SPX_CHECK(slic_tile_assign(g, a, d_img, d_img4, d_labels, d_dcplane, d_K, parity, d_overflow, st));
                 tiled = true;
                 launches++;
             }
@@ -536,7 +536,7 @@ struct SlicEngine {
 
     int enqueue_assign()
     {
-        if (use_tile) return slic_tile_assign(g, a, d_img, d_img4, d_labels, d_K, parity, d_overflow, st);
+        if (use_tile) return slic_tile_assign(g, a, d_img, d_img4, d_labels, d_dcplane, d_K, parity, d_overflow, st);
         dim3 grid(cdiv(g.w, 32), cdiv(g.h, 8));
         if (g.alg == SPX_SLIC) slic_assign_generic_kernel<100><<<grid, 256, 0, st>>>(g, a, d_img, d_labels, d_dcplane, parity, 0, 0, g.w, g.h);
         else if (g.alg == SPX_SLICO) slic_assign_generic_kernel<101><<<grid, 256, 0, st>>>(g, a, d_img, d_labels, d_dcplane, parity, 0, 0, g.w, g.h);

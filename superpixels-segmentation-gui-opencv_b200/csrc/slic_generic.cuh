@@ -52,7 +52,7 @@ __device__ __forceinline__ void slic_pixel_generic(const SlicGeom& g, const Slic
         if (bestn >= 0) { labels[li] = bestn; label = bestn; }
         else label = labels[li];                       // covered by no window: keeps its label
         if (ALG == 101) {
-            size_t pi = (size_t)y * g.w + x;
+            size_t pi = (size_t)y * g.lp + x;                      // the plane has the label pitch
             if (lastn >= 0) dcplane[pi] = lastdc; else lastdc = dcplane[pi];
         }
     }

@@ -24,6 +24,7 @@
 #include "slic_generic.cuh"
 #include <cfloat>
 #include <cmath>
+#include <type_traits>
 
 namespace spx {
 
@@ -80,10 +81,18 @@ __device__ __forceinline__ u64 bcast2(float v) { return pack2(v, v); }   // ptxa
 // one record per candidate, so that a single multiply addresses everything the inner loop reads
 struct __align__(16) CandRec {
     float4 k;                    // (-k0, -k1, -k2, n as int bits)
+    float4 m;                    // SLICO: (maxchans[n], RN(1/maxchans[n]), -maxchans[n], unused)
     float ex2[TW];               // (x-kx)^2 [times 1/xywt when it is a power of two], +inf outside the window
     float ey2[TH];               // (y-ky)^2 likewise
 };
-struct __align__(16) TileSmem {
+struct SlicoSmem {               // SLICO only
+    float dcm[TH][TW];           // colour distance to the LAST visiting cluster, per pixel (upstream's distchans plane)
+    unsigned mx[NCOPY][CAP];     // per candidate: running maximum of dcm over its pixels (float bits; values are >= 0)
+    int bad;                     // a divisor the reciprocal sequence cannot handle: the tile takes the exact generic path
+};
+struct NoSmem {};
+template <int ALG>
+struct __align__(16) TileSmemT {
     CandRec rec[CAP];            // ascending n
     int4 win[CAP];               // window: x_lo, x_hi, y_lo, y_hi (half open)
     // accumulators: NCOPY privatised copies (a lane uses copy lane&7, so lanes that sit in the same cluster rarely hit
@@ -93,6 +102,7 @@ struct __align__(16) TileSmem {
     float kxy[CAP][2];           // centre position per slot
     int list[CAP];
     unsigned char slot[TH][TW];  // winning candidate slot per pixel (0xFF: none / handled on the spot)
+    typename std::conditional<ALG == SPX_SLICO, SlicoSmem, NoSmem>::type o;
 };
 
 struct TileArgs {
@@ -101,6 +111,7 @@ struct TileArgs {
     const unsigned* img4;        // Lab1 words, pitch p4 (pixels)
     int w, h, S, Kcap, tiles_x, lp, p4;
     float xywt, rcp_xywt;
+    const float* maxc; unsigned* maxc_acc; float* dcplane;      // SLICO (dcplane has the label pitch)
 };
 
 __device__ __forceinline__ void acc_global_pixel(const TileArgs& t, int n, unsigned px, int x, int y)
@@ -111,21 +122,24 @@ __device__ __forceinline__ void acc_global_pixel(const TileArgs& t, int n, unsig
 }
 
 // exact per-pixel path for a tile whose candidate list overflowed (kept out of line: it is cold)
-__device__ __noinline__ void tile_fallback(const SlicGeom& g, const SlicArrays& a, const unsigned char* img, int* labels,
+template <int ALG>
+__device__ __noinline__ void tile_fallback(const SlicGeom& g, const SlicArrays& a, const unsigned char* img, int* labels, float* dcplane,
                                            int parity, int tx0, int ty0, int warp, int lane)
 {
     for (int r = warp; r < TH; r += NT / 32) {
         const int x = tx0 + lane, y = ty0 + r;
-        slic_pixel_generic<100>(g, a, img, labels, nullptr, parity, x, y, x < g.w && y < g.h);
+        slic_pixel_generic<ALG>(g, a, img, labels, dcplane, parity, x, y, x < g.w && y < g.h);
     }
 }
 
 // phase-1 cold path: some pixel of the warp's patch is covered by no window (or lies outside the image).
 // Everything is passed by value so that the hot loop's state never has to live in local memory.
-__device__ __noinline__ void step_slow(const TileArgs& t, TileSmem& sm, int* labels, unsigned slots4, unsigned p00, unsigned p01,
-                                       unsigned p10, unsigned p11, int x, int y, int xo, int yo)
+template <int ALG>
+__device__ __noinline__ void step_slow(const TileArgs& t, TileSmemT<ALG>& sm, int* labels, unsigned slots4, unsigned p00, unsigned p01,
+                                       unsigned p10, unsigned p11, float l00, float l01, float l10, float l11, int x, int y, int xo, int yo)
 {
     const unsigned px[4] = {p00, p01, p10, p11};
+    const float ldc[4] = {l00, l01, l10, l11};
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int r = i >> 1, k = i & 1;
@@ -133,20 +147,26 @@ __device__ __noinline__ void step_slow(const TileArgs& t, TileSmem& sm, int* lab
         const unsigned s = (slots4 >> (8 * i)) & 0xffu;         // 0xFF: no candidate
         unsigned char sb = 0xFF;
         if (xx < t.w && yy < t.h) {
-            int* lp = labels + (size_t)yy * t.lp + xx;
-            if (s != 0xffu) { *lp = __float_as_int(sm.rec[s].k.w); sb = (unsigned char)s; }
-            else acc_global_pixel(t, *lp, px[i], xx, yy);       // keeps its label; sums go straight to global
+            const size_t li = (size_t)yy * t.lp + xx;
+            if (s != 0xffu) {
+                labels[li] = __float_as_int(sm.rec[s].k.w); sb = (unsigned char)s;
+                if constexpr (ALG == SPX_SLICO) { t.dcplane[li] = ldc[i]; sm.o.dcm[yo + r][xo + k] = ldc[i]; }
+            } else {
+                const int n = labels[li];
+                acc_global_pixel(t, n, px[i], xx, yy);          // keeps its label; sums go straight to global
+                if constexpr (ALG == SPX_SLICO) atomicMax(&t.maxc_acc[n], __float_as_uint(t.dcplane[li]));   // plane keeps its value
+            }
         }
         sm.slot[yo + r][xo + k] = sb;
     }
 }
 
-template <bool POW2>
-__global__ void __launch_bounds__(NT, 8) slic_tile_kernel(const __grid_constant__ TileArgs t, const __grid_constant__ SlicGeom g,
+template <bool POW2, int ALG>
+__global__ void __launch_bounds__(NT, ALG == SPX_SLICO ? 6 : 8) slic_tile_kernel(const __grid_constant__ TileArgs t, const __grid_constant__ SlicGeom g,
                                                            const __grid_constant__ SlicArrays a, const unsigned char* __restrict__ img,
                                                            int* __restrict__ labels, int parity, int* __restrict__ d_overflow)
 {
-    __shared__ TileSmem sm;
+    __shared__ TileSmemT<ALG> sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int S = t.S;
     const int tile = blockIdx.y * t.tiles_x + blockIdx.x;
@@ -172,10 +192,15 @@ __global__ void __launch_bounds__(NT, 8) slic_tile_kernel(const __grid_constant_
     const int cnt = __ldg(&t.tl_count[tile]);
     if (cnt > CAP) {
         if (tid == 0) atomicAdd(d_overflow, 1);
-        tile_fallback(g, a, img, labels, parity, tx0, ty0, warp, lane);
+        tile_fallback<ALG>(g, a, img, labels, t.dcplane, parity, tx0, ty0, warp, lane);
         return;
     }
-    if (tid < cnt) sm.list[tid] = __float_as_int(r1.y);
+    float mxv = 1.0f;
+    if (tid < cnt) {
+        sm.list[tid] = __float_as_int(r1.y);
+        if constexpr (ALG == SPX_SLICO) mxv = __ldg(&t.maxc[__float_as_int(r1.y)]);
+    }
+    if constexpr (ALG == SPX_SLICO) { if (tid == 0) sm.o.bad = 0; }
     __syncthreads();
     // ---- rank by cluster index (upstream's visiting order), stage centres
     if (tid < cnt) {
@@ -186,12 +211,27 @@ __global__ void __launch_bounds__(NT, 8) slic_tile_kernel(const __grid_constant_
         const int ix = __float_as_int(r1.z), iy = __float_as_int(r1.w);
         sm.win[rank] = make_int4(ix - S, ix + S, iy - S, iy + S);
         sm.kxy[rank][0] = r0.x; sm.kxy[rank][1] = r0.y;
+        if constexpr (ALG == SPX_SLICO) {
+            // dc / maxchans[n] is evaluated as q = dc*r; q += fma(-q, m, dc)*r with r = RN(1/m): correctly rounded unless the
+            // significand of m is all ones
+            sm.rec[rank].m = make_float4(mxv, __fdiv_rn(1.0f, mxv), -mxv, 0.f);
+            if ((__float_as_uint(mxv) & 0x7fffffu) == 0x7fffffu) sm.o.bad = 1;
+        }
+    }
+    if constexpr (ALG == SPX_SLICO) {
+        for (int i = tid; i < NCOPY * CAP; i += NT) (&sm.o.mx[0][0])[i] = 0u;
     }
     {   // zero the accumulators of the candidates in use: copy tid>>4, candidates (tid&15), +16, ... as 16-byte stores
         unsigned* cp = sm.acc[tid >> 4];
         for (int c = tid & 15; c < cnt; c += 16) *reinterpret_cast<uint4*>(cp + 4 * c) = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
+    if constexpr (ALG == SPX_SLICO) {
+        if (sm.o.bad) {
+            tile_fallback<ALG>(g, a, img, labels, t.dcplane, parity, tx0, ty0, warp, lane);
+            return;
+        }
+    }
     // ---- separable spatial tables, two entries per job: job (c, r): r < 16 -> ex2[c][2r..2r+1], else ey2[c][2(r-16)..]
     {
         const float inf = __int_as_float(0x7f800000);
@@ -257,6 +297,7 @@ __global__ void __launch_bounds__(NT, 8) slic_tile_kernel(const __grid_constant_
         }
         float best[2][2] = {{FLT_MAX, FLT_MAX}, {FLT_MAX, FLT_MAX}};
         int slot[2][2] = {{-1, -1}, {-1, -1}};
+        float ldc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};     // SLICO: colour distance to the last cluster whose window holds the pixel
         const unsigned char* rec0 = reinterpret_cast<const unsigned char*>(&sm.rec[0]);
         const unsigned char* thr_ex = reinterpret_cast<const unsigned char*>(&sm.rec[0].ex2[xo]);
         const unsigned char* thr_ey = reinterpret_cast<const unsigned char*>(&sm.rec[0].ey2[yo]);
@@ -268,6 +309,8 @@ __global__ void __launch_bounds__(NT, 8) slic_tile_kernel(const __grid_constant_
                 m &= m - 1;
                 const int ro = c * (int)sizeof(CandRec);
                 const float4 kc = *reinterpret_cast<const float4*>(rec0 + ro);
+                float4 km = make_float4(0.f, 0.f, 0.f, 0.f);
+                if constexpr (ALG == SPX_SLICO) km = *reinterpret_cast<const float4*>(rec0 + ro + 16);
                 const u64 exv = *reinterpret_cast<const u64*>(thr_ex + ro);
                 const float2 eyv = *reinterpret_cast<const float2*>(thr_ey + ro);
 #pragma unroll
@@ -276,6 +319,17 @@ __global__ void __launch_bounds__(NT, 8) slic_tile_kernel(const __grid_constant_
                     u64 d = add2_products(mul2(t0, t0), mul2(t1, t1));
                     d = add2_products(d, mul2(t2, t2));
                     u64 sxy = add2(exv, bcast2(r ? eyv.y : eyv.x));
+                    if constexpr (ALG == SPX_SLICO) {
+                        float s0, s1, c0, c1;
+                        unpack2(sxy, s0, s1);
+                        unpack2(d, c0, c1);
+                        const float inf = __int_as_float(0x7f800000);
+                        ldc[r][0] = s0 < inf ? c0 : ldc[r][0];            // candidates come in ascending n: the last one stays
+                        ldc[r][1] = s1 < inf ? c1 : ldc[r][1];
+                        const u64 q0 = mul2(d, bcast2(km.y));
+                        const u64 e = fma2(q0, bcast2(km.z), d);
+                        d = fma2(e, bcast2(km.y), q0);
+                    }
                     if (!POW2) {
                         const u64 q0 = mul2(sxy, bcast2(t.rcp_xywt));
                         const u64 e = fma2(q0, bcast2(-t.xywt), sxy);
@@ -298,10 +352,17 @@ __global__ void __launch_bounds__(NT, 8) slic_tile_kernel(const __grid_constant_
             *reinterpret_cast<int2*>(lrow + t.lp) = make_int2(n10, n11);
             *reinterpret_cast<unsigned short*>(&sm.slot[yo][xo]) = (unsigned short)(slot[0][0] | (slot[0][1] << 8));
             *reinterpret_cast<unsigned short*>(&sm.slot[yo + 1][xo]) = (unsigned short)(slot[1][0] | (slot[1][1] << 8));
+            if constexpr (ALG == SPX_SLICO) {
+                float* prow = t.dcplane + (lrow - labels);
+                *reinterpret_cast<float2*>(prow) = make_float2(ldc[0][0], ldc[0][1]);
+                *reinterpret_cast<float2*>(prow + t.lp) = make_float2(ldc[1][0], ldc[1][1]);
+                *reinterpret_cast<float2*>(&sm.o.dcm[yo][xo]) = make_float2(ldc[0][0], ldc[0][1]);
+                *reinterpret_cast<float2*>(&sm.o.dcm[yo + 1][xo]) = make_float2(ldc[1][0], ldc[1][1]);
+            }
         } else {
             const unsigned s4 = (unsigned)(slot[0][0] & 0xff) | ((unsigned)(slot[0][1] & 0xff) << 8) |
                                 ((unsigned)(slot[1][0] & 0xff) << 16) | ((unsigned)(slot[1][1] & 0xff) << 24);
-            step_slow(t, sm, labels, s4, px[0][0], px[0][1], px[1][0], px[1][1], x, y, xo, yo);
+            step_slow<ALG>(t, sm, labels, s4, px[0][0], px[0][1], px[1][0], px[1][1], ldc[0][0], ldc[0][1], ldc[1][0], ldc[1][1], x, y, xo, yo);
         }
         pimg += p4_16;
         lrow += 16 * t.lp;
@@ -342,6 +403,12 @@ __global__ void __launch_bounds__(NT, 8) slic_tile_kernel(const __grid_constant_
             unsigned* da = &sm.acc[lane & (NCOPY - 1)][4 * A];
             atomicAdd(da + 0, (AE & 0xffffu) | (cntA << 18)); atomicAdd(da + 1, AO & 0xffffu); atomicAdd(da + 2, AE >> 16);
             atomicAdd(da + 3, (cntA * (4 * q) + jA) | ((cntA * row) << 16));
+            if constexpr (ALG == SPX_SLICO) {
+                const uint4 dv = *reinterpret_cast<const uint4*>(&sm.o.dcm[row][4 * q]);     // float bits, all >= 0
+                const unsigned mA = max(max(dv.x, dv.y & m1), max(dv.z & m2, dv.w & m3));
+                atomicMax(&sm.o.mx[lane & (NCOPY - 1)][A], mA);
+                if (A != B) atomicMax(&sm.o.mx[lane & (NCOPY - 1)][B], max(max(dv.y & ~m1, dv.z & ~m2), dv.w & ~m3));
+            }
             if (A != B) {
                 const unsigned BE = TE - AE, BO = TO - AO;
                 const unsigned cntB = BO >> 16, jB = 6u - jA;
@@ -359,6 +426,7 @@ __global__ void __launch_bounds__(NT, 8) slic_tile_kernel(const __grid_constant_
                     unsigned* d = &sm.acc[lane & (NCOPY - 1)][4 * s];
                     atomicAdd(d + 0, (pw[j] & 0xffu) | (1u << 18)); atomicAdd(d + 1, (pw[j] >> 8) & 0xffu);
                     atomicAdd(d + 2, (pw[j] >> 16) & 0xffu); atomicAdd(d + 3, (unsigned)(4 * q + j) | ((unsigned)row << 16));
+                    if constexpr (ALG == SPX_SLICO) atomicMax(&sm.o.mx[lane & (NCOPY - 1)][s], __float_as_uint(sm.o.dcm[row][4 * q + j]));
                 }
             }
         }
@@ -386,6 +454,12 @@ __global__ void __launch_bounds__(NT, 8) slic_tile_kernel(const __grid_constant_
     for (int c = tid; c < cnt; c += NT) {
         const unsigned count = (unsigned)sm.list[c];
         if (!count) continue;
+        if constexpr (ALG == SPX_SLICO) {
+            unsigned mxb = 0;
+#pragma unroll
+            for (int p = 0; p < NCOPY; p++) mxb = max(mxb, sm.o.mx[p][c]);
+            atomicMax(&t.maxc_acc[__float_as_int(sm.rec[c].k.w)], mxb);
+        }
         unsigned v = 0;
 #pragma unroll
         for (int p = 0; p < NCOPY; p++) v += sm.acc[p][4 * c + 3];
@@ -412,7 +486,7 @@ static bool markstein_ok(float w)
 
 bool slic_tile_supported(const SlicGeom& g)
 {
-    return g.alg == SPX_SLIC && g.C == 3 && g.S >= MIN_S && (is_pow2(g.xywt) || markstein_ok(g.xywt));
+    return (g.alg == SPX_SLIC || g.alg == SPX_SLICO) && g.C == 3 && g.S >= MIN_S && (is_pow2(g.xywt) || markstein_ok(g.xywt));
 }
 
 // 8UC3 rows -> Lab1 words (c0 | c1<<8 | c2<<16 | 1<<24); the padding of the tile grid stays zero
@@ -444,7 +518,7 @@ int slic_tile_prepare(const SlicGeom& g, const unsigned char* d_img, unsigned* d
 }
 
 int slic_tile_assign(const SlicGeom& g, const SlicArrays& a, const unsigned char* d_img, const unsigned* d_img4, int* d_labels,
-                     const int* d_K, int parity, int* d_overflow, cudaStream_t st)
+                     float* d_dcplane, const int* d_K, int parity, int* d_overflow, cudaStream_t st)
 {
     (void)d_K;
     dim3 grid(g.tiles_x, g.tiles_y);
@@ -453,8 +527,15 @@ int slic_tile_assign(const SlicGeom& g, const SlicArrays& a, const unsigned char
     t.img4 = d_img4;
     t.w = g.w; t.h = g.h; t.S = g.S; t.Kcap = g.Kcap; t.tiles_x = g.tiles_x; t.lp = g.lp; t.p4 = g.p4;
     t.xywt = g.xywt; t.rcp_xywt = 1.0f / g.xywt;
-    if (is_pow2(g.xywt)) slic_tile_kernel<true><<<grid, NT, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);
-    else slic_tile_kernel<false><<<grid, NT, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);
+    t.maxc = a.maxc; t.maxc_acc = a.maxc_acc; t.dcplane = d_dcplane;
+    const bool p2 = is_pow2(g.xywt);
+    if (g.alg == SPX_SLICO) {
+        if (p2) slic_tile_kernel<true, SPX_SLICO><<<grid, NT, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);
+        else slic_tile_kernel<false, SPX_SLICO><<<grid, NT, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);
+    } else {
+        if (p2) slic_tile_kernel<true, SPX_SLIC><<<grid, NT, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);
+        else slic_tile_kernel<false, SPX_SLIC><<<grid, NT, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);
+    }
     SPX_CUDA(cudaGetLastError());
     return SPX_OK;
 }

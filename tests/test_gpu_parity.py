@@ -138,6 +138,28 @@ def test_slico_mslic_match_oracle(spx, O, example_lab, alg):
     assert (a.getCentres() == b.getCentres()).all()
 
 
+@pytest.mark.parametrize("S", [16, 25])
+def test_slico_tiled_path_exact(spx, O, example_lab, S):
+    """SLICO through the tiled kernel (S >= 14): power-of-two S*S (16) and the general divisor (25, BASELINE configs[1])"""
+    img = np.ascontiguousarray(example_lab[200:900, 350:1150])
+    a, b = _run_pair(spx, O, img, spx.SLICO, S, 10.0, 7)
+    assert (a.getLabels() == b.getLabels()).all()
+    assert (a.getCentres() == b.getCentres()).all()
+    a.iterate(3); b.iterate(3)                      # a second iterate() call restarts the adaptive maxima, as upstream
+    assert (a.getLabels() == b.getLabels()).all()
+
+
+def test_slico_cfg2_4k_equals_oracle(spx, O, synthmod):
+    """BASELINE.json configs[1]: SLICO 3840x2160, region_size=25, 10 iterations, contour mask"""
+    img, _ = synthmod.synth(3840, 2160, 0)
+    lab = spx.cvtColor(img, spx.COLOR_BGR2Lab)
+    a, b = _run_pair(spx, O, lab, spx.SLICO, 25, 10.0, 10)
+    la, lb = a.getLabels(), b.getLabels()
+    assert float((la == lb).mean()) == 1.0
+    assert (a.getCentres() == b.getCentres()).all()
+    assert (a.getLabelContourMask(False) == b.getLabelContourMask(False)).all()
+
+
 def test_slic_iterate_twice_equals_oracle(spx, O, synthmod):
     img, _ = synthmod.synth(160, 120, 3)
     a = O.SuperpixelSLIC(img, O.SLIC, 10, 10.0); b = spx.createSuperpixelSLIC(img, spx.SLIC, 10, 10.0)
