@@ -50,8 +50,6 @@ struct PostWorkspace {
     int* blocksum = nullptr;    // scan scratch
     int* flag = nullptr;        // device flags / counters [8]
     unsigned char* diff = nullptr;   // contour: differing-neighbour bit masks [N]
-    unsigned char* takenA = nullptr; // contour ping-pong                      [N]
-    unsigned char* takenB = nullptr;
     int* h_flag = nullptr;      // pinned host mirror [8]
     long long launches = 0;
     int alloc(int w_, int h_);

@@ -14,6 +14,7 @@
 //  contour mask:  upstream's `istaken` recurrence only looks at causal neighbours (W,NW,N,NE), so
 //                 it has a unique fixed point; Jacobi sweeps from the all-false state reach it.
 #include "common.cuh"
+#include <algorithm>
 
 namespace spx {
 
@@ -33,18 +34,16 @@ int PostWorkspace::alloc(int w_, int h_)
     SPX_CUDA(cudaMalloc(&blocksum, (N / 1024 + 2) * sizeof(int)));
     SPX_CUDA(cudaMalloc(&flag, 8 * sizeof(int)));
     SPX_CUDA(cudaMalloc(&diff, N));
-    SPX_CUDA(cudaMalloc(&takenA, N));
-    SPX_CUDA(cudaMalloc(&takenB, N));
     SPX_CUDA(cudaMallocHost(&h_flag, 8 * sizeof(int)));
     return SPX_OK;
 }
 void PostWorkspace::release()
 {
     cudaFree(parent); cudaFree(csize); cudaFree(newid); cudaFree(link); cudaFree(blocksum); cudaFree(flag);
-    cudaFree(diff); cudaFree(takenA); cudaFree(takenB);
+    cudaFree(diff);
     if (h_flag) cudaFreeHost(h_flag);
     parent = csize = newid = link = blocksum = flag = nullptr;
-    diff = takenA = takenB = nullptr; h_flag = nullptr;
+    diff = nullptr; h_flag = nullptr;
     w = h = 0;
 }
 
@@ -251,8 +250,11 @@ int enforce_connectivity_dev(PostWorkspace& ws, int* d_labels, int lp, int numla
 // ------------------------------------------------------------------------------------------------
 // bit k of diff[p] = neighbour k is in bounds and has a different label; k follows upstream's
 // dx8/dy8 order: W, NW, N, NE, E, SE, S, SW.  Bits 0..3 are the causal (already visited) ones.
+// MODE 0: write diff and clear the mask (the flags of the recurrence live in the mask buffer itself, 0 / 255);
+// MODE 1: pure stencil (SEEDS flavour with thick_line): mask = popc(diff) > thr.
+template <int MODE>
 __global__ void contour_diff_kernel(const int* __restrict__ lab, int lp, int w, int h, unsigned char* __restrict__ diff,
-                                    unsigned char* __restrict__ taken)
+                                    unsigned char* __restrict__ mask, size_t mp, int thr)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= w) return;
@@ -265,38 +267,119 @@ __global__ void contour_diff_kernel(const int* __restrict__ lab, int lp, int w, 
         int xx = x + dx8[k], yy = y + dy8[k];
         if (xx >= 0 && xx < w && yy >= 0 && yy < h && lab[(size_t)yy * lp + xx] != me) d |= 1u << k;
     }
-    diff[(size_t)y * w + x] = (unsigned char)d;
-    taken[(size_t)y * w + x] = 0;
+    if (MODE == 0) { diff[(size_t)y * w + x] = (unsigned char)d; mask[(size_t)y * mp + x] = 0; }
+    else mask[(size_t)y * mp + x] = __popc(d) > thr ? 255 : 0;
 }
-__global__ void contour_sweep_kernel(const unsigned char* __restrict__ diff, const unsigned char* __restrict__ tin,
-                                     unsigned char* __restrict__ tout, int w, int h, int lw, int* __restrict__ changed)
+
+// The recurrence  taken(p) = popc(diff(p)) - #{causal differing neighbours already taken} > lw  only looks backwards in
+// raster order, so it has a unique fixed point and ANY evaluation order that keeps re-evaluating until nothing changes
+// reaches it.  One persistent grid (all CTAs co-resident, cooperative launch) sweeps the image; a thread owns a run of
+// 64 pixels of one row and walks it left to right in place, so dependencies along a row resolve inside the sweep and
+// every sweep moves the settled front at least one row down; a grid-wide barrier separates the sweeps; the kernel ends
+// after the first sweep that changed nothing.  No host round trip.
+constexpr int CT_RUN = 64;
+__device__ __forceinline__ void contour_grid_barrier(unsigned* counter, unsigned target)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= w) return;
-    size_t i = (size_t)y * w + x;
-    unsigned d = diff[i];
-    int np = __popc(d);
-    unsigned char t = 0;
-    if (np > lw) {
-        if ((d & 1u) && tin[i - 1]) np--;
-        if ((d & 2u) && tin[i - w - 1]) np--;
-        if ((d & 4u) && tin[i - w]) np--;
-        if ((d & 8u) && tin[i - w + 1]) np--;
-        t = np > lw ? 1 : 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (*(volatile unsigned*)counter < target) { }
+        __threadfence();
     }
-    tout[i] = t;
-    if (t != tin[i]) *changed = 1;
+    __syncthreads();
 }
-// MODE 0: from the converged `taken` flags; MODE 1: pure stencil popc(diff) > thr
-template <int MODE>
-__global__ void contour_emit_kernel(const unsigned char* __restrict__ diff, const unsigned char* __restrict__ taken,
-                                    unsigned char* __restrict__ mask, size_t mp, int w, int h, int thr)
+__global__ void __launch_bounds__(1024) contour_sweeps_kernel(const unsigned char* __restrict__ diff, unsigned char* mask, size_t mp,
+                                                               int w, int h, int lw, int vec, unsigned* bar, int* count /* [3] */,
+                                                               int* dirty, int* list0, int* list1)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= w) return;
-    size_t i = (size_t)y * w + x;
-    bool on = MODE == 0 ? taken[i] != 0 : __popc((unsigned)diff[i]) > thr;
-    mask[(size_t)y * mp + x] = on ? 255 : 0;
+    const int rpr = (w + CT_RUN - 1) / CT_RUN;
+    const int total = rpr * h;
+    const unsigned nblk = gridDim.x;
+    for (unsigned sweep = 0;; sweep++) {
+        // a run is re-evaluated only if one of its inputs (the run to its left, the three runs above) changed in the
+        // previous sweep: a changed run appends its dependents to the next sweep's work list (once: `dirty` flag).
+        // count[s%3] = length of sweep s's list, filled during sweep s-1, cleared during sweep s+1.
+        const int* cur = (sweep & 1) ? list1 : list0;
+        int* nxt = (sweep & 1) ? list0 : list1;
+        int* ncount = &count[(sweep + 1) % 3];
+        if (blockIdx.x == 0 && threadIdx.x == 0) count[(sweep + 2) % 3] = 0;
+        const int nwork = sweep == 0 ? total : *(volatile int*)&count[sweep % 3];
+        for (int wi = blockIdx.x * blockDim.x + threadIdx.x; wi < nwork; wi += nblk * blockDim.x) {
+            const int run = sweep == 0 ? wi : __ldcg(cur + wi);
+            if (sweep > 0) dirty[run] = 0;
+            bool touched = false;
+            const int y = run / rpr, rx = run - y * rpr, x0 = rx * CT_RUN;
+            const int n = min(CT_RUN, w - x0);
+            const unsigned char* drow = diff + (size_t)y * w + x0;
+            unsigned char* mrow = mask + (size_t)y * mp + x0;
+            const unsigned char* arow = mask + (size_t)(y - 1) * mp + x0;                // only read when y > 0
+            // flags are read through L2 (other CTAs wrote them in the previous sweep)
+            unsigned prev = x0 > 0 ? (__ldcg(mrow - 1) != 0) : 0;                         // W of the first pixel
+            unsigned aL = (y > 0 && x0 > 0) ? (__ldcg(arow - 1) != 0) : 0;
+            if (vec && n == CT_RUN) {
+                // whole run in registers: 4 x 16 bytes of diff, own flags and the flags of the row above
+                uint4 dq[4], mq[4], aq[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    dq[k] = __ldg(reinterpret_cast<const uint4*>(drow) + k);
+                    mq[k] = __ldcg(reinterpret_cast<const uint4*>(mrow) + k);
+                    aq[k] = y > 0 ? __ldcg(reinterpret_cast<const uint4*>(arow) + k) : make_uint4(0u, 0u, 0u, 0u);
+                }
+                const unsigned aEnd = (y > 0 && x0 + CT_RUN < w) ? (__ldcg(arow + CT_RUN) != 0) : 0;
+                const unsigned* dw = reinterpret_cast<const unsigned*>(dq);
+                unsigned* mw = reinterpret_cast<unsigned*>(mq);
+                const unsigned* aw = reinterpret_cast<const unsigned*>(aq);
+                bool rc = false;
+                unsigned aC = aw[0] & 0xffu ? 1u : 0u;
+#pragma unroll
+                for (int j = 0; j < CT_RUN; j++) {
+                    const unsigned aR = j + 1 < CT_RUN ? ((aw[(j + 1) >> 2] >> (8 * ((j + 1) & 3))) & 0xffu ? 1u : 0u) : aEnd;
+                    const unsigned d = (dw[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                    int np = __popc(d);
+                    unsigned t = 0;
+                    if (np > lw) {
+                        np -= (int)(((d & 1u) ? prev : 0u) + ((d & 2u) ? aL : 0u) + ((d & 4u) ? aC : 0u) + ((d & 8u) ? aR : 0u));
+                        t = np > lw ? 1u : 0u;
+                        const unsigned old = (mw[j >> 2] >> (8 * (j & 3))) & 0xffu ? 1u : 0u;
+                        if (old != t) { mw[j >> 2] ^= 0xffu << (8 * (j & 3)); rc = true; }
+                    }
+                    prev = t; aL = aC; aC = aR;
+                }
+                if (rc) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) reinterpret_cast<uint4*>(mrow)[k] = mq[k];
+                    touched = true;
+                }
+            } else {
+                unsigned aC = y > 0 ? (__ldcg(arow) != 0) : 0;
+                for (int j = 0; j < n; j++) {
+                    const unsigned aR = (y > 0 && x0 + j + 1 < w) ? (__ldcg(arow + j + 1) != 0) : 0;
+                    const unsigned d = drow[j];
+                    int np = __popc(d);
+                    unsigned t = 0;
+                    if (np > lw) {
+                        np -= (int)(((d & 1u) ? prev : 0u) + ((d & 2u) ? aL : 0u) + ((d & 4u) ? aC : 0u) + ((d & 8u) ? aR : 0u));
+                        t = np > lw ? 1u : 0u;
+                        const unsigned old = __ldcg(mrow + j) != 0;
+                        if (old != t) { mrow[j] = t ? 255 : 0; touched = true; }
+                    }
+                    prev = t; aL = aC; aC = aR;
+                }
+            }
+            if (touched) {
+                auto push = [&](int r) { if (atomicExch(&dirty[r], 1) == 0) nxt[atomicAdd(ncount, 1)] = r; };
+                if (rx + 1 < rpr) push(run + 1);
+                if (y + 1 < h) {
+                    if (rx > 0) push(run + rpr - 1);
+                    push(run + rpr);
+                    if (rx + 1 < rpr) push(run + rpr + 1);
+                }
+            }
+        }
+        contour_grid_barrier(bar, (sweep + 1) * nblk);
+        if (*(volatile int*)ncount == 0) break;
+    }
 }
 
 int contour_mask_dev(PostWorkspace& ws, const int* d_labels, int lp, int thick_line, int flavour,
@@ -304,32 +387,39 @@ int contour_mask_dev(PostWorkspace& ws, const int* d_labels, int lp, int thick_l
 {
     const int w = ws.w, h = ws.h;
     dim3 b2(256), g2(cdiv(w, 256), h);
-    contour_diff_kernel<<<g2, b2, 0, st>>>(d_labels, lp, w, h, ws.diff, ws.takenA);
-    ws.launches++;
     if (flavour == 1 && thick_line) {
-        contour_emit_kernel<1><<<g2, b2, 0, st>>>(ws.diff, ws.takenA, d_mask, mp, w, h, 1);
+        contour_diff_kernel<1><<<g2, b2, 0, st>>>(d_labels, lp, w, h, ws.diff, d_mask, mp, 1);
         ws.launches++;
         SPX_CUDA(cudaGetLastError());
         return SPX_OK;
     }
-    const int lw = flavour == 1 ? 1 : (thick_line ? 2 : 1);
-    unsigned char* a = ws.takenA;
-    unsigned char* b = ws.takenB;
-    const int group = lw == 1 ? 4 : 16;
-    for (int round = 0; round < 100000; round++) {
-        SPX_CUDA(cudaMemsetAsync(ws.flag + 1, 0, sizeof(int), st));
-        for (int k = 0; k < group; k++) {
-            // only the last sweep of a group reports changes: if it changed nothing we are at the fixed point
-            contour_sweep_kernel<<<g2, b2, 0, st>>>(ws.diff, a, b, w, h, lw, k == group - 1 ? ws.flag + 1 : ws.flag + 2);
-            unsigned char* t = a; a = b; b = t;
-        }
-        ws.launches += group;
-        SPX_CUDA(cudaMemcpyAsync(ws.h_flag + 1, ws.flag + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-        SPX_CUDA(cudaStreamSynchronize(st));
-        if (!ws.h_flag[1]) break;
+    int lw = flavour == 1 ? 1 : (thick_line ? 2 : 1);
+    contour_diff_kernel<0><<<g2, b2, 0, st>>>(d_labels, lp, w, h, ws.diff, d_mask, mp, 0);
+    SPX_CUDA(cudaMemsetAsync(ws.flag + 4, 0, 4 * sizeof(int), st));        // barrier counter + 3 change flags
+    // persistent grid: one CTA of 1024 threads per SM (the in-kernel barrier needs all of them running: cooperative launch)
+    static int s_sms = 0;
+    if (!s_sms) {
+        int dev = 0;
+        SPX_CUDA(cudaGetDevice(&dev));
+        SPX_CUDA(cudaDeviceGetAttribute(&s_sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    contour_emit_kernel<0><<<g2, b2, 0, st>>>(ws.diff, a, d_mask, mp, w, h, 0);
-    ws.launches++;
+    const int runs = cdiv(w, CT_RUN) * h;
+    int blocks = std::min(cdiv(runs, 1024), s_sms);
+    if (blocks < 1) blocks = 1;
+    const unsigned char* diffp = ws.diff;
+    // dirty flags and the two work lists live in the connectivity scratch, which is free here (3 * runs ints <= N ints)
+    int* dirty = ws.csize;
+    int* list0 = dirty + runs;
+    int* list1 = list0 + runs;
+    SPX_CUDA(cudaMemsetAsync(dirty, 0, (size_t)runs * sizeof(int), st));
+    unsigned* bar = reinterpret_cast<unsigned*>(ws.flag + 4);
+    int* cnt = ws.flag + 5;
+    // 16-byte vector access to diff / mask rows when every run starts aligned
+    int vec = (w % 16 == 0 && mp % 16 == 0 && (uintptr_t)d_mask % 16 == 0 && (uintptr_t)ws.diff % 16 == 0) ? 1 : 0;
+    void* args[] = {(void*)&diffp, (void*)&d_mask, (void*)&mp, (void*)&w, (void*)&h, (void*)&lw, (void*)&vec, (void*)&bar, (void*)&cnt,
+                    (void*)&dirty, (void*)&list0, (void*)&list1};
+    SPX_CUDA(cudaLaunchCooperativeKernel((const void*)contour_sweeps_kernel, dim3(blocks), dim3(1024), args, 0, st));
+    ws.launches += 2;
     SPX_CUDA(cudaGetLastError());
     return SPX_OK;
 }
