@@ -126,6 +126,51 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+def other_configs(spx, synth, L):
+    """BASELINE.json's remaining configs on rank 0 (not bench lines: device time of iterate() with the image resident,
+    wall clock around the synchronous C-ABI calls, best of 3).  MP/s = pixels / iterate time."""
+    out = {}
+
+    def best(f, n=3):
+        t = 1e30
+        for _ in range(n):
+            t0 = time.perf_counter(); f(); t = min(t, time.perf_counter() - t0)
+        return t
+
+    def slic_family(name, alg, W, H, S):
+        bgr = synth.synth(W, H, 0)[0]
+        lab = spx.cvtColor(bgr, spx.COLOR_BGR2Lab)
+        s = spx.createSuperpixelSLIC(lab, alg, S, RULER)
+        s.iterate(ITERS)
+
+        def it():
+            s.reset(lab); L.spx_slic_synchronize(s._h)
+            t0 = time.perf_counter(); s.iterate(ITERS); L.spx_slic_synchronize(s._h)
+            return time.perf_counter() - t0
+        t = min(it() for _ in range(3))
+        tm = best(lambda: s.getLabelContourMask(False))
+        out[name] = {"iterate10_ms": t * 1e3, "MP_s": W * H / 1e6 / t, "frac_of_hbm_roofline_7B_px_iter": 70.0 * W * H / t / 1e9 / peaks()[0],
+                     "contour_mask_ms_incl_d2h": tm * 1e3}
+        s.release()
+
+    slic_family("cfg2_SLICO_4K_S25", spx.SLICO, W4K, H4K, 25)
+    slic_family("cfg3_MSLIC_8K_S30", spx.MSLIC, 7680, 4320, 30)
+    bgr = synth.synth(7680, 4320, 0)[0]
+    lab = spx.cvtColor(bgr, spx.COLOR_BGR2Lab)
+    l = spx.createSuperpixelLSC(lab, 30, 0.075)
+    t = best(lambda: (l.iterate(ITERS), l.getNumberOfSuperpixels()), 2)       # further iterations on the same object
+    out["cfg3_LSC_8K_S30_ratio0.075"] = {"iterate10_ms": t * 1e3, "MP_s": 7680 * 4320 / 1e6 / t}
+    l.release()
+    bgr = synth.synth(1920, 1080, 0)[0]
+    lab = spx.cvtColor(bgr, spx.COLOR_BGR2Lab)
+    sd = spx.createSuperpixelSEEDS(1920, 1080, 3, 2000, 4, 2, 5, False)
+    sd.iterate(lab, ITERS)
+    t = best(lambda: sd.iterate(lab, ITERS))
+    out["cfg4_SEEDS_1080p_2000sp_4lv_5bins"] = {"iterate10_ms_incl_h2d": t * 1e3, "MP_s": 1920 * 1080 / 1e6 / t}
+    sd.release()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -289,6 +334,10 @@ def run_ours(args):
                "sample": "%d x one 4K frame (create + iterate(10) + getLabels), oracle restatement, OpenMP %d threads" % (nb, cores),
                "label_agreement_vs_gpu": float((ol == e2e_ref_labels).mean())}
 
+    other = None
+    if rank == 0 and not args.no_other_configs:
+        other = other_configs(spx, synth, L)
+
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -301,7 +350,7 @@ def run_ours(args):
                "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": n_host * npx * 3,
                        "d2h_bytes_per_step": n_host * npx * 4, "frames": n_host, "threads": n_thr},
                "gpu_launches": launches[0], "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
-               "wall_s_timed": wall}
+               "wall_s_timed": wall, "other_configs": other}
         print(json.dumps(out))
     if dist is not None:
         dist.barrier()
@@ -320,6 +369,7 @@ def main():
     ap.add_argument("--e2e-frames", type=int, default=8)
     ap.add_argument("--e2e-reps", type=int, default=2)
     ap.add_argument("--e2e-threads", type=int, default=4)
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the extra (non-headline) configs on rank 0")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
