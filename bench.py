@@ -243,6 +243,10 @@ def run_ours(args):
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
     elapsed = float(el.item())
     value = world * B * args.steps * npx / 1e6 / elapsed
+    nl = torch.tensor([float(launches[0])], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(nl, op=dist.ReduceOp.SUM)          # kernels launched by all ranks inside the timed region
+    total_launches = int(nl.item())
 
     # ---- e2e: host buffers in, host labels out, through the reference-facing calls (H2D + D2H timed)
     n_thr = min(args.e2e_threads, n_host)
@@ -349,7 +353,7 @@ def run_ours(args):
                "frames_per_sec": value * 1e6 / npx,
                "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": n_host * npx * 3,
                        "d2h_bytes_per_step": n_host * npx * 4, "frames": n_host, "threads": n_thr},
-               "gpu_launches": launches[0], "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+               "gpu_launches": total_launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
                "wall_s_timed": wall, "other_configs": other}
         print(json.dumps(out))
     if dist is not None:

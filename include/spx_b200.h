@@ -92,6 +92,34 @@ int spx_slic_time_assign(spx_slic_t*, int reps, int flush_l2, float* avg_ms);
 /* cv::Ptr<SuperpixelSLIC> release (the GUI overwrites `slic` on every COMPUTE, mainwindow.cpp:2105) */
 int spx_slic_destroy(spx_slic_t*);
 
+/* ---- row-strip mode: ONE image over several GPUs (north-star: gigapixel images) ----
+ * One process per GPU.  Every rank creates the object with the geometry of the WHOLE image but uploads only the rows it
+ * needs: rows [row0,row1) of the image, of which it owns (assigns) [own_row0,own_row1) -- multiples of 32 -- plus two halo
+ * rows on every inner side.  Cluster state is replicated; per iteration the host exchanges the integer accumulators:
+ *     spx_slic_create_strip(...)            seeds whose grid position lies in the owned rows, zeros elsewhere
+ *     [sum kx,ky,kc,ikx,iky over ranks]     -> every rank has all seeds     (NCCL all-reduce on the pointers below)
+ *     spx_slic_strip_rebin()
+ *     repeat: spx_slic_strip_assign()       assignment + accumulation over the owned tile rows
+ *             [sum acc over ranks]          exact: integer sums (only clusters near a cut receive pixels from two ranks)
+ *             spx_slic_strip_update()       centre update (identical on every rank) + re-binning
+ *     spx_slic_get_label_rows()             the owned rows of the label map
+ * The result is bit-identical to the single-GPU object.  SLIC (algorithm 100), 3 channels, region_size >= 14. */
+typedef struct {
+    void* kx; void* ky;      /* float[Kcap]            */
+    void* kc;                /* float[channels][Kcap]  */
+    void* ikx; void* iky;    /* int[Kcap]              */
+    void* acc;               /* uint64[channels+3][Kcap]: sums of c0..c2, x, y, count */
+    int K, Kcap, channels;
+} spx_slic_state_t;
+int spx_slic_create_strip(const uint8_t* rows, size_t stride, int width, int height, int channels, int algorithm,
+                          int region_size, float ruler, int row0, int row1, int own_row0, int own_row1,
+                          void* cuda_stream, spx_slic_t** out);
+int spx_slic_device_state(spx_slic_t*, spx_slic_state_t* out);
+int spx_slic_strip_rebin(spx_slic_t*);
+int spx_slic_strip_assign(spx_slic_t*);
+int spx_slic_strip_update(spx_slic_t*);
+int spx_slic_get_label_rows(spx_slic_t*, int32_t* dst, size_t dst_stride, int row0, int row1);
+
 /* ---- batch of independent frames on one device (BASELINE.json configs[4]) ----
  * For every frame i: createSuperpixelSLIC(frame_i) ; iterate(num_iterations) ;
  * [enforceLabelConnectivity(min_element_size) if > 0] ; getLabels -> d_labels[i]

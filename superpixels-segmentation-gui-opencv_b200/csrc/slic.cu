@@ -89,10 +89,19 @@ __global__ void slic_seed_kernel(SlicGeom g, SlicArrays a, const unsigned char* 
             if (e < best) { best = e; sx = nx; sy = ny; }
         }
     }
+    // strip mode: a seed belongs to the rank whose rows hold its grid position; the others contribute zeros to the sum
+    // that assembles the seeds (spx_slic_create_strip)
+    const bool mine = Y >= g.own_y0 && Y < g.own_y1;
     if (sx != X && sy != Y) { X = sx; Y = sy; }
-    a.kx[n] = (float)X; a.ky[n] = (float)Y;
-    a.ikx[n] = X; a.iky[n] = Y; a.ioff[n] = S;
+    a.ioff[n] = S;
     a.adaptk[n] = 1.0f;
+    if (!mine) {
+        a.kx[n] = 0.f; a.ky[n] = 0.f; a.ikx[n] = 0; a.iky[n] = 0;
+        for (int c = 0; c < g.C; c++) a.kc[(size_t)c * g.Kcap + n] = 0.f;
+        return;
+    }
+    a.kx[n] = (float)X; a.ky[n] = (float)Y;
+    a.ikx[n] = X; a.iky[n] = Y;
     for (int c = 0; c < g.C; c++) a.kc[(size_t)c * g.Kcap + n] = (float)img[(size_t)Y * g.ipitch + (size_t)X * g.C + c];
 }
 
@@ -117,7 +126,7 @@ __device__ __forceinline__ void bin_stage(const SlicGeom& g, const SlicArrays& a
         if (g.tile_on) {
             const int off = a.ioff[n];
             const int tx0 = max(ix - off, 0) / TILE_W, tx1 = min(ix + off - 1, g.w - 1) / TILE_W;
-            const int ty0 = max(iy - off, 0) / TILE_H, ty1 = min(iy + off - 1, g.h - 1) / TILE_H;
+            const int ty0 = max(max(iy - off, 0) / TILE_H, g.ty_lo), ty1 = min(min(iy + off - 1, g.h - 1) / TILE_H, g.ty_hi - 1);
             if (tx1 >= tx0 && ty1 >= ty0) span = make_int4(tx0, ty0, tx1 - tx0 + 1, ty1 - ty0 + 1);
             sh.a[slot] = make_float4(a.kx[n], a.ky[n], a.kc[n], a.kc[(size_t)g.Kcap + n]);
             sh.b[slot] = make_float4(a.kc[2 * (size_t)g.Kcap + n], __int_as_float(n), __int_as_float(ix), __int_as_float(iy));
@@ -421,6 +430,7 @@ struct SlicEngine {
         g.tiles_x = cdiv(w, TILE_W); g.tiles_y = cdiv(h, TILE_H);
         g.lp = g.tiles_x * TILE_W;
         g.p4 = g.tiles_x * TILE_W;
+        g.ty_lo = 0; g.ty_hi = g.tiles_y; g.own_y0 = 0; g.own_y1 = h;
         g.nbx = cdiv(w, S); g.nby = cdiv(h, S);
         g.radius = alg == SPX_MSLIC ? 2 : 1;
         if (alg == SPX_SLICO) g.xywt = (float)(S * S);
@@ -493,6 +503,27 @@ struct SlicEngine {
         SPX_REQUIRE(img && stride >= (size_t)g.w * g.C, SPX_ERR_BADARG, "createSuperpixelSLIC: bad image pointer/stride");
         SPX_CUDA(cudaMemcpy2DAsync(d_img, g.ipitch, img, stride, (size_t)g.w * g.C, g.h,
                                    from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        return SPX_OK;
+    }
+
+    // ---- row-strip mode (one image over several GPUs): explicit steps instead of iterate()
+    int strip_rebin()
+    {
+        // the seeds have been assembled across ranks: rebuild the bins / tile lists of parity 0 from them
+        SPX_CUDA(cudaMemsetAsync(a.head[0], 0xFF, (size_t)g.nbx * g.nby * sizeof(int), st));
+        if (use_tile) SPX_CUDA(cudaMemsetAsync(a.tl_count[0], 0, (size_t)g.tiles_x * g.tiles_y * sizeof(int), st));
+        slic_bin_kernel<<<cdiv(K0, BIN_CTA), BIN_CTA, 0, st>>>(g, a, d_K, 0);
+        launches++;
+        SPX_CUDA(cudaGetLastError());
+        return SPX_OK;
+    }
+    int strip_update()
+    {
+        const int threads_fin = max(max(g.Kcap, g.nbx * g.nby), g.tiles_x * g.tiles_y);
+        slic_finalize_kernel<<<cdiv(threads_fin, BIN_CTA), BIN_CTA, 0, st>>>(g, a, d_K, parity, 1);
+        launches++;
+        parity ^= 1;
+        SPX_CUDA(cudaGetLastError());
         return SPX_OK;
     }
 
@@ -695,6 +726,75 @@ extern "C" int spx_slic_create_dev(const void* d_image, size_t stride, int w, in
     SPX_CHECK(spx::require_device(dev));
     return slic_create_common(d_image, stride, w, h, C, alg, S, ruler, (cudaStream_t)stream, true, out);
 }
+// ---- row-strip mode ------------------------------------------------------------------------------------------
+extern "C" int spx_slic_create_strip(const uint8_t* rows, size_t stride, int w, int h, int C, int alg, int S, float ruler,
+                                     int row0, int row1, int own_row0, int own_row1, void* stream, spx_slic_t** out)
+{
+    using namespace spx;
+    SPX_REQUIRE(out, SPX_ERR_BADARG, "create_strip: out is NULL");
+    *out = nullptr;
+    SPX_REQUIRE(rows && alg == SPX_SLIC && C == 3, SPX_ERR_BADARG, "create_strip: 3-channel SLIC only");
+    SPX_REQUIRE(0 <= row0 && row0 <= own_row0 && own_row0 < own_row1 && own_row1 <= row1 && row1 <= h, SPX_ERR_BADARG,
+                "create_strip: need 0 <= row0 <= own_row0 < own_row1 <= row1 <= height");
+    SPX_REQUIRE((own_row0 % TILE_H == 0) && (own_row1 % TILE_H == 0 || own_row1 == h), SPX_ERR_BADARG,
+                "create_strip: owned rows must start and end on multiples of %d (or at the image end)", TILE_H);
+    SPX_REQUIRE((own_row0 == 0 || own_row0 - row0 >= 2) && (own_row1 == h || row1 - own_row1 >= 2), SPX_ERR_BADARG,
+                "create_strip: two halo rows are needed on every inner side (seed perturbation reads them)");
+    int dev = 0;
+    SPX_CUDA(cudaGetDevice(&dev));
+    SPX_CHECK(require_device(dev));
+    SlicEngine* e = nullptr;
+    SPX_CHECK(make_engine(w, h, C, alg, S, ruler, (cudaStream_t)stream, &e));
+    int rc = SPX_OK;
+    if (!e->use_tile) { set_error("create_strip: configuration outside the tiled path (region_size >= 14 required)"); rc = SPX_ERR_BADARG; }
+    if (rc == SPX_OK) {
+        e->g.ty_lo = own_row0 / TILE_H; e->g.ty_hi = cdiv(own_row1, TILE_H);
+        e->g.own_y0 = own_row0; e->g.own_y1 = own_row1;
+        e->use_graph = false;
+        cudaError_t ce = cudaMemcpy2DAsync(e->d_img + (size_t)row0 * e->g.ipitch, e->g.ipitch, rows, stride, (size_t)w * C, row1 - row0,
+                                           cudaMemcpyHostToDevice, e->st);
+        if (ce != cudaSuccess) { set_error("create_strip: upload failed: %s", cudaGetErrorString(ce)); rc = SPX_ERR_GPU; }
+    }
+    if (rc == SPX_OK) rc = e->seed();
+    if (rc != SPX_OK) { delete e; return rc; }
+    *out = new spx_slic{e};
+    return SPX_OK;
+}
+extern "C" int spx_slic_device_state(spx_slic_t* h, spx_slic_state_t* out)
+{
+    SLIC_ENTER(h);
+    SPX_REQUIRE(out, SPX_ERR_BADARG, "device_state: out is NULL");
+    out->kx = e->a.kx; out->ky = e->a.ky; out->kc = e->a.kc; out->ikx = e->a.ikx; out->iky = e->a.iky; out->acc = e->a.acc;
+    out->K = e->g.K; out->Kcap = e->g.Kcap; out->channels = e->g.C;
+    return SPX_OK;
+}
+extern "C" int spx_slic_strip_rebin(spx_slic_t* h)
+{
+    SLIC_ENTER(h);
+    return e->strip_rebin();
+}
+extern "C" int spx_slic_strip_assign(spx_slic_t* h)
+{
+    SLIC_ENTER(h);
+    e->launches++;
+    return e->enqueue_assign();
+}
+extern "C" int spx_slic_strip_update(spx_slic_t* h)
+{
+    SLIC_ENTER(h);
+    return e->strip_update();
+}
+extern "C" int spx_slic_get_label_rows(spx_slic_t* h, int32_t* dst, size_t dst_stride, int row0, int row1)
+{
+    SLIC_ENTER(h);
+    SPX_REQUIRE(dst && dst_stride >= (size_t)e->g.w * 4 && 0 <= row0 && row0 <= row1 && row1 <= e->g.h, SPX_ERR_BADARG, "getLabelRows: bad argument");
+    if (row1 > row0)
+        SPX_CUDA(cudaMemcpy2DAsync(dst, dst_stride, e->d_labels + (size_t)row0 * e->g.lp, (size_t)e->g.lp * 4, (size_t)e->g.w * 4, row1 - row0,
+                                   cudaMemcpyDeviceToHost, e->st));
+    SPX_CUDA(cudaStreamSynchronize(e->st));
+    return SPX_OK;
+}
+
 extern "C" int spx_slic_reset(spx_slic_t* h, const uint8_t* image, size_t stride)
 {
     SLIC_ENTER(h);

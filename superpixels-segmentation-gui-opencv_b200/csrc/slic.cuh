@@ -39,6 +39,8 @@ struct SlicGeom {
     float xywt;                      // SLIC/MSLIC: (S/ruler)^2 ; SLICO: S*S
     int tiles_x, tiles_y;            // grid of TILE_W x TILE_H tiles
     int tile_on;                     // the tiled path is in use: centres are also scattered into the tile lists
+    int ty_lo, ty_hi;                // tile rows this object assigns (strip mode; [0, tiles_y) otherwise)
+    int own_y0, own_y1;              // pixel rows whose seeds this object owns (strip mode; [0, h) otherwise)
 };
 
 }  // namespace spx

@@ -110,6 +110,7 @@ struct TileArgs {
     unsigned long long* acc;
     const unsigned* img4;        // Lab1 words, pitch p4 (pixels)
     int w, h, S, Kcap, tiles_x, lp, p4;
+    int ty_off;                  // first tile row of the launch (strip mode)
     float xywt, rcp_xywt;
     const float* maxc; unsigned* maxc_acc; float* dcplane;      // SLICO (dcplane has the label pitch)
 };
@@ -169,8 +170,9 @@ __global__ void __launch_bounds__(NT, ALG == SPX_SLICO ? 6 : 8) slic_tile_kernel
     __shared__ TileSmemT<ALG> sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int S = t.S;
-    const int tile = blockIdx.y * t.tiles_x + blockIdx.x;
-    const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
+    const int tyi = blockIdx.y + t.ty_off;
+    const int tile = tyi * t.tiles_x + blockIdx.x;
+    const int tx0 = blockIdx.x * TW, ty0 = tyi * TH;
 
     // ---- first pixels in flight before anything else (lanes 8 x 4, 2x2 pixels per thread, warps 2 x 2)
     const int lx = lane & 7, ly = lane >> 3;
@@ -521,8 +523,9 @@ int slic_tile_assign(const SlicGeom& g, const SlicArrays& a, const unsigned char
                      float* d_dcplane, const int* d_K, int parity, int* d_overflow, cudaStream_t st)
 {
     (void)d_K;
-    dim3 grid(g.tiles_x, g.tiles_y);
+    dim3 grid(g.tiles_x, g.ty_hi - g.ty_lo);
     TileArgs t;
+    t.ty_off = g.ty_lo;
     t.tl_count = a.tl_count[parity]; t.tl_rec = a.tl_rec[parity]; t.acc = a.acc;
     t.img4 = d_img4;
     t.w = g.w; t.h = g.h; t.S = g.S; t.Kcap = g.Kcap; t.tiles_x = g.tiles_x; t.lp = g.lp; t.p4 = g.p4;

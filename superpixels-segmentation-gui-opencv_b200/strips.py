@@ -1,0 +1,135 @@
+"""Row-strip SLIC: ONE image over several GPUs (BASELINE.json north-star: gigapixel images).
+
+One process per GPU (torch.distributed / NCCL).  Rank r owns a band of rows (a multiple of 32, so bands are whole tile
+rows) and uploads those rows plus two halo rows.  Cluster state is replicated; per iteration ONE exchange step sums the
+integer accumulators (pixel sums per cluster) over the ranks -- only clusters near a cut receive pixels from two ranks,
+the sums are integers, so the result is bit-identical to the single-GPU object.  torch is plumbing here: it wraps the
+library's device pointers (``__cuda_array_interface__``) so that NCCL can reduce them in place.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import SLIC, SpxError, _ck, _p, lib
+
+
+class _State(C.Structure):
+    _fields_ = [("kx", C.c_void_p), ("ky", C.c_void_p), ("kc", C.c_void_p), ("ikx", C.c_void_p), ("iky", C.c_void_p),
+                ("acc", C.c_void_p), ("K", C.c_int), ("Kcap", C.c_int), ("channels", C.c_int)]
+
+
+class _DevArray:
+    """zero-copy view of a raw device pointer for torch.as_tensor"""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def row_bands(height, world, tile=32):
+    """[own_row0, own_row1) per rank: whole tile rows, as even as possible; trailing ranks may get nothing for tiny images"""
+    tiles = (height + tile - 1) // tile
+    out = []
+    for r in range(world):
+        t0, t1 = tiles * r // world, tiles * (r + 1) // world
+        out.append((min(t0 * tile, height), min(t1 * tile, height)))
+    return out
+
+
+def halo_rows(own0, own1, height, halo=2):
+    """rows a rank has to upload: its own band plus `halo` rows on every inner side"""
+    return max(own0 - halo, 0), min(own1 + halo, height)
+
+
+class StripSLIC:
+    """cv::ximgproc::SuperpixelSLIC (algorithm SLIC) over the row band of this rank.  `image` is the whole 8UC3 image
+    or a callable rows(row0, row1) -> ndarray, so a rank never needs more than its band in host memory."""
+
+    def __init__(self, image, region_size, ruler, dist, device, width=None, height=None):
+        import torch
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        if callable(image):
+            self.w, self.h = int(width), int(height)
+            rows = image
+        else:
+            img = np.ascontiguousarray(image, dtype=np.uint8)
+            self.h, self.w = img.shape[:2]
+            rows = lambda a, b: img[a:b]
+        self.own0, self.own1 = row_bands(self.h, self.world)[self.rank]
+        if self.own1 <= self.own0:
+            raise SpxError(-5, "StripSLIC: more ranks than tile rows")
+        self.row0, self.row1 = halo_rows(self.own0, self.own1, self.h)
+        band = np.ascontiguousarray(rows(self.row0, self.row1))
+        torch.cuda.set_device(device)
+        # one explicit stream for the library's kernels AND the NCCL reductions, so that they are ordered
+        # (the legacy default stream would make the library create a private stream of its own)
+        self.stream = torch.cuda.Stream(device)
+        self._h = C.c_void_p(None)
+        L = lib()
+        L.spx_slic_create_strip.argtypes = [C.c_void_p, C.c_size_t] + [C.c_int] * 5 + [C.c_float] + [C.c_int] * 4 + [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.spx_slic_device_state.argtypes = [C.c_void_p, C.POINTER(_State)]
+        for f in (L.spx_slic_strip_rebin, L.spx_slic_strip_assign, L.spx_slic_strip_update):
+            f.argtypes = [C.c_void_p]
+        L.spx_slic_get_label_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
+        _ck(L.spx_slic_create_strip(_p(band), self.w * 3, self.w, self.h, 3, SLIC, int(region_size), float(ruler), self.row0, self.row1,
+                                    self.own0, self.own1, C.c_void_p(self.stream.cuda_stream), C.byref(self._h)))
+        st = _State()
+        _ck(L.spx_slic_device_state(self._h, C.byref(st)))
+        self.K = st.K
+        dev = torch.device("cuda", device)
+        view = lambda ptr, n, ts: torch.as_tensor(_DevArray(ptr, n, ts), device=dev)
+        self._seed_f = [view(st.kx, st.Kcap, "<f4"), view(st.ky, st.Kcap, "<f4"), view(st.kc, 3 * st.Kcap, "<f4")]
+        self._seed_i = [view(st.ikx, st.Kcap, "<i4"), view(st.iky, st.Kcap, "<i4")]
+        self._acc = view(st.acc, 6 * st.Kcap, "<i8")
+        # assemble the seeds: exactly one rank contributed a non-zero entry per cluster, so the sum is exact
+        with torch.cuda.stream(self.stream):
+            for t in self._seed_f + self._seed_i:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        _ck(L.spx_slic_strip_rebin(self._h))
+        self.exchanged_bytes = 0
+
+    def iterate(self, num_iterations=10):
+        L = lib()
+        for _ in range(int(num_iterations)):
+            _ck(L.spx_slic_strip_assign(self._h))
+            with self.torch.cuda.stream(self.stream):
+                self.dist.all_reduce(self._acc, op=self.dist.ReduceOp.SUM)  # the one exchange step of the path
+            self.exchanged_bytes += self._acc.numel() * 8
+            _ck(L.spx_slic_strip_update(self._h))
+
+    def getNumberOfSuperpixels(self):
+        return self.K
+
+    def getLabelRows(self):
+        """the owned rows [own0, own1) of the label map"""
+        out = np.empty((self.own1 - self.own0, self.w), np.int32)
+        _ck(lib().spx_slic_get_label_rows(self._h, _p(out), self.w * 4, self.own0, self.own1))
+        return out
+
+    def getLabels(self):
+        """the whole label map, gathered on every rank (for tests; a gigapixel caller keeps the bands apart)"""
+        mine = self.getLabelRows()
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, mine)
+        return np.concatenate(parts, 0)
+
+    def synchronize(self):
+        self.stream.synchronize()
+
+    def getCentres(self):
+        t = self.torch
+        self.stream.synchronize()
+        K, Kcap = self.K, self._seed_f[0].numel()
+        kc = self._seed_f[2].view(3, Kcap)[:, :K].t()
+        return t.cat([kc, self._seed_f[0][:K, None], self._seed_f[1][:K, None]], 1).cpu().numpy()
+
+    def release(self):
+        if self._h.value:
+            lib().spx_slic_destroy(self._h)
+            self._h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass

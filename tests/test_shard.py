@@ -56,3 +56,18 @@ def test_two_ranks_gloo():
     for rank, rate, units, t, got in res:
         assert units == 11 and t == 2.0 and abs(rate - 5.5) < 1e-12
         assert sorted(got[0] + got[1]) == list(range(11)) and not set(got[0]) & set(got[1])
+
+
+def test_strip_bands():
+    """row-strip mode: bands are whole tile rows, cover the image once, and every inner side gets two halo rows"""
+    strips = importlib.import_module(PKG + ".strips")
+    for h in (32, 1080, 2160, 30000):
+        for world in (1, 2, 4, 8):
+            bands = strips.row_bands(h, world)
+            assert bands[0][0] == 0 and bands[-1][1] == h
+            for (a0, a1), (b0, b1) in zip(bands, bands[1:]):
+                assert a1 == b0
+            for a0, a1 in bands:
+                assert a0 % 32 == 0 and (a1 % 32 == 0 or a1 == h)
+                r0, r1 = strips.halo_rows(a0, a1, h)
+                assert (a0 == 0 or a0 - r0 == 2) and (a1 == h or r1 - a1 == 2)
