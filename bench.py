@@ -32,6 +32,26 @@ W4K, H4K, REGION, RULER, ITERS = 3840, 2160, 20, 10.0, 10
 METRIC = "slic_megapixels_per_sec_10iters_4k"
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` summary (profiles/), or None"""
+    import glob
+    import re
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_slic_tile_v*.txt"))):
+        try:
+            txt = open(f).read()
+            rd = re.search(r"dram__bytes_read.sum\s+([0-9.]+)\s+(\w+)", txt)
+            wr = re.search(r"dram__bytes_write.sum\s+([0-9.]+)\s+(\w+)", txt)
+            if not rd or not wr:
+                continue
+            unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            best = {"bytes": float(rd.group(1)) * unit[rd.group(2)] + float(wr.group(1)) * unit[wr.group(2)],
+                    "source": os.path.relpath(f, ROOT)}
+        except Exception:
+            continue
+    return best
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -319,7 +339,8 @@ def run_ours(args):
         alg_bytes = 7.0 * npx                      # per assignment launch: 3 B Lab read + 4 B label write per pixel
         achieved = alg_bytes / (kms.value * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "slic_assign (fused assignment + centre accumulation)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": (ncu_traffic() or {}).get("bytes"), "traffic_source": (ncu_traffic() or {}).get("source"),
                 "peak_source": peak_src, "kernel_ms": kms.value, "kernel_ms_l2_warm": kms_warm.value,
                 "iterate10_ms_one_frame": it_ms, "assign_share_of_iterate": ITERS * kms_warm.value / it_ms,
                 "algorithmic_bytes_per_launch": alg_bytes,

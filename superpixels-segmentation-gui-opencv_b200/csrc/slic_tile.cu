@@ -81,14 +81,13 @@ __device__ __forceinline__ u64 bcast2(float v) { return pack2(v, v); }   // ptxa
 // one record per candidate, so that a single multiply addresses everything the inner loop reads
 struct __align__(16) CandRec {
     float4 k;                    // (-k0, -k1, -k2, n as int bits)
-    float4 m;                    // SLICO: (maxchans[n], RN(1/maxchans[n]), -maxchans[n], unused)
+    float4 m;                    // SLICO: (maxchans[n], RN(1/maxchans[n]), -maxchans[n], -); MSLIC: the same for adaptk[n]
     float ex2[TW];               // (x-kx)^2 [times 1/xywt when it is a power of two], +inf outside the window
     float ey2[TH];               // (y-ky)^2 likewise
 };
 struct SlicoSmem {               // SLICO only
     float dcm[TH][TW];           // colour distance to the LAST visiting cluster, per pixel (upstream's distchans plane)
     unsigned mx[NCOPY][CAP];     // per candidate: running maximum of dcm over its pixels (float bits; values are >= 0)
-    int bad;                     // a divisor the reciprocal sequence cannot handle: the tile takes the exact generic path
 };
 struct NoSmem {};
 template <int ALG>
@@ -103,6 +102,7 @@ struct __align__(16) TileSmemT {
     int list[CAP];
     unsigned char slot[TH][TW];  // winning candidate slot per pixel (0xFF: none / handled on the spot)
     typename std::conditional<ALG == SPX_SLICO, SlicoSmem, NoSmem>::type o;
+    int bad;                     // SLICO / MSLIC: a divisor the reciprocal sequence cannot handle -> exact generic path for the tile
 };
 
 struct TileArgs {
@@ -198,11 +198,13 @@ __global__ void __launch_bounds__(NT, ALG == SPX_SLICO ? 6 : 8) slic_tile_kernel
         return;
     }
     float mxv = 1.0f;
+    int woff = S;                                                  // window half-size (MSLIC: int(S * adaptk[n]))
     if (tid < cnt) {
         sm.list[tid] = __float_as_int(r1.y);
         if constexpr (ALG == SPX_SLICO) mxv = __ldg(&t.maxc[__float_as_int(r1.y)]);
+        if constexpr (ALG == SPX_MSLIC) { mxv = a.adaptk[__float_as_int(r1.y)]; woff = a.ioff[__float_as_int(r1.y)]; }
     }
-    if constexpr (ALG == SPX_SLICO) { if (tid == 0) sm.o.bad = 0; }
+    if (ALG != SPX_SLIC && tid == 0) sm.bad = 0;
     __syncthreads();
     // ---- rank by cluster index (upstream's visiting order), stage centres
     if (tid < cnt) {
@@ -211,13 +213,13 @@ __global__ void __launch_bounds__(NT, ALG == SPX_SLICO ? 6 : 8) slic_tile_kernel
         for (int j = 0; j < cnt; j++) rank += sm.list[j] < n ? 1 : 0;
         sm.rec[rank].k = make_float4(-r0.z, -r0.w, -r1.x, r1.y);
         const int ix = __float_as_int(r1.z), iy = __float_as_int(r1.w);
-        sm.win[rank] = make_int4(ix - S, ix + S, iy - S, iy + S);
+        sm.win[rank] = make_int4(ix - woff, ix + woff, iy - woff, iy + woff);
         sm.kxy[rank][0] = r0.x; sm.kxy[rank][1] = r0.y;
-        if constexpr (ALG == SPX_SLICO) {
-            // dc / maxchans[n] is evaluated as q = dc*r; q += fma(-q, m, dc)*r with r = RN(1/m): correctly rounded unless the
-            // significand of m is all ones
+        if constexpr (ALG != SPX_SLIC) {
+            // v / m (m = maxchans[n] or adaptk[n]) is evaluated as q = v*r; q += fma(-q, m, v)*r with r = RN(1/m): correctly
+            // rounded unless the significand of m is all ones
             sm.rec[rank].m = make_float4(mxv, __fdiv_rn(1.0f, mxv), -mxv, 0.f);
-            if ((__float_as_uint(mxv) & 0x7fffffu) == 0x7fffffu) sm.o.bad = 1;
+            if ((__float_as_uint(mxv) & 0x7fffffu) == 0x7fffffu) sm.bad = 1;
         }
     }
     if constexpr (ALG == SPX_SLICO) {
@@ -228,8 +230,8 @@ __global__ void __launch_bounds__(NT, ALG == SPX_SLICO ? 6 : 8) slic_tile_kernel
         for (int c = tid & 15; c < cnt; c += 16) *reinterpret_cast<uint4*>(cp + 4 * c) = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
-    if constexpr (ALG == SPX_SLICO) {
-        if (sm.o.bad) {
+    if constexpr (ALG != SPX_SLIC) {
+        if (sm.bad) {
             tile_fallback<ALG>(g, a, img, labels, t.dcplane, parity, tx0, ty0, warp, lane);
             return;
         }
@@ -312,7 +314,7 @@ __global__ void __launch_bounds__(NT, ALG == SPX_SLICO ? 6 : 8) slic_tile_kernel
                 const int ro = c * (int)sizeof(CandRec);
                 const float4 kc = *reinterpret_cast<const float4*>(rec0 + ro);
                 float4 km = make_float4(0.f, 0.f, 0.f, 0.f);
-                if constexpr (ALG == SPX_SLICO) km = *reinterpret_cast<const float4*>(rec0 + ro + 16);
+                if constexpr (ALG != SPX_SLIC) km = *reinterpret_cast<const float4*>(rec0 + ro + 16);
                 const u64 exv = *reinterpret_cast<const u64*>(thr_ex + ro);
                 const float2 eyv = *reinterpret_cast<const float2*>(thr_ey + ro);
 #pragma unroll
@@ -338,6 +340,11 @@ __global__ void __launch_bounds__(NT, ALG == SPX_SLICO ? 6 : 8) slic_tile_kernel
                         sxy = fma2(e, bcast2(t.rcp_xywt), q0);
                     }
                     d = add2(d, sxy);
+                    if constexpr (ALG == SPX_MSLIC) {                      // the whole distance is divided by adaptk[n]
+                        const u64 q0 = mul2(d, bcast2(km.y));
+                        const u64 e = fma2(q0, bcast2(km.z), d);
+                        d = fma2(e, bcast2(km.y), q0);
+                    }
                     float d0, d1;
                     unpack2(d, d0, d1);
                     if (d0 < best[r][0]) { best[r][0] = d0; slot[r][0] = c; }
@@ -488,7 +495,7 @@ static bool markstein_ok(float w)
 
 bool slic_tile_supported(const SlicGeom& g)
 {
-    return (g.alg == SPX_SLIC || g.alg == SPX_SLICO) && g.C == 3 && g.S >= MIN_S && (is_pow2(g.xywt) || markstein_ok(g.xywt));
+    return (g.alg == SPX_SLIC || g.alg == SPX_SLICO || g.alg == SPX_MSLIC) && g.C == 3 && g.S >= MIN_S && (is_pow2(g.xywt) || markstein_ok(g.xywt));
 }
 
 // 8UC3 rows -> Lab1 words (c0 | c1<<8 | c2<<16 | 1<<24); the padding of the tile grid stays zero
@@ -535,6 +542,9 @@ int slic_tile_assign(const SlicGeom& g, const SlicArrays& a, const unsigned char
     if (g.alg == SPX_SLICO) {
         if (p2) slic_tile_kernel<true, SPX_SLICO><<<grid, NT, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);
         else slic_tile_kernel<false, SPX_SLICO><<<grid, NT, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);
+    } else if (g.alg == SPX_MSLIC) {
+        if (p2) slic_tile_kernel<true, SPX_MSLIC><<<grid, NT, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);
+        else slic_tile_kernel<false, SPX_MSLIC><<<grid, NT, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);
     } else {
         if (p2) slic_tile_kernel<true, SPX_SLIC><<<grid, NT, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);
         else slic_tile_kernel<false, SPX_SLIC><<<grid, NT, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);

@@ -149,6 +149,16 @@ def test_slico_tiled_path_exact(spx, O, example_lab, S):
     assert (a.getLabels() == b.getLabels()).all()
 
 
+def test_mslic_tiled_path_exact(spx, O, synthmod):
+    """MSLIC through the tiled kernel: adaptive windows (up to 2S), distance / adaptk, cluster splits (K grows)"""
+    img, _ = synthmod.synth(1280, 720, 4)
+    lab = O.bgr2lab8(img)
+    a, b = _run_pair(spx, O, lab, spx.MSLIC, 30, 10.0, 6)
+    assert a.getNumberOfSuperpixels() == b.getNumberOfSuperpixels()
+    assert (a.getLabels() == b.getLabels()).all()
+    assert (a.getCentres() == b.getCentres()).all()
+
+
 def test_slico_cfg2_4k_equals_oracle(spx, O, synthmod):
     """BASELINE.json configs[1]: SLICO 3840x2160, region_size=25, 10 iterations, contour mask"""
     img, _ = synthmod.synth(3840, 2160, 0)
