@@ -43,6 +43,9 @@ extern "C" {
 int         spx_version(void);
 const char* spx_last_error(void);
 int         spx_device_count(int* count);
+/* device memory of destroyed objects stays in the device's stream-ordered pool for the next object (the GUI creates a
+ * new Superpixel object on every COMPUTE click); this returns it to the driver */
+int         spx_release_cached_memory(void);
 
 /* ---- cv::cvtColor(converted, converted, COLOR_BGR2Lab / COLOR_BGR2HSV), mainwindow.cpp:2096-2097 ----
  * 8UC3 -> 8UC3, bit-exact with OpenCV's 8-bit integer pipelines.  In-place (src == dst) is allowed. */

@@ -52,6 +52,7 @@ def lib():
     L.spx_last_error.restype = C.c_char_p
     sig = {
         "spx_device_count": [pi],
+        "spx_release_cached_memory": [],
         "spx_bgr2lab8": [vp, sz, vp, sz, i32, i32, i32],
         "spx_bgr2hsv8": [vp, sz, vp, sz, i32, i32, i32],
         "spx_bgr2lab8_dev": [vp, sz, vp, sz, i32, i32, vp],

@@ -27,8 +27,43 @@ int require_device(int device)
     SPX_CUDA(cudaSetDevice(device));
     return SPX_OK;
 }
+int pool_alloc(void** p, size_t bytes, cudaStream_t st)
+{
+    static bool tuned[64] = {false};
+    int dev = 0;
+    SPX_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !tuned[dev]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        tuned[dev] = true;
+    }
+    cudaError_t e = cudaMallocAsync(p, bytes > 0 ? bytes : 4, st);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        set_error("device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? SPX_ERR_NOMEM : SPX_ERR_GPU;
+    }
+    return SPX_OK;
+}
+void pool_free(void* p, cudaStream_t st)
+{
+    if (p) cudaFreeAsync(p, st);
+}
 }  // namespace spx
 
+extern "C" int spx_release_cached_memory(void)
+{
+    int dev = 0;
+    SPX_CUDA(cudaGetDevice(&dev));
+    cudaMemPool_t pool;
+    SPX_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    SPX_CUDA(cudaDeviceSynchronize());
+    SPX_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return SPX_OK;
+}
 extern "C" int spx_version(void) { return 100; }
 extern "C" const char* spx_last_error(void) { return spx::g_err; }
 extern "C" int spx_device_count(int* count)

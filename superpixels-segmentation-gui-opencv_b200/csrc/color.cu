@@ -145,12 +145,12 @@ static int cvt8_host(int mode, const uint8_t* src, size_t sstride, uint8_t* dst,
     SPX_CHECK(require_device(device));
     size_t pitch = round_up((size_t)w * 3, 16);
     unsigned char* d = nullptr;
-    SPX_CUDA(cudaMalloc(&d, pitch * h));
+    SPX_CHECK(pool_alloc((void**)&d, pitch * h, 0));
     int rc = SPX_OK;
     cudaError_t e = cudaMemcpy2D(d, pitch, src, sstride, (size_t)w * 3, h, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) rc = cvt8_dev(mode, d, pitch, d, pitch, w, h, 0);
     if (e == cudaSuccess && rc == SPX_OK) e = cudaMemcpy2D(dst, dstride, d, pitch, (size_t)w * 3, h, cudaMemcpyDeviceToHost);
-    cudaFree(d);
+    pool_free(d, 0);
     if (e != cudaSuccess) { set_error("cvtColor: %s", cudaGetErrorString(e)); return SPX_ERR_GPU; }
     return rc;
 }

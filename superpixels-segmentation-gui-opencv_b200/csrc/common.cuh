@@ -40,6 +40,12 @@ static inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; 
 // fails loudly when there is no usable CUDA device (no CPU fallback anywhere in this library)
 int require_device(int device);
 
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync) with the release threshold raised, so that
+// the reference's usage pattern -- a new Superpixel object on every COMPUTE click -- reuses the previous object's memory
+// instead of paying cudaMalloc/cudaFree (milliseconds for the 100+ MB buffers of a 4K frame) each time.
+int pool_alloc(void** p, size_t bytes, cudaStream_t st);
+void pool_free(void* p, cudaStream_t st);
+
 // ---- post-processing stages shared by SLIC / LSC / SEEDS engines (post.cu) ----
 struct PostWorkspace {
     int w = 0, h = 0;
@@ -52,7 +58,8 @@ struct PostWorkspace {
     unsigned char* diff = nullptr;   // contour: differing-neighbour bit masks [N]
     int* h_flag = nullptr;      // pinned host mirror [8]
     long long launches = 0;
-    int alloc(int w_, int h_);
+    cudaStream_t st_alloc = nullptr;
+    int alloc(int w_, int h_, cudaStream_t st = nullptr);
     void release();
 };
 // labels: dense int32 with pitch `lpitch` (elements). In place. numlabels_out written to ws.h_flag[0]

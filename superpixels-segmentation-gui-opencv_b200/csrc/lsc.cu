@@ -17,6 +17,9 @@
 //     graph by a single CTA (one step per small region), then a scan for the final ids.
 #include "common.cuh"
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdlib>
@@ -341,7 +344,7 @@ __global__ void __launch_bounds__(256) lsc_post_sums_kernel(LscDev L, const int*
 }
 __global__ void lsc_post_stats_kernel(const long long* __restrict__ rsum, const int* __restrict__ size, int D, int R, int threshold,
                                       float* __restrict__ cen, float* __restrict__ Wr, int* __restrict__ alive,
-                                      int* __restrict__ smallflag, int* __restrict__ done, int* __restrict__ target)
+                                      int* __restrict__ smallflag, int* __restrict__ done, int* __restrict__ cur)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
@@ -349,7 +352,7 @@ __global__ void lsc_post_stats_kernel(const long long* __restrict__ rsum, const 
     const long long sw = a[D];
     for (int j = 0; j < D; j++) cen[(size_t)r * D + j] = sw != 0 ? (float)__ddiv_rn(__ddiv_rn((double)a[j], (double)sw), 256.0) : 0.f;
     Wr[r] = (float)__ddiv_rn((double)sw, 16777216.0);
-    alive[r] = 1; done[r] = 0; target[r] = -1;
+    alive[r] = 1; done[r] = 0; cur[r] = r;
     smallflag[r] = size[r] < threshold ? 1 : 0;
 }
 
@@ -372,40 +375,61 @@ __device__ __forceinline__ unsigned lsc_prio(int r, int order)
     }
     return x;
 }
-__global__ void lsc_round_relabel_kernel(int* __restrict__ curlab, const int* __restrict__ target, int n)
+// region adjacency: one 64-bit key (min<<32 | max) per 4-neighbour pixel pair with different regions; sorted and
+// de-duplicated once, the rounds then work on the (much smaller) edge list.  Merged regions are followed through `cur`.
+__global__ void lsc_edge_count_kernel(const int* __restrict__ reg, int w, int h, unsigned long long* __restrict__ keys,
+                                      unsigned long long* __restrict__ count, unsigned long long cap)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int t = target[curlab[i]];
-    if (t >= 0) curlab[i] = t;
-}
-__global__ void lsc_round_begin_kernel(const int* __restrict__ smallflag, const int* __restrict__ done, const int* __restrict__ size,
-                                       int threshold, int R, int order, int* __restrict__ pend, unsigned* __restrict__ key, unsigned* __restrict__ a,
-                                       unsigned long long* __restrict__ best, int* __restrict__ target, int* __restrict__ npending)
-{
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool p = r < R && smallflag[r] && !done[r] && size[r] < threshold;
-    if (r < R) { pend[r] = p ? 1 : 0; key[r] = a[r] = p ? lsc_prio(r, order) : 0xffffffffu; best[r] = ~0ull; target[r] = -1; }
-    const unsigned m = __ballot_sync(0xffffffffu, p);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(npending, __popc(m));
-}
-// a[r] = min pending index over the closed neighbourhood of r; the same kernel run on (a -> b) gives distance 2
-__global__ void lsc_round_minprop_kernel(const int* __restrict__ curlab, const unsigned* __restrict__ src, unsigned* __restrict__ dst,
-                                         int w, int h, const int* __restrict__ npending)
-{
-    if (*npending == 0) return;
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= w) return;
-    const int i = y * w + x, rp = curlab[i];
+    const int i = y * w + x, rp = reg[i];
 #pragma unroll
     for (int k = 0; k < 2; k++) {
         if (k == 0 ? x + 1 >= w : y + 1 >= h) continue;
-        const int rq = curlab[k == 0 ? i + 1 : i + w];
+        const int rq = reg[k == 0 ? i + 1 : i + w];
         if (rq == rp) continue;
-        const unsigned vp = src[rp], vq = src[rq];
-        if (vq < dst[rp]) atomicMin(&dst[rp], vq);
-        if (vp < dst[rq]) atomicMin(&dst[rq], vp);
+        // skip the pair when the pixel before it on the same boundary run already emitted it (cheap partial dedupe)
+        if (k == 0 && y > 0 && reg[i - w] == rp && reg[i - w + 1] == rq) continue;
+        if (k == 1 && x > 0 && reg[i - 1] == rp && reg[i + w - 1] == rq) continue;
+        const unsigned lo = (unsigned)min(rp, rq), hi = (unsigned)max(rp, rq);
+        const unsigned long long pos = atomicAdd(count, 1ull);
+        if (pos < cap) keys[pos] = ((unsigned long long)lo << 32) | hi;
     }
+}
+__device__ __forceinline__ int lsc_cur(const int* __restrict__ cur, int r)
+{
+    int c = cur[r];
+    while (c != r) { r = c; c = cur[r]; }
+    return r;
+}
+__global__ void lsc_round_compress_kernel(int* __restrict__ cur, int R)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < R) cur[r] = lsc_cur(cur, r);
+}
+__global__ void lsc_round_begin_kernel(const int* __restrict__ smallflag, const int* __restrict__ done, const int* __restrict__ size,
+                                       int threshold, int R, int order, int* __restrict__ pend, unsigned* __restrict__ key, unsigned* __restrict__ a,
+                                       unsigned long long* __restrict__ best, int* __restrict__ npending)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool p = r < R && smallflag[r] && !done[r] && size[r] < threshold;
+    if (r < R) { pend[r] = p ? 1 : 0; key[r] = a[r] = p ? lsc_prio(r, order) : 0xffffffffu; best[r] = ~0ull; }
+    const unsigned m = __ballot_sync(0xffffffffu, p);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(npending, __popc(m));
+}
+// a[r] = min pending priority over the closed neighbourhood of r; the same kernel run on (a -> b) gives distance 2
+__global__ void lsc_round_minprop_kernel(const unsigned long long* __restrict__ edges, int E, const int* __restrict__ cur,
+                                         const unsigned* __restrict__ src, unsigned* __restrict__ dst, const int* __restrict__ npending)
+{
+    if (*npending == 0) return;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const unsigned long long k = edges[e];
+    const int rp = lsc_cur(cur, (int)(k >> 32)), rq = lsc_cur(cur, (int)(k & 0xffffffffull));
+    if (rq == rp) return;
+    const unsigned vp = src[rp], vq = src[rq];
+    if (vq < dst[rp]) atomicMin(&dst[rp], vq);
+    if (vp < dst[rq]) atomicMin(&dst[rq], vp);
 }
 __global__ void lsc_round_copy_kernel(const unsigned* __restrict__ a, unsigned* __restrict__ b, int R, const int* __restrict__ npending)
 {
@@ -419,27 +443,22 @@ __device__ __forceinline__ unsigned long long lsc_pair_key(const float* __restri
     for (int j = 0; j < D; j++) { const float u = __fsub_rn(cen[(size_t)i * D + j], cen[(size_t)r * D + j]); d = __fadd_rn(d, __fmul_rn(u, u)); }
     return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)r;
 }
-__global__ void lsc_round_best_kernel(const int* __restrict__ curlab, const int* __restrict__ pend, const unsigned* __restrict__ b,
-                                      const float* __restrict__ cen, int D, int order, unsigned long long* __restrict__ best, int w, int h,
-                                      const int* __restrict__ npending)
+__global__ void lsc_round_best_kernel(const unsigned long long* __restrict__ edges, int E, const int* __restrict__ cur,
+                                      const int* __restrict__ pend, const unsigned* __restrict__ b, const float* __restrict__ cen, int D,
+                                      int order, unsigned long long* __restrict__ best, const int* __restrict__ npending)
 {
     if (*npending == 0) return;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= w) return;
-    const int i = y * w + x, rp = curlab[i];
-    const bool sp = pend[rp] && b[rp] == lsc_prio(rp, order);
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        if (k == 0 ? x + 1 >= w : y + 1 >= h) continue;
-        const int rq = curlab[k == 0 ? i + 1 : i + w];
-        if (rq == rp) continue;
-        if (sp) { const unsigned long long key = lsc_pair_key(cen, D, rp, rq); if (key < best[rp]) atomicMin(&best[rp], key); }
-        if (pend[rq] && b[rq] == lsc_prio(rq, order)) { const unsigned long long key = lsc_pair_key(cen, D, rq, rp); if (key < best[rq]) atomicMin(&best[rq], key); }
-    }
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const unsigned long long k = edges[e];
+    const int rp = lsc_cur(cur, (int)(k >> 32)), rq = lsc_cur(cur, (int)(k & 0xffffffffull));
+    if (rq == rp) return;
+    if (pend[rp] && b[rp] == lsc_prio(rp, order)) { const unsigned long long key = lsc_pair_key(cen, D, rp, rq); if (key < best[rp]) atomicMin(&best[rp], key); }
+    if (pend[rq] && b[rq] == lsc_prio(rq, order)) { const unsigned long long key = lsc_pair_key(cen, D, rq, rp); if (key < best[rq]) atomicMin(&best[rq], key); }
 }
 __global__ void lsc_round_merge_kernel(const int* __restrict__ pend, const unsigned* __restrict__ b, const unsigned long long* __restrict__ best,
                                        int D, int R, int order, float* __restrict__ cen, float* __restrict__ Wr, int* __restrict__ size,
-                                       int* __restrict__ alive, int* __restrict__ done, int* __restrict__ target,
+                                       int* __restrict__ alive, int* __restrict__ done, int* __restrict__ cur,
                                        const int* __restrict__ npending)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -457,12 +476,13 @@ __global__ void lsc_round_merge_kernel(const int* __restrict__ pend, const unsig
     Wr[nb] = __fadd_rn(wn, wi);
     size[nb] += size[i];
     alive[i] = 0;
-    target[i] = nb;
+    cur[i] = nb;
 }
-__global__ void lsc_post_relabel_kernel(const int* __restrict__ curlab, const int* __restrict__ newid, int* __restrict__ lab, int n)
+__global__ void lsc_post_relabel_kernel(const int* __restrict__ reg, const int* __restrict__ cur, const int* __restrict__ newid,
+                                        int* __restrict__ lab, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) lab[i] = newid[curlab[i]];
+    if (i < n) lab[i] = newid[lsc_cur(cur, reg[i])];
 }
 
 struct MaxOp { __device__ __forceinline__ int operator()(int a, int b) const { return a > b ? a : b; } };
@@ -491,7 +511,7 @@ struct LscEngine {
 
     template <typename T> int dalloc(T** p, size_t n)
     {
-        SPX_CUDA(cudaMalloc((void**)p, n * sizeof(T) > 0 ? n * sizeof(T) : 4));
+        SPX_CHECK(pool_alloc((void**)p, n * sizeof(T), st));
         allocs.push_back((void*)*p);
         return SPX_OK;
     }
@@ -499,8 +519,8 @@ struct LscEngine {
     {
         cudaSetDevice(device);
         if (st) cudaStreamSynchronize(st);
-        for (void* p : allocs) cudaFree(p);
-        if (d_scan_tmp) cudaFree(d_scan_tmp);
+        for (void* p : allocs) pool_free(p, st);
+        if (d_scan_tmp) pool_free(d_scan_tmp, st);
         post.release();
         if (h_pinned) cudaFreeHost(h_pinned);
         if (st) cudaStreamDestroy(st);
@@ -508,9 +528,9 @@ struct LscEngine {
     int scan_tmp(size_t bytes)
     {
         if (bytes <= scan_tmp_bytes) return SPX_OK;
-        if (d_scan_tmp) cudaFree(d_scan_tmp);
+        if (d_scan_tmp) pool_free(d_scan_tmp, st);
         d_scan_tmp = nullptr; scan_tmp_bytes = 0;
-        SPX_CUDA(cudaMalloc(&d_scan_tmp, bytes));
+        SPX_CHECK(pool_alloc(&d_scan_tmp, bytes, st));
         scan_tmp_bytes = bytes;
         return SPX_OK;
     }
@@ -683,11 +703,11 @@ struct LscEngine {
         int *P, *csize, *rootidx, *flag, *A, *B, *Cc;
         std::vector<void*> tmp;
         auto talloc = [&](int** p, size_t cnt) -> int {
-            SPX_CUDA(cudaMalloc((void**)p, (cnt > 0 ? cnt : 1) * sizeof(int)));
+            SPX_CHECK(pool_alloc((void**)p, (cnt > 0 ? cnt : 1) * sizeof(int), st));
             tmp.push_back(*p);
             return SPX_OK;
         };
-        auto tfree = [&]() { for (void* p : tmp) cudaFree(p); tmp.clear(); };
+        auto tfree = [&]() { for (void* p : tmp) pool_free(p, st); tmp.clear(); };
         int rc = SPX_OK;
 #define LSC_TRY(expr) do { rc = (expr); if (rc != SPX_OK) { tfree(); return rc; } } while (0)
 #define LSC_TRYCUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { set_error("%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); tfree(); return SPX_ERR_GPU; } } while (0)
@@ -729,12 +749,12 @@ struct LscEngine {
         LSC_TRYCUDA(cudaMemcpyAsync(h_pinned + 1, flag + n - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         LSC_TRYCUDA(cudaStreamSynchronize(st));
         const int R = h_pinned[0] + h_pinned[1];
-        int *reg = B, *size, *alive, *smallflag, *done, *target, *pend, *rk, *ra, *rb, *newid;
+        int *reg = B, *size, *alive, *smallflag, *done, *cur, *pend, *rk, *ra, *rb, *newid;
         unsigned long long* best;
         float *cen, *Wr;
         long long* rsum;
         LSC_TRY(talloc(&size, R + 1)); LSC_TRY(talloc(&alive, R + 1)); LSC_TRY(talloc(&smallflag, R)); LSC_TRY(talloc(&done, R));
-        LSC_TRY(talloc(&target, R)); LSC_TRY(talloc(&pend, R)); LSC_TRY(talloc(&rk, R)); LSC_TRY(talloc(&ra, R)); LSC_TRY(talloc(&rb, R));
+        LSC_TRY(talloc(&cur, R)); LSC_TRY(talloc(&pend, R)); LSC_TRY(talloc(&rk, R)); LSC_TRY(talloc(&ra, R)); LSC_TRY(talloc(&rb, R));
         LSC_TRY(talloc(&newid, R + 1)); LSC_TRY(talloc((int**)&best, (size_t)R * 2));
         LSC_TRY(talloc((int**)&cen, (size_t)R * D)); LSC_TRY(talloc((int**)&Wr, R));
         LSC_TRY(talloc((int**)&rsum, (size_t)R * (D + 1) * 2));
@@ -750,20 +770,49 @@ struct LscEngine {
             default: lsc_post_sums_kernel<4><<<gp, 256, 0, st>>>(L, reg, rsum); break;
         }
         const int gr = cdiv(R, 256);
-        lsc_post_stats_kernel<<<gr, 256, 0, st>>>(rsum, size, D, R, threshold, cen, Wr, alive, smallflag, done, target);
+        lsc_post_stats_kernel<<<gr, 256, 0, st>>>(rsum, size, D, R, threshold, cen, Wr, alive, smallflag, done, cur);
         launches += 3;
-        // ---- merge rounds (see the comment above lsc_round_relabel_kernel); `reg` becomes the current region map
+        // ---- region adjacency edges, sorted and de-duplicated once
+        // (key buffers sized for the worst case: every horizontal and vertical pixel pair)
+        const unsigned long long ecap = (unsigned long long)2 * n;
+        unsigned long long *kbuf0, *kbuf1, *ecount;
+        LSC_TRY(talloc((int**)&kbuf0, (size_t)ecap * 2)); LSC_TRY(talloc((int**)&kbuf1, (size_t)ecap * 2)); LSC_TRY(talloc((int**)&ecount, 4));
+        LSC_TRYCUDA(cudaMemsetAsync(ecount, 0, 2 * sizeof(unsigned long long), st));
+        lsc_edge_count_kernel<<<g2, 256, 0, st>>>(reg, w, h, kbuf0, ecount, ecap);
+        launches++;
+        unsigned long long h_ec = 0;
+        LSC_TRYCUDA(cudaMemcpyAsync(&h_ec, ecount, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        LSC_TRYCUDA(cudaStreamSynchronize(st));
+        int E = 0;
+        unsigned long long* edges = kbuf1;
+        if (h_ec > 0) {
+            const int nraw = (int)h_ec;
+            size_t b1 = 0, b2 = 0;
+            LSC_TRYCUDA(cub::DeviceRadixSort::SortKeys(nullptr, b1, kbuf0, kbuf1, nraw, 0, 64, st));
+            int* d_nuniq = reinterpret_cast<int*>(ecount + 1);
+            LSC_TRYCUDA(cub::DeviceSelect::Unique(nullptr, b2, kbuf1, kbuf0, d_nuniq, nraw, st));
+            LSC_TRY(scan_tmp(std::max(b1, b2)));
+            LSC_TRYCUDA(cub::DeviceRadixSort::SortKeys(d_scan_tmp, b1, kbuf0, kbuf1, nraw, 0, 64, st));
+            LSC_TRYCUDA(cub::DeviceSelect::Unique(d_scan_tmp, b2, kbuf1, kbuf0, d_nuniq, nraw, st));
+            launches += 4;
+            LSC_TRYCUDA(cudaMemcpyAsync(h_pinned, d_nuniq, sizeof(int), cudaMemcpyDeviceToHost, st));
+            LSC_TRYCUDA(cudaStreamSynchronize(st));
+            E = h_pinned[0];
+            edges = kbuf0;
+        }
+        // ---- merge rounds (see the comment above lsc_round_begin_kernel) on the edge list
+        const int ge = cdiv(std::max(E, 1), 256);
         int rounds = 0;
         for (;;) {
             for (int k = 0; k < 8; k++) {
-                lsc_round_relabel_kernel<<<g1, 256, 0, st>>>(reg, target, n);
                 LSC_TRYCUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
-                lsc_round_begin_kernel<<<gr, 256, 0, st>>>(smallflag, done, size, threshold, R, merge_order, pend, (unsigned*)rk, (unsigned*)ra, best, target, d_flag);
-                lsc_round_minprop_kernel<<<g2, 256, 0, st>>>(reg, (unsigned*)rk, (unsigned*)ra, w, h, d_flag);
+                lsc_round_begin_kernel<<<gr, 256, 0, st>>>(smallflag, done, size, threshold, R, merge_order, pend, (unsigned*)rk, (unsigned*)ra, best, d_flag);
+                lsc_round_minprop_kernel<<<ge, 256, 0, st>>>(edges, E, cur, (unsigned*)rk, (unsigned*)ra, d_flag);
                 lsc_round_copy_kernel<<<gr, 256, 0, st>>>((unsigned*)ra, (unsigned*)rb, R, d_flag);
-                lsc_round_minprop_kernel<<<g2, 256, 0, st>>>(reg, (unsigned*)ra, (unsigned*)rb, w, h, d_flag);
-                lsc_round_best_kernel<<<g2, 256, 0, st>>>(reg, pend, (unsigned*)rb, cen, D, merge_order, best, w, h, d_flag);
-                lsc_round_merge_kernel<<<gr, 256, 0, st>>>(pend, (unsigned*)rb, best, D, R, merge_order, cen, Wr, size, alive, done, target, d_flag);
+                lsc_round_minprop_kernel<<<ge, 256, 0, st>>>(edges, E, cur, (unsigned*)ra, (unsigned*)rb, d_flag);
+                lsc_round_best_kernel<<<ge, 256, 0, st>>>(edges, E, cur, pend, (unsigned*)rb, cen, D, merge_order, best, d_flag);
+                lsc_round_merge_kernel<<<gr, 256, 0, st>>>(pend, (unsigned*)rb, best, D, R, merge_order, cen, Wr, size, alive, done, cur, d_flag);
+                lsc_round_compress_kernel<<<gr, 256, 0, st>>>(cur, R);
                 launches += 7;
                 rounds++;
             }
@@ -771,9 +820,9 @@ struct LscEngine {
             LSC_TRYCUDA(cudaStreamSynchronize(st));
             if (!h_pinned[0]) break;
         }
-        if (getenv("SPX_LSC_DEBUG")) fprintf(stderr, "[lsc] post-pass: %d regions, threshold %d, %d merge rounds, launches %lld\n", R, threshold, rounds, launches);
+        if (getenv("SPX_LSC_DEBUG")) fprintf(stderr, "[lsc] post-pass: %d regions, %d adjacency edges (%llu raw), threshold %d, %d merge rounds, launches %lld\n", R, E, h_ec, threshold, rounds, launches);
         LSC_TRY(exclusive_sum(alive, newid, R + 1));
-        lsc_post_relabel_kernel<<<g1, 256, 0, st>>>(reg, newid, d_labels, n);
+        lsc_post_relabel_kernel<<<g1, 256, 0, st>>>(reg, cur, newid, d_labels, n);
         launches++;
         LSC_TRYCUDA(cudaMemcpyAsync(h_pinned, newid + R, sizeof(int), cudaMemcpyDeviceToHost, st));
         LSC_TRYCUDA(cudaStreamSynchronize(st));
@@ -842,7 +891,7 @@ extern "C" int spx_lsc_get_label_contour_mask(spx_lsc_t* h, uint8_t* dst, size_t
 {
     LSC_ENTER(h);
     SPX_REQUIRE(dst && dst_stride >= (size_t)e->L.w, SPX_ERR_BADARG, "getLabelContourMask: bad destination");
-    SPX_CHECK(e->post.alloc(e->L.w, e->L.h));
+    SPX_CHECK(e->post.alloc(e->L.w, e->L.h, e->st));
     long long l0 = e->post.launches;
     SPX_CHECK(spx::contour_mask_dev(e->post, e->d_labels, e->L.w, thick_line, 0, e->d_mask, e->L.w, e->st));
     e->launches += e->post.launches - l0;

@@ -21,26 +21,27 @@ namespace spx {
 // ------------------------------------------------------------------------------------------------
 // workspace
 // ------------------------------------------------------------------------------------------------
-int PostWorkspace::alloc(int w_, int h_)
+int PostWorkspace::alloc(int w_, int h_, cudaStream_t st)
 {
     if (w_ == w && h_ == h && parent) return SPX_OK;
     release();
+    st_alloc = st;
     w = w_; h = h_;
     size_t N = (size_t)w * h;
-    SPX_CUDA(cudaMalloc(&parent, N * sizeof(int)));
-    SPX_CUDA(cudaMalloc(&csize, N * sizeof(int)));
-    SPX_CUDA(cudaMalloc(&newid, N * sizeof(int)));
-    SPX_CUDA(cudaMalloc(&link, N * sizeof(int)));
-    SPX_CUDA(cudaMalloc(&blocksum, (N / 1024 + 2) * sizeof(int)));
-    SPX_CUDA(cudaMalloc(&flag, 8 * sizeof(int)));
-    SPX_CUDA(cudaMalloc(&diff, N));
+    SPX_CHECK(pool_alloc((void**)&parent, N * sizeof(int), st));
+    SPX_CHECK(pool_alloc((void**)&csize, N * sizeof(int), st));
+    SPX_CHECK(pool_alloc((void**)&newid, N * sizeof(int), st));
+    SPX_CHECK(pool_alloc((void**)&link, N * sizeof(int), st));
+    SPX_CHECK(pool_alloc((void**)&blocksum, (N / 1024 + 2) * sizeof(int), st));
+    SPX_CHECK(pool_alloc((void**)&flag, 8 * sizeof(int), st));
+    SPX_CHECK(pool_alloc((void**)&diff, N, st));
     SPX_CUDA(cudaMallocHost(&h_flag, 8 * sizeof(int)));
     return SPX_OK;
 }
 void PostWorkspace::release()
 {
-    cudaFree(parent); cudaFree(csize); cudaFree(newid); cudaFree(link); cudaFree(blocksum); cudaFree(flag);
-    cudaFree(diff);
+    pool_free(parent, st_alloc); pool_free(csize, st_alloc); pool_free(newid, st_alloc); pool_free(link, st_alloc);
+    pool_free(blocksum, st_alloc); pool_free(flag, st_alloc); pool_free(diff, st_alloc);
     if (h_flag) cudaFreeHost(h_flag);
     parent = csize = newid = link = blocksum = flag = nullptr;
     diff = nullptr; h_flag = nullptr;
@@ -68,14 +69,20 @@ __device__ __forceinline__ void uf_unite(int* P, int a, int b)
     } while (!done);
 }
 
-// parent[i] = i-1 when the left neighbour has the same label (rows become chains), else i
+// parent[i] = first pixel of the horizontal run of equal labels that holds i (found with one ballot per warp; a run that
+// began in an earlier warp chains through the pixel left of the warp's first lane), so finds start one or two hops
+// from a run head instead of walking the run
 __global__ void ccl_init_kernel(const int* __restrict__ lab, int lp, int w, int h, int* __restrict__ P)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= w) return;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const int lane = threadIdx.x & 31;
     const int* row = lab + (size_t)y * lp;
-    int i = y * w + x;
-    P[i] = (x > 0 && row[x - 1] == row[x]) ? i - 1 : i;
+    const bool in = x < w;
+    const bool start = !in || x == 0 || row[x - 1] != row[x];
+    const unsigned heads = __ballot_sync(0xffffffffu, start) & (0xffffffffu >> (31 - lane));
+    if (!in) return;
+    const int i = y * w + x;
+    P[i] = heads ? i - (lane - (31 - __clz(heads))) : i - lane - 1;
 }
 // vertical unions; skipped when the left neighbour already carries the same union
 __global__ void ccl_merge_kernel(const int* __restrict__ lab, int lp, int w, int h, int* __restrict__ P)

@@ -331,7 +331,7 @@ struct SeedsEngine {
 
     template <typename T> int dalloc(T** p, size_t n)
     {
-        SPX_CUDA(cudaMalloc((void**)p, n * sizeof(T) > 0 ? n * sizeof(T) : 4));
+        SPX_CHECK(pool_alloc((void**)p, n * sizeof(T), st));
         allocs.push_back((void*)*p);
         return SPX_OK;
     }
@@ -340,7 +340,7 @@ struct SeedsEngine {
         cudaSetDevice(device);
         if (st) cudaStreamSynchronize(st);
         for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
-        for (void* p : allocs) cudaFree(p);
+        for (void* p : allocs) pool_free(p, st);
         post.release();
         if (st) cudaStreamDestroy(st);
     }
@@ -555,7 +555,7 @@ extern "C" int spx_seeds_get_label_contour_mask(spx_seeds_t* h, uint8_t* dst, si
 {
     SEEDS_ENTER(h);
     SPX_REQUIRE(dst && dst_stride >= (size_t)e->S.w, SPX_ERR_BADARG, "getLabelContourMask: bad destination");
-    SPX_CHECK(e->post.alloc(e->S.w, e->S.h));
+    SPX_CHECK(e->post.alloc(e->S.w, e->S.h, e->st));
     long long l0 = e->post.launches;
     SPX_CHECK(spx::contour_mask_dev(e->post, e->S.labels, e->S.w, thick_line, 1, e->d_mask, e->S.w, e->st));
     e->launches += e->post.launches - l0;

@@ -378,7 +378,7 @@ struct SlicEngine {
 
     template <typename T> int dalloc(T** p, size_t n)
     {
-        SPX_CUDA(cudaMalloc((void**)p, n * sizeof(T) > 0 ? n * sizeof(T) : 4));
+        SPX_CHECK(pool_alloc((void**)p, n * sizeof(T), st));
         allocs.push_back((void*)*p);
         return SPX_OK;
     }
@@ -387,7 +387,7 @@ struct SlicEngine {
         cudaSetDevice(device);
         if (st) cudaStreamSynchronize(st);
         for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
-        for (void* p : allocs) cudaFree(p);
+        for (void* p : allocs) pool_free(p, st);
         post.release();
         if (h_pinned) cudaFreeHost(h_pinned);
         if (own_stream && st) cudaStreamDestroy(st);
@@ -579,7 +579,7 @@ struct SlicEngine {
     {
         void* fl = nullptr;
         const size_t flbytes = 256u << 20;
-        if (flush) SPX_CUDA(cudaMalloc(&fl, flbytes));
+        if (flush) SPX_CHECK(pool_alloc(&fl, flbytes, st));
         cudaEvent_t e0, e1;
         SPX_CUDA(cudaEventCreate(&e0)); SPX_CUDA(cudaEventCreate(&e1));
         double tot = 0;
@@ -599,7 +599,7 @@ struct SlicEngine {
         cudaMemsetAsync(a.acc, 0, (size_t)g.Kcap * (g.C + 3) * sizeof(unsigned long long), st);
         cudaStreamSynchronize(st);
         cudaEventDestroy(e0); cudaEventDestroy(e1);
-        if (fl) cudaFree(fl);
+        if (fl) pool_free(fl, st);
         *avg_ms = (float)(tot / (reps > 0 ? reps : 1));
         return rc;
     }
@@ -645,7 +645,7 @@ struct SlicEngine {
 
     int ensure_post()
     {
-        return post.alloc(g.w, g.h);
+        return post.alloc(g.w, g.h, st);
     }
     int enforce(int min_element_size)
     {
