@@ -330,11 +330,13 @@ def run_ours(args):
                 if r >= 3:
                     times.append(a0.elapsed_time(a1))
         it_ms = float(np.median(times))
-        # the dominant kernel alone: CUDA events around single launches on the object's stream (state after 10
-        # iterations = steady state), L2 flushed before every launch and, for comparison, L2-warm
-        kms = C.c_float(0); kms_warm = C.c_float(0)
-        assert L.spx_slic_time_assign(h, 20, 1, C.byref(kms)) == 0, L.spx_last_error()
-        assert L.spx_slic_time_assign(h, 20, 0, C.byref(kms_warm)) == 0, L.spx_last_error()
+        # the dominant kernel alone: CUDA events around every assignment launch of iterate(10) run launch by launch on the
+        # object's stream (from the seeds, 3 runs + 1 warm-up), L2 flushed with a 256 MB memset before every launch and,
+        # for comparison, L2-warm; kernel_ms = mean over the 10 launches
+        arr = (C.c_float * ITERS)(); arr_warm = (C.c_float * ITERS)()
+        assert L.spx_slic_time_iterations(h, ITERS, 3, 1, arr) == 0, L.spx_last_error()
+        assert L.spx_slic_time_iterations(h, ITERS, 3, 0, arr_warm) == 0, L.spx_last_error()
+        kms = C.c_float(float(np.mean(list(arr)))); kms_warm = C.c_float(float(np.mean(list(arr_warm))))
         L.spx_slic_destroy(h)
         alg_bytes = 7.0 * npx                      # per assignment launch: 3 B Lab read + 4 B label write per pixel
         achieved = alg_bytes / (kms.value * 1e-3) / 1e9
@@ -342,6 +344,7 @@ def run_ours(args):
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (ncu_traffic() or {}).get("bytes"), "traffic_source": (ncu_traffic() or {}).get("source"),
                 "peak_source": peak_src, "kernel_ms": kms.value, "kernel_ms_l2_warm": kms_warm.value,
+                "kernel_ms_per_launch": [round(float(v), 5) for v in arr],
                 "iterate10_ms_one_frame": it_ms, "assign_share_of_iterate": ITERS * kms_warm.value / it_ms,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "batch_frac": (7.0 * ITERS * npx) * (value * 1e6 / npx) / 1e9 / peak}

@@ -92,6 +92,10 @@ int spx_slic_launch_count(spx_slic_t*, long long* out);
  * assignment + accumulation pass) over `reps` launches at the object's current state, timed with CUDA events on the
  * object's stream; when flush_l2 != 0 a 256 MB buffer is overwritten before every launch.  State is left unchanged. */
 int spx_slic_time_assign(spx_slic_t*, int reps, int flush_l2, float* avg_ms);
+/* measurement hook (bench.py roofline): re-seeds the object and runs iterate(iters) launch by launch (no graph), every
+ * assignment launch between its own pair of CUDA events on the object's stream; assign_ms[i] = duration of the i-th
+ * assignment launch averaged over `reps` runs (one extra warm-up run first).  Leaves the state iterate(iters) gives. */
+int spx_slic_time_iterations(spx_slic_t*, int iters, int reps, int flush_l2, float* assign_ms);
 /* cv::Ptr<SuperpixelSLIC> release (the GUI overwrites `slic` on every COMPUTE, mainwindow.cpp:2105) */
 int spx_slic_destroy(spx_slic_t*);
 

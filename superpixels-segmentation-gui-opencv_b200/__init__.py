@@ -73,6 +73,7 @@ def lib():
         "spx_slic_synchronize": [vp],
         "spx_slic_launch_count": [vp, C.POINTER(C.c_longlong)],
         "spx_slic_time_assign": [vp, i32, i32, C.POINTER(C.c_float)],
+        "spx_slic_time_iterations": [vp, i32, i32, i32, C.POINTER(C.c_float)],
         "spx_slic_destroy": [vp],
         "spx_slic_batch_dev": [pp, i32, i32, i32, i32, i32, i32, f32, i32, i32, pp, pp, i32, i32, C.POINTER(C.c_longlong)],
         "spx_slic_batch_release": [],

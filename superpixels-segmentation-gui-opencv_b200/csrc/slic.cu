@@ -527,40 +527,47 @@ struct SlicEngine {
         return SPX_OK;
     }
 
-    int enqueue_iterations(int n)
+    // one iteration: assignment (+ events around it when asked) and the centre update
+    int enqueue_iteration(cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr)
     {
         const int threads_fin = max(max(g.Kcap, g.nbx * g.nby), g.tiles_x * g.tiles_y);
+        if (e0) SPX_CUDA(cudaEventRecord(e0, st));
+        if (use_tile) {
+            SPX_CHECK(slic_tile_assign(g, a, d_img, d_img4, d_labels, d_dcplane, d_K, parity, d_overflow, st));
+        } else {
+            dim3 grid(cdiv(g.w, 32), cdiv(g.h, 8));
+            if (g.alg == SPX_SLIC) slic_assign_generic_kernel<100><<<grid, 256, 0, st>>>(g, a, d_img, d_labels, d_dcplane, parity, 0, 0, g.w, g.h);
+            else if (g.alg == SPX_SLICO) slic_assign_generic_kernel<101><<<grid, 256, 0, st>>>(g, a, d_img, d_labels, d_dcplane, parity, 0, 0, g.w, g.h);
+            else slic_assign_generic_kernel<102><<<grid, 256, 0, st>>>(g, a, d_img, d_labels, d_dcplane, parity, 0, 0, g.w, g.h);
+        }
+        launches++;
+        if (e1) SPX_CUDA(cudaEventRecord(e1, st));
+        const int do_bin = g.alg == SPX_MSLIC ? 0 : 1;
+        slic_finalize_kernel<<<cdiv(threads_fin, BIN_CTA), BIN_CTA, 0, st>>>(g, a, d_K, parity, do_bin);
+        launches++;
+        if (g.alg == SPX_MSLIC) {
+            float q = (float)g.S / ruler;
+            mslic_area_kernel<<<dim3(cdiv(g.w, 32), cdiv(g.h, 8)), 256, 0, st>>>(g, a, d_img, d_labels, q);
+            mslic_adapt_kernel<<<1, 1024, 0, st>>>(g, a, d_img, d_K, K0);
+            slic_bin_kernel<<<cdiv(g.Kcap, BIN_CTA), BIN_CTA, 0, st>>>(g, a, d_K, parity ^ 1);
+            launches += 3;
+        }
+        parity ^= 1;
+        return SPX_OK;
+    }
+    int enqueue_begin()
+    {
         if (g.alg == SPX_SLICO) {
             size_t np = (size_t)g.lp * g.tiles_y * TILE_H;       // the plane has the label pitch
             slico_begin_kernel<<<(unsigned)((max(np, (size_t)g.K) + 255) / 256), 256, 0, st>>>(g, a, d_dcplane, np);
             launches++;
         }
-        for (int it = 0; it < n; it++) {
-            bool tiled = false;
-            if (use_tile) {
-                SPX_CHECK(slic_tile_assign(g, a, d_img, d_img4, d_labels, d_dcplane, d_K, parity, d_overflow, st));
-                tiled = true;
-                launches++;
-            }
-            if (!tiled) {
-                dim3 grid(cdiv(g.w, 32), cdiv(g.h, 8));
-                if (g.alg == SPX_SLIC) slic_assign_generic_kernel<100><<<grid, 256, 0, st>>>(g, a, d_img, d_labels, d_dcplane, parity, 0, 0, g.w, g.h);
-                else if (g.alg == SPX_SLICO) slic_assign_generic_kernel<101><<<grid, 256, 0, st>>>(g, a, d_img, d_labels, d_dcplane, parity, 0, 0, g.w, g.h);
-                else slic_assign_generic_kernel<102><<<grid, 256, 0, st>>>(g, a, d_img, d_labels, d_dcplane, parity, 0, 0, g.w, g.h);
-                launches++;
-            }
-            const int do_bin = g.alg == SPX_MSLIC ? 0 : 1;
-            slic_finalize_kernel<<<cdiv(threads_fin, BIN_CTA), BIN_CTA, 0, st>>>(g, a, d_K, parity, do_bin);
-            launches++;
-            if (g.alg == SPX_MSLIC) {
-                float q = (float)g.S / ruler;
-                mslic_area_kernel<<<dim3(cdiv(g.w, 32), cdiv(g.h, 8)), 256, 0, st>>>(g, a, d_img, d_labels, q);
-                mslic_adapt_kernel<<<1, 1024, 0, st>>>(g, a, d_img, d_K, K0);
-                slic_bin_kernel<<<cdiv(g.Kcap, BIN_CTA), BIN_CTA, 0, st>>>(g, a, d_K, parity ^ 1);
-                launches += 3;
-            }
-            parity ^= 1;
-        }
+        return SPX_OK;
+    }
+    int enqueue_iterations(int n)
+    {
+        SPX_CHECK(enqueue_begin());
+        for (int it = 0; it < n; it++) SPX_CHECK(enqueue_iteration());
         SPX_CUDA(cudaGetLastError());
         return SPX_OK;
     }
@@ -601,6 +608,43 @@ struct SlicEngine {
         cudaEventDestroy(e0); cudaEventDestroy(e1);
         if (fl) pool_free(fl, st);
         *avg_ms = (float)(tot / (reps > 0 ? reps : 1));
+        return rc;
+    }
+    // The assignment launches of a whole iterate(iters) from the seeds, each between its own pair of events on the
+    // object's stream (no graph): ms[i] = duration of the i-th assignment launch averaged over `reps` runs -- what
+    // bench.py's roofline is quoted on.  Leaves the object in the state iterate(iters) on a fresh object gives.
+    int time_iterations(int iters, int reps, int flush, float* ms)
+    {
+        void* fl = nullptr;
+        const size_t flbytes = 256u << 20;
+        if (flush) SPX_CHECK(pool_alloc(&fl, flbytes, st));
+        std::vector<cudaEvent_t> ev(2 * (size_t)iters);
+        for (auto& e : ev) SPX_CUDA(cudaEventCreate(&e));
+        std::vector<double> tot((size_t)iters, 0.0);
+        int rc = SPX_OK;
+        for (int r = 0; r < reps + 1 && rc == SPX_OK; r++) {      // run 0 is a warm-up
+            rc = seed();
+            if (rc == SPX_OK) rc = enqueue_begin();
+            for (int it = 0; it < iters && rc == SPX_OK; it++) {
+                if (fl) cudaMemsetAsync(fl, r + it, flbytes, st);
+                rc = enqueue_iteration(ev[2 * it], ev[2 * it + 1]);
+            }
+            if (rc == SPX_OK && cudaStreamSynchronize(st) != cudaSuccess) { set_error("time_iterations: kernel failed"); rc = SPX_ERR_GPU; }
+            for (int it = 0; it < iters && rc == SPX_OK && r > 0; it++) {
+                float t = 0;
+                cudaEventElapsedTime(&t, ev[2 * it], ev[2 * it + 1]);
+                tot[it] += t;
+            }
+        }
+        for (auto& e : ev) cudaEventDestroy(e);
+        if (fl) pool_free(fl, st);
+        for (int it = 0; it < iters; it++) ms[it] = (float)(tot[it] / (reps > 0 ? reps : 1));
+        if (rc == SPX_OK && g.alg == SPX_MSLIC) {
+            SPX_CUDA(cudaMemcpyAsync(h_pinned, d_K, sizeof(int), cudaMemcpyDeviceToHost, st));
+            SPX_CUDA(cudaStreamSynchronize(st));
+            g.K = h_pinned[0];
+        }
+        numlabels = g.K;
         return rc;
     }
 
@@ -895,6 +939,13 @@ extern "C" int spx_slic_time_assign(spx_slic_t* h, int reps, int flush_l2, float
     SLIC_ENTER(h);
     SPX_REQUIRE(avg_ms && reps >= 1, SPX_ERR_BADARG, "time_assign: bad argument");
     return e->time_assign(reps, flush_l2, avg_ms);
+}
+extern "C" int spx_slic_time_iterations(spx_slic_t* h, int iters, int reps, int flush_l2, float* assign_ms)
+{
+    SLIC_ENTER(h);
+    SPX_REQUIRE(assign_ms && reps >= 1 && iters >= 1, SPX_ERR_BADARG, "time_iterations: bad argument");
+    SPX_REQUIRE(e->g.ty_lo == 0 && e->g.ty_hi == e->g.tiles_y, SPX_ERR_BADARG, "time_iterations: not for strip objects");
+    return e->time_iterations(iters, reps, flush_l2, assign_ms);
 }
 extern "C" int spx_slic_destroy(spx_slic_t* h)
 {

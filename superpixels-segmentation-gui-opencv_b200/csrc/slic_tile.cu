@@ -1,4 +1,4 @@
-// slic_tile.cu -- tiled fast path of the SLIC assignment + centre accumulation (3-channel, SLIC=100).   [v5]
+// slic_tile.cu -- tiled fast path of the SLIC assignment + centre accumulation (3-channel, SLIC / SLICO / MSLIC).   [v6]
 //
 // One CTA (128 threads) owns a 32x32 pixel tile of the "Lab1" image (one 32-bit word per pixel: c0,c1,c2,1; rows and
 // columns padded to the tile grid with zero words, so no load or store in the hot loop needs a bounds check).
@@ -80,7 +80,7 @@ __device__ __forceinline__ u64 bcast2(float v) { return pack2(v, v); }   // ptxa
 // ---- shared memory layout -----------------------------------------------------------------------
 // one record per candidate, so that a single multiply addresses everything the inner loop reads
 struct __align__(16) CandRec {
-    float4 k;                    // (-k0, -k1, -k2, n as int bits)
+    float4 k;                    // (-k0, -k1, -k2, key = (n << 6) | slot as int bits)
     float4 m;                    // SLICO: (maxchans[n], RN(1/maxchans[n]), -maxchans[n], -); MSLIC: the same for adaptk[n]
     float ex2[TW];               // (x-kx)^2 [times 1/xywt when it is a power of two], +inf outside the window
     float ey2[TH];               // (y-ky)^2 likewise
@@ -90,6 +90,10 @@ struct SlicoSmem {               // SLICO only
     unsigned mx[NCOPY][CAP];     // per candidate: running maximum of dcm over its pixels (float bits; values are >= 0)
 };
 struct NoSmem {};
+// rec[].k.w carries key = (n << 6) | slot: the inner loop selects one register and both the label and the slot follow
+__device__ __forceinline__ int key_n(int key) { return key >> 6; }
+__device__ __forceinline__ int key_slot(int key) { return key & 63; }
+static_assert(CAP <= 64, "slot must fit the 6 low bits of the key");
 template <int ALG>
 struct __align__(16) TileSmemT {
     CandRec rec[CAP];            // ascending n
@@ -121,7 +125,6 @@ __device__ __forceinline__ void acc_global_pixel(const TileArgs& t, int n, unsig
     atomicAdd(&t.acc[2 * (size_t)t.Kcap + n], (u64)((px >> 16) & 0xffu)); atomicAdd(&t.acc[3 * (size_t)t.Kcap + n], (u64)x);
     atomicAdd(&t.acc[4 * (size_t)t.Kcap + n], (u64)y); atomicAdd(&t.acc[5 * (size_t)t.Kcap + n], 1ull);
 }
-
 // exact per-pixel path for a tile whose candidate list overflowed (kept out of line: it is cold)
 template <int ALG>
 __device__ __noinline__ void tile_fallback(const SlicGeom& g, const SlicArrays& a, const unsigned char* img, int* labels, float* dcplane,
@@ -136,21 +139,23 @@ __device__ __noinline__ void tile_fallback(const SlicGeom& g, const SlicArrays& 
 // phase-1 cold path: some pixel of the warp's patch is covered by no window (or lies outside the image).
 // Everything is passed by value so that the hot loop's state never has to live in local memory.
 template <int ALG>
-__device__ __noinline__ void step_slow(const TileArgs& t, TileSmemT<ALG>& sm, int* labels, unsigned slots4, unsigned p00, unsigned p01,
-                                       unsigned p10, unsigned p11, float l00, float l01, float l10, float l11, int x, int y, int xo, int yo)
+__device__ __noinline__ void step_slow(const TileArgs& t, TileSmemT<ALG>& sm, int* labels, int k00, int k01, int k10, int k11,
+                                       unsigned p00, unsigned p01, unsigned p10, unsigned p11, float l00, float l01, float l10, float l11,
+                                       int x, int y, int xo, int yo)
 {
     const unsigned px[4] = {p00, p01, p10, p11};
     const float ldc[4] = {l00, l01, l10, l11};
+    const int keys[4] = {k00, k01, k10, k11};
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int r = i >> 1, k = i & 1;
         const int xx = x + k, yy = y + r;
-        const unsigned s = (slots4 >> (8 * i)) & 0xffu;         // 0xFF: no candidate
+        const int key = keys[i];                                // < 0: no candidate
         unsigned char sb = 0xFF;
         if (xx < t.w && yy < t.h) {
             const size_t li = (size_t)yy * t.lp + xx;
-            if (s != 0xffu) {
-                labels[li] = __float_as_int(sm.rec[s].k.w); sb = (unsigned char)s;
+            if (key >= 0) {
+                labels[li] = key_n(key); sb = (unsigned char)key_slot(key);
                 if constexpr (ALG == SPX_SLICO) { t.dcplane[li] = ldc[i]; sm.o.dcm[yo + r][xo + k] = ldc[i]; }
             } else {
                 const int n = labels[li];
@@ -211,7 +216,7 @@ __global__ void __launch_bounds__(NT, ALG == SPX_SLICO ? 6 : 8) slic_tile_kernel
         const int n = __float_as_int(r1.y);
         int rank = 0;
         for (int j = 0; j < cnt; j++) rank += sm.list[j] < n ? 1 : 0;
-        sm.rec[rank].k = make_float4(-r0.z, -r0.w, -r1.x, r1.y);
+        sm.rec[rank].k = make_float4(-r0.z, -r0.w, -r1.x, __int_as_float((n << 6) | rank));
         const int ix = __float_as_int(r1.z), iy = __float_as_int(r1.w);
         sm.win[rank] = make_int4(ix - woff, ix + woff, iy - woff, iy + woff);
         sm.kxy[rank][0] = r0.x; sm.kxy[rank][1] = r0.y;
@@ -300,7 +305,7 @@ __global__ void __launch_bounds__(NT, ALG == SPX_SLICO ? 6 : 8) slic_tile_kernel
             }
         }
         float best[2][2] = {{FLT_MAX, FLT_MAX}, {FLT_MAX, FLT_MAX}};
-        int slot[2][2] = {{-1, -1}, {-1, -1}};
+        int key[2][2] = {{-1, -1}, {-1, -1}};           // (n << 6) | slot of the best candidate so far
         float ldc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};     // SLICO: colour distance to the last cluster whose window holds the pixel
         const unsigned char* rec0 = reinterpret_cast<const unsigned char*>(&sm.rec[0]);
         const unsigned char* thr_ex = reinterpret_cast<const unsigned char*>(&sm.rec[0].ex2[xo]);
@@ -313,6 +318,7 @@ __global__ void __launch_bounds__(NT, ALG == SPX_SLICO ? 6 : 8) slic_tile_kernel
                 m &= m - 1;
                 const int ro = c * (int)sizeof(CandRec);
                 const float4 kc = *reinterpret_cast<const float4*>(rec0 + ro);
+                const int kw = __float_as_int(kc.w);
                 float4 km = make_float4(0.f, 0.f, 0.f, 0.f);
                 if constexpr (ALG != SPX_SLIC) km = *reinterpret_cast<const float4*>(rec0 + ro + 16);
                 const u64 exv = *reinterpret_cast<const u64*>(thr_ex + ro);
@@ -347,20 +353,19 @@ __global__ void __launch_bounds__(NT, ALG == SPX_SLICO ? 6 : 8) slic_tile_kernel
                     }
                     float d0, d1;
                     unpack2(d, d0, d1);
-                    if (d0 < best[r][0]) { best[r][0] = d0; slot[r][0] = c; }
-                    if (d1 < best[r][1]) { best[r][1] = d1; slot[r][1] = c; }
+                    if (d0 < best[r][0]) { best[r][0] = d0; key[r][0] = kw; }
+                    if (d1 < best[r][1]) { best[r][1] = d1; key[r][1] = kw; }
                 }
             }
         }
         // ---- labels + slot map.  Fast path: every pixel of the patch found a candidate and the tile is interior.
-        const int any_neg = slot[0][0] | slot[0][1] | slot[1][0] | slot[1][1];
+        const int any_neg = key[0][0] | key[0][1] | key[1][0] | key[1][1];
         if (interior && !__any_sync(0xffffffffu, any_neg < 0)) {
-            const int n00 = __float_as_int(sm.rec[slot[0][0]].k.w), n01 = __float_as_int(sm.rec[slot[0][1]].k.w);
-            const int n10 = __float_as_int(sm.rec[slot[1][0]].k.w), n11 = __float_as_int(sm.rec[slot[1][1]].k.w);
+            const int n00 = key_n(key[0][0]), n01 = key_n(key[0][1]), n10 = key_n(key[1][0]), n11 = key_n(key[1][1]);
             *reinterpret_cast<int2*>(lrow) = make_int2(n00, n01);
             *reinterpret_cast<int2*>(lrow + t.lp) = make_int2(n10, n11);
-            *reinterpret_cast<unsigned short*>(&sm.slot[yo][xo]) = (unsigned short)(slot[0][0] | (slot[0][1] << 8));
-            *reinterpret_cast<unsigned short*>(&sm.slot[yo + 1][xo]) = (unsigned short)(slot[1][0] | (slot[1][1] << 8));
+            *reinterpret_cast<unsigned short*>(&sm.slot[yo][xo]) = (unsigned short)(key_slot(key[0][0]) | (key_slot(key[0][1]) << 8));
+            *reinterpret_cast<unsigned short*>(&sm.slot[yo + 1][xo]) = (unsigned short)(key_slot(key[1][0]) | (key_slot(key[1][1]) << 8));
             if constexpr (ALG == SPX_SLICO) {
                 float* prow = t.dcplane + (lrow - labels);
                 *reinterpret_cast<float2*>(prow) = make_float2(ldc[0][0], ldc[0][1]);
@@ -369,13 +374,13 @@ __global__ void __launch_bounds__(NT, ALG == SPX_SLICO ? 6 : 8) slic_tile_kernel
                 *reinterpret_cast<float2*>(&sm.o.dcm[yo + 1][xo]) = make_float2(ldc[1][0], ldc[1][1]);
             }
         } else {
-            const unsigned s4 = (unsigned)(slot[0][0] & 0xff) | ((unsigned)(slot[0][1] & 0xff) << 8) |
-                                ((unsigned)(slot[1][0] & 0xff) << 16) | ((unsigned)(slot[1][1] & 0xff) << 24);
-            step_slow<ALG>(t, sm, labels, s4, px[0][0], px[0][1], px[1][0], px[1][1], ldc[0][0], ldc[0][1], ldc[1][0], ldc[1][1], x, y, xo, yo);
+            step_slow<ALG>(t, sm, labels, key[0][0], key[0][1], key[1][0], key[1][1], px[0][0], px[0][1], px[1][0], px[1][1],
+                                  ldc[0][0], ldc[0][1], ldc[1][0], ldc[1][1], x, y, xo, yo);
         }
         pimg += p4_16;
         lrow += 16 * t.lp;
     }
+
     // phase 2's pixels (L1 hits) are requested before the barrier
     uint4 pv2[2];
 #pragma unroll
@@ -443,38 +448,28 @@ __global__ void __launch_bounds__(NT, ALG == SPX_SLICO ? 6 : 8) slic_tile_kernel
     __syncthreads();
     // ---- flush: fold the copies, then one global atomic per field per candidate that received pixels
     for (int i = tid; i < cnt * 4; i += NT) {
-        unsigned v = 0;
-#pragma unroll
-        for (int p = 0; p < NCOPY; p++) v += sm.acc[p][i];
         const int c = i >> 2, f = i & 3;
-        const int n = __float_as_int(sm.rec[c].k.w);
+        unsigned v = 0, v0 = 0;
+#pragma unroll
+        for (int p = 0; p < NCOPY; p++) { v += sm.acc[p][i]; v0 += sm.acc[p][4 * c]; }
+        const unsigned count = v0 >> 18;
+        if (!count) continue;
+        const int n = key_n(__float_as_int(sm.rec[c].k.w));
         if (f == 0) {
-            const unsigned count = v >> 18;
-            if (count) {
-                atomicAdd(&t.acc[n], (u64)(v & 0x3ffffu));
-                atomicAdd(&t.acc[(size_t)5 * t.Kcap + n], (u64)count);
-                sm.list[c] = (int)count;
-            } else sm.list[c] = 0;
+            atomicAdd(&t.acc[n], (u64)(v & 0x3ffffu));
+            atomicAdd(&t.acc[(size_t)5 * t.Kcap + n], (u64)count);
+            if constexpr (ALG == SPX_SLICO) {
+                unsigned mxb = 0;
+#pragma unroll
+                for (int p = 0; p < NCOPY; p++) mxb = max(mxb, sm.o.mx[p][c]);
+                atomicMax(&t.maxc_acc[n], mxb);
+            }
         } else if (f < 3) {
             if (v) atomicAdd(&t.acc[(size_t)f * t.Kcap + n], (u64)v);
+        } else {
+            atomicAdd(&t.acc[(size_t)3 * t.Kcap + n], (u64)(v & 0xffffu) + (u64)count * (u64)tx0);
+            atomicAdd(&t.acc[(size_t)4 * t.Kcap + n], (u64)(v >> 16) + (u64)count * (u64)ty0);
         }
-    }
-    __syncthreads();
-    for (int c = tid; c < cnt; c += NT) {
-        const unsigned count = (unsigned)sm.list[c];
-        if (!count) continue;
-        if constexpr (ALG == SPX_SLICO) {
-            unsigned mxb = 0;
-#pragma unroll
-            for (int p = 0; p < NCOPY; p++) mxb = max(mxb, sm.o.mx[p][c]);
-            atomicMax(&t.maxc_acc[__float_as_int(sm.rec[c].k.w)], mxb);
-        }
-        unsigned v = 0;
-#pragma unroll
-        for (int p = 0; p < NCOPY; p++) v += sm.acc[p][4 * c + 3];
-        const int n = __float_as_int(sm.rec[c].k.w);
-        atomicAdd(&t.acc[(size_t)3 * t.Kcap + n], (u64)(v & 0xffffu) + (u64)count * (u64)tx0);
-        atomicAdd(&t.acc[(size_t)4 * t.Kcap + n], (u64)(v >> 16) + (u64)count * (u64)ty0);
     }
 }
 

@@ -18,6 +18,11 @@ for flush in (1, 0):
     ms = C.c_float(0)
     assert L.spx_slic_time_assign(s._h, 20, flush, C.byref(ms)) == 0
     print("assign kernel: %.2f us (%s)" % (ms.value * 1e3, "L2 flushed" if flush else "L2 warm"))
+for flush in (1, 0):
+    arr = (C.c_float * 10)()
+    assert L.spx_slic_time_iterations(s._h, 10, 5, flush, arr) == 0, L.spx_last_error()
+    v = [x * 1e3 for x in arr]
+    print("assign launches of iterate(10), us (%s): %s  mean %.2f" % ("L2 flushed" if flush else "L2 warm", " ".join("%.1f" % x for x in v), sum(v) / 10))
 best = 1e9
 for r in range(5):
     s.reset(lab)
