@@ -25,7 +25,7 @@ namespace spx {
 bool slic_tile_supported(const SlicGeom& g);
 int slic_tile_prepare(const SlicGeom& g, const unsigned char* d_img, unsigned* d_img4, cudaStream_t st);
 int slic_tile_assign(const SlicGeom& g, const SlicArrays& a, const unsigned char* d_img, const unsigned* d_img4, int* d_labels,
-                     float* d_dcplane, const int* d_K, int parity, int* d_overflow, cudaStream_t st);
+                     float* d_dcplane, const float* d_area_px, const int* d_K, int parity, int* d_overflow, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------
 // device helpers
@@ -246,33 +246,46 @@ __device__ __forceinline__ float tri_area5(const float* a, const float* b, const
     if (gg < 0.f) gg = 0.f;
     return __fmul_rn(0.5f, __fsqrt_rn(gg));
 }
-__global__ void __launch_bounds__(256) mslic_area_kernel(SlicGeom g, SlicArrays a, const unsigned char* __restrict__ img,
-                                                          const int* __restrict__ labels, float q)
+// The manifold area of the pixel quad at (x, y) depends on the image only: it is computed once per image into a float
+// plane (label pitch) ...
+__global__ void __launch_bounds__(256) mslic_area_px_kernel(SlicGeom g, const unsigned char* __restrict__ img, float* __restrict__ plane, float q)
+{
+    int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= g.w - 1 || y >= g.h - 1) return;
+    float P[4][5];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int xx = x + (j & 1), yy = y + (j >> 1);
+        P[j][0] = (float)xx; P[j][1] = (float)yy;
+        const unsigned char* p = img + (size_t)yy * g.ipitch + (size_t)xx * g.C;
+#pragma unroll
+        for (int c = 0; c < 3; c++) P[j][2 + c] = c < g.C ? __fmul_rn(q, (float)p[c]) : 0.f;
+    }
+    plane[(size_t)y * g.lp + x] = __fadd_rn(tri_area5(P[0], P[1], P[2]), tri_area5(P[3], P[1], P[2]));
+}
+// ... and every iteration only sums the plane per label (fixed point x256, exact 64-bit integer sums)
+__global__ void __launch_bounds__(256) mslic_area_sum_kernel(SlicGeom g, SlicArrays a, const float* __restrict__ plane,
+                                                              const int* __restrict__ labels)
 {
     int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
     bool inside = x < g.w - 1 && y < g.h - 1;
     long long fx = 0;
     int label = -1;
     if (inside) {
-        float P[4][5];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            int xx = x + (j & 1), yy = y + (j >> 1);
-            P[j][0] = (float)xx; P[j][1] = (float)yy;
-            const unsigned char* p = img + (size_t)yy * g.ipitch + (size_t)xx * g.C;
-#pragma unroll
-            for (int c = 0; c < 3; c++) P[j][2 + c] = c < g.C ? __fmul_rn(q, (float)p[c]) : 0.f;
-        }
-        float ar = __fadd_rn(tri_area5(P[0], P[1], P[2]), tri_area5(P[3], P[1], P[2]));
-        fx = (long long)__fmul_rn(ar, 256.0f);
+        fx = (long long)__fmul_rn(plane[(size_t)y * g.lp + x], 256.0f);
         label = labels[(size_t)y * g.lp + x];
     }
+    // warp sum per label: the lanes of a row mostly share one label, so one ballot against lane 0's label settles the
+    // common case; the 64-bit sum goes through three 32-bit REDUX (21-bit limbs: 32 lanes x 2^21 < 2^32)
     int key = inside ? label : -1 - (int)(threadIdx.x & 31);
-    unsigned m = __match_any_sync(0xffffffffu, key);
-    // 64-bit warp sum over the match group
-    long long s = 0;
-    for (unsigned rem = m; rem; rem &= rem - 1) s += __shfl_sync(m, fx, __ffs(rem) - 1);
-    if (inside && (int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd((unsigned long long*)&a.area[label], (unsigned long long)s);
+    const int key0 = __shfl_sync(0xffffffffu, key, 0);
+    unsigned m = __ballot_sync(0xffffffffu, key == key0);
+    if (m != 0xffffffffu) m = __match_any_sync(0xffffffffu, key);
+    const unsigned long long u = (unsigned long long)fx;                 // areas are >= 0 and < 2^63
+    const unsigned l0 = (unsigned)(u & 0x1fffffu), l1 = (unsigned)((u >> 21) & 0x1fffffu), l2 = (unsigned)(u >> 42);
+    const unsigned s0 = __reduce_add_sync(m, l0), s1 = __reduce_add_sync(m, l1), s2 = __reduce_add_sync(m, l2);
+    if (inside && (int)(threadIdx.x & 31) == __ffs(m) - 1)
+        atomicAdd((unsigned long long*)&a.area[label], (unsigned long long)s0 + ((unsigned long long)s1 << 21) + ((unsigned long long)s2 << 42));
 }
 // single CTA: mean area, adaptk, split list (ascending k), append new centres, window half-sizes
 __global__ void __launch_bounds__(1024) mslic_adapt_kernel(SlicGeom g, SlicArrays a, const unsigned char* __restrict__ img,
@@ -362,6 +375,7 @@ struct SlicEngine {
     unsigned* d_img4 = nullptr;      // tiled path: padded Lab1 words (c0,c1,c2,1)
     int* d_labels = nullptr;
     float* d_dcplane = nullptr;      // SLICO only
+    float* d_area_px = nullptr;      // MSLIC only: manifold area of every pixel quad (label pitch)
     unsigned char* d_mask = nullptr;
     int* d_K = nullptr;
     int* d_overflow = nullptr;
@@ -455,6 +469,10 @@ struct SlicEngine {
         SPX_CHECK(dalloc(&a.area, kc));
         SPX_CHECK(dalloc(&d_K, 4)); SPX_CHECK(dalloc(&d_overflow, 4));
         if (alg == SPX_SLICO) SPX_CHECK(dalloc(&d_dcplane, (size_t)g.lp * g.tiles_y * TILE_H));
+        if (alg == SPX_MSLIC) {
+            SPX_CHECK(dalloc(&d_area_px, (size_t)g.lp * g.tiles_y * TILE_H));
+            SPX_CUDA(cudaMemsetAsync(d_area_px, 0, (size_t)g.lp * g.tiles_y * TILE_H * sizeof(float), st));   // last row / column and padding stay 0
+        }
         SPX_CUDA(cudaMallocHost(&h_pinned, 4 * sizeof(int)));
         SPX_CUDA(cudaMemsetAsync(d_img, 0, g.ipitch * (size_t)(h + 1), st));
         use_tile = slic_tile_supported(g) && !getenv("SPX_SLIC_GENERIC");
@@ -491,6 +509,10 @@ struct SlicEngine {
         int K = 0;
         SeedParams sp = seed_params(&K);
         if (use_tile) { SPX_CHECK(slic_tile_prepare(g, d_img, d_img4, st)); launches++; }
+        if (g.alg == SPX_MSLIC) {
+            mslic_area_px_kernel<<<dim3(cdiv(g.w, 32), cdiv(g.h, 8)), 256, 0, st>>>(g, d_img, d_area_px, (float)g.S / ruler);
+            launches++;
+        }
         slic_seed_kernel<<<cdiv(K0, 128), 128, 0, st>>>(g, a, d_img, sp);
         slic_bin_kernel<<<cdiv(K0, BIN_CTA), BIN_CTA, 0, st>>>(g, a, d_K, 0);
         launches += 2;
@@ -533,7 +555,7 @@ struct SlicEngine {
         const int threads_fin = max(max(g.Kcap, g.nbx * g.nby), g.tiles_x * g.tiles_y);
         if (e0) SPX_CUDA(cudaEventRecord(e0, st));
         if (use_tile) {
-            SPX_CHECK(slic_tile_assign(g, a, d_img, d_img4, d_labels, d_dcplane, d_K, parity, d_overflow, st));
+            SPX_CHECK(slic_tile_assign(g, a, d_img, d_img4, d_labels, d_dcplane, d_area_px, d_K, parity, d_overflow, st));
         } else {
             dim3 grid(cdiv(g.w, 32), cdiv(g.h, 8));
             if (g.alg == SPX_SLIC) slic_assign_generic_kernel<100><<<grid, 256, 0, st>>>(g, a, d_img, d_labels, d_dcplane, parity, 0, 0, g.w, g.h);
@@ -546,11 +568,11 @@ struct SlicEngine {
         slic_finalize_kernel<<<cdiv(threads_fin, BIN_CTA), BIN_CTA, 0, st>>>(g, a, d_K, parity, do_bin);
         launches++;
         if (g.alg == SPX_MSLIC) {
-            float q = (float)g.S / ruler;
-            mslic_area_kernel<<<dim3(cdiv(g.w, 32), cdiv(g.h, 8)), 256, 0, st>>>(g, a, d_img, d_labels, q);
+            // the tiled assignment kernel already summed the manifold areas per cluster; the generic path does it here
+            if (!use_tile) { mslic_area_sum_kernel<<<dim3(cdiv(g.w, 32), cdiv(g.h, 8)), 256, 0, st>>>(g, a, d_area_px, d_labels); launches++; }
             mslic_adapt_kernel<<<1, 1024, 0, st>>>(g, a, d_img, d_K, K0);
             slic_bin_kernel<<<cdiv(g.Kcap, BIN_CTA), BIN_CTA, 0, st>>>(g, a, d_K, parity ^ 1);
-            launches += 3;
+            launches += 2;
         }
         parity ^= 1;
         return SPX_OK;
@@ -574,7 +596,7 @@ struct SlicEngine {
 
     int enqueue_assign()
     {
-        if (use_tile) return slic_tile_assign(g, a, d_img, d_img4, d_labels, d_dcplane, d_K, parity, d_overflow, st);
+        if (use_tile) return slic_tile_assign(g, a, d_img, d_img4, d_labels, d_dcplane, d_area_px, d_K, parity, d_overflow, st);
         dim3 grid(cdiv(g.w, 32), cdiv(g.h, 8));
         if (g.alg == SPX_SLIC) slic_assign_generic_kernel<100><<<grid, 256, 0, st>>>(g, a, d_img, d_labels, d_dcplane, parity, 0, 0, g.w, g.h);
         else if (g.alg == SPX_SLICO) slic_assign_generic_kernel<101><<<grid, 256, 0, st>>>(g, a, d_img, d_labels, d_dcplane, parity, 0, 0, g.w, g.h);
@@ -604,6 +626,7 @@ struct SlicEngine {
         }
         // the accumulators were fed `reps+1` times: clear them (centres / labels are unchanged)
         cudaMemsetAsync(a.acc, 0, (size_t)g.Kcap * (g.C + 3) * sizeof(unsigned long long), st);
+        cudaMemsetAsync(a.area, 0, (size_t)g.Kcap * sizeof(long long), st);
         cudaStreamSynchronize(st);
         cudaEventDestroy(e0); cudaEventDestroy(e1);
         if (fl) pool_free(fl, st);

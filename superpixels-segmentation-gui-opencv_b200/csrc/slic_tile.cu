@@ -89,6 +89,9 @@ struct SlicoSmem {               // SLICO only
     float dcm[TH][TW];           // colour distance to the LAST visiting cluster, per pixel (upstream's distchans plane)
     unsigned mx[NCOPY][CAP];     // per candidate: running maximum of dcm over its pixels (float bits; values are >= 0)
 };
+struct MslicSmem {               // MSLIC only: manifold area (fixed point x256) per candidate, as 16-bit limbs
+    unsigned ar[NCOPY][CAP][2];  // [0]: sum of (v & 0xffff), [1]: sum of (v >> 16); a tile has 1024 pixels, v < 2^32
+};
 struct NoSmem {};
 // rec[].k.w carries key = (n << 6) | slot: the inner loop selects one register and both the label and the slot follow
 __device__ __forceinline__ int key_n(int key) { return key >> 6; }
@@ -106,6 +109,7 @@ struct __align__(16) TileSmemT {
     int list[CAP];
     unsigned char slot[TH][TW];  // winning candidate slot per pixel (0xFF: none / handled on the spot)
     typename std::conditional<ALG == SPX_SLICO, SlicoSmem, NoSmem>::type o;
+    typename std::conditional<ALG == SPX_MSLIC, MslicSmem, NoSmem>::type ms;
     int bad;                     // SLICO / MSLIC: a divisor the reciprocal sequence cannot handle -> exact generic path for the tile
 };
 
@@ -117,6 +121,7 @@ struct TileArgs {
     int ty_off;                  // first tile row of the launch (strip mode)
     float xywt, rcp_xywt;
     const float* maxc; unsigned* maxc_acc; float* dcplane;      // SLICO (dcplane has the label pitch)
+    const float* area_px; unsigned long long* area;              // MSLIC: per-pixel manifold area (label pitch), per-cluster sums
 };
 
 __device__ __forceinline__ void acc_global_pixel(const TileArgs& t, int n, unsigned px, int x, int y)
@@ -125,14 +130,23 @@ __device__ __forceinline__ void acc_global_pixel(const TileArgs& t, int n, unsig
     atomicAdd(&t.acc[2 * (size_t)t.Kcap + n], (u64)((px >> 16) & 0xffu)); atomicAdd(&t.acc[3 * (size_t)t.Kcap + n], (u64)x);
     atomicAdd(&t.acc[4 * (size_t)t.Kcap + n], (u64)y); atomicAdd(&t.acc[5 * (size_t)t.Kcap + n], 1ull);
 }
+// MSLIC: fixed-point area of a pixel quad, as mslic_adapt reads it (x256, truncated)
+__device__ __forceinline__ unsigned long long area_fx(float a) { return (unsigned long long)(long long)__fmul_rn(a, 256.0f); }
+
 // exact per-pixel path for a tile whose candidate list overflowed (kept out of line: it is cold)
 template <int ALG>
 __device__ __noinline__ void tile_fallback(const SlicGeom& g, const SlicArrays& a, const unsigned char* img, int* labels, float* dcplane,
-                                           int parity, int tx0, int ty0, int warp, int lane)
+                                           const float* area_px, unsigned long long* area, int parity, int tx0, int ty0, int warp, int lane)
 {
     for (int r = warp; r < TH; r += NT / 32) {
         const int x = tx0 + lane, y = ty0 + r;
         slic_pixel_generic<ALG>(g, a, img, labels, dcplane, parity, x, y, x < g.w && y < g.h);
+        if constexpr (ALG == SPX_MSLIC) {                        // the tile's share of the per-cluster manifold areas
+            if (x < g.w - 1 && y < g.h - 1) {
+                const size_t li = (size_t)y * g.lp + x;
+                atomicAdd(&area[labels[li]], area_fx(area_px[li]));
+            }
+        }
     }
 }
 
@@ -160,6 +174,7 @@ __device__ __noinline__ void step_slow(const TileArgs& t, TileSmemT<ALG>& sm, in
             } else {
                 const int n = labels[li];
                 acc_global_pixel(t, n, px[i], xx, yy);          // keeps its label; sums go straight to global
+                if constexpr (ALG == SPX_MSLIC) { if (xx < t.w - 1 && yy < t.h - 1) atomicAdd(&t.area[n], area_fx(t.area_px[li])); }
                 if constexpr (ALG == SPX_SLICO) atomicMax(&t.maxc_acc[n], __float_as_uint(t.dcplane[li]));   // plane keeps its value
             }
         }
@@ -199,7 +214,7 @@ __global__ void __launch_bounds__(NT, ALG == SPX_SLICO ? 6 : 8) slic_tile_kernel
     const int cnt = __ldg(&t.tl_count[tile]);
     if (cnt > CAP) {
         if (tid == 0) atomicAdd(d_overflow, 1);
-        tile_fallback<ALG>(g, a, img, labels, t.dcplane, parity, tx0, ty0, warp, lane);
+        tile_fallback<ALG>(g, a, img, labels, t.dcplane, t.area_px, t.area, parity, tx0, ty0, warp, lane);
         return;
     }
     float mxv = 1.0f;
@@ -230,6 +245,9 @@ __global__ void __launch_bounds__(NT, ALG == SPX_SLICO ? 6 : 8) slic_tile_kernel
     if constexpr (ALG == SPX_SLICO) {
         for (int i = tid; i < NCOPY * CAP; i += NT) (&sm.o.mx[0][0])[i] = 0u;
     }
+    if constexpr (ALG == SPX_MSLIC) {
+        for (int i = tid; i < NCOPY * CAP * 2; i += NT) (&sm.ms.ar[0][0][0])[i] = 0u;
+    }
     {   // zero the accumulators of the candidates in use: copy tid>>4, candidates (tid&15), +16, ... as 16-byte stores
         unsigned* cp = sm.acc[tid >> 4];
         for (int c = tid & 15; c < cnt; c += 16) *reinterpret_cast<uint4*>(cp + 4 * c) = make_uint4(0u, 0u, 0u, 0u);
@@ -237,7 +255,7 @@ __global__ void __launch_bounds__(NT, ALG == SPX_SLICO ? 6 : 8) slic_tile_kernel
     __syncthreads();
     if constexpr (ALG != SPX_SLIC) {
         if (sm.bad) {
-            tile_fallback<ALG>(g, a, img, labels, t.dcplane, parity, tx0, ty0, warp, lane);
+            tile_fallback<ALG>(g, a, img, labels, t.dcplane, t.area_px, t.area, parity, tx0, ty0, warp, lane);
             return;
         }
     }
@@ -397,6 +415,24 @@ __global__ void __launch_bounds__(NT, ALG == SPX_SLICO ? 6 : 8) slic_tile_kernel
         const int row = (lane >> 3) * 8 + warp * 2 + it;               // rows r, r+8, r+16, r+24 within a warp
         const unsigned sl = *reinterpret_cast<const unsigned*>(&sm.slot[row][4 * q]);
         const uint4 pv = pv2[it];
+        if constexpr (ALG == SPX_MSLIC) {
+            // manifold area of the 4 pixel quads (zero in the last row / column and in the padding), added to the winner's
+            // limbs; a value beyond 32 bits (absurd ruler) goes straight to the global sum
+            const float4 av = __ldg(reinterpret_cast<const float4*>(t.area_px + (size_t)(ty0 + row) * t.lp + tx0 + 4 * q));
+            const float avs[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const unsigned s = (sl >> (8 * j)) & 0xffu;
+                const unsigned long long v = area_fx(avs[j]);
+                if (s != 0xffu && v) {
+                    if (v >> 32) atomicAdd(&t.area[key_n(__float_as_int(sm.rec[s].k.w))], v);
+                    else {
+                        atomicAdd(&sm.ms.ar[lane & (NCOPY - 1)][s][0], (unsigned)v & 0xffffu);
+                        atomicAdd(&sm.ms.ar[lane & (NCOPY - 1)][s][1], (unsigned)v >> 16);
+                    }
+                }
+            }
+        }
         // the segment's pixels belong to at most two candidates A (the first pixel's) and B (the first one that differs)
         const unsigned s0 = sl & 0xffu, s1 = (sl >> 8) & 0xffu, s2 = (sl >> 16) & 0xffu, s3 = sl >> 24;
         const unsigned A = s0;
@@ -458,6 +494,12 @@ __global__ void __launch_bounds__(NT, ALG == SPX_SLICO ? 6 : 8) slic_tile_kernel
         if (f == 0) {
             atomicAdd(&t.acc[n], (u64)(v & 0x3ffffu));
             atomicAdd(&t.acc[(size_t)5 * t.Kcap + n], (u64)count);
+            if constexpr (ALG == SPX_MSLIC) {
+                u64 lo = 0, hi = 0;
+#pragma unroll
+                for (int p = 0; p < NCOPY; p++) { lo += sm.ms.ar[p][c][0]; hi += sm.ms.ar[p][c][1]; }
+                if (lo | hi) atomicAdd(&t.area[n], lo + (hi << 16));
+            }
             if constexpr (ALG == SPX_SLICO) {
                 unsigned mxb = 0;
 #pragma unroll
@@ -522,7 +564,7 @@ int slic_tile_prepare(const SlicGeom& g, const unsigned char* d_img, unsigned* d
 }
 
 int slic_tile_assign(const SlicGeom& g, const SlicArrays& a, const unsigned char* d_img, const unsigned* d_img4, int* d_labels,
-                     float* d_dcplane, const int* d_K, int parity, int* d_overflow, cudaStream_t st)
+                     float* d_dcplane, const float* d_area_px, const int* d_K, int parity, int* d_overflow, cudaStream_t st)
 {
     (void)d_K;
     dim3 grid(g.tiles_x, g.ty_hi - g.ty_lo);
@@ -533,6 +575,7 @@ int slic_tile_assign(const SlicGeom& g, const SlicArrays& a, const unsigned char
     t.w = g.w; t.h = g.h; t.S = g.S; t.Kcap = g.Kcap; t.tiles_x = g.tiles_x; t.lp = g.lp; t.p4 = g.p4;
     t.xywt = g.xywt; t.rcp_xywt = 1.0f / g.xywt;
     t.maxc = a.maxc; t.maxc_acc = a.maxc_acc; t.dcplane = d_dcplane;
+    t.area_px = d_area_px; t.area = reinterpret_cast<unsigned long long*>(a.area);
     const bool p2 = is_pow2(g.xywt);
     if (g.alg == SPX_SLICO) {
         if (p2) slic_tile_kernel<true, SPX_SLICO><<<grid, NT, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);
