@@ -173,6 +173,9 @@ def other_configs(spx, synth, L):
                      "contour_mask_ms_incl_d2h": tm * 1e3}
         s.release()
 
+    slic_family("SLIC_1080p_S20", spx.SLIC, 1920, 1080, 20)          # north-star: 1080p / 4K / 8K at one GPU
+    slic_family("SLIC_4K_S20", spx.SLIC, W4K, H4K, 20)
+    slic_family("SLIC_8K_S20", spx.SLIC, 7680, 4320, 20)
     slic_family("cfg2_SLICO_4K_S25", spx.SLICO, W4K, H4K, 25)
     slic_family("cfg3_MSLIC_8K_S30", spx.MSLIC, 7680, 4320, 30)
     bgr = synth.synth(7680, 4320, 0)[0]
@@ -388,14 +391,14 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=32, help="frames per GPU per step")
     ap.add_argument("--distinct", type=int, default=4, help="distinct synthetic frames generated (cycled)")
     ap.add_argument("--streams", type=int, default=4)
-    ap.add_argument("--e2e-frames", type=int, default=8)
-    ap.add_argument("--e2e-reps", type=int, default=2)
+    ap.add_argument("--e2e-frames", type=int, default=16)
+    ap.add_argument("--e2e-reps", type=int, default=4)
     ap.add_argument("--e2e-threads", type=int, default=4)
     ap.add_argument("--no-other-configs", action="store_true", help="skip the extra (non-headline) configs on rank 0")
     args = ap.parse_args()

@@ -383,3 +383,15 @@ def test_cpp_adapter_compute_click():
     r = subprocess.run([os.path.join(cpp, "compute_click")], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("nb_cells") == 6
+
+
+@pytest.mark.gpu
+def test_golden_hashes_on_gpu(spx, example_bgr):
+    """the CUDA path reproduces the committed golden hashes byte for byte (no oracle involved)"""
+    import importlib.util, json
+    spec = importlib.util.spec_from_file_location("gen_golden", os.path.join(os.path.dirname(__file__), "..", "tools", "gen_golden.py"))
+    gg = importlib.util.module_from_spec(spec); spec.loader.exec_module(gg)
+    want = json.load(open(gg.OUT))
+    got = gg.compute(spx, example_bgr, lambda bgr: spx.cvtColor(bgr, spx.COLOR_BGR2Lab),
+                     lambda lab, S, r: spx.createSuperpixelSLIC(lab, spx.SLIC, S, r))
+    assert got == want

@@ -167,3 +167,13 @@ def test_lsc_merge_orders_agree_statistically(O, synthmod):
     # same-segment relation of horizontal neighbours agrees almost everywhere
     same0 = L0[:, 1:] == L0[:, :-1]; same1 = L1[:, 1:] == L1[:, :-1]
     assert float((same0 == same1).mean()) > 0.98
+
+
+def test_golden_hashes_reproduce(O, example_bgr):
+    """tests/golden/cfg1_hashes.json (tools/gen_golden.py): every stage of configs[0] and of the reference's fixture run"""
+    import importlib.util, json, os
+    spec = importlib.util.spec_from_file_location("gen_golden", os.path.join(os.path.dirname(__file__), "..", "tools", "gen_golden.py"))
+    gg = importlib.util.module_from_spec(spec); spec.loader.exec_module(gg)
+    want = json.load(open(gg.OUT))
+    got = gg.compute(O, example_bgr, O.bgr2lab8, lambda lab, S, r: O.SuperpixelSLIC(lab, O.SLIC, S, r))
+    assert got == want
