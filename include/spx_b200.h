@@ -184,6 +184,43 @@ int spx_seeds_get_label_contour_mask(spx_seeds_t*, uint8_t* dst, size_t dst_stri
 int spx_seeds_launch_count(spx_seeds_t*, long long* out);
 int spx_seeds_destroy(spx_seeds_t*);
 
+/* ---- the Segmentation tab's working set on the device (the callers either side of the path) ----
+ * Replaces the full-size Mats the GUI keeps next to the image (mainwindow.h:176-185: labels, labels_mask CV_32SC1; mask, grid,
+ * selection CV_8UC3) and the full-image passes it runs over them.  Plane ids: 0 image, 1 mask, 2 grid, 3 selection (8UC3, BGR),
+ * 4 labels, 5 labels_mask (32SC1).  Every call is synchronous; results are bit-identical to the cv:: calls they replace
+ * (addWeighted / dilate / compare / setTo / inRange / countNonZero / minMaxIdx of OpenCV 4.13). */
+typedef struct spx_session spx_session_t;
+int spx_session_create(int width, int height, int device, spx_session_t** out);
+int spx_session_destroy(spx_session_t*);
+int spx_session_upload(spx_session_t*, int plane, const void* src, size_t stride);      /* uploading plane 4 rebuilds the cell index */
+int spx_session_download(spx_session_t*, int plane, void* dst, size_t stride);
+/* the GUI's post-step after COMPUTE (mainwindow.cpp:2130-2138): labels <- getLabels(), labels_mask = 0, mask = 0,
+ * selection = 0, grid = cvtColor(contour, GRAY2RGB) with setTo(colour, grid); builds the per-cell index */
+int spx_session_begin(spx_session_t*, const int32_t* labels, size_t labels_stride, const uint8_t* contour_mask, size_t contour_stride,
+                      const uint8_t colour[3]);
+/* grid.setTo(colour, gray(grid) > 0) -- on_comboBox_grid_color_currentIndexChanged, mainwindow.cpp:1085-1104 */
+int spx_session_recolour_grid(spx_session_t*, const uint8_t colour[3]);
+/* Mat1b m = plane == value (plane 4 or 5) -- mainwindow.cpp:2159, 228, 258, 1334 */
+int spx_session_eq_mask(spx_session_t*, int plane, int value, uint8_t* dst, size_t stride);
+/* WhichCell(posX, posY), mainwindow.cpp:2153-2171: the cell under (x, y) is erased from mask and labels_mask (paint == 0) or
+ * painted with `colour` and claimed for `label_id`; one pass over the cell's bounding box.  cell_out (optional): its label */
+int spx_session_which_cell(spx_session_t*, int x, int y, int paint, const uint8_t colour[3], int label_id, int* cell_out);
+/* where plane `key_plane` (4 / 5) == value: colour plane p3 (1..3, or -1) <- colour, int plane p1 (4 / 5, or -1) <- newval:
+ * label delete (mainwindow.cpp:228-229), join (258-260), colour change (1334-1335) */
+int spx_session_set_where_eq(spx_session_t*, int key_plane, int value, int p3, const uint8_t colour[3], int p1, int newval);
+/* "update the cells from the white mask" (mainwindow.cpp:313-331): pure-white mask pixels become cell max(labels)+1 */
+int spx_session_new_cell_from_white(spx_session_t*, const uint8_t colour[3], int label_id, int* new_cell, int* hits);
+/* minMaxIdx(labels) maximum -- mainwindow.cpp:313 */
+int spx_session_max_label(spx_session_t*, int* out);
+/* per-cell index: boxes[k] = x0, y0, x1, y1 (inclusive; x1 < x0: unused id), counts[k] = pixels; rows = capacity of both */
+int spx_session_cell_index(spx_session_t*, int32_t* boxes, int32_t* counts, int rows, int* cells);
+/* ShowSegmentation(), mainwindow.cpp:1936-1969, as one pass: disp = image*a, + mask*b, + grid*c (addWeighted, blend = slider
+ * value 0..100), selection dilated by `dilation` copied over where non-zero, holes (pure-black mask pixels) in white;
+ * dst = vh rows of vw BGR pixels; holes (optional) = countNonZero over the whole mask */
+int spx_session_compose(spx_session_t*, int vx, int vy, int vw, int vh, int show_image, int blend_image, int show_mask, int blend_mask,
+                        int show_grid, int blend_grid, int show_selection, int dilation, int show_holes, uint8_t* dst, size_t stride,
+                        int* holes);
+
 #ifdef __cplusplus
 }
 #endif

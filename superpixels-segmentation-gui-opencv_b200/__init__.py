@@ -75,6 +75,19 @@ def lib():
         "spx_slic_time_assign": [vp, i32, i32, C.POINTER(C.c_float)],
         "spx_slic_time_iterations": [vp, i32, i32, i32, C.POINTER(C.c_float)],
         "spx_slic_destroy": [vp],
+        "spx_session_create": [i32, i32, i32, pp],
+        "spx_session_destroy": [vp],
+        "spx_session_upload": [vp, i32, vp, sz],
+        "spx_session_download": [vp, i32, vp, sz],
+        "spx_session_begin": [vp, vp, sz, vp, sz, vp],
+        "spx_session_recolour_grid": [vp, vp],
+        "spx_session_eq_mask": [vp, i32, i32, vp, sz],
+        "spx_session_which_cell": [vp, i32, i32, i32, vp, i32, pi],
+        "spx_session_set_where_eq": [vp, i32, i32, i32, vp, i32, i32],
+        "spx_session_new_cell_from_white": [vp, vp, i32, pi, pi],
+        "spx_session_max_label": [vp, pi],
+        "spx_session_cell_index": [vp, vp, vp, i32, pi],
+        "spx_session_compose": [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, sz, pi],
         "spx_slic_batch_dev": [pp, i32, i32, i32, i32, i32, i32, f32, i32, i32, pp, pp, i32, i32, C.POINTER(C.c_longlong)],
         "spx_slic_batch_release": [],
         "spx_enforce_label_connectivity": [vp, sz, i32, i32, i32, i32, i32, pi],
@@ -343,3 +356,91 @@ def slic_batch_dev(frame_ptrs, width, height, channels, algorithm, region_size, 
                                  int(num_iterations), int(min_element_size), LA, MA, int(bool(thick_line)),
                                  int(n_streams), C.byref(launches)))
     return launches.value
+
+
+class Session:
+    """The Segmentation tab's working set on the device (include/spx_b200.h, spx_session_*): labels, labels_mask, mask, grid,
+    selection and the image, with the passes the GUI runs over them (WhichCell, label list actions, ShowSegmentation)."""
+    IMAGE, MASK, GRID, SELECTION, LABELS, LABELS_MASK = 0, 1, 2, 3, 4, 5
+
+    def __init__(self, width, height, device=0):
+        self._h = C.c_void_p(None)
+        self.w, self.h = int(width), int(height)
+        _ck(lib().spx_session_create(self.w, self.h, int(device), C.byref(self._h)))
+
+    def release(self):
+        if self._h:
+            lib().spx_session_destroy(self._h)
+            self._h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    def _colour(self, c):
+        return np.ascontiguousarray(np.asarray(c, dtype=np.uint8).reshape(3))
+
+    def upload(self, plane, a):
+        a = np.ascontiguousarray(a, dtype=np.uint8 if plane < 4 else np.int32)
+        assert a.shape[:2] == (self.h, self.w)
+        _ck(lib().spx_session_upload(self._h, int(plane), _p(a), a.strides[0]))
+
+    def download(self, plane):
+        out = np.empty((self.h, self.w, 3), np.uint8) if plane < 4 else np.empty((self.h, self.w), np.int32)
+        _ck(lib().spx_session_download(self._h, int(plane), _p(out), out.strides[0]))
+        return out
+
+    def begin(self, labels, contour_mask, colour):
+        labels = np.ascontiguousarray(labels, dtype=np.int32); contour_mask = np.ascontiguousarray(contour_mask, dtype=np.uint8)
+        c = self._colour(colour)
+        _ck(lib().spx_session_begin(self._h, _p(labels), labels.strides[0], _p(contour_mask), contour_mask.strides[0], _p(c)))
+
+    def recolourGrid(self, colour):
+        c = self._colour(colour)
+        _ck(lib().spx_session_recolour_grid(self._h, _p(c)))
+
+    def eqMask(self, plane, value):
+        out = np.empty((self.h, self.w), np.uint8)
+        _ck(lib().spx_session_eq_mask(self._h, int(plane), int(value), _p(out), out.strides[0]))
+        return out
+
+    def whichCell(self, x, y, paint, colour=(0, 0, 0), label_id=0):
+        c = self._colour(colour)
+        cell = C.c_int(-1)
+        _ck(lib().spx_session_which_cell(self._h, int(x), int(y), int(bool(paint)), _p(c), int(label_id), C.byref(cell)))
+        return cell.value
+
+    def setWhereEq(self, key_plane, value, p3=-1, colour=(0, 0, 0), p1=-1, newval=0):
+        c = self._colour(colour)
+        _ck(lib().spx_session_set_where_eq(self._h, int(key_plane), int(value), int(p3), _p(c), int(p1), int(newval)))
+
+    def newCellFromWhite(self, colour, label_id):
+        c = self._colour(colour)
+        cell, hits = C.c_int(-1), C.c_int(0)
+        _ck(lib().spx_session_new_cell_from_white(self._h, _p(c), int(label_id), C.byref(cell), C.byref(hits)))
+        return cell.value, hits.value
+
+    def maxLabel(self):
+        v = C.c_int(0)
+        _ck(lib().spx_session_max_label(self._h, C.byref(v)))
+        return v.value
+
+    def cellIndex(self):
+        k = C.c_int(0)
+        _ck(lib().spx_session_cell_index(self._h, None, None, 0, C.byref(k)))
+        boxes = np.empty((k.value, 4), np.int32); counts = np.empty(k.value, np.int32)
+        _ck(lib().spx_session_cell_index(self._h, _p(boxes), _p(counts), k.value, C.byref(k)))
+        return boxes, counts
+
+    def compose(self, viewport, image=None, mask=None, grid=None, selection=None, holes=False):
+        """viewport = (x, y, w, h); image / mask / grid = blend slider value 0..100 or None (unchecked);
+        selection = dilation size or None.  Returns (disp, holes_count or None)."""
+        vx, vy, vw, vh = [int(v) for v in viewport]
+        out = np.empty((vh, vw, 3), np.uint8)
+        nh = C.c_int(0)
+        _ck(lib().spx_session_compose(self._h, vx, vy, vw, vh, int(image is not None), int(image or 0), int(mask is not None), int(mask or 0),
+                                      int(grid is not None), int(grid or 0), int(selection is not None), int(selection or 0), int(bool(holes)),
+                                      _p(out), out.strides[0], C.byref(nh)))
+        return out, (nh.value if holes else None)

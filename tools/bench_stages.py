@@ -112,5 +112,59 @@ def run():
         tc = best(lambda: so.iterate(lab3, 10), 1)[0]
     line("SEEDS iterate(img, 10)", "1920x1080 2000 superpixels 4 levels 5 bins", 1920 * 1080, 3 + 20 * 10, t, tc, {"cpu_threads": 1, "launches": sd.launchCount()})
 
+    # ---- the GUI's passes over the segmentation working set, next to the cv2 calls the
+    # reference makes (cv2 = OpenCV 4.13 on the host cores, its own thread pool)
+    import cv2
+    W, H = 3840, 2160
+    bgr, _ = synth.synth(W, H, 0)
+    lab = spx.cvtColor(bgr, spx.COLOR_BGR2Lab)
+    s = spx.createSuperpixelSLIC(lab, spx.SLIC, 20, 10.0); s.iterate(10); s.enforceLabelConnectivity(25)
+    labels = s.getLabels(); contour = s.getLabelContourMask(False)
+    ses = spx.Session(W, H)
+    t, _ = best(lambda: ses.begin(labels, contour, (0, 0, 255)), 3)
+    ses.upload(0, bgr)
+    line("session begin (labels + grid upload, cell index)", "3840x2160", W * H, 4 + 1 + 3 + 12, t, None)
+    rng = np.random.default_rng(0)
+    pts = [(int(rng.integers(0, W)), int(rng.integers(0, H))) for _ in range(64)]
+    t0 = time.perf_counter()
+    for (x, y) in pts:
+        ses.whichCell(x, y, True, (0, 255, 0), 1)
+    t = (time.perf_counter() - t0) / len(pts)
+    mask = np.zeros((H, W, 3), np.uint8); lm = np.zeros((H, W), np.int32)
+
+    def cv_click(x, y):
+        m = cv2.compare(labels, int(labels[y, x]), cv2.CMP_EQ)       # Mat1b superpixel_mask = labels == label
+        mask[m != 0] = 0; lm[m != 0] = 0                               # setTo(0, superpixel_mask) x2
+        mask[m != 0] = (0, 255, 0); lm[m != 0] = 1                     # setTo(color / label, superpixel_mask)
+    tc = None
+    if cpu:
+        t0 = time.perf_counter()
+        for (x, y) in pts[:8]:
+            cv_click(x, y)
+        tc = (time.perf_counter() - t0) / 8
+    line("WhichCell click (one cell painted)", "3840x2160, ~400 px cells", W * H, 4, t, tc, {"cpu": "cv2.compare + numpy masked stores", "cpu_threads": cv2.getNumThreads()})
+    for (vw, vh) in ((1920, 1080), (3840, 2160)):
+        vp = (0, 0, vw, vh)
+        t, _ = best(lambda: ses.compose(vp, image=50, mask=50, grid=100, selection=1, holes=True), 5)
+        tc = None
+        if cpu:
+            img_c = np.ascontiguousarray(bgr[:vh, :vw]); mk = ses.download(1); gr = ses.download(2); sel = ses.download(3)
+
+            def cv_show():
+                d = np.zeros((vh, vw, 3), np.uint8)
+                d = cv2.addWeighted(d, 0.5, img_c, 0.5, 0)
+                d = cv2.addWeighted(d, 1, np.ascontiguousarray(mk[:vh, :vw]), 0.5, 0)
+                d = cv2.addWeighted(d, 1, np.ascontiguousarray(gr[:vh, :vw]), 1.0, 0)
+                sd = cv2.dilate(np.ascontiguousarray(sel[:vh, :vw]), cv2.getStructuringElement(cv2.MORPH_RECT, (3, 3)))
+                cv2.copyTo(sd, sd, d)
+                hm = cv2.inRange(mk, (0, 0, 0), (0, 0, 0))
+                holes = np.zeros((H, W, 3), np.uint8); holes[hm != 0] = (255, 255, 255)
+                d = cv2.addWeighted(d, 1, np.ascontiguousarray(holes[:vh, :vw]), 1, 0)
+                return d, cv2.countNonZero(hm)
+            tc = best(cv_show, 3)[0]
+        line("ShowSegmentation (image+mask+grid+selection+holes)", "viewport %dx%d of 3840x2160" % (vw, vh), vw * vh, 15, t, tc,
+             {"cpu": "cv2 4.13 call sequence of mainwindow.cpp:1936-1969", "cpu_threads": cv2.getNumThreads()})
+    ses.release()
+
 
 run()
