@@ -221,6 +221,16 @@ int spx_session_compose(spx_session_t*, int vx, int vy, int vw, int vh, int show
                         int show_grid, int blend_grid, int show_selection, int dilation, int show_holes, uint8_t* dst, size_t stride,
                         int* holes);
 
+/* ---- the reference's session data file <base>-segmentation-data.xml (OpenCV FileStorage XML; mainwindow.cpp:673-706 writes it,
+ * 775-820 reads it): GridColor, LabelsCount, LabelId<i> / LabelName<i> / LabelColor<i>, and the CV_32SC1 matrices Labels and
+ * LabelsMask.  Host side only (no GPU, no OpenCV); files round-trip with cv::FileStorage. */
+typedef struct { int id; char name[128]; uint8_t colour[3]; } spx_label_t;
+int spx_session_xml_write(const char* path, int grid_colour, const spx_label_t* list, int n_labels, const int32_t* labels,
+                          size_t labels_stride, const int32_t* labels_mask, size_t mask_stride, int width, int height);
+/* labels / labels_mask may be NULL (size query: rows, cols, n_labels are still returned); list holds list_capacity entries */
+int spx_session_xml_read(const char* path, int* grid_colour, spx_label_t* list, int list_capacity, int* n_labels, int32_t* labels,
+                         size_t labels_stride, int32_t* labels_mask, size_t mask_stride, int* rows, int* cols);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,6 +88,8 @@ def lib():
         "spx_session_max_label": [vp, pi],
         "spx_session_cell_index": [vp, vp, vp, i32, pi],
         "spx_session_compose": [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, sz, pi],
+        "spx_session_xml_write": [C.c_char_p, i32, vp, i32, vp, sz, vp, sz, i32, i32],
+        "spx_session_xml_read": [C.c_char_p, pi, vp, i32, pi, vp, sz, vp, sz, pi, pi],
         "spx_slic_batch_dev": [pp, i32, i32, i32, i32, i32, i32, f32, i32, i32, pp, pp, i32, i32, C.POINTER(C.c_longlong)],
         "spx_slic_batch_release": [],
         "spx_enforce_label_connectivity": [vp, sz, i32, i32, i32, i32, i32, pi],
@@ -444,3 +446,33 @@ class Session:
                                       int(grid is not None), int(grid or 0), int(selection is not None), int(selection or 0), int(bool(holes)),
                                       _p(out), out.strides[0], C.byref(nh)))
         return out, (nh.value if holes else None)
+
+
+class _Label(C.Structure):
+    _fields_ = [("id", C.c_int), ("name", C.c_char * 128), ("colour", C.c_uint8 * 3)]
+
+
+def writeSessionXml(path, grid_colour, label_list, labels, labels_mask):
+    """<base>-segmentation-data.xml as the reference GUI writes it (mainwindow.cpp:673-706).
+    label_list: [(id, name, (c0, c1, c2)), ...] in list order."""
+    labels = np.ascontiguousarray(labels, dtype=np.int32); labels_mask = np.ascontiguousarray(labels_mask, dtype=np.int32)
+    assert labels.shape == labels_mask.shape and labels.ndim == 2
+    arr = (_Label * max(1, len(label_list)))()
+    for i, (lid, name, col) in enumerate(label_list):
+        arr[i].id = int(lid); arr[i].name = name.encode("utf-8")[:127]
+        for k in range(3):
+            arr[i].colour[k] = int(col[k])
+    _ck(lib().spx_session_xml_write(str(path).encode(), int(grid_colour), C.cast(arr, C.c_void_p), len(label_list), _p(labels), labels.strides[0],
+                                    _p(labels_mask), labels_mask.strides[0], labels.shape[1], labels.shape[0]))
+
+
+def readSessionXml(path):
+    """-> (grid_colour, [(id, name, (c0, c1, c2)), ...], labels, labels_mask)  (mainwindow.cpp:775-820)"""
+    g, n, r, c = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+    _ck(lib().spx_session_xml_read(str(path).encode(), C.byref(g), None, 0, C.byref(n), None, 0, None, 0, C.byref(r), C.byref(c)))
+    arr = (_Label * max(1, n.value))()
+    labels = np.empty((r.value, c.value), np.int32); mask = np.empty((r.value, c.value), np.int32)
+    _ck(lib().spx_session_xml_read(str(path).encode(), C.byref(g), C.cast(arr, C.c_void_p), n.value, C.byref(n), _p(labels), labels.strides[0],
+                                   _p(mask), mask.strides[0], C.byref(r), C.byref(c)))
+    lst = [(arr[i].id, arr[i].name.decode("utf-8", "replace"), tuple(int(arr[i].colour[k]) for k in range(3))) for i in range(n.value)]
+    return g.value, lst, labels, mask
