@@ -231,6 +231,14 @@ int spx_session_xml_write(const char* path, int grid_colour, const spx_label_t* 
 int spx_session_xml_read(const char* path, int* grid_colour, spx_label_t* list, int list_capacity, int* n_labels, int32_t* labels,
                          size_t labels_stride, int32_t* labels_mask, size_t mask_stride, int* rows, int* cols);
 
+/* ---- the pre-processing that feeds the path (MainWindow::on_button_apply_clicked, mainwindow.cpp:1979-2047) ----
+ * flags: 1 equalize (EqualizeHistogram, mat-image-tools.cpp:184-202), 2 normalize (cv::normalize(1, 255, NORM_MINMAX),
+ * mainwindow.cpp:2029), 4 colour balance (SimplestColorBalance(image, percent), mat-image-tools.cpp:204-229), 8 gaussian
+ * blur (cv::GaussianBlur 3x3, mainwindow.cpp:2031); applied in that order, bit-identical to OpenCV 4.13's 8-bit arithmetic.
+ * src / dst: 8UC3 (BGR) host images, may alias. */
+int spx_preprocess_8uc3(const uint8_t* src, size_t src_stride, uint8_t* dst, size_t dst_stride, int width, int height, int flags,
+                        int percent, int device);
+
 #ifdef __cplusplus
 }
 #endif

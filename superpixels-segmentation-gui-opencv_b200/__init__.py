@@ -88,6 +88,7 @@ def lib():
         "spx_session_max_label": [vp, pi],
         "spx_session_cell_index": [vp, vp, vp, i32, pi],
         "spx_session_compose": [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, sz, pi],
+        "spx_preprocess_8uc3": [vp, sz, vp, sz, i32, i32, i32, i32, i32],
         "spx_session_xml_write": [C.c_char_p, i32, vp, i32, vp, sz, vp, sz, i32, i32],
         "spx_session_xml_read": [C.c_char_p, pi, vp, i32, pi, vp, sz, vp, sz, pi, pi],
         "spx_slic_batch_dev": [pp, i32, i32, i32, i32, i32, i32, f32, i32, i32, pp, pp, i32, i32, C.POINTER(C.c_longlong)],
@@ -476,3 +477,16 @@ def readSessionXml(path):
                                    _p(mask), mask.strides[0], C.byref(r), C.byref(c)))
     lst = [(arr[i].id, arr[i].name.decode("utf-8", "replace"), tuple(int(arr[i].colour[k]) for k in range(3))) for i in range(n.value)]
     return g.value, lst, labels, mask
+
+
+PRE_EQUALIZE, PRE_NORMALIZE, PRE_COLOR_BALANCE, PRE_GAUSSIAN_BLUR = 1, 2, 4, 8
+
+
+def preprocess(bgr, equalize=False, normalize=False, color_balance=None, gaussian_blur=False, device=0):
+    """on_button_apply_clicked (mainwindow.cpp:1979-2047): equalize -> normalize -> colour balance(percent) -> 3x3 blur"""
+    a = np.ascontiguousarray(bgr, dtype=np.uint8)
+    assert a.ndim == 3 and a.shape[2] == 3
+    out = np.empty_like(a)
+    flags = (1 if equalize else 0) | (2 if normalize else 0) | (4 if color_balance is not None else 0) | (8 if gaussian_blur else 0)
+    _ck(lib().spx_preprocess_8uc3(_p(a), a.strides[0], _p(out), out.strides[0], a.shape[1], a.shape[0], flags, int(color_balance or 0), int(device)))
+    return out

@@ -165,6 +165,23 @@ def run():
         line("ShowSegmentation (image+mask+grid+selection+holes)", "viewport %dx%d of 3840x2160" % (vw, vh), vw * vh, 15, t, tc,
              {"cpu": "cv2 4.13 call sequence of mainwindow.cpp:1936-1969", "cpu_threads": cv2.getNumThreads()})
     ses.release()
+    # ---- pre-processing that feeds the path next to the cv2 calls of on_button_apply_clicked
+    t, _ = best(lambda: spx.preprocess(bgr, equalize=True, normalize=True, color_balance=2, gaussian_blur=True), 5)
+    tc = None
+    if cpu:
+        def cv_pre():
+            a = cv2.cvtColor(bgr, cv2.COLOR_BGR2YCrCb); ch = list(cv2.split(a)); ch[0] = cv2.equalizeHist(ch[0])
+            a = cv2.cvtColor(cv2.merge(ch), cv2.COLOR_YCrCb2BGR)
+            a = cv2.normalize(a, None, 1, 255, cv2.NORM_MINMAX, -1)
+            ch = list(cv2.split(a))
+            for i in range(3):
+                flat = np.sort(ch[i].reshape(1, -1), axis=1); n = flat.shape[1]
+                lo, hi = int(flat[0, int(n * 0.01)]), int(flat[0, min(int(np.ceil(n * 0.99)), n - 1)])
+                c = np.clip(ch[i], lo, hi); ch[i] = cv2.normalize(c, None, 0, 255, cv2.NORM_MINMAX)
+            return cv2.GaussianBlur(cv2.merge(ch), (3, 3), 0, 0)
+        tc = best(cv_pre, 2)[0]
+    line("preprocess (equalize+normalize+balance 2%+blur 3x3)", "3840x2160", W * H, 6 * 4 + 3 * 3, t, tc,
+         {"cpu": "cv2 4.13 call sequence of mainwindow.cpp:2028-2031 (sort by numpy)", "cpu_threads": cv2.getNumThreads()})
 
 
 run()
