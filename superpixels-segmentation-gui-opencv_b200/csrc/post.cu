@@ -69,65 +69,112 @@ __device__ __forceinline__ void uf_unite(int* P, int a, int b)
     } while (!done);
 }
 
-// parent[i] = first pixel of the horizontal run of equal labels that holds i (found with one ballot per warp; a run that
-// began in an earlier warp chains through the pixel left of the warp's first lane), so finds start one or two hops
-// from a run head instead of walking the run
-__global__ void ccl_init_kernel(const int* __restrict__ lab, int lp, int w, int h, int* __restrict__ P)
+// Block-local union-find first (shared memory), global unions only along tile borders:
+//   ccl_local_kernel   32x32 tile per CTA of 256 threads (a warp = one tile row at a time, 4 rows per thread): parent = head of the horizontal run
+//                      (one ballot), vertical unions inside the tile with shared-memory atomicMin (skipped when the left
+//                      neighbour already carries the same union), flatten, P[i] = global index of the local root.  The local
+//                      root is the tile's smallest raster index of the component, so global roots stay "smallest raster index".
+//   ccl_border_kernel  unions across tile borders (top row with the row above, left column with the column to the left).
+constexpr int CT = 32;
+__device__ __forceinline__ int sm_find(const int* P, int a)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    const int lane = threadIdx.x & 31;
-    const int* row = lab + (size_t)y * lp;
-    const bool in = x < w;
-    const bool start = !in || x == 0 || row[x - 1] != row[x];
-    const unsigned heads = __ballot_sync(0xffffffffu, start) & (0xffffffffu >> (31 - lane));
-    if (!in) return;
-    const int i = y * w + x;
-    P[i] = heads ? i - (lane - (31 - __clz(heads))) : i - lane - 1;
+    int p = P[a];
+    while (p != a) { a = p; p = P[a]; }
+    return a;
 }
-// vertical unions; skipped when the left neighbour already carries the same union
-__global__ void ccl_merge_kernel(const int* __restrict__ lab, int lp, int w, int h, int* __restrict__ P)
+__global__ void __launch_bounds__(256) ccl_local_kernel(const int* __restrict__ lab, int lp, int w, int h, int* __restrict__ P,
+                                                        int* __restrict__ csize)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y + 1;
-    if (x >= w || y >= h) return;
-    const int* row = lab + (size_t)y * lp;
-    const int* up = row - lp;
-    int me = row[x];
-    if (up[x] != me) return;
-    if (x > 0 && row[x - 1] == me && up[x - 1] == me) return;
-    uf_unite(P, y * w + x, (y - 1) * w + x);
+    __shared__ int sl[CT][CT + 1];
+    __shared__ int sp[CT * CT];
+    const int lx = threadIdx.x & 31, ly0 = threadIdx.x >> 5;             // 8 warps; warp q owns tile rows q, q+8, q+16, q+24
+    const int x = blockIdx.x * CT + lx;
+    int me[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int y = blockIdx.y * CT + ly0 + 8 * k;
+        me[k] = (x < w && y < h) ? lab[(size_t)y * lp + x] : -1 - lx;    // outside: never equal to a neighbour
+    }
+    int prev[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int ly = ly0 + 8 * k;
+        sl[ly][lx] = me[k];
+        prev[k] = __shfl_up_sync(0xffffffffu, me[k], 1);
+        const unsigned heads = __ballot_sync(0xffffffffu, lx == 0 || prev[k] != me[k]) & (0xffffffffu >> (31 - lx));
+        sp[ly * CT + lx] = ly * CT + lx - (lx - (31 - __clz(heads)));
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int ly = ly0 + 8 * k, t = ly * CT + lx;
+        if (me[k] >= 0 && ly > 0 && sl[ly - 1][lx] == me[k] && !(lx > 0 && prev[k] == me[k] && sl[ly - 1][lx - 1] == me[k])) {
+            int a = t, b = t - CT;
+            bool done;
+            do {
+                a = sm_find(sp, a); b = sm_find(sp, b);
+                if (a < b) { const int old = atomicMin(&sp[b], a); done = old == b; b = old; }
+                else if (b < a) { const int old = atomicMin(&sp[a], b); done = old == a; a = old; }
+                else done = true;
+            } while (!done);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int ly = ly0 + 8 * k, y = blockIdx.y * CT + ly;
+        if (x < w && y < h) {
+            const int r = sm_find(sp, ly * CT + lx);
+            P[y * w + x] = (blockIdx.y * CT + (r >> 5)) * w + blockIdx.x * CT + (r & 31);
+            csize[y * w + x] = 0;
+        }
+    }
 }
+// one thread per pixel of a tile's top row / left column
+__global__ void ccl_border_kernel(const int* __restrict__ lab, int lp, int w, int h, int* __restrict__ P)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tiles_y = (h + CT - 1) / CT, tiles_x = (w + CT - 1) / CT;
+    const int nh = (tiles_y - 1) * w;                                    // horizontal borders: rows CT, 2CT, ...
+    if (i < nh) {
+        const int y = (i / w + 1) * CT, x = i % w;
+        const int* row = lab + (size_t)y * lp;
+        const int me = row[x];
+        if (row[x - lp] != me) return;
+        if (x % CT != 0 && row[x - 1] == me && row[x - lp - 1] == me) return;   // the left neighbour (same tile pair) carries it
+        uf_unite(P, y * w + x, (y - 1) * w + x);
+        return;
+    }
+    const int j = i - nh;
+    if (j >= (tiles_x - 1) * h) return;
+    const int x = (j / h + 1) * CT, y = j % h;
+    const int* row = lab + (size_t)y * lp;
+    if (row[x] == row[x - 1]) uf_unite(P, y * w + x, y * w + x - 1);
+}
+// flatten + component sizes: warp-aggregated atomics (a warp covers 32 consecutive pixels, i.e. 1-3 roots; the ballot against
+// lane 0's root settles the common single-root case without MATCH)
 __global__ void ccl_flatten_kernel(int* __restrict__ P, int* __restrict__ csize, int n)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    P[i] = uf_find(P, i);
-    csize[i] = 0;
-}
-// component sizes: warp-aggregated atomics (a warp covers 32 consecutive pixels, i.e. 1-3 roots)
-__global__ void ccl_size_kernel(const int* __restrict__ P, int* __restrict__ csize, int n)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool act = i < n;
-    int r = act ? P[i] : -1 - (int)(threadIdx.x & 31);
-    unsigned m = __match_any_sync(0xffffffffu, r);
+    const bool act = i < n;
+    int r = -1 - (int)(threadIdx.x & 31);
+    if (act) { r = uf_find(P, i); P[i] = r; }
+    const int r0 = __shfl_sync(0xffffffffu, r, 0);
+    unsigned m = __ballot_sync(0xffffffffu, r == r0);
+    if (m != 0xffffffffu) m = __match_any_sync(0xffffffffu, r);
     if (act && (int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&csize[r], __popc(m));
 }
-// per root pixel: kept flag or link to the component supplying upstream's `adjlabel`
-// link encoding in newid[] for small roots: adjacent root index, or -1 (no neighbour labelled: pixel 0)
-__global__ void ccl_link_kernel(const int* __restrict__ P, const int* __restrict__ csize, int* __restrict__ link,
-                                int w, int h, int min_sp)
+// a small root's link: the component supplying upstream's `adjlabel` = last of the L,U,R,D neighbours of the root pixel whose
+// component starts earlier (left and up always do); -1: no neighbour labelled yet (pixel 0)
+__device__ __forceinline__ int small_root_link(const int* __restrict__ P, int i, int w, int h)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= w) return;
-    int i = y * w + x;
-    if (P[i] != i) return;
-    if (csize[i] > min_sp) return;   // kept: newid written by the scan
+    const int x = i % w, y = i / w;
     int adj = -1;
     if (x > 0) adj = P[i - 1];
     if (y > 0) adj = P[i - w];
     if (x < w - 1) { int r = P[i + 1]; if (r < i) adj = r; }
     if (y < h - 1) { int r = P[i + w]; if (r < i) adj = r; }
-    link[i] = adj;
+    return adj;
 }
 
 // exclusive scan of kept-root flags over raster order: block counts -> block offsets -> ids
@@ -136,13 +183,20 @@ __device__ __forceinline__ int kept_flag(const int* P, const int* csize, int i, 
 {
     return (i < n && P[i] == i && csize[i] > min_sp) ? 1 : 0;
 }
+// block counts of kept roots; the small roots met on the way get their link (one pass over P serves both)
 __global__ void __launch_bounds__(256) scan_count_kernel(const int* __restrict__ P, const int* __restrict__ csize, int n,
-                                                          int min_sp, int* __restrict__ blocksum)
+                                                          int min_sp, int* __restrict__ blocksum, int* __restrict__ link, int w, int h)
 {
     __shared__ int s[8];
     int base = blockIdx.x * SCAN_CHUNK;
     int c = 0;
-    for (int k = threadIdx.x; k < SCAN_CHUNK; k += 256) c += kept_flag(P, csize, base + k, n, min_sp);
+    for (int k = threadIdx.x; k < SCAN_CHUNK; k += 256) {
+        const int i = base + k;
+        if (i < n && P[i] == i) {
+            if (csize[i] > min_sp) c++;
+            else link[i] = small_root_link(P, i, w, h);
+        }
+    }
     c = __reduce_add_sync(0xffffffffu, c);
     if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
     __syncthreads();
@@ -199,23 +253,16 @@ __global__ void __launch_bounds__(256) scan_apply_kernel(const int* __restrict__
         __syncthreads();
     }
 }
-// small roots: chase links to a kept root (links strictly decrease, so the walk terminates)
-__global__ void ccl_resolve_kernel(const int* __restrict__ P, const int* __restrict__ csize, const int* __restrict__ link,
-                                   int* __restrict__ newid, int n, int min_sp)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || P[i] != i || csize[i] > min_sp) return;
-    int r = link[i];
-    while (r >= 0 && csize[r] <= min_sp) r = link[r];
-    // r < 0: the chain ends at a small component containing pixel 0 -> upstream's adjlabel is still 0
-    newid[i] = r >= 0 ? newid[r] : 0;
-}
-__global__ void ccl_relabel_kernel(const int* __restrict__ P, const int* __restrict__ newid, int* __restrict__ lab, int lp,
-                                   int w, int h)
+// new label of a pixel = id of its component's root if kept, otherwise of the kept root its chain of links ends at (links
+// strictly decrease, so the walk terminates; a chain that ends at a small component holding pixel 0 keeps upstream's adjlabel 0)
+__global__ void ccl_relabel_kernel(const int* __restrict__ P, const int* __restrict__ csize, const int* __restrict__ link,
+                                   const int* __restrict__ newid, int* __restrict__ lab, int lp, int w, int h, int min_sp)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= w) return;
-    lab[(size_t)y * lp + x] = newid[P[y * w + x]];
+    int r = P[y * w + x];
+    while (r >= 0 && csize[r] <= min_sp) r = link[r];
+    lab[(size_t)y * lp + x] = r >= 0 ? newid[r] : 0;
 }
 
 int enforce_connectivity_dev(PostWorkspace& ws, int* d_labels, int lp, int numlabels, int min_element_size,
@@ -233,18 +280,16 @@ int enforce_connectivity_dev(PostWorkspace& ws, int* d_labels, int lp, int numla
     int* d_link = ws.link;
     dim3 b2(256), g2(cdiv(w, 256), h);
     int g1 = cdiv(n, 256);
-    ccl_init_kernel<<<g2, b2, 0, st>>>(d_labels, lp, w, h, ws.parent);
-    if (h > 1) ccl_merge_kernel<<<dim3(cdiv(w, 256), h - 1), b2, 0, st>>>(d_labels, lp, w, h, ws.parent);
+    ccl_local_kernel<<<dim3(cdiv(w, CT), cdiv(h, CT)), 256, 0, st>>>(d_labels, lp, w, h, ws.parent, ws.csize);
+    const int nborder = (cdiv(h, CT) - 1) * w + (cdiv(w, CT) - 1) * h;
+    if (nborder > 0) ccl_border_kernel<<<cdiv(nborder, 256), 256, 0, st>>>(d_labels, lp, w, h, ws.parent);
     ccl_flatten_kernel<<<g1, 256, 0, st>>>(ws.parent, ws.csize, n);
-    ccl_size_kernel<<<g1, 256, 0, st>>>(ws.parent, ws.csize, n);
-    ccl_link_kernel<<<g2, b2, 0, st>>>(ws.parent, ws.csize, d_link, w, h, min_sp);
     int nb = cdiv(n, SCAN_CHUNK);
-    scan_count_kernel<<<nb, 256, 0, st>>>(ws.parent, ws.csize, n, min_sp, ws.blocksum);
+    scan_count_kernel<<<nb, 256, 0, st>>>(ws.parent, ws.csize, n, min_sp, ws.blocksum, d_link, w, h);
     scan_blocks_kernel<<<1, 1024, 0, st>>>(ws.blocksum, nb, ws.flag);
     scan_apply_kernel<<<nb, 256, 0, st>>>(ws.parent, ws.csize, n, min_sp, ws.blocksum, ws.newid);
-    ccl_resolve_kernel<<<g1, 256, 0, st>>>(ws.parent, ws.csize, d_link, ws.newid, n, min_sp);
-    ccl_relabel_kernel<<<g2, b2, 0, st>>>(ws.parent, ws.newid, d_labels, lp, w, h);
-    ws.launches += (h > 1) ? 10 : 9;
+    ccl_relabel_kernel<<<g2, b2, 0, st>>>(ws.parent, ws.csize, d_link, ws.newid, d_labels, lp, w, h, min_sp);
+    ws.launches += nborder > 0 ? 7 : 6;
     SPX_CUDA(cudaGetLastError());
     SPX_CUDA(cudaMemcpyAsync(ws.h_flag, ws.flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     SPX_CUDA(cudaStreamSynchronize(st));
