@@ -143,7 +143,7 @@ def run_reference(args):
            "cpu_baseline": {"value": mps, "unit": "MP/s", "cores": cores, "kind": "port",
                             "sample": "%d x one 4K frame, oracle restatement of ximgproc SLIC with OpenMP row bands" % args.steps},
            "e2e": {"value": mps, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
 
 
 def other_configs(spx, synth, L):
@@ -382,13 +382,30 @@ def run_ours(args):
                        "d2h_bytes_per_step": n_host * npx * 4, "frames": n_host, "threads": n_thr},
                "gpu_launches": total_launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
                "wall_s_timed": wall, "other_configs": other}
-        print(json.dumps(out))
+        emit(out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """the ONE JSON line of the contract goes to the real stdout; everything else a library prints (NCCL's version banner,
+    warnings) was redirected to stderr at start-up"""
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, line)
+    else:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                      # fd 1 -> stderr for the rest of the process (C libraries included)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
