@@ -1,4 +1,4 @@
-// slic_tile.cu -- tiled fast path of the SLIC assignment + centre accumulation (3-channel, SLIC / SLICO / MSLIC).   [v6]
+// slic_tile.cu -- tiled fast path of the SLIC assignment + centre accumulation (3-channel, SLIC / SLICO / MSLIC).   [v7]
 //
 // One CTA (128 threads) owns a 32x32 pixel tile of the "Lab1" image (one 32-bit word per pixel: c0,c1,c2,1; rows and
 // columns padded to the tile grid with zero words, so no load or store in the hot loop needs a bounds check).
@@ -15,10 +15,11 @@
 //             constant xywt is a multiply when xywt is a power of two (folded into the tables), otherwise Markstein's
 //             correctly rounded q = a*r; q += fma(-q, w, a)*r with r = RN(1/w).  Labels go out as 8-byte stores, the
 //             winning candidate slot of every pixel into a 1 KB shared-memory map.
-//   phase 2 : accumulation over the slot map with a scattered thread->pixel mapping (the 32 lanes of a warp sit in
-//             different clusters, so their shared-memory atomics rarely collide): a thread sums 4 consecutive pixels
-//             split by at most two slots with byte-SIMD masks and adds (c0,c1,c2,count,x,y) to the CTA's per-candidate
-//             accumulators; then one 64-bit global atomic per field per candidate that received pixels.
+//   accumulate : SLIC / MSLIC: right after the assignment a thread adds its 2x2 pixels (split by at most two winners with
+//             byte-SIMD masks) to the CTA's per-candidate accumulators -- packed words (c0 | count, c1, c2, x | y) in 8
+//             privatised copies; MSLIC adds the manifold-area limbs the same way, SLICO the maximum of the pixels'
+//             colour distance to their last visitor.  Then one 64-bit global atomic per field per candidate that received
+//             pixels.
 // Algorithmic traffic: 3 B/px read + 4 B/px written per iteration (the padded word layout moves 4 + 4).
 #include "slic.cuh"
 #include "slic_generic.cuh"
@@ -86,9 +87,8 @@ struct __align__(16) CandRec {
     float ey2[TH];               // (y-ky)^2 likewise
 };
 struct SlicoSmem {               // SLICO only
-    float dcm[TH][TW];           // colour distance to the LAST visiting cluster, per pixel (upstream's distchans plane)
-    unsigned mx[NCOPY][CAP];     // per candidate: running maximum of dcm over its pixels (float bits; values are >= 0)
-};
+    unsigned mx[NCOPY][CAP];     // per candidate: running maximum, over its pixels, of the colour distance to the pixel's LAST
+};                               // visiting cluster (upstream's distchans plane; float bits, values are >= 0)
 struct MslicSmem {               // MSLIC only: manifold area (fixed point x256) per candidate, as 16-bit limbs
     unsigned ar[NCOPY][CAP][2];  // [0]: sum of (v & 0xffff), [1]: sum of (v >> 16); a tile has 1024 pixels, v < 2^32
 };
@@ -107,7 +107,6 @@ struct __align__(16) TileSmemT {
     __align__(16) unsigned acc[NCOPY][CAP * 4 + 4];
     float kxy[CAP][2];           // centre position per slot
     int list[CAP];
-    unsigned char slot[TH][TW];  // winning candidate slot per pixel (0xFF: none / handled on the spot)
     typename std::conditional<ALG == SPX_SLICO, SlicoSmem, NoSmem>::type o;
     typename std::conditional<ALG == SPX_MSLIC, MslicSmem, NoSmem>::type ms;
     int bad;                     // SLICO / MSLIC: a divisor the reciprocal sequence cannot handle -> exact generic path for the tile
@@ -150,6 +149,69 @@ __device__ __noinline__ void tile_fallback(const SlicGeom& g, const SlicArrays& 
     }
 }
 
+// SLIC / MSLIC: the thread's 2x2 pixels go into the CTA's per-candidate accumulators right after the assignment (no slot map,
+// no second pass).  The block belongs to at most two candidates A (the first pixel's) and B in all but ~1 % of the cases:
+// byte-SIMD sums (even bytes c0,c2 / odd bytes c1,1 as 16-bit lanes) split by masks, 4 packed atomics per candidate.
+template <int ALG>
+__device__ __forceinline__ void acc_block(TileSmemT<ALG>& sm, int lane, unsigned s00, unsigned s01, unsigned s10, unsigned s11,
+                                          unsigned p00, unsigned p01, unsigned p10, unsigned p11, unsigned xo, unsigned yo,
+                                          float l00 = 0.f, float l01 = 0.f, float l10 = 0.f, float l11 = 0.f)
+{
+    const unsigned A = s00;
+    const bool e1 = s01 == A, e2 = s10 == A, e3 = s11 == A;
+    const unsigned B = !e1 ? s01 : (!e2 ? s10 : s11);
+    const bool two = (e1 || s01 == B) && (e2 || s10 == B) && (e3 || s11 == B);
+    unsigned* const cp = sm.acc[lane & (NCOPY - 1)];
+    if (two) {
+        const unsigned E0 = p00 & 0x00ff00ffu, E1 = p01 & 0x00ff00ffu, E2 = p10 & 0x00ff00ffu, E3 = p11 & 0x00ff00ffu;
+        const unsigned O0 = (p00 >> 8) & 0x00ff00ffu, O1 = (p01 >> 8) & 0x00ff00ffu, O2 = (p10 >> 8) & 0x00ff00ffu, O3 = (p11 >> 8) & 0x00ff00ffu;
+        const unsigned m1 = e1 ? 0xffffffffu : 0u, m2 = e2 ? 0xffffffffu : 0u, m3 = e3 ? 0xffffffffu : 0u;
+        const unsigned AE = E0 + (E1 & m1) + (E2 & m2) + (E3 & m3);
+        const unsigned AO = O0 + (O1 & m1) + (O2 & m2) + (O3 & m3);
+        const unsigned cntA = AO >> 16;
+        const unsigned dxA = (m1 & 1u) + (m3 & 1u), dyA = (m2 & 1u) + (m3 & 1u);       // offsets of A's pixels inside the block
+        unsigned* da = cp + 4 * A;
+        atomicAdd(da + 0, (AE & 0xffffu) | (cntA << 18)); atomicAdd(da + 1, AO & 0xffffu); atomicAdd(da + 2, AE >> 16);
+        atomicAdd(da + 3, (cntA * xo + dxA) | ((cntA * yo + dyA) << 16));
+        if constexpr (ALG == SPX_SLICO) {
+            const unsigned d0 = __float_as_uint(l00), d1 = __float_as_uint(l01), d2 = __float_as_uint(l10), d3 = __float_as_uint(l11);
+            atomicMax(&sm.o.mx[lane & (NCOPY - 1)][A], max(max(d0, d1 & m1), max(d2 & m2, d3 & m3)));
+            if (A != B) atomicMax(&sm.o.mx[lane & (NCOPY - 1)][B], max(max(d1 & ~m1, d2 & ~m2), d3 & ~m3));
+        }
+        if (A != B) {
+            const unsigned BE = (E0 + E1 + E2 + E3) - AE, BO = (O0 + O1 + O2 + O3) - AO;
+            const unsigned cntB = 4u - cntA;
+            unsigned* db = cp + 4 * B;
+            atomicAdd(db + 0, (BE & 0xffffu) | (cntB << 18)); atomicAdd(db + 1, BO & 0xffffu); atomicAdd(db + 2, BE >> 16);
+            atomicAdd(db + 3, (cntB * xo + (2u - dxA)) | ((cntB * yo + (2u - dyA)) << 16));
+        }
+    } else {
+        const unsigned ss[4] = {s00, s01, s10, s11}, pw[4] = {p00, p01, p10, p11};
+        const float ll[4] = {l00, l01, l10, l11};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            unsigned* d = cp + 4 * ss[j];
+            atomicAdd(d + 0, (pw[j] & 0xffu) | (1u << 18)); atomicAdd(d + 1, (pw[j] >> 8) & 0xffu);
+            atomicAdd(d + 2, (pw[j] >> 16) & 0xffu); atomicAdd(d + 3, (xo + (j & 1)) | ((yo + (j >> 1)) << 16));
+            if constexpr (ALG == SPX_SLICO) atomicMax(&sm.o.mx[lane & (NCOPY - 1)][ss[j]], __float_as_uint(ll[j]));
+        }
+    }
+}
+// MSLIC: manifold area (fixed point x256) of one pixel quad into the winner's limbs; beyond 32 bits straight to the global sum
+template <int ALG>
+__device__ __forceinline__ void acc_area(const TileArgs& t, TileSmemT<ALG>& sm, int lane, unsigned s, float a)
+{
+    if constexpr (ALG == SPX_MSLIC) {
+        const unsigned long long v = area_fx(a);
+        if (!v) return;
+        if (v >> 32) atomicAdd(&t.area[key_n(__float_as_int(sm.rec[s].k.w))], v);
+        else {
+            atomicAdd(&sm.ms.ar[lane & (NCOPY - 1)][s][0], (unsigned)v & 0xffffu);
+            atomicAdd(&sm.ms.ar[lane & (NCOPY - 1)][s][1], (unsigned)v >> 16);
+        }
+    }
+}
+
 // phase-1 cold path: some pixel of the warp's patch is covered by no window (or lies outside the image).
 // Everything is passed by value so that the hot loop's state never has to live in local memory.
 template <int ALG>
@@ -165,12 +227,20 @@ __device__ __noinline__ void step_slow(const TileArgs& t, TileSmemT<ALG>& sm, in
         const int r = i >> 1, k = i & 1;
         const int xx = x + k, yy = y + r;
         const int key = keys[i];                                // < 0: no candidate
-        unsigned char sb = 0xFF;
         if (xx < t.w && yy < t.h) {
             const size_t li = (size_t)yy * t.lp + xx;
             if (key >= 0) {
-                labels[li] = key_n(key); sb = (unsigned char)key_slot(key);
-                if constexpr (ALG == SPX_SLICO) { t.dcplane[li] = ldc[i]; sm.o.dcm[yo + r][xo + k] = ldc[i]; }
+                labels[li] = key_n(key);
+                if constexpr (ALG == SPX_SLICO) {
+                    t.dcplane[li] = ldc[i];
+                    atomicMax(&sm.o.mx[threadIdx.x & (NCOPY - 1)][key_slot(key)], __float_as_uint(ldc[i]));
+                }
+                {
+                    unsigned* d = sm.acc[threadIdx.x & (NCOPY - 1)] + 4 * key_slot(key);
+                    atomicAdd(d + 0, (px[i] & 0xffu) | (1u << 18)); atomicAdd(d + 1, (px[i] >> 8) & 0xffu);
+                    atomicAdd(d + 2, (px[i] >> 16) & 0xffu); atomicAdd(d + 3, (unsigned)(xo + k) | ((unsigned)(yo + r) << 16));
+                    if constexpr (ALG == SPX_MSLIC) { if (xx < t.w - 1 && yy < t.h - 1) acc_area<ALG>(t, sm, threadIdx.x & 31, (unsigned)key_slot(key), t.area_px[li]); }
+                }
             } else {
                 const int n = labels[li];
                 acc_global_pixel(t, n, px[i], xx, yy);          // keeps its label; sums go straight to global
@@ -178,12 +248,11 @@ __device__ __noinline__ void step_slow(const TileArgs& t, TileSmemT<ALG>& sm, in
                 if constexpr (ALG == SPX_SLICO) atomicMax(&t.maxc_acc[n], __float_as_uint(t.dcplane[li]));   // plane keeps its value
             }
         }
-        sm.slot[yo + r][xo + k] = sb;
     }
 }
 
 template <bool POW2, int ALG>
-__global__ void __launch_bounds__(NT, ALG == SPX_SLICO ? 6 : 8) slic_tile_kernel(const __grid_constant__ TileArgs t, const __grid_constant__ SlicGeom g,
+__global__ void __launch_bounds__(NT, 8) slic_tile_kernel(const __grid_constant__ TileArgs t, const __grid_constant__ SlicGeom g,
                                                            const __grid_constant__ SlicArrays a, const unsigned char* __restrict__ img,
                                                            int* __restrict__ labels, int parity, int* __restrict__ d_overflow)
 {
@@ -382,14 +451,29 @@ __global__ void __launch_bounds__(NT, ALG == SPX_SLICO ? 6 : 8) slic_tile_kernel
             const int n00 = key_n(key[0][0]), n01 = key_n(key[0][1]), n10 = key_n(key[1][0]), n11 = key_n(key[1][1]);
             *reinterpret_cast<int2*>(lrow) = make_int2(n00, n01);
             *reinterpret_cast<int2*>(lrow + t.lp) = make_int2(n10, n11);
-            *reinterpret_cast<unsigned short*>(&sm.slot[yo][xo]) = (unsigned short)(key_slot(key[0][0]) | (key_slot(key[0][1]) << 8));
-            *reinterpret_cast<unsigned short*>(&sm.slot[yo + 1][xo]) = (unsigned short)(key_slot(key[1][0]) | (key_slot(key[1][1]) << 8));
+            acc_block<ALG>(sm, lane, key_slot(key[0][0]), key_slot(key[0][1]), key_slot(key[1][0]), key_slot(key[1][1]), px[0][0], px[0][1],
+                           px[1][0], px[1][1], (unsigned)xo, (unsigned)yo, ldc[0][0], ldc[0][1], ldc[1][0], ldc[1][1]);
+            if constexpr (ALG == SPX_MSLIC) {                      // (zero in the image's last row / column: the plane holds 0 there)
+                const float2 a0 = __ldg(reinterpret_cast<const float2*>(t.area_px + (lrow - labels)));
+                const float2 a1 = __ldg(reinterpret_cast<const float2*>(t.area_px + (lrow - labels) + t.lp));
+                const unsigned s0 = key_slot(key[0][0]), s1 = key_slot(key[0][1]), s2 = key_slot(key[1][0]), s3 = key_slot(key[1][1]);
+                const unsigned long long v0 = area_fx(a0.x), v1 = area_fx(a0.y), v2 = area_fx(a1.x), v3 = area_fx(a1.y);
+                if (s0 == s1 && s0 == s2 && s0 == s3 && !((v0 | v1 | v2 | v3) >> 32)) {      // one candidate, ordinary values: one pair of atomics
+                    const unsigned lo = ((unsigned)v0 & 0xffffu) + ((unsigned)v1 & 0xffffu) + ((unsigned)v2 & 0xffffu) + ((unsigned)v3 & 0xffffu);
+                    const unsigned hi = ((unsigned)v0 >> 16) + ((unsigned)v1 >> 16) + ((unsigned)v2 >> 16) + ((unsigned)v3 >> 16);
+                    if (lo | hi) {
+                        atomicAdd(&sm.ms.ar[lane & (NCOPY - 1)][s0][0], lo);
+                        atomicAdd(&sm.ms.ar[lane & (NCOPY - 1)][s0][1], hi);
+                    }
+                } else {
+                    acc_area<ALG>(t, sm, lane, s0, a0.x); acc_area<ALG>(t, sm, lane, s1, a0.y);
+                    acc_area<ALG>(t, sm, lane, s2, a1.x); acc_area<ALG>(t, sm, lane, s3, a1.y);
+                }
+            }
             if constexpr (ALG == SPX_SLICO) {
                 float* prow = t.dcplane + (lrow - labels);
                 *reinterpret_cast<float2*>(prow) = make_float2(ldc[0][0], ldc[0][1]);
                 *reinterpret_cast<float2*>(prow + t.lp) = make_float2(ldc[1][0], ldc[1][1]);
-                *reinterpret_cast<float2*>(&sm.o.dcm[yo][xo]) = make_float2(ldc[0][0], ldc[0][1]);
-                *reinterpret_cast<float2*>(&sm.o.dcm[yo + 1][xo]) = make_float2(ldc[1][0], ldc[1][1]);
             }
         } else {
             step_slow<ALG>(t, sm, labels, key[0][0], key[0][1], key[1][0], key[1][1], px[0][0], px[0][1], px[1][0], px[1][1],
@@ -399,88 +483,6 @@ __global__ void __launch_bounds__(NT, ALG == SPX_SLICO ? 6 : 8) slic_tile_kernel
         lrow += 16 * t.lp;
     }
 
-    // phase 2's pixels (L1 hits) are requested before the barrier
-    uint4 pv2[2];
-#pragma unroll
-    for (int it = 0; it < 2; it++)
-        pv2[it] = __ldg(reinterpret_cast<const uint4*>(t.img4 + (size_t)(ty0 + (lane >> 3) * 8 + warp * 2 + it) * t.p4 + tx0 + 4 * (lane & 7)));
-    __syncthreads();
-
-    // ---- phase 2: accumulate over the slot map.  Thread -> two 4-pixel row segments; the lanes of a warp are spread
-    // over the whole tile (8 column groups x 4 rows 8 apart), so concurrent shared-memory atomics mostly hit
-    // different candidates.
-#pragma unroll
-    for (int it = 0; it < 2; it++) {
-        const int q = lane & 7;                                        // column group: pixels 4q .. 4q+3
-        const int row = (lane >> 3) * 8 + warp * 2 + it;               // rows r, r+8, r+16, r+24 within a warp
-        const unsigned sl = *reinterpret_cast<const unsigned*>(&sm.slot[row][4 * q]);
-        const uint4 pv = pv2[it];
-        if constexpr (ALG == SPX_MSLIC) {
-            // manifold area of the 4 pixel quads (zero in the last row / column and in the padding), added to the winner's
-            // limbs; a value beyond 32 bits (absurd ruler) goes straight to the global sum
-            const float4 av = __ldg(reinterpret_cast<const float4*>(t.area_px + (size_t)(ty0 + row) * t.lp + tx0 + 4 * q));
-            const float avs[4] = {av.x, av.y, av.z, av.w};
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const unsigned s = (sl >> (8 * j)) & 0xffu;
-                const unsigned long long v = area_fx(avs[j]);
-                if (s != 0xffu && v) {
-                    if (v >> 32) atomicAdd(&t.area[key_n(__float_as_int(sm.rec[s].k.w))], v);
-                    else {
-                        atomicAdd(&sm.ms.ar[lane & (NCOPY - 1)][s][0], (unsigned)v & 0xffffu);
-                        atomicAdd(&sm.ms.ar[lane & (NCOPY - 1)][s][1], (unsigned)v >> 16);
-                    }
-                }
-            }
-        }
-        // the segment's pixels belong to at most two candidates A (the first pixel's) and B (the first one that differs)
-        const unsigned s0 = sl & 0xffu, s1 = (sl >> 8) & 0xffu, s2 = (sl >> 16) & 0xffu, s3 = sl >> 24;
-        const unsigned A = s0;
-        const bool e1 = s1 == A, e2 = s2 == A, e3 = s3 == A;
-        const unsigned B = !e1 ? s1 : (!e2 ? s2 : s3);
-        const bool two = (e1 || s1 == B) && (e2 || s2 == B) && (e3 || s3 == B);
-        if (two && A != 0xffu && B != 0xffu) {
-            // even bytes (c0,c2) and odd bytes (c1,1) of every pixel, as two 16-bit lanes each
-            const unsigned E0 = pv.x & 0x00ff00ffu, E1 = pv.y & 0x00ff00ffu, E2 = pv.z & 0x00ff00ffu, E3 = pv.w & 0x00ff00ffu;
-            const unsigned O0 = (pv.x >> 8) & 0x00ff00ffu, O1 = (pv.y >> 8) & 0x00ff00ffu, O2 = (pv.z >> 8) & 0x00ff00ffu,
-                           O3 = (pv.w >> 8) & 0x00ff00ffu;
-            const unsigned m1 = e1 ? 0xffffffffu : 0u, m2 = e2 ? 0xffffffffu : 0u, m3 = e3 ? 0xffffffffu : 0u;
-            const unsigned TE = E0 + E1 + E2 + E3, TO = O0 + O1 + O2 + O3;
-            const unsigned AE = E0 + (E1 & m1) + (E2 & m2) + (E3 & m3);
-            const unsigned AO = O0 + (O1 & m1) + (O2 & m2) + (O3 & m3);
-            const unsigned cntA = AO >> 16;
-            const unsigned jA = (m1 & 1u) + (m2 & 2u) + (m3 & 3u);       // sum of the in-segment offsets of A's pixels
-            unsigned* da = &sm.acc[lane & (NCOPY - 1)][4 * A];
-            atomicAdd(da + 0, (AE & 0xffffu) | (cntA << 18)); atomicAdd(da + 1, AO & 0xffffu); atomicAdd(da + 2, AE >> 16);
-            atomicAdd(da + 3, (cntA * (4 * q) + jA) | ((cntA * row) << 16));
-            if constexpr (ALG == SPX_SLICO) {
-                const uint4 dv = *reinterpret_cast<const uint4*>(&sm.o.dcm[row][4 * q]);     // float bits, all >= 0
-                const unsigned mA = max(max(dv.x, dv.y & m1), max(dv.z & m2, dv.w & m3));
-                atomicMax(&sm.o.mx[lane & (NCOPY - 1)][A], mA);
-                if (A != B) atomicMax(&sm.o.mx[lane & (NCOPY - 1)][B], max(max(dv.y & ~m1, dv.z & ~m2), dv.w & ~m3));
-            }
-            if (A != B) {
-                const unsigned BE = TE - AE, BO = TO - AO;
-                const unsigned cntB = BO >> 16, jB = 6u - jA;
-                unsigned* db = &sm.acc[lane & (NCOPY - 1)][4 * B];
-                atomicAdd(db + 0, (BE & 0xffffu) | (cntB << 18)); atomicAdd(db + 1, BO & 0xffffu); atomicAdd(db + 2, BE >> 16);
-                atomicAdd(db + 3, (cntB * (4 * q) + jB) | ((cntB * row) << 16));
-            }
-        } else {
-            // three slots in four pixels, or pixels handled on the spot in phase 1 (0xFF): one by one
-            const unsigned pw[4] = {pv.x, pv.y, pv.z, pv.w};
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const unsigned s = (sl >> (8 * j)) & 0xffu;
-                if (s != 0xffu) {
-                    unsigned* d = &sm.acc[lane & (NCOPY - 1)][4 * s];
-                    atomicAdd(d + 0, (pw[j] & 0xffu) | (1u << 18)); atomicAdd(d + 1, (pw[j] >> 8) & 0xffu);
-                    atomicAdd(d + 2, (pw[j] >> 16) & 0xffu); atomicAdd(d + 3, (unsigned)(4 * q + j) | ((unsigned)row << 16));
-                    if constexpr (ALG == SPX_SLICO) atomicMax(&sm.o.mx[lane & (NCOPY - 1)][s], __float_as_uint(sm.o.dcm[row][4 * q + j]));
-                }
-            }
-        }
-    }
     __syncthreads();
     // ---- flush: fold the copies, then one global atomic per field per candidate that received pixels
     for (int i = tid; i < cnt * 4; i += NT) {

@@ -395,3 +395,15 @@ def test_golden_hashes_on_gpu(spx, example_bgr):
     got = gg.compute(spx, example_bgr, lambda bgr: spx.cvtColor(bgr, spx.COLOR_BGR2Lab),
                      lambda lab, S, r: spx.createSuperpixelSLIC(lab, spx.SLIC, S, r))
     assert got == want
+
+
+@pytest.mark.gpu
+def test_sanity_sweep():
+    """ragged / degenerate sizes of all five algorithms (tools/sanity_sweep.py): bit-exact against the oracle or rejected with
+    SPX_ERR_BAD_ARG -- never a CUDA error, never a mismatch"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("sanity_sweep", os.path.join(os.path.dirname(__file__), "..", "tools", "sanity_sweep.py"))
+    sw = importlib.util.module_from_spec(spec); spec.loader.exec_module(sw)
+    ok, rejected, failed = sw.run(sw.SMALL)
+    assert not failed, failed[:5]
+    assert ok > 100
