@@ -138,13 +138,48 @@ __global__ void lsc_bin_kernel(LscDev L)
 }
 
 // ---- assignment + exact accumulation -----------------------------------------------------------------------------
+// The CTA's 32x8 pixels search the bins (bx-1..bx+1) x (by-1..by+1) of their own bin; the union over the CTA is a small
+// block of bins, so its seeds and centres are staged in shared memory once (a thread per bin walks the list) and every pixel
+// loops over the staged set with the window test -- instead of each pixel chasing nine linked lists through L2.  The explicit
+// (d, k) tie-break makes the result independent of the staging order.  More than LSC_STAGE seeds: the per-pixel walk.
+constexpr int LSC_STAGE = 96;
 template <int C>
 __global__ void __launch_bounds__(256) lsc_assign_kernel(LscDev L, int* __restrict__ labels, int do_assign)
 {
     constexpr int D = 2 * C + 4;
+    __shared__ int s_n;
+    __shared__ int s_k[LSC_STAGE];
+    __shared__ int2 s_xy[LSC_STAGE];
+    __shared__ float s_cen[LSC_STAGE][D];
     const int lane = threadIdx.x & 31;
     const int x = blockIdx.x * 32 + lane, y = blockIdx.y * 8 + (threadIdx.x >> 5);
     const bool inside = x < L.w && y < L.h;
+    int staged = -1;                                              // -1: per-pixel walk
+    if (do_assign) {
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        const int X0 = blockIdx.x * 32, Y0 = blockIdx.y * 8;
+        const int bx0 = max(X0 / L.stepx - 1, 0), bx1 = min(min(X0 + 31, L.w - 1) / L.stepx + 1, L.nbx - 1);
+        const int by0 = max(Y0 / L.stepy - 1, 0), by1 = min(min(Y0 + 7, L.h - 1) / L.stepy + 1, L.nby - 1);
+        const int nbw = bx1 - bx0 + 1, nb = nbw * (by1 - by0 + 1);
+        for (int b = threadIdx.x; b < nb; b += 256)
+            for (int k = L.head[(by0 + b / nbw) * L.nbx + bx0 + b % nbw]; k >= 0; k = L.next[k]) {
+                const int pos = atomicAdd(&s_n, 1);
+                if (pos < LSC_STAGE) s_k[pos] = k;
+            }
+        __syncthreads();
+        const int n = s_n;
+        if (n <= LSC_STAGE) {
+            staged = n;
+            for (int i = threadIdx.x; i < n * (D + 2); i += 256) {
+                const int j = i / (D + 2), f = i % (D + 2), k = s_k[j];
+                if (f < D) s_cen[j][f] = L.cen[(size_t)k * D + f];
+                else if (f == D) s_xy[j].x = L.sx[k];
+                else s_xy[j].y = L.sy[k];
+            }
+        }
+        __syncthreads();
+    }
     float f[D];
     float Wt = 0.f;
     int label = -1 - lane;
@@ -154,17 +189,29 @@ __global__ void __launch_bounds__(256) lsc_assign_kernel(LscDev L, int* __restri
         if (do_assign) {
             float best = FLT_MAX;
             int bestk = -1;
-            const int bx = x / L.stepx, by = y / L.stepy;
-            for (int yy = max(by - 1, 0); yy <= min(by + 1, L.nby - 1); yy++)
-                for (int xx = max(bx - 1, 0); xx <= min(bx + 1, L.nbx - 1); xx++)
-                    for (int k = L.head[yy * L.nbx + xx]; k >= 0; k = L.next[k]) {
-                        if (abs(x - L.sx[k]) > L.stepx || abs(y - L.sy[k]) > L.stepy) continue;
-                        const float* c = L.cen + (size_t)k * D;
-                        float d = 0.f;
+            if (staged >= 0) {
+                for (int j = 0; j < staged; j++) {
+                    const int2 sxy = s_xy[j];
+                    if (abs(x - sxy.x) > L.stepx || abs(y - sxy.y) > L.stepy) continue;
+                    float d = 0.f;
 #pragma unroll
-                        for (int i = 0; i < D; i++) { const float t = __fsub_rn(f[i], c[i]); d = __fadd_rn(d, __fmul_rn(t, t)); }
-                        if (d < best || (d == best && k < bestk)) { best = d; bestk = k; }
-                    }
+                    for (int i = 0; i < D; i++) { const float t = __fsub_rn(f[i], s_cen[j][i]); d = __fadd_rn(d, __fmul_rn(t, t)); }
+                    const int k = s_k[j];
+                    if (d < best || (d == best && k < bestk)) { best = d; bestk = k; }
+                }
+            } else {
+                const int bx = x / L.stepx, by = y / L.stepy;
+                for (int yy = max(by - 1, 0); yy <= min(by + 1, L.nby - 1); yy++)
+                    for (int xx = max(bx - 1, 0); xx <= min(bx + 1, L.nbx - 1); xx++)
+                        for (int k = L.head[yy * L.nbx + xx]; k >= 0; k = L.next[k]) {
+                            if (abs(x - L.sx[k]) > L.stepx || abs(y - L.sy[k]) > L.stepy) continue;
+                            const float* c = L.cen + (size_t)k * D;
+                            float d = 0.f;
+#pragma unroll
+                            for (int i = 0; i < D; i++) { const float t = __fsub_rn(f[i], c[i]); d = __fadd_rn(d, __fmul_rn(t, t)); }
+                            if (d < best || (d == best && k < bestk)) { best = d; bestk = k; }
+                        }
+            }
             if (bestk >= 0) { labels[li] = bestk; label = bestk; }
             else label = labels[li];                       // covered by no window: keeps its label
         } else label = labels[li];
