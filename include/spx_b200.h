@@ -67,6 +67,10 @@ int spx_slic_create_dev(const void* d_image, size_t stride, int width, int heigh
                         int algorithm, int region_size, float ruler, void* cuda_stream, spx_slic_t** out);
 /* re-run the constructor on a new frame of identical geometry/parameters, reusing all device
  * allocations (what `slic = createSuperpixelSLIC(...)` does on every COMPUTE click, minus malloc). */
+/* the same with the GUI's cvtColor(converted, converted, COLOR_BGR2Lab | COLOR_BGR2HSV) (mainwindow.cpp:2096-2097) folded in: the
+ * BGR image is uploaded once and converted on the device (colour_code = 44 / 40), saving a host round trip of the image */
+int spx_slic_create_bgr(const uint8_t* bgr, size_t stride, int width, int height, int colour_code, int algorithm, int region_size,
+                        float ruler, int device, spx_slic_t** out);
 int spx_slic_reset(spx_slic_t*, const uint8_t* image, size_t stride);
 int spx_slic_reset_dev(spx_slic_t*, const void* d_image, size_t stride);
 /* SuperpixelSLIC::iterate(num_iterations) -- mainwindow.cpp:2106 */
@@ -157,6 +161,8 @@ int spx_selftest_division(float w, int n, int device, int* mismatches);
 typedef struct spx_lsc spx_lsc_t;
 int spx_lsc_create(const uint8_t* image, size_t stride, int width, int height, int channels,
                    int region_size, float ratio, int device, spx_lsc_t** out);
+int spx_lsc_create_bgr(const uint8_t* bgr, size_t stride, int width, int height, int colour_code, int region_size, float ratio, int device,
+                       spx_lsc_t** out);
 int spx_lsc_iterate(spx_lsc_t*, int num_iterations);
 int spx_lsc_enforce_label_connectivity(spx_lsc_t*, int min_element_size);
 int spx_lsc_get_number_of_superpixels(spx_lsc_t*, int* out);

@@ -43,12 +43,18 @@ inline int device()
 // ---- cv::ximgproc::SuperpixelSLIC (mainwindow.h:170) ------------------------------------------------
 class SuperpixelSLIC : public cv::Algorithm {
 public:
-    SuperpixelSLIC(cv::InputArray image, int algorithm, int region_size, float ruler) : h_(nullptr), w_(0), hgt_(0)
+    // colour_code < 0: `image` is what the GUI passes today (already Lab / HSV).  COLOR_BGR2Lab (44) / COLOR_BGR2HSV (40): `image`
+    // is BGR and the cvtColor of mainwindow.cpp:2096-2097 runs on the device after the upload.
+    SuperpixelSLIC(cv::InputArray image, int algorithm, int region_size, float ruler, int colour_code = -1) : h_(nullptr), w_(0), hgt_(0)
     {
         cv::Mat m = detail::image8u(image, "createSuperpixelSLIC");
         w_ = m.cols; hgt_ = m.rows;
-        detail::check(spx_slic_create(m.data, m.step, m.cols, m.rows, m.channels(), algorithm, region_size, ruler,
-                                      detail::device(), &h_), "createSuperpixelSLIC");
+        if (colour_code < 0)
+            detail::check(spx_slic_create(m.data, m.step, m.cols, m.rows, m.channels(), algorithm, region_size, ruler,
+                                          detail::device(), &h_), "createSuperpixelSLIC");
+        else
+            detail::check(spx_slic_create_bgr(m.data, m.step, m.cols, m.rows, colour_code, algorithm, region_size, ruler,
+                                              detail::device(), &h_), "createSuperpixelSLIC");
     }
     ~SuperpixelSLIC() { spx_slic_destroy(h_); }
     SuperpixelSLIC(const SuperpixelSLIC&) = delete;
@@ -89,6 +95,12 @@ inline cv::Ptr<SuperpixelSLIC> createSuperpixelSLIC(cv::InputArray image, int al
                                                     float ruler = 10.0f)       // mainwindow.cpp:2105
 {
     return cv::makePtr<SuperpixelSLIC>(image, algorithm, region_size, ruler);
+}
+// cvtColor(image, converted, code) + createSuperpixelSLIC(converted, ...) of mainwindow.cpp:2096-2105 in one call
+inline cv::Ptr<SuperpixelSLIC> createSuperpixelSLIC_BGR(cv::InputArray bgr, int code, int algorithm = SLICO, int region_size = 10,
+                                                        float ruler = 10.0f)
+{
+    return cv::makePtr<SuperpixelSLIC>(bgr, algorithm, region_size, ruler, code);
 }
 
 // ---- cv::ximgproc::SuperpixelLSC (mainwindow.h:171) -------------------------------------------------

@@ -58,6 +58,8 @@ def lib():
         "spx_bgr2lab8_dev": [vp, sz, vp, sz, i32, i32, vp],
         "spx_bgr2hsv8_dev": [vp, sz, vp, sz, i32, i32, vp],
         "spx_slic_create": [vp, sz, i32, i32, i32, i32, i32, f32, i32, pp],
+        "spx_slic_create_bgr": [vp, sz, i32, i32, i32, i32, i32, f32, i32, pp],
+        "spx_lsc_create_bgr": [vp, sz, i32, i32, i32, i32, f32, i32, pp],
         "spx_slic_create_dev": [vp, sz, i32, i32, i32, i32, i32, f32, vp, pp],
         "spx_slic_reset": [vp, vp, sz],
         "spx_slic_reset_dev": [vp, vp, sz],
@@ -230,12 +232,20 @@ class SuperpixelSLIC(_Superpixel):
     """cv::ximgproc::SuperpixelSLIC; construct with createSuperpixelSLIC."""
     _pfx = "spx_slic_"
 
-    def __init__(self, image, algorithm=SLICO, region_size=10, ruler=10.0, device=0):
+    def __init__(self, image, algorithm=SLICO, region_size=10, ruler=10.0, device=0, colour_code=None):
+        """colour_code = COLOR_BGR2Lab / COLOR_BGR2HSV: `image` is BGR and the GUI's cvtColor (mainwindow.cpp:2096-2097) runs on the
+        device right after the upload (spx_slic_create_bgr)"""
         super().__init__()
         img = _img(image)
         self.h, self.w, self.c = img.shape
-        _ck(lib().spx_slic_create(_p(img), self.w * self.c, self.w, self.h, self.c, int(algorithm), int(region_size),
-                                  float(ruler), int(device), C.byref(self._h)))
+        if colour_code is None:
+            _ck(lib().spx_slic_create(_p(img), self.w * self.c, self.w, self.h, self.c, int(algorithm), int(region_size),
+                                      float(ruler), int(device), C.byref(self._h)))
+        else:
+            if self.c != 3:
+                raise SpxError(-5, "createSuperpixelSLIC: the fused colour conversion needs a 3-channel BGR image")
+            _ck(lib().spx_slic_create_bgr(_p(img), self.w * 3, self.w, self.h, int(colour_code), int(algorithm), int(region_size),
+                                          float(ruler), int(device), C.byref(self._h)))
 
     def reset(self, image):
         img = _img(image)
@@ -269,12 +279,18 @@ class SuperpixelLSC(_Superpixel):
     """cv::ximgproc::SuperpixelLSC; construct with createSuperpixelLSC."""
     _pfx = "spx_lsc_"
 
-    def __init__(self, image, region_size=10, ratio=0.075, device=0):
+    def __init__(self, image, region_size=10, ratio=0.075, device=0, colour_code=None):
         super().__init__()
         img = _img(image)
         self.h, self.w, self.c = img.shape
-        _ck(lib().spx_lsc_create(_p(img), self.w * self.c, self.w, self.h, self.c, int(region_size), float(ratio),
-                                 int(device), C.byref(self._h)))
+        if colour_code is None:
+            _ck(lib().spx_lsc_create(_p(img), self.w * self.c, self.w, self.h, self.c, int(region_size), float(ratio),
+                                     int(device), C.byref(self._h)))
+        else:
+            if self.c != 3:
+                raise SpxError(-5, "createSuperpixelLSC: the fused colour conversion needs a 3-channel BGR image")
+            _ck(lib().spx_lsc_create_bgr(_p(img), self.w * 3, self.w, self.h, int(colour_code), int(region_size), float(ratio),
+                                         int(device), C.byref(self._h)))
 
     def iterate(self, num_iterations=10):
         _ck(lib().spx_lsc_iterate(self._h, int(num_iterations)))
@@ -329,14 +345,14 @@ class SuperpixelSEEDS(_Superpixel):
         return n.value
 
 
-def createSuperpixelSLIC(image, algorithm=SLICO, region_size=10, ruler=10.0, device=0):
-    """mainwindow.cpp:2105"""
-    return SuperpixelSLIC(image, algorithm, region_size, ruler, device)
+def createSuperpixelSLIC(image, algorithm=SLICO, region_size=10, ruler=10.0, device=0, colour_code=None):
+    """mainwindow.cpp:2105 (colour_code: fold the cvtColor of :2096-2097 into the upload)"""
+    return SuperpixelSLIC(image, algorithm, region_size, ruler, device, colour_code)
 
 
-def createSuperpixelLSC(image, region_size=10, ratio=0.075, device=0):
+def createSuperpixelLSC(image, region_size=10, ratio=0.075, device=0, colour_code=None):
     """mainwindow.cpp:2114"""
-    return SuperpixelLSC(image, region_size, ratio, device)
+    return SuperpixelLSC(image, region_size, ratio, device, colour_code)
 
 
 def createSuperpixelSEEDS(image_width, image_height, image_channels, num_superpixels, num_levels, prior=2,

@@ -46,6 +46,9 @@ int require_device(int device);
 int pool_alloc(void** p, size_t bytes, cudaStream_t st);
 void pool_free(void* p, cudaStream_t st);
 
+// 8-bit BGR -> Lab (mode 0) / HSV (mode 1) on device buffers, in place allowed (color.cu)
+int cvt8_dev(int mode, const void* d_src, size_t sstride, void* d_dst, size_t dstride, int w, int h, cudaStream_t st);
+
 // ---- post-processing stages shared by SLIC / LSC / SEEDS engines (post.cu) ----
 struct PostWorkspace {
     int w = 0, h = 0;

@@ -679,7 +679,7 @@ struct LscEngine {
         return SPX_OK;
     }
 
-    int create(const uint8_t* image, size_t stride, int w, int h, int C, int S_, float ratio_)
+    int create(const uint8_t* image, size_t stride, int w, int h, int C, int S_, float ratio_, int cvt_mode = -1)
     {
         SPX_REQUIRE(image && w > 0 && h > 0 && (long long)w * h < (1ll << 30) && stride >= (size_t)w * C, SPX_ERR_BADARG,
                     "createSuperpixelLSC: bad image");
@@ -711,6 +711,11 @@ struct LscEngine {
         SPX_CUDA(cudaMallocHost(&h_pinned, 8 * sizeof(int)));
         L.img = d_img;
         SPX_CUDA(cudaMemcpy2DAsync(d_img, L.ipitch, image, stride, (size_t)w * C, h, cudaMemcpyHostToDevice, st));
+        if (cvt_mode >= 0) {                  // cvtColor of mainwindow.cpp:2096-2097 on the uploaded image, in place
+            SPX_REQUIRE(C == 3, SPX_ERR_BADARG, "createSuperpixelLSC: the fused colour conversion needs a 3-channel BGR image");
+            SPX_CHECK(cvt8_dev(cvt_mode, d_img, L.ipitch, d_img, L.ipitch, w, h, st));
+            launches++;
+        }
         SPX_CUDA(cudaMemsetAsync(d_labels, 0, N * sizeof(int), st));
         SPX_CUDA(cudaMemsetAsync(L.sums, 0, (size_t)L.K * (L.D + 4) * sizeof(long long), st));
         SPX_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)C * 256 * sizeof(unsigned long long), st));
@@ -990,6 +995,20 @@ extern "C" int spx_lsc_create(const uint8_t* image, size_t stride, int w, int h,
     LscEngine* e = new LscEngine();
     e->device = device;
     int rc = e->create(image, stride, w, h, C, S, ratio);
+    if (rc != SPX_OK) { delete e; return rc; }
+    *out = new spx_lsc{e};
+    return SPX_OK;
+}
+extern "C" int spx_lsc_create_bgr(const uint8_t* bgr, size_t stride, int w, int h, int colour_code, int S, float ratio, int device, spx_lsc_t** out)
+{
+    using namespace spx;
+    SPX_REQUIRE(out, SPX_ERR_BADARG, "createSuperpixelLSC: out is NULL");
+    *out = nullptr;
+    SPX_REQUIRE(colour_code == 44 || colour_code == 40, SPX_ERR_BADARG, "createSuperpixelLSC: colour code must be COLOR_BGR2Lab (44) or COLOR_BGR2HSV (40)");
+    SPX_CHECK(require_device(device));
+    LscEngine* e = new LscEngine();
+    e->device = device;
+    int rc = e->create(bgr, stride, w, h, 3, S, ratio, colour_code == 44 ? 0 : 1);
     if (rc != SPX_OK) { delete e; return rc; }
     *out = new spx_lsc{e};
     return SPX_OK;

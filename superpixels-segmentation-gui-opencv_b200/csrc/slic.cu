@@ -764,15 +764,18 @@ struct spx_slic { SlicEngine* e; };
     SPX_CUDA(cudaSetDevice(e->device))
 
 static int slic_create_common(const void* image, size_t stride, int w, int h, int C, int alg, int S, float ruler,
-                              cudaStream_t stream, bool from_device, spx_slic_t** out)
+                              cudaStream_t stream, bool from_device, spx_slic_t** out, int cvt_mode = -1)
 {
     using namespace spx;
     SPX_REQUIRE(out, SPX_ERR_BADARG, "createSuperpixelSLIC: out is NULL");
     *out = nullptr;
     SPX_REQUIRE(image, SPX_ERR_BADARG, "createSuperpixelSLIC: image is NULL");
+    SPX_REQUIRE(cvt_mode < 0 || C == 3, SPX_ERR_BADARG, "createSuperpixelSLIC: the fused colour conversion needs a 3-channel BGR image");
     SlicEngine* e = nullptr;
     SPX_CHECK(make_engine(w, h, C, alg, S, ruler, stream, &e));
     int rc = e->upload((const uint8_t*)image, stride, from_device);
+    // cvtColor(BGR2Lab / BGR2HSV) of mainwindow.cpp:2096-2097 on the freshly uploaded image, in place: no extra host round trip
+    if (rc == SPX_OK && cvt_mode >= 0) { rc = cvt8_dev(cvt_mode, e->d_img, e->g.ipitch, e->d_img, e->g.ipitch, w, h, e->st); e->launches++; }
     if (rc == SPX_OK) rc = e->seed();
     if (rc != SPX_OK) { delete e; return rc; }
     *out = new spx_slic{e};
@@ -784,6 +787,14 @@ extern "C" int spx_slic_create(const uint8_t* image, size_t stride, int w, int h
 {
     SPX_CHECK(spx::require_device(device));
     return slic_create_common(image, stride, w, h, C, alg, S, ruler, nullptr, false, out);
+}
+extern "C" int spx_slic_create_bgr(const uint8_t* bgr, size_t stride, int w, int h, int colour_code, int alg, int S, float ruler,
+                                   int device, spx_slic_t** out)
+{
+    SPX_REQUIRE(colour_code == 44 || colour_code == 40, SPX_ERR_BADARG, "createSuperpixelSLIC: colour code must be COLOR_BGR2Lab (44) or COLOR_BGR2HSV (40)");
+    SPX_CHECK(spx::require_device(device));
+    SPX_CUDA(cudaSetDevice(device));
+    return slic_create_common(bgr, stride, w, h, 3, alg, S, ruler, nullptr, false, out, colour_code == 44 ? 0 : 1);
 }
 extern "C" int spx_slic_create_dev(const void* d_image, size_t stride, int w, int h, int C, int alg, int S, float ruler,
                                    void* stream, spx_slic_t** out)

@@ -407,3 +407,21 @@ def test_sanity_sweep():
     ok, rejected, failed = sw.run(sw.SMALL)
     assert not failed, failed[:5]
     assert ok > 100
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("code", ["COLOR_BGR2Lab", "COLOR_BGR2HSV"])
+def test_create_with_fused_colour_conversion(spx, synthmod, code):
+    """spx_slic_create_bgr / spx_lsc_create_bgr == cvtColor on the host side + create (mainwindow.cpp:2096-2105)"""
+    bgr, _ = synthmod.synth(333, 211, 5)
+    cc = getattr(spx, code)
+    conv = spx.cvtColor(bgr, cc)
+    for alg, S in ((spx.SLIC, 20), (spx.SLICO, 9)):
+        a = spx.createSuperpixelSLIC(conv, alg, S, 10.0); b = spx.createSuperpixelSLIC(bgr, alg, S, 10.0, colour_code=cc)
+        a.iterate(4); b.iterate(4)
+        assert (a.getLabels() == b.getLabels()).all() and (a.getCentres() == b.getCentres()).all()
+    a = spx.createSuperpixelLSC(conv, 15, 0.075); b = spx.createSuperpixelLSC(bgr, 15, 0.075, colour_code=cc)
+    a.iterate(3); b.iterate(3)
+    assert (a.getLabels() == b.getLabels()).all()
+    with pytest.raises(spx.SpxError):
+        spx.createSuperpixelSLIC(bgr, spx.SLIC, 20, 10.0, colour_code=7)
