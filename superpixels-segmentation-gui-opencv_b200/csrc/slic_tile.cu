@@ -252,7 +252,7 @@ __device__ __noinline__ void step_slow(const TileArgs& t, TileSmemT<ALG>& sm, in
 }
 
 template <bool POW2, int ALG>
-__global__ void __launch_bounds__(NT, 8) slic_tile_kernel(const __grid_constant__ TileArgs t, const __grid_constant__ SlicGeom g,
+__global__ void __launch_bounds__(NT, ALG == SPX_SLIC ? 9 : 8) slic_tile_kernel(const __grid_constant__ TileArgs t, const __grid_constant__ SlicGeom g,
                                                            const __grid_constant__ SlicArrays a, const unsigned char* __restrict__ img,
                                                            int* __restrict__ labels, int parity, int* __restrict__ d_overflow)
 {
