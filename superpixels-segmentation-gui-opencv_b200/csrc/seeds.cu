@@ -137,21 +137,25 @@ __device__ __forceinline__ bool split_vb(int a21, int a22, int a23, int a31, int
 }
 
 // ---- block level --------------------------------------------------------------------------------------------------
-// gain of giving block (level, sub), currently part of superpixel `own`, to superpixel `tgt`
-__device__ float seeds_intersect_conditional(const SeedsDev& S, int tgt, int own, int level, int sub)
+// gain of giving block (level, sub), currently part of superpixel `own`, to superpixel `tgt`.  One warp per call: the lanes
+// split the histogram bins (coalesced reads of the three histograms), integer partial sums, butterfly reduction -- every
+// lane ends with the same exact totals and evaluates the same float expression.
+__device__ __forceinline__ float seeds_intersect_conditional(const SeedsDev& S, int tgt, int own, int level, int sub, int lane)
 {
     const int* hA = S.hist[S.top] + (size_t)tgt * S.hsize;
     const int* hB = S.hist[S.top] + (size_t)own * S.hsize;
     const int* h2 = S.hist[level] + (size_t)sub * S.hsize;
     const long long cA = S.T[S.top][tgt], c2 = S.T[level][sub], cB = (long long)S.T[S.top][own] - c2;
     long long sumA = 0, sumB = 0;
-    for (int n = 0; n < S.hsize; n++) {
+    for (int n = lane; n < S.hsize; n += 32) {
         const long long v2 = h2[n];
         const long long a = hA[n] * c2, b = v2 * cA;
         sumA += a < b ? a : b;
         const long long c = (hB[n] - v2) * c2, d = v2 * cB;
         sumB += c < d ? c : d;
     }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { sumA += __shfl_xor_sync(0xffffffffu, sumA, o); sumB += __shfl_xor_sync(0xffffffffu, sumB, o); }
     const float iA = __fdiv_rn(__ll2float_rn(sumA), __fmul_rn(__ll2float_rn(cA), __ll2float_rn(c2)));
     const float iB = cB > 0 ? __fdiv_rn(__ll2float_rn(sumB), __fmul_rn(__ll2float_rn(cB), __ll2float_rn(c2))) : 0.f;
     return __fsub_rn(iA, iB);
@@ -163,11 +167,13 @@ __device__ __forceinline__ bool seeds_phase_coords(int i, int j, int vertical, i
     x = c2 + 2 * i; y = c4 + 4 * j;
     return x >= 1 && x < nw - 1 && y >= 1 && y < nh - 2;
 }
-__global__ void seeds_block_decide_kernel(SeedsDev S, int level, int vertical, int c4, int c2, float req)
+// one warp per pair (all lanes take the same branches: the pair, its labels and the split checks are warp-uniform)
+__global__ void seeds_block_decide_kernel(SeedsDev S, int level, int vertical, int c4, int c2, float req, int ni)
 {
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     int x, y;
     const int nw = S.nr_w[level], nh = S.nr_h[level];
-    if (!seeds_phase_coords(blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y, vertical, c4, c2, nw, nh, x, y)) return;
+    if (!seeds_phase_coords(gw % ni, gw / ni, vertical, c4, c2, nw, nh, x, y)) return;
     const int* P = S.parent[level];
     const int st = nw;
 #define PP(yy, xx) P[(yy) * st + (xx)]
@@ -177,18 +183,18 @@ __global__ void seeds_block_decide_kernel(SeedsDev S, int level, int vertical, i
         const int nA = S.nrp[A], nB = S.nrp[B];
         if (!vertical) {
             if (nA == 2 || (nA > 2 && split_hf(PP(y - 1, x - 1), PP(y - 1, x), PP(y, x - 1), A, PP(y + 1, x - 1), PP(y + 1, x))))
-                if (seeds_intersect_conditional(S, B, A, level, y * st + x) > req) d = 1;
+                if (seeds_intersect_conditional(S, B, A, level, y * st + x, lane) > req) d = 1;
             if (!d && (nB == 2 || (nB > 2 && split_hb(PP(y - 1, x + 1), PP(y - 1, x + 2), B, PP(y, x + 2), PP(y + 1, x + 1), PP(y + 1, x + 2)))))
-                if (seeds_intersect_conditional(S, A, B, level, y * st + x + 1) > req) d = 2;
+                if (seeds_intersect_conditional(S, A, B, level, y * st + x + 1, lane) > req) d = 2;
         } else {
             if (nA == 2 || (nA > 2 && split_vf(PP(y - 1, x - 1), PP(y - 1, x), PP(y - 1, x + 1), PP(y, x - 1), A, PP(y, x + 1))))
-                if (seeds_intersect_conditional(S, B, A, level, y * st + x) > req) d = 1;
+                if (seeds_intersect_conditional(S, B, A, level, y * st + x, lane) > req) d = 1;
             if (!d && (nB == 2 || (nB > 2 && split_vb(PP(y + 1, x - 1), B, PP(y + 1, x + 1), PP(y + 2, x - 1), PP(y + 2, x), PP(y + 2, x + 1)))))
-                if (seeds_intersect_conditional(S, A, B, level, (y + 1) * st + x) > req) d = 2;
+                if (seeds_intersect_conditional(S, A, B, level, (y + 1) * st + x, lane) > req) d = 2;
         }
     }
 #undef PP
-    S.dec[y * nw + x] = (unsigned char)d;
+    if (lane == 0) S.dec[y * nw + x] = (unsigned char)d;
 }
 // one warp per pair: the lanes split the histogram bins
 __global__ void seeds_block_apply_kernel(SeedsDev S, int level, int vertical, int c4, int c2, int ni)
@@ -410,7 +416,7 @@ struct SeedsEngine {
             const int nj = grid.y;
             for (int c2 = 0; c2 < 2; c2++)
                 for (int c4 = 0; c4 < 4; c4++) {
-                    seeds_block_decide_kernel<<<grid, 128, 0, st>>>(S, level, vertical, c4, c2, req);
+                    seeds_block_decide_kernel<<<cdiv(ni * nj * 32, 128), 128, 0, st>>>(S, level, vertical, c4, c2, req, ni);
                     seeds_block_apply_kernel<<<cdiv(ni * nj * 32, 128), 128, 0, st>>>(S, level, vertical, c4, c2, ni);
                     launches += 2;
                 }
