@@ -287,78 +287,121 @@ __global__ void __launch_bounds__(256) mslic_area_sum_kernel(SlicGeom g, SlicArr
     if (inside && (int)(threadIdx.x & 31) == __ffs(m) - 1)
         atomicAdd((unsigned long long*)&a.area[label], (unsigned long long)s0 + ((unsigned long long)s1 << 21) + ((unsigned long long)s2 << 42));
 }
-// single CTA: mean area, adaptk, split list (ascending k), append new centres, window half-sizes
-__global__ void __launch_bounds__(1024) mslic_adapt_kernel(SlicGeom g, SlicArrays a, const unsigned char* __restrict__ img,
-                                                            int* __restrict__ d_K, int K0)
+// The content-adaptive step as four small grid-wide kernels (a single CTA walking 37 k clusters took 86 us at 8K):
+//   total   sum of the cluster areas (exact 64-bit integer)
+//   adaptk  mean area -> adaptk[k]; clusters to split counted per block and in total
+//   split   (when the growth cap allows) new centres appended in ascending k: n = K + 3 * (flagged clusters before k)
+//   finish  window half-sizes for all (old and new) clusters, areas cleared, K published
+constexpr int MA = 256;
+__device__ __forceinline__ bool mslic_flag(const SlicArrays& a, int k, float abar)
 {
-    __shared__ long long s_red[32];
-    __shared__ int s_scan[32];
-    __shared__ long long s_tot;
-    __shared__ int s_nsplit, s_carry;
-    const int K = *d_K;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    long long part = 0;
-    for (int k = tid; k < K; k += 1024) part += a.area[k];
+    const float ak = __fdiv_rn((float)a.area[k], 256.0f);
+    return ak > __fmul_rn(4.0f, abar);                       // split = 4
+}
+__device__ __forceinline__ float mslic_abar(const SlicArrays& a, int K)
+{
+    const long long tot = *reinterpret_cast<const long long*>(a.ms_scratch);
+    return __fdiv_rn((float)tot, __fmul_rn((float)K, 256.0f));
+}
+__global__ void __launch_bounds__(MA) mslic_total_kernel(SlicArrays a, const int* __restrict__ d_K)
+{
+    __shared__ long long s_red[MA / 32];
+    const int k = blockIdx.x * MA + threadIdx.x, lane = threadIdx.x & 31;
+    long long part = k < *d_K ? a.area[k] : 0;
     for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if (lane == 0) s_red[wid] = part;
+    if (lane == 0) s_red[threadIdx.x >> 5] = part;
     __syncthreads();
-    if (tid == 0) { long long t = 0; for (int i = 0; i < 32; i++) t += s_red[i]; s_tot = t; s_nsplit = 0; s_carry = 0; }
-    __syncthreads();
-    const float target = 2.0f, split = 4.0f;
-    const float abar = __fdiv_rn((float)s_tot, __fmul_rn((float)K, 256.0f));
-    int mysplits = 0;
-    for (int k = tid; k < K; k += 1024) {
-        float ak = __fdiv_rn((float)a.area[k], 256.0f);
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int i = 0; i < MA / 32; i++) t += s_red[i];
+        if (t) atomicAdd(reinterpret_cast<unsigned long long*>(a.ms_scratch), (unsigned long long)t);
+    }
+}
+__global__ void __launch_bounds__(MA) mslic_adaptk_kernel(SlicArrays a, const int* __restrict__ d_K)
+{
+    __shared__ int s_cnt[MA / 32];
+    const int K = *d_K;
+    const int k = blockIdx.x * MA + threadIdx.x, lane = threadIdx.x & 31;
+    const float target = 2.0f;
+    const float abar = mslic_abar(a, K);
+    bool f = false;
+    if (k < K) {
+        const float ak = __fdiv_rn((float)a.area[k], 256.0f);
         float r = ak > 0.f ? __fsqrt_rn(__fdiv_rn(abar, ak)) : target;
         r = fminf(fmaxf(r, __fdiv_rn(1.0f, target)), target);
         a.adaptk[k] = r;
-        if (ak > __fmul_rn(split, abar)) mysplits++;
+        f = mslic_flag(a, k, abar);
     }
-    atomicAdd(&s_nsplit, mysplits);
+    const unsigned m = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) s_cnt[threadIdx.x >> 5] = __popc(m);
     __syncthreads();
-    const int nsplit = s_nsplit;
+    if (threadIdx.x == 0) {
+        int c = 0;
+        for (int i = 0; i < MA / 32; i++) c += s_cnt[i];
+        a.ms_scratch[4 + blockIdx.x] = c;
+        if (c) atomicAdd(&a.ms_scratch[2], c);
+    }
+}
+__global__ void __launch_bounds__(MA) mslic_split_kernel(SlicGeom g, SlicArrays a, const unsigned char* __restrict__ img,
+                                                         const int* __restrict__ d_K, int K0)
+{
+    __shared__ int s_w[MA / 32];
+    __shared__ int s_base;
+    const int K = *d_K, nsplit = a.ms_scratch[2];
     const bool do_split = nsplit > 0 && K + 3 * nsplit <= 4 * K0 && K + 3 * nsplit <= g.Kcap;
-    if (do_split) {
-        for (int base = 0; base < K; base += 1024) {
-            int k = base + tid;
-            int f = 0;
-            float ak = 0.f;
-            if (k < K) { ak = __fdiv_rn((float)a.area[k], 256.0f); f = ak > __fmul_rn(split, abar) ? 1 : 0; }
-            unsigned b = __ballot_sync(0xffffffffu, f);
-            int pre = __popc(b & ((1u << lane) - 1));
-            if (lane == 0) s_scan[wid] = __popc(b);
-            __syncthreads();
-            int off = s_carry;
-            for (int q2 = 0; q2 < wid; q2++) off += s_scan[q2];
-            if (f) {
-                int n = K + 3 * (off + pre);
-                float o = __fmul_rn(__fmul_rn(0.5f, (float)g.S), a.adaptk[k]);
-                float cx = a.kx[k], cy = a.ky[k];
-                const float ox[4] = {-o, o, -o, o}, oy[4] = {-o, -o, o, o};
-                for (int j = 0; j < 4; j++) {
-                    float nx = __fadd_rn(cx, ox[j]), ny = __fadd_rn(cy, oy[j]);
-                    nx = fminf(fmaxf(nx, 0.f), (float)(g.w - 1));
-                    ny = fminf(fmaxf(ny, 0.f), (float)(g.h - 1));
-                    int dst = j == 0 ? k : n++;
-                    a.kx[dst] = nx; a.ky[dst] = ny;
-                    a.ikx[dst] = (int)nx; a.iky[dst] = (int)ny;
-                    for (int c = 0; c < g.C; c++)
-                        a.kc[(size_t)c * g.Kcap + dst] = (float)img[(size_t)(int)ny * g.ipitch + (size_t)(int)nx * g.C + c];
-                    a.adaptk[dst] = a.adaptk[k];
-                }
-            }
-            __syncthreads();
-            if (tid == 0) { int t = 0; for (int i = 0; i < 32; i++) t += s_scan[i]; s_carry += t; }
-            __syncthreads();
-        }
-    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.ms_scratch[3] = do_split ? K + 3 * nsplit : K;
+    if (!do_split) return;                                    // uniform
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // flagged clusters in the blocks before this one
+    int part = 0;
+    for (int b = tid; b < (int)blockIdx.x; b += MA) part += a.ms_scratch[4 + b];
+    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) s_w[wid] = part;
     __syncthreads();
-    const int newK = do_split ? K + 3 * nsplit : K;
-    for (int k = tid; k < newK; k += 1024) {
+    if (tid == 0) { int t = 0; for (int i = 0; i < MA / 32; i++) t += s_w[i]; s_base = t; }
+    __syncthreads();
+    const int base = s_base;
+    const int k = blockIdx.x * MA + tid;
+    const float abar = mslic_abar(a, K);
+    const bool f = k < K && mslic_flag(a, k, abar);
+    const unsigned m = __ballot_sync(0xffffffffu, f);
+    __syncthreads();
+    if (lane == 0) s_w[wid] = __popc(m);
+    __syncthreads();
+    if (!f) return;
+    int off = base + __popc(m & ((1u << lane) - 1));
+    for (int q = 0; q < wid; q++) off += s_w[q];
+    int n = K + 3 * off;
+    const float o = __fmul_rn(__fmul_rn(0.5f, (float)g.S), a.adaptk[k]);
+    const float cx = a.kx[k], cy = a.ky[k];
+    const float ox[4] = {-o, o, -o, o}, oy[4] = {-o, -o, o, o};
+    const float ad = a.adaptk[k];
+    for (int j = 0; j < 4; j++) {
+        float nx = __fadd_rn(cx, ox[j]), ny = __fadd_rn(cy, oy[j]);
+        nx = fminf(fmaxf(nx, 0.f), (float)(g.w - 1));
+        ny = fminf(fmaxf(ny, 0.f), (float)(g.h - 1));
+        const int dst = j == 0 ? k : n++;
+        a.kx[dst] = nx; a.ky[dst] = ny;
+        a.ikx[dst] = (int)nx; a.iky[dst] = (int)ny;
+        for (int c = 0; c < g.C; c++)
+            a.kc[(size_t)c * g.Kcap + dst] = (float)img[(size_t)(int)ny * g.ipitch + (size_t)(int)nx * g.C + c];
+        a.adaptk[dst] = ad;
+    }
+}
+__global__ void __launch_bounds__(MA) mslic_finish_kernel(SlicGeom g, SlicArrays a, int* __restrict__ d_K)
+{
+    const int newK = a.ms_scratch[3];
+    const int k = blockIdx.x * MA + threadIdx.x;
+    if (k < newK) {
         a.ioff[k] = (int)__fmul_rn((float)g.S, a.adaptk[k]);
         a.area[k] = 0;
     }
-    if (tid == 0) *d_K = newK;
+    if (k == 0) *d_K = newK;                                  // nobody in this kernel reads *d_K
+}
+// scratch cleared for the next iteration (after finish: total and split count are read by the kernels before it)
+__global__ void mslic_scratch_clear_kernel(SlicArrays a)
+{
+    if (threadIdx.x < 3) a.ms_scratch[threadIdx.x] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -467,6 +510,7 @@ struct SlicEngine {
         SPX_CHECK(dalloc(&a.next, kc));
         SPX_CHECK(dalloc(&a.head[0], (size_t)g.nbx * g.nby)); SPX_CHECK(dalloc(&a.head[1], (size_t)g.nbx * g.nby));
         SPX_CHECK(dalloc(&a.area, kc));
+        SPX_CHECK(dalloc(&a.ms_scratch, (size_t)8 + kc / 256 + 8));
         SPX_CHECK(dalloc(&d_K, 4)); SPX_CHECK(dalloc(&d_overflow, 4));
         if (alg == SPX_SLICO) SPX_CHECK(dalloc(&d_dcplane, (size_t)g.lp * g.tiles_y * TILE_H));
         if (alg == SPX_MSLIC) {
@@ -499,6 +543,7 @@ struct SlicEngine {
         SPX_CUDA(cudaMemsetAsync(d_labels, 0, (size_t)g.lp * g.tiles_y * TILE_H * sizeof(int), st));
         SPX_CUDA(cudaMemsetAsync(a.acc, 0, kc * (g.C + 3) * sizeof(unsigned long long), st));
         SPX_CUDA(cudaMemsetAsync(a.area, 0, kc * sizeof(long long), st));
+        SPX_CUDA(cudaMemsetAsync(a.ms_scratch, 0, 4 * sizeof(int), st));
         SPX_CUDA(cudaMemsetAsync(a.head[0], 0xFF, (size_t)g.nbx * g.nby * sizeof(int), st));
         SPX_CUDA(cudaMemsetAsync(a.head[1], 0xFF, (size_t)g.nbx * g.nby * sizeof(int), st));
         SPX_CUDA(cudaMemsetAsync(d_overflow, 0, 4 * sizeof(int), st));
@@ -570,7 +615,13 @@ struct SlicEngine {
         if (g.alg == SPX_MSLIC) {
             // the tiled assignment kernel already summed the manifold areas per cluster; the generic path does it here
             if (!use_tile) { mslic_area_sum_kernel<<<dim3(cdiv(g.w, 32), cdiv(g.h, 8)), 256, 0, st>>>(g, a, d_area_px, d_labels); launches++; }
-            mslic_adapt_kernel<<<1, 1024, 0, st>>>(g, a, d_img, d_K, K0);
+            const int nbk = cdiv(g.Kcap, MA);
+            mslic_total_kernel<<<nbk, MA, 0, st>>>(a, d_K);
+            mslic_adaptk_kernel<<<nbk, MA, 0, st>>>(a, d_K);
+            mslic_split_kernel<<<nbk, MA, 0, st>>>(g, a, d_img, d_K, K0);
+            mslic_finish_kernel<<<nbk, MA, 0, st>>>(g, a, d_K);
+            mslic_scratch_clear_kernel<<<1, 32, 0, st>>>(a);
+            launches += 4;                     // + the two counted below
             slic_bin_kernel<<<cdiv(g.Kcap, BIN_CTA), BIN_CTA, 0, st>>>(g, a, d_K, parity ^ 1);
             launches += 2;
         }

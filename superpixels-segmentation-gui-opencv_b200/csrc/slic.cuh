@@ -18,6 +18,7 @@ struct SlicArrays {
     int* next;                       // per-bin linked lists of centres
     int* head[2];                    // bin heads, double buffered by iteration parity
     long long* area;                 // MSLIC fixed-point manifold area per cluster
+    int* ms_scratch;                 // MSLIC adapt step: [0..1] total area (64 bit), [2] splits, [3] new K, [4..] splits per block
     int* tl_count[2];                // tiled path: candidates per 32x32 tile, double buffered like head[]
     struct TileRec* tl_rec[2];       // tiled path: candidate records, TILE_CAP per tile
 };
