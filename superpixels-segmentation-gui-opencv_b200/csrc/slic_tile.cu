@@ -13,9 +13,9 @@
 //             is evaluated with the sm_100 packed instructions FADD2/FMUL2 (same rounding per element, half the issue
 //             slots; scalar operands are broadcast by the instruction), never contracted.  The IEEE division by the
 //             constant xywt is a multiply when xywt is a power of two (folded into the tables), otherwise Markstein's
-//             correctly rounded q = a*r; q += fma(-q, w, a)*r with r = RN(1/w).  Labels go out as 8-byte stores, the
-//             winning candidate slot of every pixel into a 1 KB shared-memory map.
-//   accumulate : SLIC / MSLIC: right after the assignment a thread adds its 2x2 pixels (split by at most two winners with
+//             correctly rounded q = a*r; q += fma(-q, w, a)*r with r = RN(1/w).  The winner travels as one key
+//             (n << 6) | slot; labels go out as 8-byte stores.
+//   accumulate : right after the assignment a thread adds its 2x2 pixels (split by at most two winners with
 //             byte-SIMD masks) to the CTA's per-candidate accumulators -- packed words (c0 | count, c1, c2, x | y) in 8
 //             privatised copies; MSLIC adds the manifold-area limbs the same way, SLICO the maximum of the pixels'
 //             colour distance to their last visitor.  Then one 64-bit global atomic per field per candidate that received
@@ -149,8 +149,8 @@ __device__ __noinline__ void tile_fallback(const SlicGeom& g, const SlicArrays& 
     }
 }
 
-// SLIC / MSLIC: the thread's 2x2 pixels go into the CTA's per-candidate accumulators right after the assignment (no slot map,
-// no second pass).  The block belongs to at most two candidates A (the first pixel's) and B in all but ~1 % of the cases:
+// The thread's 2x2 pixels go into the CTA's per-candidate accumulators right after the assignment (no slot map, no second
+// pass).  The block belongs to at most two candidates A (the first pixel's) and B in all but ~1 % of the cases:
 // byte-SIMD sums (even bytes c0,c2 / odd bytes c1,1 as 16-bit lanes) split by masks, 4 packed atomics per candidate.
 template <int ALG>
 __device__ __forceinline__ void acc_block(TileSmemT<ALG>& sm, int lane, unsigned s00, unsigned s01, unsigned s10, unsigned s11,
@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(NT, ALG == SPX_SLIC ? 9 : 8) slic_tile_kernel(
                 }
             }
         }
-        // ---- labels + slot map.  Fast path: every pixel of the patch found a candidate and the tile is interior.
+        // ---- labels + accumulation.  Fast path: every pixel of the patch found a candidate and the tile is interior.
         const int any_neg = key[0][0] | key[0][1] | key[1][0] | key[1][1];
         if (interior && !__any_sync(0xffffffffu, any_neg < 0)) {
             const int n00 = key_n(key[0][0]), n01 = key_n(key[0][1]), n10 = key_n(key[1][0]), n11 = key_n(key[1][1]);
