@@ -16,6 +16,7 @@
 //     pixel lists in parallel, then the inherently sequential nearest-neighbour merge of small regions on the region
 //     graph by a single CTA (one step per small region), then a scan for the final ids.
 #include "common.cuh"
+#include "f32x2.cuh"
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
@@ -237,6 +238,8 @@ __global__ void __launch_bounds__(256) lsc_assign_kernel(LscDev L, int* __restri
         }
     }
 }
+
+#include "lsc_tile.cuh"
 
 // centres = W-weighted means, seeds = integer mean position; sums cleared; seeds re-binned
 __global__ void lsc_finalize_kernel(LscDev L)
@@ -630,6 +633,7 @@ struct LscEngine {
     void* d_scan_tmp = nullptr;
     size_t scan_tmp_bytes = 0;
     int* d_flag = nullptr;
+    int* d_tile_overflow = nullptr;         // tiles of the tiled assignment whose candidate list overflowed (diagnostic)
     int* h_pinned = nullptr;
     long long launches = 0;
     PostWorkspace post;
@@ -708,6 +712,8 @@ struct LscEngine {
         SPX_CHECK(dalloc(&L.sums, (size_t)L.K * (L.D + 4)));
         SPX_CHECK(dalloc(&L.head, (size_t)L.nbx * L.nby)); SPX_CHECK(dalloc(&L.next, (size_t)L.K));
         SPX_CHECK(dalloc(&d_flag, 8));
+        SPX_CHECK(dalloc(&d_tile_overflow, 1));
+        SPX_CUDA(cudaMemsetAsync(d_tile_overflow, 0, sizeof(int), st));
         SPX_CUDA(cudaMallocHost(&h_pinned, 8 * sizeof(int)));
         L.img = d_img;
         SPX_CUDA(cudaMemcpy2DAsync(d_img, L.ipitch, image, stride, (size_t)w * C, h, cudaMemcpyHostToDevice, st));
@@ -807,8 +813,10 @@ struct LscEngine {
     {
         SPX_REQUIRE(n >= 0, SPX_ERR_BADARG, "iterate: num_iterations must be >= 0");
         const dim3 grid(cdiv(L.w, 32), cdiv(L.h, 8));
+        const bool tiled = L.C == 3 && L.stepx >= LSC_TILE_MIN_STEP && L.stepy >= LSC_TILE_MIN_STEP && !getenv("SPX_LSC_NO_TILE");
         for (int it = 0; it < n; it++) {
-            switch (L.C) {
+            if (tiled) lsc_tile_kernel<<<dim3(cdiv(L.w, 32), cdiv(L.h, 32)), 128, 0, st>>>(L, d_labels, d_tile_overflow);
+            else switch (L.C) {
                 case 1: lsc_assign_kernel<1><<<grid, 256, 0, st>>>(L, d_labels, 1); break;
                 case 2: lsc_assign_kernel<2><<<grid, 256, 0, st>>>(L, d_labels, 1); break;
                 case 3: lsc_assign_kernel<3><<<grid, 256, 0, st>>>(L, d_labels, 1); break;

@@ -88,6 +88,16 @@ def test_no_stray_fma_contraction_in_tile_kernel():
             assert n_ffma2 >= 2 and n_ffma2 % 2 == 0, (name, n_ffma2)
 
 
+def test_no_fma_contraction_in_lsc_tile_kernel():
+    """the tiled LSC assignment evaluates the 10-D distance with FADD2 / FMUL2 only: 2 rows x (10 sub + 10 mul + 9 add + 2
+    penalty adds) = 62 packed instructions in the candidate loop, and no FFMA2 anywhere (the oracle never contracts)"""
+    funcs = _sass_functions()
+    k = [v for n, v in funcs.items() if "lsc_tile_kernel" in n]
+    assert len(k) == 1
+    assert sum(1 for l in k[0] if " FFMA2 " in l) == 0
+    assert sum(1 for l in k[0] if " FADD2" in l or " FMUL2" in l) == 62
+
+
 def test_cpp_adapter_builds_and_fails_loudly_without_gpu(spx):
     """include/spx_ximgproc.hpp (the cv::ximgproc-shaped adapter) compiles against a mock <opencv2/core.hpp>, links to
     libspx_b200.so, and the reference's COMPUTE click written against it throws cv::Exception(-217) on a CPU box."""

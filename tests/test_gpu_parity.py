@@ -267,6 +267,35 @@ def test_lsc_labels_and_centres_exact(spx, O, synthmod, w, h, S, ratio, iters):
     assert (ca == cb).all()
 
 
+@pytest.mark.parametrize("w,h,S,ratio,iters", [(333, 251, 16, 0.075, 5), (97, 65, 14, 0.075, 4), (257, 200, 20, 0.3, 6), (64, 33, 15, 0.075, 3),
+                                               (1920, 1080, 30, 0.075, 3)])
+def test_lsc_tiled_path_exact(spx, O, synthmod, w, h, S, ratio, iters):
+    """the tiled assignment kernel (3 channels, steps >= 14): ragged tile grids, odd widths (scalar label stores), image
+    borders (pixels no window covers keep their label), against the oracle"""
+    bgr, _ = synthmod.synth(w, h, 9)
+    lab = O.bgr2lab8(bgr)
+    a, b = _lsc_pair(spx, O, lab, S, ratio)
+    a.iterate(iters); b.iterate(iters)
+    assert (a.getLabels() == b.getLabels()).all()
+    assert (a.getCentres() == b.getCentres()).all()
+
+
+def test_lsc_tiled_equals_per_pixel_kernel_8k(spx, synthmod):
+    """cfg3 size (7680x4320, S=30): the tiled kernel against the per-pixel gather kernel (SPX_LSC_NO_TILE=1), bit for bit"""
+    bgr, _ = synthmod.synth(7680, 4320, 0)
+    lab = spx.cvtColor(bgr, spx.COLOR_BGR2Lab)
+    a = spx.createSuperpixelLSC(lab, 30, 0.075)
+    a.iterate(3)
+    os.environ["SPX_LSC_NO_TILE"] = "1"
+    try:
+        b = spx.createSuperpixelLSC(lab, 30, 0.075)
+        b.iterate(3)
+    finally:
+        del os.environ["SPX_LSC_NO_TILE"]
+    assert (a.getLabels() == b.getLabels()).all()
+    assert (a.getCentres() == b.getCentres()).all()
+
+
 @pytest.mark.parametrize("order", [1, 0])
 @pytest.mark.parametrize("p", [25, 5, 60])
 def test_lsc_full_pipeline_exact(spx, O, example_lab, p, order):
