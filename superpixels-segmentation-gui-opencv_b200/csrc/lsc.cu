@@ -42,6 +42,11 @@ struct LscDev {
     float* cen;                                   // K x D
     long long* sums;                              // K x (D+4): D features, W, x, y, count
     int *head, *next;                             // bins of stepx x stepy pixels
+    // tiled assignment (lsc_tile.cuh): colour tables interleaved per value (cos, sin, w, 0) [3][256]; per 32x32 tile the seeds
+    // whose window meets it, appended by the kernels that move the seeds (null: not tiled)
+    const float4* ctab;
+    int *tl_count, *tl_k;
+    int tiles_x, tiles_y;
 };
 
 template <int C>
@@ -130,12 +135,28 @@ __global__ void __launch_bounds__(128) lsc_init_centres_kernel(LscDev L)
     }
 }
 
+constexpr int LSC_CAP = 32;                        // candidates per tile of the tiled assignment
+// seed k into the list of every 32x32 tile its window [s - step, s + step] meets
+__device__ __forceinline__ void lsc_tile_append(const LscDev& L, int k, int sx, int sy)
+{
+    if (!L.tl_count) return;
+    const int tx0 = max(sx - L.stepx, 0) >> 5, tx1 = min(sx + L.stepx, L.w - 1) >> 5;
+    const int ty0 = max(sy - L.stepy, 0) >> 5, ty1 = min(sy + L.stepy, L.h - 1) >> 5;
+    for (int ty = ty0; ty <= ty1; ty++)
+        for (int tx = tx0; tx <= tx1; tx++) {
+            const int t = ty * L.tiles_x + tx;
+            const int pos = atomicAdd(&L.tl_count[t], 1);
+            if (pos < LSC_CAP) L.tl_k[(size_t)t * LSC_CAP + pos] = k;
+        }
+}
+
 __global__ void lsc_bin_kernel(LscDev L)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= L.K) return;
     const int bx = min(max(L.sx[k], 0) / L.stepx, L.nbx - 1), by = min(max(L.sy[k], 0) / L.stepy, L.nby - 1);
     L.next[k] = atomicExch(&L.head[by * L.nbx + bx], k);
+    lsc_tile_append(L, k, L.sx[k], L.sy[k]);
 }
 
 // ---- assignment + exact accumulation -----------------------------------------------------------------------------
@@ -257,6 +278,7 @@ __global__ void lsc_finalize_kernel(LscDev L)
     L.sx[k] = sx; L.sy[k] = sy;
     const int bx = min(sx / L.stepx, L.nbx - 1), by = min(sy / L.stepy, L.nby - 1);
     L.next[k] = atomicExch(&L.head[by * L.nbx + bx], k);
+    lsc_tile_append(L, k, sx, sy);
 }
 
 // ---- connected components (union-find, root = smallest raster index) ----------------------------------------------
@@ -634,6 +656,7 @@ struct LscEngine {
     size_t scan_tmp_bytes = 0;
     int* d_flag = nullptr;
     int* d_tile_overflow = nullptr;         // tiles of the tiled assignment whose candidate list overflowed (diagnostic)
+    bool tiled = false;                     // 3 channels and steps >= LSC_TILE_MIN_STEP: lsc_tile_kernel
     int* h_pinned = nullptr;
     long long launches = 0;
     PostWorkspace post;
@@ -714,6 +737,17 @@ struct LscEngine {
         SPX_CHECK(dalloc(&d_flag, 8));
         SPX_CHECK(dalloc(&d_tile_overflow, 1));
         SPX_CUDA(cudaMemsetAsync(d_tile_overflow, 0, sizeof(int), st));
+        tiled = C == 3 && L.stepx >= LSC_TILE_MIN_STEP && L.stepy >= LSC_TILE_MIN_STEP && !getenv("SPX_LSC_NO_TILE");
+        L.tiles_x = cdiv(w, 32); L.tiles_y = cdiv(h, 32);
+        L.ctab = nullptr; L.tl_count = nullptr; L.tl_k = nullptr;
+        float4* d_ctab = nullptr;
+        if (tiled) {
+            SPX_CHECK(dalloc(&d_ctab, (size_t)3 * 256));
+            SPX_CHECK(dalloc(&L.tl_count, (size_t)L.tiles_x * L.tiles_y));
+            SPX_CHECK(dalloc(&L.tl_k, (size_t)L.tiles_x * L.tiles_y * LSC_CAP));
+            SPX_CUDA(cudaMemsetAsync(L.tl_count, 0, (size_t)L.tiles_x * L.tiles_y * sizeof(int), st));
+            L.ctab = d_ctab;
+        }
         SPX_CUDA(cudaMallocHost(&h_pinned, 8 * sizeof(int)));
         L.img = d_img;
         SPX_CUDA(cudaMemcpy2DAsync(d_img, L.ipitch, image, stride, (size_t)w * C, h, cudaMemcpyHostToDevice, st));
@@ -789,6 +823,11 @@ struct LscEngine {
                 }
             }
         }
+        std::vector<float4> ctab((size_t)3 * 256);
+        if (tiled) {
+            for (int i = 0; i < 3 * 256; i++) ctab[i] = make_float4(colcos[i], colsin[i], wcol[i], 0.f);
+            SPX_CUDA(cudaMemcpyAsync(d_ctab, ctab.data(), ctab.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
+        }
         SPX_CUDA(cudaMemcpyAsync(d_tab, tab.data(), ntab * sizeof(float), cudaMemcpyHostToDevice, st));
         SPX_CUDA(cudaMemcpyAsync(L.sx, seeds.data(), (size_t)L.K * sizeof(int), cudaMemcpyHostToDevice, st));
         SPX_CUDA(cudaMemcpyAsync(L.sy, seeds.data() + L.K, (size_t)L.K * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -813,9 +852,12 @@ struct LscEngine {
     {
         SPX_REQUIRE(n >= 0, SPX_ERR_BADARG, "iterate: num_iterations must be >= 0");
         const dim3 grid(cdiv(L.w, 32), cdiv(L.h, 8));
-        const bool tiled = L.C == 3 && L.stepx >= LSC_TILE_MIN_STEP && L.stepy >= LSC_TILE_MIN_STEP && !getenv("SPX_LSC_NO_TILE");
         for (int it = 0; it < n; it++) {
-            if (tiled) lsc_tile_kernel<<<dim3(cdiv(L.w, 32), cdiv(L.h, 32)), 128, 0, st>>>(L, d_labels, d_tile_overflow);
+            if (tiled) {
+                const dim3 tg(cdiv(L.w, 32), cdiv(L.h, 32));
+                lsc_tile_kernel<<<tg, 128, 0, st>>>(L, d_labels, d_tile_overflow);
+                SPX_CUDA(cudaMemsetAsync(L.tl_count, 0, (size_t)L.tiles_x * L.tiles_y * sizeof(int), st));
+            }
             else switch (L.C) {
                 case 1: lsc_assign_kernel<1><<<grid, 256, 0, st>>>(L, d_labels, 1); break;
                 case 2: lsc_assign_kernel<2><<<grid, 256, 0, st>>>(L, d_labels, 1); break;

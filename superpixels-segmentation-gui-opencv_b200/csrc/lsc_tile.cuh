@@ -3,8 +3,8 @@
 // fixed-point integers and the arg-min is taken in (distance, seed index) order either way); ~5x fewer instructions.
 //
 // One CTA (128 threads) per 32x32 tile.
-//   setup      : a thread per bin of the tile's bin neighbourhood walks the bin's seed list and keeps the seeds whose window
-//                [s - step, s + step] meets the tile (13 at S = 20, 10 at S = 30); they are ranked by seed index (ascending
+//   setup      : the kernels that move the seeds (lsc_bin_kernel, lsc_finalize_kernel) append every seed to the list of each
+//                tile its window [s - step, s + step] meets (13 per tile at S = 20, 10 at S = 30); they are ranked by seed index (ascending
 //                index + strict '<' = the oracle's (distance, index) order) and staged as one record each: the negated
 //                centre, the key (k << 6) | slot, and two 32-entry penalty rows (0 inside the window, +inf outside; adding
 //                0 to a distance >= 0 is exact, +inf can never win).
@@ -18,7 +18,6 @@
 // Tiles whose list overflows LSC_CAP and pixels covered by no window take exact per-pixel paths.
 // (no include guard needed: included once, inside namespace spx, by lsc.cu, which includes f32x2.cuh at file scope)
 
-constexpr int LSC_CAP = 32;
 constexpr int LSC_NCOPY = 8;
 constexpr int LSC_TILE_MIN_STEP = 14;
 constexpr int LSC_SLOTW = 24;                      // words per slot: 10 feature sums + W as {lo, hi}; x | y << 16; count
@@ -33,8 +32,6 @@ struct LscTileSmem {
     int4 win[LSC_CAP];                             // window, inclusive: x_lo, x_hi, y_lo, y_hi
     unsigned acc[LSC_NCOPY][LSC_COPYW];
     int k[LSC_CAP];
-    int2 sxy[LSC_CAP];
-    int n;
 };
 
 __device__ __forceinline__ void lsc_sadd64(unsigned* p, unsigned long long v)
@@ -138,30 +135,15 @@ __device__ __forceinline__ void lsc_acc_pixel(unsigned* cp, const u64 (&P)[2][10
     atomicAdd(d + 23, 1u);
 }
 
-__global__ void __launch_bounds__(128, 4) lsc_tile_kernel(const __grid_constant__ LscDev L, int* __restrict__ labels, int* __restrict__ d_overflow)
+__global__ void __launch_bounds__(128, 5) lsc_tile_kernel(const __grid_constant__ LscDev L, int* __restrict__ labels, int* __restrict__ d_overflow)
 {
     constexpr int D = 10;
     __shared__ LscTileSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx0 = blockIdx.x * 32, ty0 = blockIdx.y * 32;
-    if (tid == 0) sm.n = 0;
-    __syncthreads();
-    // ---- candidates: seeds of the bin neighbourhood whose window meets the tile
-    {
-        const int xr = min(tx0 + 31, L.w - 1), yr = min(ty0 + 31, L.h - 1);
-        const int bx0 = max(tx0 / L.stepx - 1, 0), bx1 = min(xr / L.stepx + 1, L.nbx - 1);
-        const int by0 = max(ty0 / L.stepy - 1, 0), by1 = min(yr / L.stepy + 1, L.nby - 1);
-        const int nbw = bx1 - bx0 + 1, nb = nbw * (by1 - by0 + 1);
-        for (int b = tid; b < nb; b += 128)
-            for (int k = L.head[(by0 + b / nbw) * L.nbx + bx0 + b % nbw]; k >= 0; k = L.next[k]) {
-                const int sx = L.sx[k], sy = L.sy[k];
-                if (sx + L.stepx < tx0 || sx - L.stepx > xr || sy + L.stepy < ty0 || sy - L.stepy > yr) continue;
-                const int pos = atomicAdd(&sm.n, 1);
-                if (pos < LSC_CAP) { sm.k[pos] = k; sm.sxy[pos] = make_int2(sx, sy); }
-            }
-    }
-    __syncthreads();
-    const int cnt = sm.n;
+    // ---- candidates: the kernels that move the seeds appended every seed whose window meets this tile
+    const int tile = blockIdx.y * L.tiles_x + blockIdx.x;
+    const int cnt = __ldg(&L.tl_count[tile]);
     if (cnt > LSC_CAP) {
         if (tid == 0) atomicAdd(d_overflow, 1);
         for (int r = warp; r < 32; r += 4) {
@@ -170,9 +152,13 @@ __global__ void __launch_bounds__(128, 4) lsc_tile_kernel(const __grid_constant_
         }
         return;
     }
+    int my_k = 0;
+    if (tid < cnt) { my_k = L.tl_k[(size_t)tile * LSC_CAP + tid]; sm.k[tid] = my_k; }
+    for (int i = tid; i < LSC_NCOPY * LSC_COPYW; i += 128) (&sm.acc[0][0])[i] = 0u;
+    __syncthreads();
     // ---- rank by seed index, stage the records; clear the accumulators
     if (tid < cnt) {
-        const int k = sm.k[tid];
+        const int k = my_k;
         int rank = 0;
         for (int j = 0; j < cnt; j++) rank += sm.k[j] < k ? 1 : 0;
         const float2* c = reinterpret_cast<const float2*>(L.cen + (size_t)k * D);
@@ -181,10 +167,9 @@ __global__ void __launch_bounds__(128, 4) lsc_tile_kernel(const __grid_constant_
         R.c0 = make_float4(-a0.x, -a0.y, -a1.x, -a1.y);
         R.c1 = make_float4(-a2.x, -a2.y, -a3.x, -a3.y);
         R.c2 = make_float4(-a4.x, -a4.y, __int_as_float((k << 6) | rank), 0.f);
-        const int2 s = sm.sxy[tid];
+        const int2 s = make_int2(L.sx[k], L.sy[k]);
         sm.win[rank] = make_int4(s.x - L.stepx, s.x + L.stepx, s.y - L.stepy, s.y + L.stepy);
     }
-    for (int i = tid; i < LSC_NCOPY * LSC_COPYW; i += 128) (&sm.acc[0][0])[i] = 0u;
     __syncthreads();
     {
         const float inf = __int_as_float(0x7f800000);
@@ -228,15 +213,14 @@ __global__ void __launch_bounds__(128, 4) lsc_tile_kernel(const __grid_constant_
             for (int k = 0; k < 2; k++) {
                 const unsigned char* p = L.img + (size_t)yc * L.ipitch + (size_t)(k ? xc1 : xc0) * 3;
                 const int v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2);
-                float wc = __ldg(&L.wcol[v0]);
-                wc = __fadd_rn(wc, __ldg(&L.wcol[256 + v1]));
-                wc = __fadd_rn(wc, __ldg(&L.wcol[512 + v2]));
+                const float4 t0 = __ldg(&L.ctab[v0]), t1 = __ldg(&L.ctab[256 + v1]), t2 = __ldg(&L.ctab[512 + v2]);   // (cos, sin, w, -)
+                const float wc = __fadd_rn(__fadd_rn(t0.z, t1.z), t2.z);
                 const float W = __fadd_rn(wc, __fadd_rn(wxv[k], wyv));
                 const float inv = __fdiv_rn(1.0f, W);
                 Wt[r][k] = W;
-                f[k][0] = __fmul_rn(__ldg(&L.colcos[v0]), inv); f[k][1] = __fmul_rn(__ldg(&L.colsin[v0]), inv);
-                f[k][2] = __fmul_rn(__ldg(&L.colcos[256 + v1]), inv); f[k][3] = __fmul_rn(__ldg(&L.colsin[256 + v1]), inv);
-                f[k][4] = __fmul_rn(__ldg(&L.colcos[512 + v2]), inv); f[k][5] = __fmul_rn(__ldg(&L.colsin[512 + v2]), inv);
+                f[k][0] = __fmul_rn(t0.x, inv); f[k][1] = __fmul_rn(t0.y, inv);
+                f[k][2] = __fmul_rn(t1.x, inv); f[k][3] = __fmul_rn(t1.y, inv);
+                f[k][4] = __fmul_rn(t2.x, inv); f[k][5] = __fmul_rn(t2.y, inv);
                 f[k][6] = __fmul_rn(xcs[k], inv); f[k][7] = __fmul_rn(xsn[k], inv);
                 f[k][8] = __fmul_rn(ycs, inv); f[k][9] = __fmul_rn(ysn, inv);
             }
