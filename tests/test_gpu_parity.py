@@ -427,6 +427,18 @@ def test_golden_hashes_on_gpu(spx, example_bgr):
 
 
 @pytest.mark.gpu
+def test_golden_hashes_other_algorithms_on_gpu(spx, example_bgr):
+    """SLICO, MSLIC, LSC and SEEDS reproduce tests/golden/algs_hashes.json byte for byte on the CUDA path (no oracle involved)"""
+    import importlib.util, json
+    spec = importlib.util.spec_from_file_location("gen_golden_algs", os.path.join(os.path.dirname(__file__), "..", "tools", "gen_golden_algs.py"))
+    gg = importlib.util.module_from_spec(spec); spec.loader.exec_module(gg)
+    want = json.load(open(gg.OUT))
+    got = gg.compute(spx.cvtColor(example_bgr, spx.COLOR_BGR2Lab), lambda lab, alg, S, r: spx.createSuperpixelSLIC(lab, alg, S, r),
+                     spx.createSuperpixelLSC, spx.createSuperpixelSEEDS)
+    assert got == want
+
+
+@pytest.mark.gpu
 def test_sanity_sweep():
     """ragged / degenerate sizes of all five algorithms (tools/sanity_sweep.py): bit-exact against the oracle or rejected with
     SPX_ERR_BAD_ARG -- never a CUDA error, never a mismatch"""

@@ -177,3 +177,14 @@ def test_golden_hashes_reproduce(O, example_bgr):
     want = json.load(open(gg.OUT))
     got = gg.compute(O, example_bgr, O.bgr2lab8, lambda lab, S, r: O.SuperpixelSLIC(lab, O.SLIC, S, r))
     assert got == want
+
+
+def test_golden_hashes_other_algorithms_reproduce(O, example_bgr):
+    """tests/golden/algs_hashes.json (tools/gen_golden_algs.py): SLICO, MSLIC, LSC, SEEDS on a crop of the example image --
+    regression anchors of our restatement where upstream ships no vector (parity unpinned)"""
+    import importlib.util, json, os
+    spec = importlib.util.spec_from_file_location("gen_golden_algs", os.path.join(os.path.dirname(__file__), "..", "tools", "gen_golden_algs.py"))
+    gg = importlib.util.module_from_spec(spec); spec.loader.exec_module(gg)
+    want = json.load(open(gg.OUT))
+    got = gg.compute(O.bgr2lab8(example_bgr), lambda lab, alg, S, r: O.SuperpixelSLIC(lab, alg, S, r), O.SuperpixelLSC, O.SuperpixelSEEDS)
+    assert got == want
