@@ -78,23 +78,6 @@ __device__ __noinline__ void lsc_pixel_exact(const LscDev& L, int* __restrict__ 
     atomicAdd(&dst[D + 1], (unsigned long long)x); atomicAdd(&dst[D + 2], (unsigned long long)y); atomicAdd(&dst[D + 3], 1ull);
 }
 
-// the bytes of the thread's 2x2 block (rows y, y + 1; pixels xc0, xc1) as three 16-bit words per row: b0 | b1 << 8, ...
-// interior tiles: x is even and the pitch a multiple of 16, so the six bytes are three aligned 16-bit loads
-__device__ __forceinline__ void lsc_load_rows(const LscDev& L, bool interior, int xc0, int xc1, int y, unsigned (&o)[2][3])
-{
-#pragma unroll
-    for (int r = 0; r < 2; r++) {
-        const unsigned char* row = L.img + (size_t)min(y + r, L.h - 1) * L.ipitch;
-        if (interior) {
-            const unsigned short* p = reinterpret_cast<const unsigned short*>(row + (size_t)xc0 * 3);
-            o[r][0] = __ldg(p); o[r][1] = __ldg(p + 1); o[r][2] = __ldg(p + 2);
-        } else {
-            const unsigned char *p = row + (size_t)xc0 * 3, *q = row + (size_t)xc1 * 3;
-            o[r][0] = __ldg(p) | (__ldg(p + 1) << 8); o[r][1] = __ldg(p + 2) | (__ldg(q) << 8); o[r][2] = __ldg(q + 1) | (__ldg(q + 2) << 8);
-        }
-    }
-}
-
 // the thread's 2x2 block into the per-candidate accumulators.  SPLIT = false: all four pixels belong to slot A.
 template <bool SPLIT>
 __device__ __forceinline__ void lsc_acc_block(unsigned* cp, const u64 (&P)[2][10], const float (&Wt)[2][2], unsigned A, unsigned B,
@@ -158,14 +141,6 @@ __global__ void __launch_bounds__(128, 5) lsc_tile_kernel(const __grid_constant_
     __shared__ LscTileSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx0 = blockIdx.x * 32, ty0 = blockIdx.y * 32;
-    // ---- first pixels in flight before anything else (lanes 8 x 4, 2x2 pixels per thread, warps 2 x 2)
-    const int lx = lane & 7, ly = lane >> 3, wx = warp & 1, wy = warp >> 1;
-    const int xo = 16 * wx + 2 * lx;
-    const int x = tx0 + xo;
-    const int xc0 = min(x, L.w - 1), xc1 = min(x + 1, L.w - 1);
-    const bool interior = tx0 + 32 <= L.w && ty0 + 32 <= L.h;
-    unsigned nx[2][3];                                            // the 2x2 block's bytes of the coming step: 3 x u16 per row
-    lsc_load_rows(L, interior, xc0, xc1, ty0 + 8 * wy + 2 * ly, nx);
     // ---- candidates: the kernels that move the seeds appended every seed whose window meets this tile
     const int tile = blockIdx.y * L.tiles_x + blockIdx.x;
     const int cnt = __ldg(&L.tl_count[tile]);
@@ -209,9 +184,14 @@ __global__ void __launch_bounds__(128, 5) lsc_tile_kernel(const __grid_constant_
     }
     __syncthreads();
 
-    // ---- assignment: two steps of 16 rows
+    // ---- assignment: lanes 8 x 4, 2x2 pixels per thread, warps 2 x 2, two steps of 16 rows
+    const int lx = lane & 7, ly = lane >> 3, wx = warp & 1, wy = warp >> 1;
+    const int xo = 16 * wx + 2 * lx;
+    const int x = tx0 + xo;
+    const int xc0 = min(x, L.w - 1), xc1 = min(x + 1, L.w - 1);
     const float xcs[2] = {__ldg(&L.xcos[xc0]), __ldg(&L.xcos[xc1])}, xsn[2] = {__ldg(&L.xsin[xc0]), __ldg(&L.xsin[xc1])};
     const float wxv[2] = {__ldg(&L.wx[xc0]), __ldg(&L.wx[xc1])};
+    const bool interior = tx0 + 32 <= L.w && ty0 + 32 <= L.h;
     const bool pair_store = (L.w & 1) == 0;
     const int X0 = tx0 + 16 * wx, X1 = X0 + 15;
     unsigned* const cp = sm.acc[lane & (LSC_NCOPY - 1)];
@@ -224,10 +204,6 @@ __global__ void __launch_bounds__(128, 5) lsc_tile_kernel(const __grid_constant_
         // features of the 2x2 block, packed by row: P[r][i] = (f_i(x, y + r), f_i(x + 1, y + r))
         u64 P[2][D];
         float Wt[2][2];
-        unsigned cur[2][3];
-#pragma unroll
-        for (int r = 0; r < 2; r++) { cur[r][0] = nx[r][0]; cur[r][1] = nx[r][1]; cur[r][2] = nx[r][2]; }
-        if (step == 0) lsc_load_rows(L, interior, xc0, xc1, y + 16, nx);      // the next step's pixels
 #pragma unroll
         for (int r = 0; r < 2; r++) {
             const int yc = min(y + r, L.h - 1);
@@ -235,8 +211,8 @@ __global__ void __launch_bounds__(128, 5) lsc_tile_kernel(const __grid_constant_
             float f[2][D];
 #pragma unroll
             for (int k = 0; k < 2; k++) {
-                const int v0 = k ? cur[r][1] >> 8 : cur[r][0] & 0xffu, v1 = k ? cur[r][2] & 0xffu : cur[r][0] >> 8;
-                const int v2 = k ? cur[r][2] >> 8 : cur[r][1] & 0xffu;
+                const unsigned char* p = L.img + (size_t)yc * L.ipitch + (size_t)(k ? xc1 : xc0) * 3;
+                const int v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2);
                 const float4 t0 = __ldg(&L.ctab[v0]), t1 = __ldg(&L.ctab[256 + v1]), t2 = __ldg(&L.ctab[512 + v2]);   // (cos, sin, w, -)
                 const float wc = __fadd_rn(__fadd_rn(t0.z, t1.z), t2.z);
                 const float W = __fadd_rn(wc, __fadd_rn(wxv[k], wyv));
