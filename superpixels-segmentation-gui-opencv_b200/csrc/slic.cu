@@ -407,6 +407,71 @@ __global__ void mslic_scratch_clear_kernel(SlicArrays a)
 // ------------------------------------------------------------------------------------------------
 // engine
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// Row-strip mode, peer exchange: the ONE exchange step of an iteration -- every rank needs the sums of
+// the integer accumulators over all ranks -- done by the ranks' own kernels over NVLink peer memory instead of an NCCL
+// all-reduce.  Every rank owns an exchange buffer (cudaMalloc, exported with cudaIpcGetMemHandle, mapped by all peers):
+//     recv[2][world][n6] u64   slot [iteration parity][source rank]: the source's partial sums, written by the source
+//     flag[world]        int   flag[source] = number of the last iteration whose sums the source has delivered
+// push: plain coalesced stores of the local partial sums into the slot of every peer, a system-scope fence, and -- by the
+//       last CTA to finish -- the iteration number into every peer's flag.
+// wait+sum: spins on the local flags (the peers write them), then adds the peers' slots to the local accumulators; the
+//       ordinary centre update follows.  Integer sums: the result is bit-identical to the single-GPU object.
+// Slots are double-buffered by iteration parity: a peer can deliver iteration i+2 only after it has seen this rank's flag
+// for i+1, which is written after this rank's wait+sum of iteration i has finished reading slot i (stream order).
+// ------------------------------------------------------------------------------------------------
+constexpr int STRIP_MAX_WORLD = 16;
+struct StripPeers {
+    unsigned long long* base[STRIP_MAX_WORLD];     // exchange buffer of every rank in THIS process's address space
+    int world, rank;
+    size_t n6;                                     // (channels + 3) * Kcap
+};
+__device__ __forceinline__ unsigned long long* strip_slot(unsigned long long* base, const StripPeers& P, int par, int src)
+{
+    return base + ((size_t)par * P.world + src) * P.n6;
+}
+__device__ __forceinline__ int* strip_flags(unsigned long long* base, const StripPeers& P)
+{
+    return reinterpret_cast<int*>(base + (size_t)2 * P.world * P.n6);
+}
+__global__ void __launch_bounds__(256) strip_push_kernel(const __grid_constant__ StripPeers P, const unsigned long long* __restrict__ acc,
+                                                          int iter, unsigned* __restrict__ done)
+{
+    const int par = iter & 1;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < P.n6; i += (size_t)gridDim.x * 256) {
+        const unsigned long long v = acc[i];
+        for (int p = 0; p < P.world; p++)
+            if (p != P.rank) strip_slot(P.base[p], P, par, P.rank)[i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned ticket = atomicAdd(done, 1u);
+        if (ticket == gridDim.x - 1) {             // every CTA's stores are fenced: publish
+            *done = 0;
+            __threadfence_system();
+            for (int p = 0; p < P.world; p++)
+                if (p != P.rank) *reinterpret_cast<volatile int*>(&strip_flags(P.base[p], P)[P.rank]) = iter;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) strip_wait_sum_kernel(const __grid_constant__ StripPeers P, unsigned long long* __restrict__ acc, int iter)
+{
+    if (threadIdx.x < P.world && threadIdx.x != P.rank) {
+        const volatile int* f = strip_flags(P.base[P.rank], P) + threadIdx.x;
+        while (*f < iter) __nanosleep(200);
+        __threadfence_system();
+    }
+    __syncthreads();
+    const int par = iter & 1;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < P.n6; i += (size_t)gridDim.x * 256) {
+        unsigned long long v = acc[i];
+        for (int p = 0; p < P.world; p++)
+            if (p != P.rank) v += __ldcv(&strip_slot(P.base[P.rank], P, par, p)[i]);      // (not through a stale L1 line)
+        acc[i] = v;
+    }
+}
+
 struct SlicEngine {
     int device = 0;
     cudaStream_t st = nullptr;
@@ -432,6 +497,13 @@ struct SlicEngine {
     PostWorkspace post;
     std::map<long long, cudaGraphExec_t> graphs;
     std::vector<void*> allocs;
+    // row-strip mode, peer exchange
+    StripPeers peers{};
+    void* xchg = nullptr;            // this rank's exchange buffer (cudaMalloc: exportable)
+    size_t xchg_bytes = 0;
+    unsigned* d_push_done = nullptr;
+    int xchg_iter = 0;
+    bool peers_open = false;
 
     template <typename T> int dalloc(T** p, size_t n)
     {
@@ -447,7 +519,66 @@ struct SlicEngine {
         for (void* p : allocs) pool_free(p, st);
         post.release();
         if (h_pinned) cudaFreeHost(h_pinned);
+        strip_peer_close();
         if (own_stream && st) cudaStreamDestroy(st);
+    }
+    void strip_peer_close()
+    {
+        if (peers_open)
+            for (int p = 0; p < peers.world; p++)
+                if (p != peers.rank && peers.base[p]) cudaIpcCloseMemHandle(peers.base[p]);
+        peers_open = false;
+        if (xchg) cudaFree(xchg);
+        xchg = nullptr;
+    }
+    int strip_peer_alloc(int world, int rank, void* handle_out, size_t* bytes_out)
+    {
+        SPX_REQUIRE(world >= 1 && world <= STRIP_MAX_WORLD && rank >= 0 && rank < world && handle_out, SPX_ERR_BADARG,
+                    "strip_peer_alloc: need 1 <= world <= %d, 0 <= rank < world", STRIP_MAX_WORLD);
+        SPX_REQUIRE(!xchg, SPX_ERR_BADARG, "strip_peer_alloc: called twice");
+        peers = StripPeers{};
+        peers.world = world; peers.rank = rank; peers.n6 = (size_t)(g.C + 3) * g.Kcap;
+        xchg_bytes = (size_t)2 * world * peers.n6 * sizeof(unsigned long long) + (size_t)STRIP_MAX_WORLD * sizeof(int);
+        SPX_CUDA(cudaMalloc(&xchg, xchg_bytes));
+        SPX_CUDA(cudaMemsetAsync(xchg, 0, xchg_bytes, st));
+        SPX_CHECK(dalloc(&d_push_done, 1));
+        SPX_CUDA(cudaMemsetAsync(d_push_done, 0, sizeof(unsigned), st));
+        SPX_CUDA(cudaStreamSynchronize(st));                      // zeroed before any peer can map and write it
+        cudaIpcMemHandle_t hd;
+        SPX_CUDA(cudaIpcGetMemHandle(&hd, xchg));
+        static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        memcpy(handle_out, &hd, sizeof(hd));
+        if (bytes_out) *bytes_out = xchg_bytes;
+        peers.base[rank] = (unsigned long long*)xchg;
+        xchg_iter = 0;
+        return SPX_OK;
+    }
+    int strip_peer_open(const void* handles)
+    {
+        SPX_REQUIRE(xchg && handles && !peers_open, SPX_ERR_BADARG, "strip_peer_open: call strip_peer_alloc first (once)");
+        for (int p = 0; p < peers.world; p++) {
+            if (p == peers.rank) continue;
+            cudaIpcMemHandle_t hd;
+            memcpy(&hd, (const char*)handles + (size_t)p * sizeof(hd), sizeof(hd));
+            void* ptr = nullptr;
+            SPX_CUDA(cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+            peers.base[p] = (unsigned long long*)ptr;
+        }
+        peers_open = true;
+        return SPX_OK;
+    }
+    // the exchange step: deliver the local partial sums to every peer, wait for theirs, add them up
+    int strip_exchange()
+    {
+        SPX_REQUIRE(peers_open || peers.world == 1, SPX_ERR_BADARG, "strip_exchange: peers are not mapped");
+        if (peers.world == 1) return SPX_OK;
+        xchg_iter++;
+        const int nb = (int)std::min<size_t>((peers.n6 + 255) / 256, 4 * 148);
+        strip_push_kernel<<<nb, 256, 0, st>>>(peers, a.acc, xchg_iter, d_push_done);
+        strip_wait_sum_kernel<<<nb, 256, 0, st>>>(peers, a.acc, xchg_iter);
+        launches += 2;
+        SPX_CUDA(cudaGetLastError());
+        return SPX_OK;
     }
 
     SeedParams seed_params(int* K_out) const
@@ -912,6 +1043,21 @@ extern "C" int spx_slic_strip_update(spx_slic_t* h)
 {
     SLIC_ENTER(h);
     return e->strip_update();
+}
+extern "C" int spx_slic_strip_peer_alloc(spx_slic_t* h, int world, int rank, void* ipc_handle_out, size_t* bytes_out)
+{
+    SLIC_ENTER(h);
+    return e->strip_peer_alloc(world, rank, ipc_handle_out, bytes_out);
+}
+extern "C" int spx_slic_strip_peer_open(spx_slic_t* h, const void* ipc_handles)
+{
+    SLIC_ENTER(h);
+    return e->strip_peer_open(ipc_handles);
+}
+extern "C" int spx_slic_strip_exchange(spx_slic_t* h)
+{
+    SLIC_ENTER(h);
+    return e->strip_exchange();
 }
 extern "C" int spx_slic_get_label_rows(spx_slic_t* h, int32_t* dst, size_t dst_stride, int row0, int row1)
 {

@@ -3,8 +3,13 @@
 One process per GPU (torch.distributed / NCCL).  Rank r owns a band of rows (a multiple of 32, so bands are whole tile
 rows) and uploads those rows plus two halo rows.  Cluster state is replicated; per iteration ONE exchange step sums the
 integer accumulators (pixel sums per cluster) over the ranks -- only clusters near a cut receive pixels from two ranks,
-the sums are integers, so the result is bit-identical to the single-GPU object.  torch is plumbing here: it wraps the
-library's device pointers (``__cuda_array_interface__``) so that NCCL can reduce them in place.
+the sums are integers, so the result is bit-identical to the single-GPU object.
+
+The exchange step runs over NVLink peer memory by default (``exchange="peer"``): every rank's exchange buffer is mapped
+into its peers through CUDA IPC, the library's own kernels store the partial sums into the peers' buffers, publish a
+flag, wait for the peers' flags and add (``spx_slic_strip_exchange``; csrc/slic.cu).  ``exchange="nccl"`` keeps the
+NCCL all-reduce on the library's device pointers (``__cuda_array_interface__`` views) for comparison.  torch is plumbing:
+the process group carries the 64-byte IPC handles, the one-off assembly of the seeds and the barriers.
 """
 import ctypes as C
 
@@ -44,8 +49,11 @@ class StripSLIC:
     """cv::ximgproc::SuperpixelSLIC (algorithm SLIC) over the row band of this rank.  `image` is the whole 8UC3 image
     or a callable rows(row0, row1) -> ndarray, so a rank never needs more than its band in host memory."""
 
-    def __init__(self, image, region_size, ruler, dist, device, width=None, height=None):
+    def __init__(self, image, region_size, ruler, dist, device, width=None, height=None, exchange="peer"):
         import torch
+        if exchange not in ("peer", "nccl"):
+            raise SpxError(-5, "StripSLIC: exchange must be 'peer' or 'nccl'")
+        self.exchange = exchange
         self.torch, self.dist = torch, dist
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         if callable(image):
@@ -87,14 +95,32 @@ class StripSLIC:
                 dist.all_reduce(t, op=dist.ReduceOp.SUM)
         _ck(L.spx_slic_strip_rebin(self._h))
         self.exchanged_bytes = 0
+        if exchange == "peer" and self.world > 1:
+            L.spx_slic_strip_peer_alloc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_size_t)]
+            L.spx_slic_strip_peer_open.argtypes = [C.c_void_p, C.c_void_p]
+            L.spx_slic_strip_exchange.argtypes = [C.c_void_p]
+            mine = C.create_string_buffer(64)
+            nbytes = C.c_size_t(0)
+            _ck(L.spx_slic_strip_peer_alloc(self._h, self.world, self.rank, mine, C.byref(nbytes)))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, mine.raw)              # 64 bytes per rank
+            allh = C.create_string_buffer(b"".join(handles), 64 * self.world)
+            _ck(L.spx_slic_strip_peer_open(self._h, allh))
+            self.stream.synchronize()
+            dist.barrier()                                         # every buffer is zeroed and mapped before the first push
 
     def iterate(self, num_iterations=10):
         L = lib()
+        peer = self.exchange == "peer" and self.world > 1
         for _ in range(int(num_iterations)):
             _ck(L.spx_slic_strip_assign(self._h))
-            with self.torch.cuda.stream(self.stream):
-                self.dist.all_reduce(self._acc, op=self.dist.ReduceOp.SUM)  # the one exchange step of the path
-            self.exchanged_bytes += self._acc.numel() * 8
+            if peer:
+                _ck(L.spx_slic_strip_exchange(self._h))            # the one exchange step of the path: NVLink peer stores + flags
+                self.exchanged_bytes += self._acc.numel() * 8 * (self.world - 1)
+            else:
+                with self.torch.cuda.stream(self.stream):
+                    self.dist.all_reduce(self._acc, op=self.dist.ReduceOp.SUM)
+                self.exchanged_bytes += self._acc.numel() * 8
             _ck(L.spx_slic_strip_update(self._h))
 
     def getNumberOfSuperpixels(self):
@@ -123,13 +149,17 @@ class StripSLIC:
         kc = self._seed_f[2].view(3, Kcap)[:, :K].t()
         return t.cat([kc, self._seed_f[0][:K, None], self._seed_f[1][:K, None]], 1).cpu().numpy()
 
-    def release(self):
+    def release(self, barrier=True):
+        """collective when exchange == "peer": no rank may free its exchange buffer while a peer can still write to it"""
         if self._h.value:
+            if barrier and self.exchange == "peer" and self.world > 1:
+                self.stream.synchronize()
+                self.dist.barrier()
             lib().spx_slic_destroy(self._h)
             self._h = C.c_void_p(None)
 
     def __del__(self):
         try:
-            self.release()
+            self.release(barrier=False)
         except Exception:
             pass

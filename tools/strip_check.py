@@ -16,23 +16,31 @@ W, H = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (4096, 409
 S, RULER, IT = 20, 10.0, 10
 bgr, _ = synth.synth(W, H, 3)                               # every rank builds the same image and slices its band
 lab = spx.cvtColor(bgr, spx.COLOR_BGR2Lab, device=local)
-s = strips.StripSLIC(lab, S, RULER, dist, local)
-s.iterate(1)                                                # NCCL / kernel warm-up (one more iteration than the reference below)
-s2 = strips.StripSLIC(lab, S, RULER, dist, local)
-s = s2
-torch.cuda.synchronize(); dist.barrier()
-t0 = time.perf_counter(); s.iterate(IT); torch.cuda.synchronize(); dist.barrier(); t = time.perf_counter() - t0
-Ls = s.getLabels()
-Cs = s.getCentres()
+def run(exchange):
+    w = strips.StripSLIC(lab, S, RULER, dist, local, exchange=exchange)
+    w.iterate(1)                                            # kernel / NCCL / peer-mapping warm-up
+    w.release()
+    s = strips.StripSLIC(lab, S, RULER, dist, local, exchange=exchange)
+    torch.cuda.synchronize(); dist.barrier()
+    t0 = time.perf_counter(); s.iterate(IT); torch.cuda.synchronize(); dist.barrier(); t = time.perf_counter() - t0
+    out = (s.getLabels(), s.getCentres(), t, s.exchanged_bytes, s.getNumberOfSuperpixels())
+    s.release()
+    return out
+
+
+Ls, Cs, t, xb, K = run("peer")                              # NVLink peer stores + flags by the library's own kernels
+Ln, Cn, tn, xbn, _ = run("nccl")                            # NCCL all-reduce of the accumulators
 if rank == 0:
     g = spx.createSuperpixelSLIC(lab, spx.SLIC, S, RULER, device=local)
     spx.lib().spx_slic_synchronize(g._h)
     t1 = time.perf_counter(); g.iterate(IT); spx.lib().spx_slic_synchronize(g._h); t1 = time.perf_counter() - t1
     Lg, Cg = g.getLabels(), g.getCentres()
     print(json.dumps({"strip_check": "%dx%d SLIC S=%d %d iterations" % (W, H, S, IT), "n_gpus": world, "bands": strips.row_bands(H, world),
-                      "labels_identical": bool((Ls == Lg).all()), "centres_identical": bool((Cs == Cg).all()),
-                      "strip_iterate_ms": t * 1e3, "single_gpu_iterate_ms": t1 * 1e3,
-                      "exchanged_MB_per_iteration": s.exchanged_bytes / IT / 1e6, "K": s.getNumberOfSuperpixels()}))
-    assert (Ls == Lg).all() and (Cs == Cg).all()
+                      "labels_identical": bool((Ls == Lg).all() and (Ln == Lg).all()),
+                      "centres_identical": bool((Cs == Cg).all() and (Cn == Cg).all()),
+                      "strip_iterate_ms": t * 1e3, "strip_iterate_ms_nccl_allreduce": tn * 1e3, "single_gpu_iterate_ms": t1 * 1e3,
+                      "exchange": "peer memory (CUDA IPC over NVLink): stores + flags by the library's kernels",
+                      "exchanged_MB_per_iteration": xb / IT / 1e6, "exchanged_MB_per_iteration_nccl": xbn / IT / 1e6, "K": K}))
+    assert (Ls == Lg).all() and (Cs == Cg).all() and (Ln == Lg).all() and (Cn == Cg).all()
 dist.barrier()
 dist.destroy_process_group()
