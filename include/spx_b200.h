@@ -134,12 +134,14 @@ int spx_slic_strip_update(spx_slic_t*);
  *     [all-gather the handles]      world x 64 bytes, any transport (torch.distributed in strips.py)
  *     spx_slic_strip_peer_open()    maps every peer's buffer
  *     repeat: spx_slic_strip_assign(); spx_slic_strip_exchange(); spx_slic_strip_update();
- * strip_exchange = the rank's kernels store its partial sums into every peer's buffer, publish a flag, wait for the
- * peers' flags and add their sums (integers: bit-identical to the all-reduce).  Every rank must destroy its object only
+ * strip_exchange = the rank's kernels store its partial sums (only the index range of clusters its band touched) into every
+ * peer's buffer, publish the range and a flag, wait for the peers' flags and add their sums (integers: bit-identical to the
+ * all-reduce).  Every rank must destroy its object only
  * after all ranks have finished iterating (a barrier on the host side). */
 int spx_slic_strip_peer_alloc(spx_slic_t*, int world, int rank, void* ipc_handle_out /* 64 bytes */, size_t* bytes_out);
 int spx_slic_strip_peer_open(spx_slic_t*, const void* ipc_handles /* world x 64 bytes, rank order */);
 int spx_slic_strip_exchange(spx_slic_t*);
+int spx_slic_strip_exchanged_bytes(spx_slic_t*, unsigned long long* out);   /* bytes this rank has stored into its peers so far */
 int spx_slic_get_label_rows(spx_slic_t*, int32_t* dst, size_t dst_stride, int row0, int row1);
 
 /* ---- batch of independent frames on one device (BASELINE.json configs[4]) ----

@@ -413,8 +413,10 @@ __global__ void mslic_scratch_clear_kernel(SlicArrays a)
 // all-reduce.  Every rank owns an exchange buffer (cudaMalloc, exported with cudaIpcGetMemHandle, mapped by all peers):
 //     recv[2][world][n6] u64   slot [iteration parity][source rank]: the source's partial sums, written by the source
 //     flag[world]        int   flag[source] = number of the last iteration whose sums the source has delivered
-// push: plain coalesced stores of the local partial sums into the slot of every peer, a system-scope fence, and -- by the
-//       last CTA to finish -- the iteration number into every peer's flag.
+//     range[2][world]    int2  [lo, hi): the cluster index range the source delivered in that slot
+// push: only the index range of clusters that received pixels from this rank's band travels (~K/world entries per field):
+//       plain coalesced stores into the slot of every peer, a system-scope fence, and -- by the last CTA to finish -- the
+//       range and then the iteration number into every peer's buffer.
 // wait+sum: spins on the local flags (the peers write them), then adds the peers' slots to the local accumulators; the
 //       ordinary centre update follows.  Integer sums: the result is bit-identical to the single-GPU object.
 // Slots are double-buffered by iteration parity: a peer can deliver iteration i+2 only after it has seen this rank's flag
@@ -423,9 +425,10 @@ __global__ void mslic_scratch_clear_kernel(SlicArrays a)
 constexpr int STRIP_MAX_WORLD = 16;
 struct StripPeers {
     unsigned long long* base[STRIP_MAX_WORLD];     // exchange buffer of every rank in THIS process's address space
-    int world, rank;
-    size_t n6;                                     // (channels + 3) * Kcap
+    int world, rank, Kcap, nf;                     // nf = channels + 3 fields of Kcap entries each
+    size_t n6;                                     // nf * Kcap
 };
+// layout of an exchange buffer: recv[2][world][n6] u64 | flag[MAX_WORLD] int | range[2][MAX_WORLD] int2
 __device__ __forceinline__ unsigned long long* strip_slot(unsigned long long* base, const StripPeers& P, int par, int src)
 {
     return base + ((size_t)par * P.world + src) * P.n6;
@@ -434,21 +437,48 @@ __device__ __forceinline__ int* strip_flags(unsigned long long* base, const Stri
 {
     return reinterpret_cast<int*>(base + (size_t)2 * P.world * P.n6);
 }
+__device__ __forceinline__ int2* strip_range(unsigned long long* base, const StripPeers& P, int par, int src)
+{
+    return reinterpret_cast<int2*>(strip_flags(base, P) + STRIP_MAX_WORLD) + par * STRIP_MAX_WORLD + src;
+}
+// the index range [lo, hi) of the clusters that received pixels from this rank's band (cluster indices are row-major in
+// the seed grid, so a band of rows is nearly a contiguous index range: ~K/world entries instead of K)
+__global__ void __launch_bounds__(256) strip_range_kernel(const unsigned long long* __restrict__ count, int K, int* __restrict__ range)
+{
+    int lo = 0x7fffffff, hi = -1;
+    for (int k = blockIdx.x * 256 + threadIdx.x; k < K; k += gridDim.x * 256)
+        if (count[k]) { lo = min(lo, k); hi = max(hi, k); }
+    for (int o = 16; o; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    if ((threadIdx.x & 31) == 0 && hi >= 0) { atomicMin(&range[0], lo); atomicMax(&range[1], hi); }
+}
 __global__ void __launch_bounds__(256) strip_push_kernel(const __grid_constant__ StripPeers P, const unsigned long long* __restrict__ acc,
-                                                          int iter, unsigned* __restrict__ done)
+                                                          int iter, int* __restrict__ range, unsigned* __restrict__ done,
+                                                          unsigned long long* __restrict__ bytes_sent)
 {
     const int par = iter & 1;
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < P.n6; i += (size_t)gridDim.x * 256) {
-        const unsigned long long v = acc[i];
+    int lo = range[0], hi = range[1] + 1;
+    if (hi <= lo) lo = hi = 0;                     // the band received no pixel at all
+    const int len = hi - lo;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < (size_t)P.nf * len; i += (size_t)gridDim.x * 256) {
+        const int f = (int)(i / len);
+        const size_t j = (size_t)f * P.Kcap + lo + (i - (size_t)f * len);
+        const unsigned long long v = acc[j];
         for (int p = 0; p < P.world; p++)
-            if (p != P.rank) strip_slot(P.base[p], P, par, P.rank)[i] = v;
+            if (p != P.rank) strip_slot(P.base[p], P, par, P.rank)[j] = v;
     }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned ticket = atomicAdd(done, 1u);
-        if (ticket == gridDim.x - 1) {             // every CTA's stores are fenced: publish
+        if (ticket == gridDim.x - 1) {             // every CTA's stores are fenced: publish the range, then the flag
             *done = 0;
+            range[0] = 0x7fffffff; range[1] = -1;
+            *bytes_sent += (unsigned long long)P.nf * len * 8ull * (P.world - 1);
+            for (int p = 0; p < P.world; p++)
+                if (p != P.rank) {
+                    volatile int* r = reinterpret_cast<volatile int*>(strip_range(P.base[p], P, par, P.rank));
+                    r[0] = lo; r[1] = hi;
+                }
             __threadfence_system();
             for (int p = 0; p < P.world; p++)
                 if (p != P.rank) *reinterpret_cast<volatile int*>(&strip_flags(P.base[p], P)[P.rank]) = iter;
@@ -457,18 +487,26 @@ __global__ void __launch_bounds__(256) strip_push_kernel(const __grid_constant__
 }
 __global__ void __launch_bounds__(256) strip_wait_sum_kernel(const __grid_constant__ StripPeers P, unsigned long long* __restrict__ acc, int iter)
 {
+    __shared__ int2 rg[STRIP_MAX_WORLD];
+    const int par = iter & 1;
     if (threadIdx.x < P.world && threadIdx.x != P.rank) {
         const volatile int* f = strip_flags(P.base[P.rank], P) + threadIdx.x;
         while (*f < iter) __nanosleep(200);
         __threadfence_system();
+        const volatile int2* r = strip_range(P.base[P.rank], P, par, threadIdx.x);
+        rg[threadIdx.x] = make_int2(r->x, r->y);
     }
     __syncthreads();
-    const int par = iter & 1;
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < P.n6; i += (size_t)gridDim.x * 256) {
-        unsigned long long v = acc[i];
-        for (int p = 0; p < P.world; p++)
-            if (p != P.rank) v += __ldcv(&strip_slot(P.base[P.rank], P, par, p)[i]);      // (not through a stale L1 line)
-        acc[i] = v;
+    for (int p = 0; p < P.world; p++) {
+        if (p == P.rank) continue;
+        const int lo = rg[p].x, len = rg[p].y - rg[p].x;
+        const unsigned long long* slot = strip_slot(P.base[P.rank], P, par, p);
+        for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < (size_t)P.nf * len; i += (size_t)gridDim.x * 256) {
+            const int f = (int)(i / len);
+            const size_t j = (size_t)f * P.Kcap + lo + (i - (size_t)f * len);
+            const unsigned long long v = __ldcv(&slot[j]);       // (not through a stale L1 line)
+            if (v) atomicAdd(&acc[j], v);                        // ranges of different sources may overlap: another thread may own j there
+        }
     }
 }
 
@@ -502,6 +540,8 @@ struct SlicEngine {
     void* xchg = nullptr;            // this rank's exchange buffer (cudaMalloc: exportable)
     size_t xchg_bytes = 0;
     unsigned* d_push_done = nullptr;
+    int* d_range = nullptr;
+    unsigned long long* d_bytes_sent = nullptr;
     int xchg_iter = 0;
     bool peers_open = false;
 
@@ -537,12 +577,18 @@ struct SlicEngine {
                     "strip_peer_alloc: need 1 <= world <= %d, 0 <= rank < world", STRIP_MAX_WORLD);
         SPX_REQUIRE(!xchg, SPX_ERR_BADARG, "strip_peer_alloc: called twice");
         peers = StripPeers{};
-        peers.world = world; peers.rank = rank; peers.n6 = (size_t)(g.C + 3) * g.Kcap;
-        xchg_bytes = (size_t)2 * world * peers.n6 * sizeof(unsigned long long) + (size_t)STRIP_MAX_WORLD * sizeof(int);
+        peers.world = world; peers.rank = rank; peers.Kcap = g.Kcap; peers.nf = g.C + 3; peers.n6 = (size_t)(g.C + 3) * g.Kcap;
+        xchg_bytes = (size_t)2 * world * peers.n6 * sizeof(unsigned long long) + (size_t)STRIP_MAX_WORLD * sizeof(int) +
+                     (size_t)2 * STRIP_MAX_WORLD * sizeof(int2);
         SPX_CUDA(cudaMalloc(&xchg, xchg_bytes));
         SPX_CUDA(cudaMemsetAsync(xchg, 0, xchg_bytes, st));
         SPX_CHECK(dalloc(&d_push_done, 1));
         SPX_CUDA(cudaMemsetAsync(d_push_done, 0, sizeof(unsigned), st));
+        SPX_CHECK(dalloc(&d_range, 2));
+        const int r0[2] = {0x7fffffff, -1};
+        SPX_CUDA(cudaMemcpyAsync(d_range, r0, sizeof(r0), cudaMemcpyHostToDevice, st));
+        SPX_CHECK(dalloc(&d_bytes_sent, 1));
+        SPX_CUDA(cudaMemsetAsync(d_bytes_sent, 0, sizeof(unsigned long long), st));
         SPX_CUDA(cudaStreamSynchronize(st));                      // zeroed before any peer can map and write it
         cudaIpcMemHandle_t hd;
         SPX_CUDA(cudaIpcGetMemHandle(&hd, xchg));
@@ -574,9 +620,10 @@ struct SlicEngine {
         if (peers.world == 1) return SPX_OK;
         xchg_iter++;
         const int nb = (int)std::min<size_t>((peers.n6 + 255) / 256, 4 * 148);
-        strip_push_kernel<<<nb, 256, 0, st>>>(peers, a.acc, xchg_iter, d_push_done);
+        strip_range_kernel<<<std::min(cdiv(g.Kcap, 256), 148), 256, 0, st>>>(a.acc + (size_t)(g.C + 2) * g.Kcap, g.Kcap, d_range);
+        strip_push_kernel<<<nb, 256, 0, st>>>(peers, a.acc, xchg_iter, d_range, d_push_done, d_bytes_sent);
         strip_wait_sum_kernel<<<nb, 256, 0, st>>>(peers, a.acc, xchg_iter);
-        launches += 2;
+        launches += 3;
         SPX_CUDA(cudaGetLastError());
         return SPX_OK;
     }
@@ -1058,6 +1105,16 @@ extern "C" int spx_slic_strip_exchange(spx_slic_t* h)
 {
     SLIC_ENTER(h);
     return e->strip_exchange();
+}
+extern "C" int spx_slic_strip_exchanged_bytes(spx_slic_t* h, unsigned long long* out)
+{
+    SLIC_ENTER(h);
+    SPX_REQUIRE(out, SPX_ERR_BADARG, "strip_exchanged_bytes: out is NULL");
+    *out = 0;
+    if (!e->d_bytes_sent) return SPX_OK;
+    SPX_CUDA(cudaMemcpyAsync(out, e->d_bytes_sent, sizeof(*out), cudaMemcpyDeviceToHost, e->st));
+    SPX_CUDA(cudaStreamSynchronize(e->st));
+    return SPX_OK;
 }
 extern "C" int spx_slic_get_label_rows(spx_slic_t* h, int32_t* dst, size_t dst_stride, int row0, int row1)
 {

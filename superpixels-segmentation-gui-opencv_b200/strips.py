@@ -116,7 +116,6 @@ class StripSLIC:
             _ck(L.spx_slic_strip_assign(self._h))
             if peer:
                 _ck(L.spx_slic_strip_exchange(self._h))            # the one exchange step of the path: NVLink peer stores + flags
-                self.exchanged_bytes += self._acc.numel() * 8 * (self.world - 1)
             else:
                 with self.torch.cuda.stream(self.stream):
                     self.dist.all_reduce(self._acc, op=self.dist.ReduceOp.SUM)
@@ -125,6 +124,16 @@ class StripSLIC:
 
     def getNumberOfSuperpixels(self):
         return self.K
+
+    def exchangedBytes(self):
+        """bytes this rank has sent in exchange steps so far (peer mode: counted on the device by the push kernel)"""
+        if self.exchange == "peer" and self.world > 1:
+            L = lib()
+            L.spx_slic_strip_exchanged_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong)]
+            v = C.c_ulonglong(0)
+            _ck(L.spx_slic_strip_exchanged_bytes(self._h, C.byref(v)))
+            return int(v.value)
+        return self.exchanged_bytes
 
     def getLabelRows(self):
         """the owned rows [own0, own1) of the label map"""

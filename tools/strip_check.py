@@ -23,7 +23,7 @@ def run(exchange):
     s = strips.StripSLIC(lab, S, RULER, dist, local, exchange=exchange)
     torch.cuda.synchronize(); dist.barrier()
     t0 = time.perf_counter(); s.iterate(IT); torch.cuda.synchronize(); dist.barrier(); t = time.perf_counter() - t0
-    out = (s.getLabels(), s.getCentres(), t, s.exchanged_bytes, s.getNumberOfSuperpixels())
+    out = (s.getLabels(), s.getCentres(), t, s.exchangedBytes(), s.getNumberOfSuperpixels())
     s.release()
     return out
 
@@ -40,7 +40,7 @@ if rank == 0:
                       "centres_identical": bool((Cs == Cg).all() and (Cn == Cg).all()),
                       "strip_iterate_ms": t * 1e3, "strip_iterate_ms_nccl_allreduce": tn * 1e3, "single_gpu_iterate_ms": t1 * 1e3,
                       "exchange": "peer memory (CUDA IPC over NVLink): stores + flags by the library's kernels",
-                      "exchanged_MB_per_iteration": xb / IT / 1e6, "exchanged_MB_per_iteration_nccl": xbn / IT / 1e6, "K": K}))
+                      "sent_MB_per_rank_per_iteration": xb / IT / 1e6, "allreduce_payload_MB_per_iteration": xbn / IT / 1e6, "K": K}))
     assert (Ls == Lg).all() and (Cs == Cg).all() and (Ln == Lg).all() and (Cn == Cg).all()
 dist.barrier()
 dist.destroy_process_group()
