@@ -194,6 +194,31 @@ def other_configs(spx, synth, L):
     return out
 
 
+def bind_to_gpu_numa_node(index):
+    """pin this process (and the pinned host buffers it allocates from now on: first touch) to the CPUs of the NUMA node the
+    GPU hangs off (sysfs local_cpulist of its PCI function); returns the CPU count, or None when the topology is not exposed"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = "/sys/bus/pci/devices/%s:%s/local_cpulist" % (dom[-4:].lower(), rest.lower())
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if not part:
+                continue
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -204,13 +229,20 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available() or spx.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device; this engine has no CPU fallback")
+    L = spx.lib()
+    numa_cpus = None if args.no_numa_bind else bind_to_gpu_numa_node(local)
+    # measured on the 8-GPU box (profiles/r1_e2e_host_sweep_8gpu.log): 2..6 pipeline threads per rank, spinning or sleeping
+    # waits, NUMA binding on or off all give the same end-to-end rate -- the box's host I/O path is the limit -- and at one GPU
+    # sleeping waits cost 6 %, so the driver's default (spin) stays unless asked otherwise
+    blocking = 1 if args.blocking_sync else 0
+    L.spx_set_blocking_sync.argtypes = [C.c_int, C.c_int]
+    assert L.spx_set_blocking_sync(local, blocking) == 0, L.spx_last_error()
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    L = spx.lib()
     B = args.frames
     npx = W4K * H4K
 
@@ -379,7 +411,8 @@ def run_ours(args):
                           "l2": "inputs larger than L2: %d distinct frame buffers = %.0f MB per GPU" % (B, B * npx * 3 / 1e6)},
                "frames_per_sec": value * 1e6 / npx,
                "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": n_host * npx * 3,
-                       "d2h_bytes_per_step": n_host * npx * 4, "frames": n_host, "threads": n_thr},
+                       "d2h_bytes_per_step": n_host * npx * 4, "frames": n_host, "threads": n_thr,
+                       "host": {"cores": os.cpu_count(), "numa_bound_cpus": numa_cpus, "blocking_sync": bool(blocking)}},
                "gpu_launches": total_launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
                "wall_s_timed": wall, "other_configs": other}
         emit(out)
@@ -416,7 +449,9 @@ def main():
     ap.add_argument("--streams", type=int, default=4)
     ap.add_argument("--e2e-frames", type=int, default=16)
     ap.add_argument("--e2e-reps", type=int, default=4)
-    ap.add_argument("--e2e-threads", type=int, default=4)
+    ap.add_argument("--e2e-threads", type=int, default=4, help="pipeline threads per rank for the end-to-end leg")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to the CPUs of its GPU's NUMA node")
+    ap.add_argument("--blocking-sync", action="store_true", help="host threads sleep while waiting for the device (spx_set_blocking_sync)")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the extra (non-headline) configs on rank 0")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -103,6 +103,10 @@ int spx_slic_time_iterations(spx_slic_t*, int iters, int reps, int flush_l2, flo
 /* cv::Ptr<SuperpixelSLIC> release (the GUI overwrites `slic` on every COMPUTE, mainwindow.cpp:2105) */
 int spx_slic_destroy(spx_slic_t*);
 
+/* Host-side waiting policy of this process on `device`: on = 1 makes threads that wait for the device sleep
+ * (cudaDeviceScheduleBlockingSync) instead of spinning; for hosts with more pipeline threads than cores. */
+int spx_set_blocking_sync(int device, int on);
+
 /* ---- row-strip mode: ONE image over several GPUs (north-star: gigapixel images) ----
  * One process per GPU.  Every rank creates the object with the geometry of the WHOLE image but uploads only the rows it
  * needs: rows [row0,row1) of the image, of which it owns (assigns) [own_row0,own_row1) -- multiples of 32 -- plus two halo

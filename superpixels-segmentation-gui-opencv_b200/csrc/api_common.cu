@@ -75,3 +75,13 @@ extern "C" int spx_device_count(int* count)
     *count = n;
     return SPX_OK;
 }
+
+// Host threads waiting for the device sleep instead of spinning (cudaDeviceScheduleBlockingSync) -- for hosts that run more
+// worker threads than they have cores (8 ranks x 4 pipeline threads on a 32-core box); 0 restores the driver's default.
+extern "C" int spx_set_blocking_sync(int device, int on)
+{
+    using namespace spx;
+    SPX_CHECK(require_device(device));
+    SPX_CUDA(cudaSetDeviceFlags(on ? cudaDeviceScheduleBlockingSync : cudaDeviceScheduleAuto));
+    return SPX_OK;
+}
