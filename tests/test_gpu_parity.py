@@ -451,6 +451,17 @@ def test_sanity_sweep():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("tool,cases", [("fuzz_lsc.py", 80), ("fuzz_slic.py", 120)])
+def test_randomised_parity(tool, cases):
+    """tools/fuzz_lsc.py / tools/fuzz_slic.py: random sizes, region sizes, ratios / rulers, iteration counts and image kinds
+    through create -> iterate -> enforceLabelConnectivity -> contour, every stage bit-exact against the oracle"""
+    import subprocess, sys
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "..", "tools", tool), str(cases), "11"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("code", ["COLOR_BGR2Lab", "COLOR_BGR2HSV"])
 def test_create_with_fused_colour_conversion(spx, synthmod, code):
     """spx_slic_create_bgr / spx_lsc_create_bgr == cvtColor on the host side + create (mainwindow.cpp:2096-2105)"""
