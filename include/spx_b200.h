@@ -125,6 +125,8 @@ typedef struct {
     void* ikx; void* iky;    /* int[Kcap]              */
     void* acc;               /* uint64[channels+3][Kcap]: sums of c0..c2, x, y, count */
     int K, Kcap, channels;
+    void* labels;            /* int32 label map of the WHOLE image on this device (rows outside the owned band: unspecified) */
+    int label_pitch;         /* elements per label row */
 } spx_slic_state_t;
 int spx_slic_create_strip(const uint8_t* rows, size_t stride, int width, int height, int channels, int algorithm,
                           int region_size, float ruler, int row0, int row1, int own_row0, int own_row1,

@@ -136,12 +136,13 @@ __global__ void __launch_bounds__(128) lsc_init_centres_kernel(LscDev L)
 }
 
 constexpr int LSC_CAP = 32;                        // candidates per tile of the tiled assignment
-// seed k into the list of every 32x32 tile its window [s - step, s + step] meets
+constexpr int LSC_TH = 32;                         // tile height (32 x 64 tiles measured: same speed at S = 30, lists overflow below S = 16)
+// seed k into the list of every 32 x LSC_TH tile its window [s - step, s + step] meets
 __device__ __forceinline__ void lsc_tile_append(const LscDev& L, int k, int sx, int sy)
 {
     if (!L.tl_count) return;
     const int tx0 = max(sx - L.stepx, 0) >> 5, tx1 = min(sx + L.stepx, L.w - 1) >> 5;
-    const int ty0 = max(sy - L.stepy, 0) >> 5, ty1 = min(sy + L.stepy, L.h - 1) >> 5;
+    const int ty0 = max(sy - L.stepy, 0) / LSC_TH, ty1 = min(sy + L.stepy, L.h - 1) / LSC_TH;
     for (int ty = ty0; ty <= ty1; ty++)
         for (int tx = tx0; tx <= tx1; tx++) {
             const int t = ty * L.tiles_x + tx;
@@ -738,7 +739,7 @@ struct LscEngine {
         SPX_CHECK(dalloc(&d_tile_overflow, 1));
         SPX_CUDA(cudaMemsetAsync(d_tile_overflow, 0, sizeof(int), st));
         tiled = C == 3 && L.stepx >= LSC_TILE_MIN_STEP && L.stepy >= LSC_TILE_MIN_STEP && !getenv("SPX_LSC_NO_TILE");
-        L.tiles_x = cdiv(w, 32); L.tiles_y = cdiv(h, 32);
+        L.tiles_x = cdiv(w, 32); L.tiles_y = cdiv(h, LSC_TH);
         L.ctab = nullptr; L.tl_count = nullptr; L.tl_k = nullptr;
         float4* d_ctab = nullptr;
         if (tiled) {
@@ -854,7 +855,7 @@ struct LscEngine {
         const dim3 grid(cdiv(L.w, 32), cdiv(L.h, 8));
         for (int it = 0; it < n; it++) {
             if (tiled) {
-                const dim3 tg(cdiv(L.w, 32), cdiv(L.h, 32));
+                const dim3 tg(L.tiles_x, L.tiles_y);
                 lsc_tile_kernel<<<tg, 128, 0, st>>>(L, d_labels, d_tile_overflow);
                 SPX_CUDA(cudaMemsetAsync(L.tl_count, 0, (size_t)L.tiles_x * L.tiles_y * sizeof(int), st));
             }

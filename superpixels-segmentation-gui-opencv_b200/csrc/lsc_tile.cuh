@@ -2,7 +2,7 @@
 // Included by lsc.cu after LscDev / lsc_features.  Same results as lsc_assign_kernel, bit for bit (the sums are exact
 // fixed-point integers and the arg-min is taken in (distance, seed index) order either way); ~5x fewer instructions.
 //
-// One CTA (128 threads) per 32x32 tile.
+// One CTA (128 threads) per 32 x LSC_TH (32) tile.
 //   setup      : the kernels that move the seeds (lsc_bin_kernel, lsc_finalize_kernel) append every seed to the list of each
 //                tile its window [s - step, s + step] meets (13 per tile at S = 20, 10 at S = 30); they are ranked by seed index (ascending
 //                index + strict '<' = the oracle's (distance, index) order) and staged as one record each: the negated
@@ -25,12 +25,12 @@ constexpr int LSC_COPYW = LSC_CAP * LSC_SLOTW + 4; // the +4 words rotate the co
 
 struct __align__(16) LscRec {
     float4 c0, c1, c2;                             // -cen[0..3], -cen[4..7], (-cen[8], -cen[9], key as int bits, 0)
-    float px[32], py[32];
+    float px[32], py[LSC_TH];
 };
 struct LscTileSmem {
     LscRec rec[LSC_CAP];                           // ascending seed index
     int4 win[LSC_CAP];                             // window, inclusive: x_lo, x_hi, y_lo, y_hi
-    unsigned acc[LSC_NCOPY][LSC_COPYW];
+    __align__(16) unsigned acc[LSC_NCOPY][LSC_COPYW];
     int k[LSC_CAP];
 };
 
@@ -140,13 +140,13 @@ __global__ void __launch_bounds__(128, 5) lsc_tile_kernel(const __grid_constant_
     constexpr int D = 10;
     __shared__ LscTileSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tx0 = blockIdx.x * 32, ty0 = blockIdx.y * 32;
+    const int tx0 = blockIdx.x * 32, ty0 = blockIdx.y * LSC_TH;
     // ---- candidates: the kernels that move the seeds appended every seed whose window meets this tile
     const int tile = blockIdx.y * L.tiles_x + blockIdx.x;
     const int cnt = __ldg(&L.tl_count[tile]);
     if (cnt > LSC_CAP) {
         if (tid == 0) atomicAdd(d_overflow, 1);
-        for (int r = warp; r < 32; r += 4) {
+        for (int r = warp; r < LSC_TH; r += 4) {
             const int x = tx0 + lane, y = ty0 + r;
             if (x < L.w && y < L.h) lsc_pixel_exact(L, labels, x, y, false);
         }
@@ -154,7 +154,10 @@ __global__ void __launch_bounds__(128, 5) lsc_tile_kernel(const __grid_constant_
     }
     int my_k = 0;
     if (tid < cnt) { my_k = L.tl_k[(size_t)tile * LSC_CAP + tid]; sm.k[tid] = my_k; }
-    for (int i = tid; i < LSC_NCOPY * LSC_COPYW; i += 128) (&sm.acc[0][0])[i] = 0u;
+    {   // zero the accumulators of the slots in use: copy tid >> 4, 16-byte stores
+        unsigned* cpz = sm.acc[tid >> 4];
+        for (int i = tid & 15; i < cnt * (LSC_SLOTW / 4); i += 16) *reinterpret_cast<uint4*>(cpz + 4 * i) = make_uint4(0u, 0u, 0u, 0u);
+    }
     __syncthreads();
     // ---- rank by seed index, stage the records; clear the accumulators
     if (tid < cnt) {
@@ -173,9 +176,10 @@ __global__ void __launch_bounds__(128, 5) lsc_tile_kernel(const __grid_constant_
     __syncthreads();
     {
         const float inf = __int_as_float(0x7f800000);
-        for (int i = tid; i < cnt * 64; i += 128) {
-            const int c = i >> 6, j = i & 31;
-            const bool isy = i & 32;
+        for (int i = tid; i < cnt * (32 + LSC_TH); i += 128) {
+            const int c = i / (32 + LSC_TH), e = i - c * (32 + LSC_TH);
+            const bool isy = e >= 32;
+            const int j = isy ? e - 32 : e;
             const int4 wn = sm.win[c];
             const int p = (isy ? ty0 : tx0) + j;
             const int lo = isy ? wn.z : wn.x, hi = isy ? wn.w : wn.y;
@@ -191,14 +195,14 @@ __global__ void __launch_bounds__(128, 5) lsc_tile_kernel(const __grid_constant_
     const int xc0 = min(x, L.w - 1), xc1 = min(x + 1, L.w - 1);
     const float xcs[2] = {__ldg(&L.xcos[xc0]), __ldg(&L.xcos[xc1])}, xsn[2] = {__ldg(&L.xsin[xc0]), __ldg(&L.xsin[xc1])};
     const float wxv[2] = {__ldg(&L.wx[xc0]), __ldg(&L.wx[xc1])};
-    const bool interior = tx0 + 32 <= L.w && ty0 + 32 <= L.h;
+    const bool interior = tx0 + 32 <= L.w && ty0 + LSC_TH <= L.h;
     const bool pair_store = (L.w & 1) == 0;
     const int X0 = tx0 + 16 * wx, X1 = X0 + 15;
     unsigned* const cp = sm.acc[lane & (LSC_NCOPY - 1)];
     const unsigned char* rec0 = reinterpret_cast<const unsigned char*>(&sm.rec[0]);
     const unsigned char* thr_px = reinterpret_cast<const unsigned char*>(&sm.rec[0].px[xo]);
 #pragma unroll 1
-    for (int step = 0; step < 2; step++) {
+    for (int step = 0; step < LSC_TH / 16; step++) {
         const int yo = 16 * step + 8 * wy + 2 * ly;
         const int y = ty0 + yo;
         // features of the 2x2 block, packed by row: P[r][i] = (f_i(x, y + r), f_i(x + 1, y + r))

@@ -1073,6 +1073,7 @@ extern "C" int spx_slic_device_state(spx_slic_t* h, spx_slic_state_t* out)
     SPX_REQUIRE(out, SPX_ERR_BADARG, "device_state: out is NULL");
     out->kx = e->a.kx; out->ky = e->a.ky; out->kc = e->a.kc; out->ikx = e->a.ikx; out->iky = e->a.iky; out->acc = e->a.acc;
     out->K = e->g.K; out->Kcap = e->g.Kcap; out->channels = e->g.C;
+    out->labels = e->d_labels; out->label_pitch = e->g.lp;
     return SPX_OK;
 }
 extern "C" int spx_slic_strip_rebin(spx_slic_t* h)

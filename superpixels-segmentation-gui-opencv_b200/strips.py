@@ -20,7 +20,8 @@ from . import SLIC, SpxError, _ck, _p, lib
 
 class _State(C.Structure):
     _fields_ = [("kx", C.c_void_p), ("ky", C.c_void_p), ("kc", C.c_void_p), ("ikx", C.c_void_p), ("iky", C.c_void_p),
-                ("acc", C.c_void_p), ("K", C.c_int), ("Kcap", C.c_int), ("channels", C.c_int)]
+                ("acc", C.c_void_p), ("K", C.c_int), ("Kcap", C.c_int), ("channels", C.c_int),
+                ("labels", C.c_void_p), ("label_pitch", C.c_int)]
 
 
 class _DevArray:
@@ -89,6 +90,9 @@ class StripSLIC:
         self._seed_f = [view(st.kx, st.Kcap, "<f4"), view(st.ky, st.Kcap, "<f4"), view(st.kc, 3 * st.Kcap, "<f4")]
         self._seed_i = [view(st.ikx, st.Kcap, "<i4"), view(st.iky, st.Kcap, "<i4")]
         self._acc = view(st.acc, 6 * st.Kcap, "<i8")
+        self._lp = st.label_pitch
+        self._labels = view(st.labels, self.h * st.label_pitch, "<i4")     # the device's whole-image label map, pitched rows
+        self._gathered = False
         # assemble the seeds: exactly one rank contributed a non-zero entry per cluster, so the sum is exact
         with torch.cuda.stream(self.stream):
             for t in self._seed_f + self._seed_i:
@@ -141,8 +145,56 @@ class StripSLIC:
         _ck(lib().spx_slic_get_label_rows(self._h, _p(out), self.w * 4, self.own0, self.own1))
         return out
 
+    def gatherLabels(self):
+        """the bands of all ranks into rank 0's device label map, device to device (NCCL send / recv of whole pitched rows);
+        collective"""
+        bands = row_bands(self.h, self.world)
+        with self.torch.cuda.stream(self.stream):
+            if self.rank == 0:
+                for r in range(1, self.world):
+                    a, b = bands[r]
+                    if b > a:
+                        self.dist.recv(self._labels[a * self._lp:b * self._lp], src=r)
+            elif self.own1 > self.own0:
+                self.dist.send(self._labels[self.own0 * self._lp:self.own1 * self._lp], dst=0)
+        self.stream.synchronize()
+        self._gathered = True
+
+    def enforceLabelConnectivity(self, min_element_size=25):
+        """mainwindow.cpp:2108 on a strip object: connectivity is not strip-parallel, so the bands are
+        gathered on rank 0's device -- no host staging -- and the single-device kernels run there; collective.  Afterwards
+        rank 0 holds the label map (getLabels / getLabelContourMask return None on the other ranks)."""
+        if not self._gathered:
+            self.gatherLabels()
+        k = [self.K]
+        if self.rank == 0:
+            L = lib()
+            _ck(L.spx_slic_enforce_label_connectivity(self._h, int(min_element_size)))
+            n = C.c_int(0)
+            _ck(L.spx_slic_get_number_of_superpixels(self._h, C.byref(n)))
+            k = [int(n.value)]
+        self.dist.broadcast_object_list(k, src=0)
+        self.K = k[0]
+
+    def getLabelContourMask(self, thick_line=True):
+        """mainwindow.cpp:2111; rank 0 returns the mask of the whole image, the others None; collective"""
+        if not self._gathered:
+            self.gatherLabels()
+        if self.rank != 0:
+            return None
+        out = np.empty((self.h, self.w), np.uint8)
+        _ck(lib().spx_slic_get_label_contour_mask(self._h, _p(out), self.w, 1 if thick_line else 0))
+        return out
+
     def getLabels(self):
-        """the whole label map, gathered on every rank (for tests; a gigapixel caller keeps the bands apart)"""
+        """the whole label map.  Before connectivity: gathered on every rank through the host (for tests; a gigapixel caller
+        keeps the bands apart).  After enforceLabelConnectivity / gatherLabels: rank 0's device map (None elsewhere)."""
+        if self._gathered:
+            if self.rank != 0:
+                return None
+            out = np.empty((self.h, self.w), np.int32)
+            _ck(lib().spx_slic_get_labels(self._h, _p(out), self.w * 4))
+            return out
         mine = self.getLabelRows()
         parts = [None] * self.world
         self.dist.all_gather_object(parts, mine)

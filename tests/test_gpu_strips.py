@@ -24,4 +24,4 @@ def test_strip_mode_two_gpus_bit_identical():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     d = json.loads(line)
-    assert d["labels_identical"] and d["centres_identical"] and d["n_gpus"] == 2
+    assert d["labels_identical"] and d["centres_identical"] and d["connectivity_and_contour_identical"] and d["n_gpus"] == 2

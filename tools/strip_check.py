@@ -23,24 +23,31 @@ def run(exchange):
     s = strips.StripSLIC(lab, S, RULER, dist, local, exchange=exchange)
     torch.cuda.synchronize(); dist.barrier()
     t0 = time.perf_counter(); s.iterate(IT); torch.cuda.synchronize(); dist.barrier(); t = time.perf_counter() - t0
-    out = (s.getLabels(), s.getCentres(), t, s.exchangedBytes(), s.getNumberOfSuperpixels())
+    out = [s.getLabels(), s.getCentres(), t, s.exchangedBytes(), s.getNumberOfSuperpixels()]
+    if exchange == "peer":                                  # the rest of the COMPUTE click on the strip object (gathered on rank 0's device)
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter(); s.enforceLabelConnectivity(25); torch.cuda.synchronize(); dist.barrier(); tc = time.perf_counter() - t0
+        out += [s.getLabels(), s.getLabelContourMask(False), s.getNumberOfSuperpixels(), tc]
     s.release()
     return out
 
 
-Ls, Cs, t, xb, K = run("peer")                              # NVLink peer stores + flags by the library's own kernels
+Ls, Cs, t, xb, K, Lc, Mc, Kc, tc = run("peer")                              # NVLink peer stores + flags by the library's own kernels
 Ln, Cn, tn, xbn, _ = run("nccl")                            # NCCL all-reduce of the accumulators
 if rank == 0:
     g = spx.createSuperpixelSLIC(lab, spx.SLIC, S, RULER, device=local)
     spx.lib().spx_slic_synchronize(g._h)
     t1 = time.perf_counter(); g.iterate(IT); spx.lib().spx_slic_synchronize(g._h); t1 = time.perf_counter() - t1
     Lg, Cg = g.getLabels(), g.getCentres()
+    g.enforceLabelConnectivity(25)
+    post_ok = bool(Kc == g.getNumberOfSuperpixels() and (Lc == g.getLabels()).all() and (Mc == g.getLabelContourMask(False)).all())
     print(json.dumps({"strip_check": "%dx%d SLIC S=%d %d iterations" % (W, H, S, IT), "n_gpus": world, "bands": strips.row_bands(H, world),
                       "labels_identical": bool((Ls == Lg).all() and (Ln == Lg).all()),
                       "centres_identical": bool((Cs == Cg).all() and (Cn == Cg).all()),
+                      "connectivity_and_contour_identical": post_ok, "gather_plus_connectivity_ms": tc * 1e3, "K_connected": Kc,
                       "strip_iterate_ms": t * 1e3, "strip_iterate_ms_nccl_allreduce": tn * 1e3, "single_gpu_iterate_ms": t1 * 1e3,
                       "exchange": "peer memory (CUDA IPC over NVLink): stores + flags by the library's kernels",
                       "sent_MB_per_rank_per_iteration": xb / IT / 1e6, "allreduce_payload_MB_per_iteration": xbn / IT / 1e6, "K": K}))
-    assert (Ls == Lg).all() and (Cs == Cg).all() and (Ln == Lg).all() and (Cn == Cg).all()
+    assert (Ls == Lg).all() and (Cs == Cg).all() and (Ln == Lg).all() and (Cn == Cg).all() and post_ok
 dist.barrier()
 dist.destroy_process_group()
