@@ -12,9 +12,9 @@
 //                tables; candidates whose window misses the patch are culled by one ballot; the distance runs on the
 //                packed f32x2 pipe in the oracle's order ((((t0^2 + t1^2) + t2^2) + ...) + t9^2), never contracted.
 //   sums       : the thread's 2x2 pixels are split by at most two winners and added, field by field, to the CTA's
-//                per-candidate 64-bit accumulators (two 32-bit shared-memory atomics, the carry taken from the returned
-//                low word; 8 privatised copies picked by lane, so a warp sitting inside one superpixel is a 4-way, not a
-//                32-way, conflict); one 64-bit global atomic per field per candidate at the end.
+//                per-candidate 64-bit accumulators (two fire-and-forget 32-bit shared-memory atomics: low 24 bits / signed
+//                rest, no carry to wait for; 8 privatised copies picked by lane, so a warp sitting inside one superpixel is a
+//                4-way, not a 32-way, conflict); one 64-bit global atomic per field per candidate at the end.
 // Tiles whose list overflows LSC_CAP and pixels covered by no window take exact per-pixel paths.
 // (no include guard needed: included once, inside namespace spx, by lsc.cu, which includes f32x2.cuh at file scope)
 
@@ -34,12 +34,18 @@ struct LscTileSmem {
     int k[LSC_CAP];
 };
 
+// a 64-bit value into a {lo, hi} pair of 32-bit shared-memory words WITHOUT waiting for a carry: lo takes the low 24 bits,
+// hi the (signed) rest.  A word receives at most 64 adds per tile (a copy serves 4 lanes of 4 warps for 2 steps, two winners
+// each), so lo stays below 2^30; |v| < 2^45 here (fixed point x 2^32 of features <= 51, four pixels), so hi fits easily.
+// Both atomics are fire-and-forget (no returned value, no dependent instruction).  lsc_fold64 undoes the split.
 __device__ __forceinline__ void lsc_sadd64(unsigned* p, unsigned long long v)
 {
-    const unsigned lo = (unsigned)v;
-    const unsigned old = atomicAdd(p, lo);
-    const unsigned hi = (unsigned)(v >> 32) + ((unsigned)(old + lo) < lo ? 1u : 0u);
-    if (hi) atomicAdd(p + 1, hi);
+    atomicAdd(p, (unsigned)v & 0xffffffu);
+    atomicAdd(p + 1, (unsigned)(int)((long long)v >> 24));
+}
+__device__ __forceinline__ unsigned long long lsc_fold64(unsigned lo, unsigned hi)
+{
+    return (unsigned long long)((long long)lo + ((long long)(int)hi << 24));
 }
 __device__ __forceinline__ unsigned long long lsc_q32(float Wt, float f)
 {
@@ -320,7 +326,7 @@ __global__ void __launch_bounds__(128, 5) lsc_tile_kernel(const __grid_constant_
 #pragma unroll
             for (int p = 0; p < LSC_NCOPY; p++) {
                 const unsigned* a = sm.acc[p] + LSC_SLOTW * c + 2 * f;
-                v += (unsigned long long)a[0] + ((unsigned long long)a[1] << 32);
+                v += lsc_fold64(a[0], a[1]);
             }
             if (v) atomicAdd(&dst[f], v);
         } else {
