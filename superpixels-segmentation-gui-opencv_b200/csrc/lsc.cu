@@ -20,6 +20,7 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -361,34 +362,39 @@ __global__ void lsc_pre_init_kernel(const int* __restrict__ P, const int* __rest
     FL[i] = csize[i] <= bound ? LSC_UNK : lab[i];
     ADJ[i] = LSC_UNK;
 }
-// adj_k = (final label of the component left of / above the root differs from L_k) ? that label : adj_{k-1}
-__global__ void lsc_pre_relax_kernel(const int* __restrict__ P, const int* __restrict__ lab, const int* __restrict__ csize,
-                                     const int* __restrict__ prevroot, volatile int* FL, volatile int* ADJ, int w, int n,
-                                     int bound, int* __restrict__ pending)
+// adj_k = (final label of the component left of / above the root differs from L_k) ? that label : adj_{k-1},
+// relaxed over the compacted list of component roots (1.1 M roots instead of 33 M pixels at 8K)
+__global__ void __launch_bounds__(256) lsc_pre_relax_list_kernel(const int* __restrict__ roots, const int* __restrict__ d_nroots,
+                                                                  const int* __restrict__ P, const int* __restrict__ lab,
+                                                                  const int* __restrict__ csize, const int* __restrict__ prevroot,
+                                                                  volatile int* FL, volatile int* ADJ, int w, int bound, int* __restrict__ pending)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || P[i] != i || ADJ[i] != LSC_UNK) return;
-    const int x = i % w;
-    const int nb = x > 0 ? i - 1 : (i >= w ? i - w : -1);
-    int adj;
-    if (nb < 0) adj = 0;                           // pixel 0: nothing is visited yet, adj keeps its initial value
-    else {
-        const int fl = FL[P[nb]];
-        if (fl == LSC_UNK) { *pending = 1; return; }
-        if (fl != lab[i]) adj = fl;
+    const int nr = *d_nroots;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nr; t += gridDim.x * blockDim.x) {
+        const int i = roots[t];
+        if (ADJ[i] != LSC_UNK) continue;
+        const int x = i % w;
+        const int nb = x > 0 ? i - 1 : (i >= w ? i - w : -1);
+        int adj;
+        if (nb < 0) adj = 0;                       // pixel 0: nothing is visited yet, adj keeps its initial value
         else {
-            const int pr = prevroot[i];
-            if (pr < 0) adj = 0;
+            const int fl = FL[P[nb]];
+            if (fl == LSC_UNK) { *pending = 1; continue; }
+            if (fl != lab[i]) adj = fl;
             else {
-                const int a = ADJ[pr];
-                if (a == LSC_UNK) { *pending = 1; return; }
-                adj = a;
+                const int pr = prevroot[i];
+                if (pr < 0) adj = 0;
+                else {
+                    const int a = ADJ[pr];
+                    if (a == LSC_UNK) { *pending = 1; continue; }
+                    adj = a;
+                }
             }
         }
+        if (csize[i] <= bound) FL[i] = adj;
+        __threadfence();
+        ADJ[i] = adj;
     }
-    if (csize[i] <= bound) FL[i] = adj;
-    __threadfence();
-    ADJ[i] = adj;
 }
 __global__ void lsc_pre_relabel_kernel(const int* __restrict__ P, const int* __restrict__ FL, int* __restrict__ lab, int n)
 {
@@ -908,9 +914,21 @@ struct LscEngine {
         int* FL = A; int* ADJ = B;
         lsc_pre_init_kernel<<<g1, 256, 0, st>>>(P, d_labels, csize, FL, ADJ, n, min_element_size);
         launches++;
+        // the relaxation only concerns component roots: compact them once (rootidx is free after the scan above)
+        int* roots = rootidx;
+        int* d_nroots = d_flag + 1;
+        {
+            size_t bytes = 0;
+            cub::CountingInputIterator<int> idx(0);
+            LSC_TRYCUDA(cub::DeviceSelect::Flagged(nullptr, bytes, idx, flag, roots, d_nroots, n, st));
+            LSC_TRY(scan_tmp(bytes));
+            LSC_TRYCUDA(cub::DeviceSelect::Flagged(d_scan_tmp, bytes, idx, flag, roots, d_nroots, n, st));
+            launches += 2;
+        }
         for (int round = 0; round < 1000000; round++) {
             LSC_TRYCUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
-            for (int k = 0; k < 4; k++) lsc_pre_relax_kernel<<<g1, 256, 0, st>>>(P, d_labels, csize, prevroot, FL, ADJ, w, n, min_element_size, d_flag);
+            for (int k = 0; k < 4; k++)
+                lsc_pre_relax_list_kernel<<<148 * 8, 256, 0, st>>>(roots, d_nroots, P, d_labels, csize, prevroot, FL, ADJ, w, min_element_size, d_flag);
             launches += 4;
             LSC_TRYCUDA(cudaMemcpyAsync(h_pinned, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
             LSC_TRYCUDA(cudaStreamSynchronize(st));
