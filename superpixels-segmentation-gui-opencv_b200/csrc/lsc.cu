@@ -515,7 +515,8 @@ struct LscRounds {
     unsigned long long* edges[2]; int E;          // live edges, double buffered
     int* plist[2];                                // pending regions, double buffered
     const int* smallflag; int* done; int* size; int threshold; int R; int order;
-    int* pend; unsigned* ra; unsigned* rb; unsigned long long* best;
+    uint4* rr;                                    // per region (ra, rb, pending, -): one 16-byte record, one sector per visit
+    unsigned long long* best;
     float* cen; int D; float* Wr; int* alive; int* cur;
     int* cnt;                                     // [0..3] pending-list lengths by round & 3, [4..7] edge-list lengths, [8] barrier, [9] rounds
     int max_rounds;
@@ -561,8 +562,9 @@ __global__ void __launch_bounds__(1024) lsc_rounds_kernel(LscRounds a)
             if (i < nP) {
                 r = round ? pin[i] : i;
                 p = a.smallflag[r] && !a.done[r] && a.size[r] < a.threshold;
-                a.pend[r] = p ? 1 : 0;
-                if (p) { const unsigned pr = lsc_prio(r, a.order); a.ra[r] = pr; a.rb[r] = pr; a.best[r] = ~0ull; }
+                const unsigned pr = p ? lsc_prio(r, a.order) : 0xffffffffu;
+                a.rr[r] = make_uint4(pr, pr, p ? 1u : 0u, 0u);
+                if (p) a.best[r] = ~0ull;
             }
             const int slot = lsc_warp_append(p, cP, lane);
             if (p) pout[slot] = r;
@@ -578,9 +580,9 @@ __global__ void __launch_bounds__(1024) lsc_rounds_kernel(LscRounds a)
             if (e < nE) {
                 const unsigned long long k = ein[e];
                 rp = lsc_cur(a.cur, (int)(k >> 32)); rq = lsc_cur(a.cur, (int)(k & 0xffffffffull));
-                const bool pp = a.pend[rp], pq = a.pend[rq];
+                const bool pp = a.rr[rp].z, pq = a.rr[rq].z;
                 keep = rp != rq && (pp || pq);
-                if (keep) { if (!pp) a.ra[rp] = 0xffffffffu; if (!pq) a.ra[rq] = 0xffffffffu; }
+                if (keep) { if (!pp) a.rr[rp].x = 0xffffffffu; if (!pq) a.rr[rq].x = 0xffffffffu; }
             }
             const int slot = lsc_warp_append(keep, cE, lane);
             if (keep) eout[slot] = ((unsigned long long)(unsigned)rp << 32) | (unsigned)rq;
@@ -591,31 +593,34 @@ __global__ void __launch_bounds__(1024) lsc_rounds_kernel(LscRounds a)
         for (int e = tid; e < nE; e += nth) {
             const unsigned long long k = eout[e];
             const int rp = (int)(k >> 32), rq = (int)(k & 0xffffffffull);
-            if (a.pend[rq]) { const unsigned v = lsc_prio(rq, a.order); if (v < a.ra[rp]) atomicMin(&a.ra[rp], v); }
-            if (a.pend[rp]) { const unsigned v = lsc_prio(rp, a.order); if (v < a.ra[rq]) atomicMin(&a.ra[rq], v); }
+            const uint4 P = a.rr[rp], Q = a.rr[rq];
+            if (Q.z) { const unsigned v = lsc_prio(rq, a.order); if (v < P.x) atomicMin(&a.rr[rp].x, v); }
+            if (P.z) { const unsigned v = lsc_prio(rp, a.order); if (v < Q.x) atomicMin(&a.rr[rq].x, v); }
         }
         lsc_grid_barrier(bar, ++epoch * nblk);
         // ---- rb (pending regions only) = the same over distance 2
         for (int e = tid; e < nE; e += nth) {
             const unsigned long long k = eout[e];
             const int rp = (int)(k >> 32), rq = (int)(k & 0xffffffffull);
-            const unsigned m = min(a.ra[rp], a.ra[rq]);
-            if (a.pend[rp] && m < a.rb[rp]) atomicMin(&a.rb[rp], m);
-            if (a.pend[rq] && m < a.rb[rq]) atomicMin(&a.rb[rq], m);
+            const uint4 P = a.rr[rp], Q = a.rr[rq];
+            const unsigned m = min(P.x, Q.x);
+            if (P.z && m < P.y) atomicMin(&a.rr[rp].y, m);
+            if (Q.z && m < Q.y) atomicMin(&a.rr[rq].y, m);
         }
         lsc_grid_barrier(bar, ++epoch * nblk);
         // ---- best neighbour of every region that merges in this round
         for (int e = tid; e < nE; e += nth) {
             const unsigned long long k = eout[e];
             const int rp = (int)(k >> 32), rq = (int)(k & 0xffffffffull);
-            if (a.pend[rp] && a.rb[rp] == lsc_prio(rp, a.order)) { const unsigned long long key = lsc_pair_key(a.cen, a.D, rp, rq); if (key < a.best[rp]) atomicMin(&a.best[rp], key); }
-            if (a.pend[rq] && a.rb[rq] == lsc_prio(rq, a.order)) { const unsigned long long key = lsc_pair_key(a.cen, a.D, rq, rp); if (key < a.best[rq]) atomicMin(&a.best[rq], key); }
+            const uint4 P = a.rr[rp], Q = a.rr[rq];
+            if (P.z && P.y == lsc_prio(rp, a.order)) { const unsigned long long key = lsc_pair_key(a.cen, a.D, rp, rq); if (key < a.best[rp]) atomicMin(&a.best[rp], key); }
+            if (Q.z && Q.y == lsc_prio(rq, a.order)) { const unsigned long long key = lsc_pair_key(a.cen, a.D, rq, rp); if (key < a.best[rq]) atomicMin(&a.best[rq], key); }
         }
         lsc_grid_barrier(bar, ++epoch * nblk);
         // ---- merge
         for (int q = tid; q < nP; q += nth) {
             const int i = pout[q];
-            if (a.rb[i] != lsc_prio(i, a.order)) continue;
+            if (a.rr[i].y != lsc_prio(i, a.order)) continue;
             a.done[i] = 1;
             const unsigned long long k = a.best[i];
             if (k == ~0ull) continue;                                            // no neighbour at all (one region covers the image)
@@ -950,12 +955,13 @@ struct LscEngine {
         LSC_TRYCUDA(cudaMemcpyAsync(h_pinned + 1, flag + n - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         LSC_TRYCUDA(cudaStreamSynchronize(st));
         const int R = h_pinned[0] + h_pinned[1];
-        int *reg = B, *size, *alive, *smallflag, *done, *cur, *pend, *rk, *ra, *rb, *newid;
+        int *reg = B, *size, *alive, *smallflag, *done, *cur, *newid;
+        uint4* rr;
         unsigned long long* best;
         float *cen, *Wr;
         long long* rsum;
         LSC_TRY(talloc(&size, R + 1)); LSC_TRY(talloc(&alive, R + 1)); LSC_TRY(talloc(&smallflag, R)); LSC_TRY(talloc(&done, R));
-        LSC_TRY(talloc(&cur, R)); LSC_TRY(talloc(&pend, R)); LSC_TRY(talloc(&rk, R)); LSC_TRY(talloc(&ra, R)); LSC_TRY(talloc(&rb, R));
+        LSC_TRY(talloc(&cur, R)); LSC_TRY(talloc((int**)&rr, (size_t)R * 4));
         LSC_TRY(talloc(&newid, R + 1)); LSC_TRY(talloc((int**)&best, (size_t)R * 2));
         LSC_TRY(talloc((int**)&cen, (size_t)R * D)); LSC_TRY(talloc((int**)&Wr, R));
         LSC_TRY(talloc((int**)&rsum, (size_t)R * (D + 1) * 2));
@@ -1017,7 +1023,7 @@ struct LscEngine {
             ra_.edges[0] = edges; ra_.edges[1] = edges == kbuf0 ? kbuf1 : kbuf0; ra_.E = E;
             ra_.plist[0] = plist0; ra_.plist[1] = plist1;
             ra_.smallflag = smallflag; ra_.done = done; ra_.size = size; ra_.threshold = threshold; ra_.R = R;
-            ra_.order = merge_order; ra_.pend = pend; ra_.ra = (unsigned*)ra; ra_.rb = (unsigned*)rb; ra_.best = best;
+            ra_.order = merge_order; ra_.rr = rr; ra_.best = best;
             ra_.cen = cen; ra_.D = D; ra_.Wr = Wr; ra_.alive = alive; ra_.cur = cur;
             ra_.cnt = rcnt; ra_.max_rounds = R + 2;
             int blocks = std::min(std::max(cdiv(std::max(R, E), 1024), 1), s_sms);   // one CTA per SM at most: all co-resident
