@@ -477,3 +477,21 @@ def test_create_with_fused_colour_conversion(spx, synthmod, code):
     assert (a.getLabels() == b.getLabels()).all()
     with pytest.raises(spx.SpxError):
         spx.createSuperpixelSLIC(bgr, spx.SLIC, 20, 10.0, colour_code=7)
+
+
+@pytest.mark.gpu
+def test_blocking_sync_policy_roundtrip(spx, synthmod):
+    """spx_set_blocking_sync switches the host waiting policy of the process without disturbing results"""
+    import ctypes as C
+    L = spx.lib()
+    L.spx_set_blocking_sync.argtypes = [C.c_int, C.c_int]
+    bgr, _ = synthmod.synth(200, 120, 2)
+    lab = spx.cvtColor(bgr, spx.COLOR_BGR2Lab)
+    ref = spx.createSuperpixelSLIC(lab, spx.SLIC, 16, 10.0); ref.iterate(3)
+    try:
+        assert L.spx_set_blocking_sync(0, 1) == 0, L.spx_last_error()
+        s = spx.createSuperpixelSLIC(lab, spx.SLIC, 16, 10.0); s.iterate(3)
+        assert (s.getLabels() == ref.getLabels()).all()
+    finally:
+        assert L.spx_set_blocking_sync(0, 0) == 0, L.spx_last_error()
+    assert L.spx_set_blocking_sync(99, 1) != 0          # no such device
