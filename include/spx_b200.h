@@ -191,8 +191,9 @@ int spx_lsc_set_labels(spx_lsc_t*, const int32_t* src, size_t src_stride, int nu
 /* test hooks: centres = rows of (2*channels+4 feature means, seed x, seed y) float32; kernel launch count */
 int spx_lsc_get_centres(spx_lsc_t*, float* dst, int rows);
 int spx_lsc_launch_count(spx_lsc_t*, long long* out);
-/* visiting order of the small regions in enforceLabelConnectivity's merge pass: 1 (default) = hashed region index
- * (short dependency chains, fast on a GPU), 0 = ascending region index (the authors' order; thousands of rounds). */
+/* visiting order of the small regions in enforceLabelConnectivity's merge pass: 0 (DEFAULT) = ascending region index, the
+ * authors' order -- what upstream computes, and what the cv::ximgproc adapter therefore runs; 1 (opt-in) = hashed region
+ * index: the same rule in a different order (final superpixel count differs by about 1 %), NOT upstream's result. */
 int spx_lsc_set_merge_order(spx_lsc_t*, int order);
 int spx_lsc_destroy(spx_lsc_t*);
 

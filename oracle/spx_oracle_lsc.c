@@ -42,7 +42,7 @@ struct spxo_lsc {
     int w, h, C, D, S;
     float ratio;
     int K, ColNum, RowNum, stepx, stepy;
-    int merge_order;         /* post-pass visiting order: 0 = ascending region index (authors), 1 = hashed index (CUDA default) */
+    int merge_order;         /* post-pass visiting order: 0 = ascending region index (authors; default here and in the CUDA path), 1 = hashed index (CUDA opt-in) */
     uint8_t* img;            /* dense interleaved copy */
     int32_t* labels;
     int* sx; int* sy;        /* seed positions */

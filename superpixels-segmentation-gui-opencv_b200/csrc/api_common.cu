@@ -54,7 +54,7 @@ void pool_free(void* p, cudaStream_t st)
 }
 }  // namespace spx
 
-extern "C" int spx_release_cached_memory(void)
+extern "C" int spx_release_cached_memory(void) try
 {
     int dev = 0;
     SPX_CUDA(cudaGetDevice(&dev));
@@ -63,10 +63,10 @@ extern "C" int spx_release_cached_memory(void)
     SPX_CUDA(cudaDeviceSynchronize());
     SPX_CUDA(cudaMemPoolTrimTo(pool, 0));
     return SPX_OK;
-}
+} SPX_API_CATCH
 extern "C" int spx_version(void) { return 100; }
 extern "C" const char* spx_last_error(void) { return spx::g_err; }
-extern "C" int spx_device_count(int* count)
+extern "C" int spx_device_count(int* count) try
 {
     SPX_REQUIRE(count, SPX_ERR_BADARG, "count is NULL");
     int n = 0;
@@ -74,14 +74,14 @@ extern "C" int spx_device_count(int* count)
     if (e != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
     *count = n;
     return SPX_OK;
-}
+} SPX_API_CATCH
 
 // Host threads waiting for the device sleep instead of spinning (cudaDeviceScheduleBlockingSync) -- for hosts that run more
 // worker threads than they have cores (8 ranks x 4 pipeline threads on a 32-core box); 0 restores the driver's default.
-extern "C" int spx_set_blocking_sync(int device, int on)
+extern "C" int spx_set_blocking_sync(int device, int on) try
 {
     using namespace spx;
     SPX_CHECK(require_device(device));
     SPX_CUDA(cudaSetDeviceFlags(on ? cudaDeviceScheduleBlockingSync : cudaDeviceScheduleAuto));
     return SPX_OK;
-}
+} SPX_API_CATCH

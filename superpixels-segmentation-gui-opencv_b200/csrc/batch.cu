@@ -15,18 +15,18 @@ std::mutex g_mu;
 std::map<PoolKey, std::vector<spx_slic_t*>> g_pool;
 }  // namespace
 
-extern "C" int spx_slic_batch_release(void)
+extern "C" int spx_slic_batch_release(void) try
 {
     std::lock_guard<std::mutex> lk(g_mu);
     for (auto& kv : g_pool)
         for (spx_slic_t* e : kv.second) spx_slic_destroy(e);
     g_pool.clear();
     return SPX_OK;
-}
+} SPX_API_CATCH
 
 extern "C" int spx_slic_batch_dev(const void* const* d_frames, int n_frames, int w, int h, int C, int alg, int S, float ruler,
                                   int iters, int min_element_size, void* const* d_labels, void* const* d_masks,
-                                  int thick_line, int n_streams, long long* launches_out)
+                                  int thick_line, int n_streams, long long* launches_out) try
 {
     using namespace spx;
     SPX_REQUIRE(d_frames && d_labels && n_frames >= 0, SPX_ERR_BADARG, "slic_batch: bad argument");
@@ -66,4 +66,4 @@ extern "C" int spx_slic_batch_dev(const void* const* d_frames, int n_frames, int
     }
     if (launches_out) *launches_out = launches;
     return rc;
-}
+} SPX_API_CATCH

@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <cstdarg>
 #include <cstring>
+#include <exception>
+#include <new>
 #include "../../include/spx_b200.h"
 
 namespace spx {
@@ -34,6 +36,15 @@ void set_error(const char* fmt, ...);
         }                                     \
     } while (0)
 
+// Every extern "C" entry point is a function-try-block ending in SPX_API_CATCH: nothing may throw across the C ABI
+// (std::bad_alloc from new / std::vector / std::map on the host side becomes SPX_ERR_NOMEM).
+#define SPX_API_CATCH                                                                          \
+    catch (const std::bad_alloc&) { spx::set_error("out of host memory"); return SPX_ERR_NOMEM; } \
+    catch (const std::exception& ex__) { spx::set_error("internal error: %s", ex__.what()); return SPX_ERR_INTERNAL; } \
+    catch (...) { spx::set_error("internal error (unknown exception)"); return SPX_ERR_INTERNAL; }
+
+// several kernels launch one grid row per image row (gridDim.y <= 65535): taller images are rejected up front
+#define SPX_MAX_HEIGHT 65535
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 

@@ -658,7 +658,7 @@ struct LscEngine {
     int S = 0;
     float ratio = 0.f;
     int numlabels = 0;
-    int merge_order = 1;                    // post-pass visiting order: 1 = hashed (default), 0 = upstream's raster order
+    int merge_order = 0;                    // post-pass visiting order: 0 = the authors' raster order (default, what upstream computes), 1 = hashed (opt-in)
     unsigned char* d_img = nullptr;
     int* d_labels = nullptr;
     unsigned char* d_mask = nullptr;
@@ -720,7 +720,7 @@ struct LscEngine {
 
     int create(const uint8_t* image, size_t stride, int w, int h, int C, int S_, float ratio_, int cvt_mode = -1)
     {
-        SPX_REQUIRE(image && w > 0 && h > 0 && (long long)w * h < (1ll << 30) && stride >= (size_t)w * C, SPX_ERR_BADARG,
+        SPX_REQUIRE(image && w > 0 && h > 0 && h <= SPX_MAX_HEIGHT && (long long)w * h < (1ll << 30) && stride >= (size_t)w * C, SPX_ERR_BADARG,
                     "createSuperpixelLSC: bad image");
         SPX_REQUIRE(C >= 1 && C <= LSC_MAXC, SPX_ERR_BADARG, "createSuperpixelLSC: 1..4 channels supported, got %d", C);
         SPX_REQUIRE(S_ >= 1, SPX_ERR_BADARG, "createSuperpixelLSC: region_size must be >= 1");
@@ -1062,7 +1062,7 @@ struct spx_lsc { LscEngine* e; };
     LscEngine* e = (h)->e;                                                                \
     SPX_CUDA(cudaSetDevice(e->device))
 
-extern "C" int spx_lsc_create(const uint8_t* image, size_t stride, int w, int h, int C, int S, float ratio, int device, spx_lsc_t** out)
+extern "C" int spx_lsc_create(const uint8_t* image, size_t stride, int w, int h, int C, int S, float ratio, int device, spx_lsc_t** out) try
 {
     using namespace spx;
     SPX_REQUIRE(out, SPX_ERR_BADARG, "createSuperpixelLSC: out is NULL");
@@ -1074,8 +1074,8 @@ extern "C" int spx_lsc_create(const uint8_t* image, size_t stride, int w, int h,
     if (rc != SPX_OK) { delete e; return rc; }
     *out = new spx_lsc{e};
     return SPX_OK;
-}
-extern "C" int spx_lsc_create_bgr(const uint8_t* bgr, size_t stride, int w, int h, int colour_code, int S, float ratio, int device, spx_lsc_t** out)
+} SPX_API_CATCH
+extern "C" int spx_lsc_create_bgr(const uint8_t* bgr, size_t stride, int w, int h, int colour_code, int S, float ratio, int device, spx_lsc_t** out) try
 {
     using namespace spx;
     SPX_REQUIRE(out, SPX_ERR_BADARG, "createSuperpixelLSC: out is NULL");
@@ -1088,34 +1088,34 @@ extern "C" int spx_lsc_create_bgr(const uint8_t* bgr, size_t stride, int w, int 
     if (rc != SPX_OK) { delete e; return rc; }
     *out = new spx_lsc{e};
     return SPX_OK;
-}
-extern "C" int spx_lsc_iterate(spx_lsc_t* h, int n)
+} SPX_API_CATCH
+extern "C" int spx_lsc_iterate(spx_lsc_t* h, int n) try
 {
     LSC_ENTER(h);
     return e->iterate(n);
-}
-extern "C" int spx_lsc_enforce_label_connectivity(spx_lsc_t* h, int min_element_size)
+} SPX_API_CATCH
+extern "C" int spx_lsc_enforce_label_connectivity(spx_lsc_t* h, int min_element_size) try
 {
     LSC_ENTER(h);
     return e->enforce(min_element_size);
-}
-extern "C" int spx_lsc_get_number_of_superpixels(spx_lsc_t* h, int* out)
+} SPX_API_CATCH
+extern "C" int spx_lsc_get_number_of_superpixels(spx_lsc_t* h, int* out) try
 {
     LSC_ENTER(h);
     SPX_REQUIRE(out, SPX_ERR_BADARG, "getNumberOfSuperpixels: out is NULL");
     SPX_CUDA(cudaStreamSynchronize(e->st));
     *out = e->numlabels;
     return SPX_OK;
-}
-extern "C" int spx_lsc_get_labels(spx_lsc_t* h, int32_t* dst, size_t dst_stride)
+} SPX_API_CATCH
+extern "C" int spx_lsc_get_labels(spx_lsc_t* h, int32_t* dst, size_t dst_stride) try
 {
     LSC_ENTER(h);
     SPX_REQUIRE(dst && dst_stride >= (size_t)e->L.w * 4, SPX_ERR_BADARG, "getLabels: bad destination");
     SPX_CUDA(cudaMemcpy2DAsync(dst, dst_stride, e->d_labels, (size_t)e->L.w * 4, (size_t)e->L.w * 4, e->L.h, cudaMemcpyDeviceToHost, e->st));
     SPX_CUDA(cudaStreamSynchronize(e->st));
     return SPX_OK;
-}
-extern "C" int spx_lsc_get_label_contour_mask(spx_lsc_t* h, uint8_t* dst, size_t dst_stride, int thick_line)
+} SPX_API_CATCH
+extern "C" int spx_lsc_get_label_contour_mask(spx_lsc_t* h, uint8_t* dst, size_t dst_stride, int thick_line) try
 {
     LSC_ENTER(h);
     SPX_REQUIRE(dst && dst_stride >= (size_t)e->L.w, SPX_ERR_BADARG, "getLabelContourMask: bad destination");
@@ -1126,8 +1126,8 @@ extern "C" int spx_lsc_get_label_contour_mask(spx_lsc_t* h, uint8_t* dst, size_t
     SPX_CUDA(cudaMemcpy2DAsync(dst, dst_stride, e->d_mask, e->L.w, e->L.w, e->L.h, cudaMemcpyDeviceToHost, e->st));
     SPX_CUDA(cudaStreamSynchronize(e->st));
     return SPX_OK;
-}
-extern "C" int spx_lsc_set_labels(spx_lsc_t* h, const int32_t* src, size_t src_stride, int numlabels)
+} SPX_API_CATCH
+extern "C" int spx_lsc_set_labels(spx_lsc_t* h, const int32_t* src, size_t src_stride, int numlabels) try
 {
     LSC_ENTER(h);
     SPX_REQUIRE(src && src_stride >= (size_t)e->L.w * 4, SPX_ERR_BADARG, "setLabels: bad source");
@@ -1135,8 +1135,8 @@ extern "C" int spx_lsc_set_labels(spx_lsc_t* h, const int32_t* src, size_t src_s
     SPX_CUDA(cudaStreamSynchronize(e->st));
     if (numlabels > 0) e->numlabels = numlabels;
     return SPX_OK;
-}
-extern "C" int spx_lsc_get_centres(spx_lsc_t* h, float* dst, int rows)
+} SPX_API_CATCH
+extern "C" int spx_lsc_get_centres(spx_lsc_t* h, float* dst, int rows) try
 {
     LSC_ENTER(h);
     const int K = e->L.K, D = e->L.D;
@@ -1153,23 +1153,23 @@ extern "C" int spx_lsc_get_centres(spx_lsc_t* h, float* dst, int rows)
         dst[(size_t)k * (D + 2) + D + 1] = (float)sy[k];
     }
     return SPX_OK;
-}
-extern "C" int spx_lsc_set_merge_order(spx_lsc_t* h, int order)
+} SPX_API_CATCH
+extern "C" int spx_lsc_set_merge_order(spx_lsc_t* h, int order) try
 {
     SPX_REQUIRE(h && h->e && (order == 0 || order == 1), SPX_ERR_BADARG, "set_merge_order: bad argument");
     h->e->merge_order = order;
     return SPX_OK;
-}
-extern "C" int spx_lsc_launch_count(spx_lsc_t* h, long long* out)
+} SPX_API_CATCH
+extern "C" int spx_lsc_launch_count(spx_lsc_t* h, long long* out) try
 {
     SPX_REQUIRE(h && h->e && out, SPX_ERR_BADARG, "launch_count: bad argument");
     *out = h->e->launches;
     return SPX_OK;
-}
-extern "C" int spx_lsc_destroy(spx_lsc_t* h)
+} SPX_API_CATCH
+extern "C" int spx_lsc_destroy(spx_lsc_t* h) try
 {
     if (!h) return SPX_OK;
     delete h->e;
     delete h;
     return SPX_OK;
-}
+} SPX_API_CATCH

@@ -482,10 +482,10 @@ int contour_mask_dev(PostWorkspace& ws, const int* d_labels, int lp, int thick_l
 // stand-alone C ABI (host buffers)
 // ------------------------------------------------------------------------------------------------
 extern "C" int spx_enforce_label_connectivity(int32_t* labels, size_t stride, int width, int height,
-                                              int numlabels, int min_element_size, int device, int* numlabels_out)
+                                              int numlabels, int min_element_size, int device, int* numlabels_out) try
 {
     using namespace spx;
-    SPX_REQUIRE(labels && width > 0 && height > 0 && stride >= (size_t)width * 4 && stride % 4 == 0, SPX_ERR_BADARG,
+    SPX_REQUIRE(labels && width > 0 && height > 0 && height <= SPX_MAX_HEIGHT && (long long)width * height < (1ll << 31) && stride >= (size_t)width * 4 && stride % 4 == 0, SPX_ERR_BADARG,
                 "enforceLabelConnectivity: bad argument");
     SPX_CHECK(require_device(device));
     PostWorkspace ws;
@@ -504,13 +504,13 @@ extern "C" int spx_enforce_label_connectivity(int32_t* labels, size_t stride, in
     cudaFree(d);
     ws.release();
     return rc;
-}
+} SPX_API_CATCH
 
 extern "C" int spx_label_contour_mask(const int32_t* labels, size_t stride, int width, int height, int thick_line,
-                                      int flavour, uint8_t* dst, size_t dst_stride, int device)
+                                      int flavour, uint8_t* dst, size_t dst_stride, int device) try
 {
     using namespace spx;
-    SPX_REQUIRE(labels && dst && width > 0 && height > 0 && stride >= (size_t)width * 4 && stride % 4 == 0 &&
+    SPX_REQUIRE(labels && dst && width > 0 && height > 0 && height <= SPX_MAX_HEIGHT && (long long)width * height < (1ll << 31) && stride >= (size_t)width * 4 && stride % 4 == 0 &&
                     dst_stride >= (size_t)width && (flavour == 0 || flavour == 1),
                 SPX_ERR_BADARG, "getLabelContourMask: bad argument");
     SPX_CHECK(require_device(device));
@@ -531,4 +531,4 @@ extern "C" int spx_label_contour_mask(const int32_t* labels, size_t stride, int 
     cudaFree(d); cudaFree(m);
     ws.release();
     return rc;
-}
+} SPX_API_CATCH

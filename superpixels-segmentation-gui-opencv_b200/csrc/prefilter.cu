@@ -122,10 +122,10 @@ struct PrefilterBuffers {
 // flags: bit 0 equalize, bit 1 normalize, bit 2 colour balance (with `percent`), bit 3 gaussian blur; applied in the order of
 // on_button_apply_clicked (mainwindow.cpp:2028-2032).  src / dst: 8UC3 host images (may be the same buffer).
 extern "C" int spx_preprocess_8uc3(const uint8_t* src, size_t src_stride, uint8_t* dst, size_t dst_stride, int width, int height, int flags,
-                                   int percent, int device)
+                                   int percent, int device) try
 {
     using namespace spx;
-    SPX_REQUIRE(src && dst && width > 0 && height > 0 && src_stride >= (size_t)width * 3 && dst_stride >= (size_t)width * 3, SPX_ERR_BADARG,
+    SPX_REQUIRE(src && dst && width > 0 && height > 0 && height <= SPX_MAX_HEIGHT && src_stride >= (size_t)width * 3 && dst_stride >= (size_t)width * 3, SPX_ERR_BADARG,
                 "preprocess: bad image / stride");
     SPX_REQUIRE(percent >= 0 && percent <= 100, SPX_ERR_BADARG, "preprocess: percent must lie in 0..100");
     SPX_CHECK(require_device(device));
@@ -207,4 +207,4 @@ extern "C" int spx_preprocess_8uc3(const uint8_t* src, size_t src_stride, uint8_
     SPX_CUDA(cudaMemcpy2DAsync(dst, dst_stride, result, B.pitch, (size_t)w * 3, h, cudaMemcpyDeviceToHost, B.st));
     SPX_CUDA(cudaStreamSynchronize(B.st));
     return SPX_OK;
-}
+} SPX_API_CATCH

@@ -353,7 +353,7 @@ struct SeedsEngine {
 
     int create(int w, int h, int C, int num_superpixels, int num_levels, int prior, int bins, int dstep)
     {
-        SPX_REQUIRE(w > 0 && h > 0 && (long long)w * h < (1ll << 30), SPX_ERR_BADARG, "createSuperpixelSEEDS: bad image size %dx%d", w, h);
+        SPX_REQUIRE(w > 0 && h > 0 && h <= SPX_MAX_HEIGHT && (long long)w * h < (1ll << 30), SPX_ERR_BADARG, "createSuperpixelSEEDS: bad image size %dx%d", w, h);
         SPX_REQUIRE(C >= 1 && C <= 4, SPX_ERR_BADARG, "createSuperpixelSEEDS: 1..4 channels supported, got %d", C);
         SPX_REQUIRE(num_superpixels >= 1 && num_levels >= 1 && bins >= 1, SPX_ERR_BADARG, "createSuperpixelSEEDS: bad parameter");
         double hs = 1.0;
@@ -524,7 +524,7 @@ struct spx_seeds { SeedsEngine* e; };
     SPX_CUDA(cudaSetDevice(e->device))
 
 extern "C" int spx_seeds_create(int w, int h, int C, int num_superpixels, int num_levels, int prior, int bins, int double_step,
-                                int device, spx_seeds_t** out)
+                                int device, spx_seeds_t** out) try
 {
     using namespace spx;
     SPX_REQUIRE(out, SPX_ERR_BADARG, "createSuperpixelSEEDS: out is NULL");
@@ -536,28 +536,28 @@ extern "C" int spx_seeds_create(int w, int h, int C, int num_superpixels, int nu
     if (rc != SPX_OK) { delete e; return rc; }
     *out = new spx_seeds{e};
     return SPX_OK;
-}
-extern "C" int spx_seeds_iterate(spx_seeds_t* h, const uint8_t* image, size_t stride, int n)
+} SPX_API_CATCH
+extern "C" int spx_seeds_iterate(spx_seeds_t* h, const uint8_t* image, size_t stride, int n) try
 {
     SEEDS_ENTER(h);
     return e->iterate(image, stride, n);
-}
-extern "C" int spx_seeds_get_number_of_superpixels(spx_seeds_t* h, int* out)
+} SPX_API_CATCH
+extern "C" int spx_seeds_get_number_of_superpixels(spx_seeds_t* h, int* out) try
 {
     SEEDS_ENTER(h);
     SPX_REQUIRE(out, SPX_ERR_BADARG, "getNumberOfSuperpixels: out is NULL");
     *out = e->S.K;
     return SPX_OK;
-}
-extern "C" int spx_seeds_get_labels(spx_seeds_t* h, int32_t* dst, size_t dst_stride)
+} SPX_API_CATCH
+extern "C" int spx_seeds_get_labels(spx_seeds_t* h, int32_t* dst, size_t dst_stride) try
 {
     SEEDS_ENTER(h);
     SPX_REQUIRE(dst && dst_stride >= (size_t)e->S.w * 4, SPX_ERR_BADARG, "getLabels: bad destination");
     SPX_CUDA(cudaMemcpy2DAsync(dst, dst_stride, e->S.labels, (size_t)e->S.w * 4, (size_t)e->S.w * 4, e->S.h, cudaMemcpyDeviceToHost, e->st));
     SPX_CUDA(cudaStreamSynchronize(e->st));
     return SPX_OK;
-}
-extern "C" int spx_seeds_get_label_contour_mask(spx_seeds_t* h, uint8_t* dst, size_t dst_stride, int thick_line)
+} SPX_API_CATCH
+extern "C" int spx_seeds_get_label_contour_mask(spx_seeds_t* h, uint8_t* dst, size_t dst_stride, int thick_line) try
 {
     SEEDS_ENTER(h);
     SPX_REQUIRE(dst && dst_stride >= (size_t)e->S.w, SPX_ERR_BADARG, "getLabelContourMask: bad destination");
@@ -568,17 +568,17 @@ extern "C" int spx_seeds_get_label_contour_mask(spx_seeds_t* h, uint8_t* dst, si
     SPX_CUDA(cudaMemcpy2DAsync(dst, dst_stride, e->d_mask, e->S.w, e->S.w, e->S.h, cudaMemcpyDeviceToHost, e->st));
     SPX_CUDA(cudaStreamSynchronize(e->st));
     return SPX_OK;
-}
-extern "C" int spx_seeds_launch_count(spx_seeds_t* h, long long* out)
+} SPX_API_CATCH
+extern "C" int spx_seeds_launch_count(spx_seeds_t* h, long long* out) try
 {
     SPX_REQUIRE(h && h->e && out, SPX_ERR_BADARG, "launch_count: bad argument");
     *out = h->e->launches;
     return SPX_OK;
-}
-extern "C" int spx_seeds_destroy(spx_seeds_t* h)
+} SPX_API_CATCH
+extern "C" int spx_seeds_destroy(spx_seeds_t* h) try
 {
     if (!h) return SPX_OK;
     delete h->e;
     delete h;
     return SPX_OK;
-}
+} SPX_API_CATCH

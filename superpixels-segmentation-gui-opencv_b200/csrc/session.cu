@@ -228,12 +228,12 @@ struct spx_session { Session* s; };
     Session* s = (h)->s;                                                              \
     SPX_CUDA(cudaSetDevice(s->device))
 
-extern "C" int spx_session_create(int w, int h, int device, spx_session_t** out)
+extern "C" int spx_session_create(int w, int h, int device, spx_session_t** out) try
 {
     using namespace spx;
     SPX_REQUIRE(out, SPX_ERR_BADARG, "session_create: out is NULL");
     *out = nullptr;
-    SPX_REQUIRE(w > 0 && h > 0 && (long long)w * h < (1ll << 29), SPX_ERR_BADARG, "session_create: bad size %dx%d", w, h);
+    SPX_REQUIRE(w > 0 && h > 0 && h <= SPX_MAX_HEIGHT && (long long)w * h < (1ll << 29), SPX_ERR_BADARG, "session_create: bad size %dx%d", w, h);
     SPX_CHECK(require_device(device));
     SPX_CUDA(cudaSetDevice(device));
     Session* s = new Session();
@@ -256,16 +256,16 @@ extern "C" int spx_session_create(int w, int h, int device, spx_session_t** out)
     if (rc != SPX_OK) { delete s; return rc; }
     *out = new spx_session{s};
     return SPX_OK;
-}
-extern "C" int spx_session_destroy(spx_session_t* h)
+} SPX_API_CATCH
+extern "C" int spx_session_destroy(spx_session_t* h) try
 {
     if (!h) return SPX_OK;
     delete h->s;
     delete h;
     return SPX_OK;
-}
+} SPX_API_CATCH
 // plane ids: 0 image, 1 mask, 2 grid, 3 selection (8UC3); 4 labels, 5 labels_mask (32SC1)
-extern "C" int spx_session_upload(spx_session_t* h, int plane, const void* src, size_t stride)
+extern "C" int spx_session_upload(spx_session_t* h, int plane, const void* src, size_t stride) try
 {
     SES_ENTER(h);
     SPX_REQUIRE(src && plane >= 0 && plane <= 5, SPX_ERR_BADARG, "session_upload: bad plane / source");
@@ -276,8 +276,8 @@ extern "C" int spx_session_upload(spx_session_t* h, int plane, const void* src, 
     SPX_CUDA(cudaStreamSynchronize(s->st));
     if (plane == 4) SPX_CHECK(spx::build_index(s));
     return SPX_OK;
-}
-extern "C" int spx_session_download(spx_session_t* h, int plane, void* dst, size_t stride)
+} SPX_API_CATCH
+extern "C" int spx_session_download(spx_session_t* h, int plane, void* dst, size_t stride) try
 {
     SES_ENTER(h);
     SPX_REQUIRE(dst && plane >= 0 && plane <= 5, SPX_ERR_BADARG, "session_download: bad plane / destination");
@@ -287,11 +287,11 @@ extern "C" int spx_session_download(spx_session_t* h, int plane, void* dst, size
     SPX_CUDA(cudaMemcpy2DAsync(dst, stride, src, rowb, rowb, s->h, cudaMemcpyDeviceToHost, s->st));
     SPX_CUDA(cudaStreamSynchronize(s->st));
     return SPX_OK;
-}
+} SPX_API_CATCH
 // the GUI's post-step after COMPUTE (mainwindow.cpp:2130-2138): new labels, labels_mask = 0, mask = 0, selection = 0,
 // grid = contour mask in `colour`
 extern "C" int spx_session_begin(spx_session_t* h, const int32_t* labels, size_t lstride, const uint8_t* contour, size_t cstride,
-                                 const uint8_t colour[3])
+                                 const uint8_t colour[3]) try
 {
     using namespace spx;
     SES_ENTER(h);
@@ -305,8 +305,8 @@ extern "C" int spx_session_begin(spx_session_t* h, const int32_t* labels, size_t
     grid_from_contour_kernel<<<cdiv((int)n, 256), 256, 0, s->st>>>(s->scratch, (int)n, make_uchar3(colour[0], colour[1], colour[2]), s->planes[2]);
     SPX_CUDA(cudaGetLastError());
     return build_index(s);
-}
-extern "C" int spx_session_recolour_grid(spx_session_t* h, const uint8_t colour[3])
+} SPX_API_CATCH
+extern "C" int spx_session_recolour_grid(spx_session_t* h, const uint8_t colour[3]) try
 {
     using namespace spx;
     SES_ENTER(h);
@@ -316,9 +316,9 @@ extern "C" int spx_session_recolour_grid(spx_session_t* h, const uint8_t colour[
     SPX_CUDA(cudaGetLastError());
     SPX_CUDA(cudaStreamSynchronize(s->st));
     return SPX_OK;
-}
+} SPX_API_CATCH
 // Mat1b m = plane == value  (plane: 4 labels, 5 labels_mask)
-extern "C" int spx_session_eq_mask(spx_session_t* h, int plane, int value, uint8_t* dst, size_t stride)
+extern "C" int spx_session_eq_mask(spx_session_t* h, int plane, int value, uint8_t* dst, size_t stride) try
 {
     using namespace spx;
     SES_ENTER(h);
@@ -329,10 +329,10 @@ extern "C" int spx_session_eq_mask(spx_session_t* h, int plane, int value, uint8
     SPX_CUDA(cudaMemcpy2DAsync(dst, stride, s->scratch, s->w, s->w, s->h, cudaMemcpyDeviceToHost, s->st));
     SPX_CUDA(cudaStreamSynchronize(s->st));
     return SPX_OK;
-}
+} SPX_API_CATCH
 // WhichCell (mainwindow.cpp:2153-2171): the cell under (x, y) is erased from mask and labels_mask, or (paint != 0) painted
 // with `colour` and claimed for `label_id`.  One launch over the cell's bounding box.
-extern "C" int spx_session_which_cell(spx_session_t* h, int x, int y, int paint, const uint8_t colour[3], int label_id, int* cell_out)
+extern "C" int spx_session_which_cell(spx_session_t* h, int x, int y, int paint, const uint8_t colour[3], int label_id, int* cell_out) try
 {
     using namespace spx;
     SES_ENTER(h);
@@ -352,11 +352,11 @@ extern "C" int spx_session_which_cell(spx_session_t* h, int x, int y, int paint,
     SPX_CUDA(cudaStreamSynchronize(s->st));
     if (cell_out) *cell_out = cell;
     return SPX_OK;
-}
+} SPX_API_CATCH
 // where key plane (4 labels / 5 labels_mask) == value: colour plane `p3` (1 mask, 2 grid, 3 selection, -1 none) <- colour,
 // int plane `p1` (4, 5, -1 none) <- newval.  Covers the label list actions: delete (mainwindow.cpp:228-229), join
 // (258-260), colour change (1334-1335).
-extern "C" int spx_session_set_where_eq(spx_session_t* h, int key_plane, int value, int p3, const uint8_t colour[3], int p1, int newval)
+extern "C" int spx_session_set_where_eq(spx_session_t* h, int key_plane, int value, int p3, const uint8_t colour[3], int p1, int newval) try
 {
     using namespace spx;
     SES_ENTER(h);
@@ -375,11 +375,11 @@ extern "C" int spx_session_set_where_eq(spx_session_t* h, int key_plane, int val
     SPX_CUDA(cudaStreamSynchronize(s->st));
     if (p1 == 4) SPX_CHECK(build_index(s));
     return SPX_OK;
-}
+} SPX_API_CATCH
 // the "update cells from the white mask" action (mainwindow.cpp:313-331): every pixel of `mask` that is pure white becomes
 // a new cell: labels <- max(labels)+1, labels_mask <- label_id, mask <- colour, grid <- 0 there (the new cell's outline
 // is drawn by the caller: findContours/drawContours stay on the host).  hits = pixels updated.
-extern "C" int spx_session_new_cell_from_white(spx_session_t* h, const uint8_t colour[3], int label_id, int* new_cell, int* hits)
+extern "C" int spx_session_new_cell_from_white(spx_session_t* h, const uint8_t colour[3], int label_id, int* new_cell, int* hits) try
 {
     using namespace spx;
     SES_ENTER(h);
@@ -397,16 +397,16 @@ extern "C" int spx_session_new_cell_from_white(spx_session_t* h, const uint8_t c
     if (new_cell) *new_cell = cell;
     if (s->h_flag[1] > 0) SPX_CHECK(build_index(s));
     return SPX_OK;
-}
-extern "C" int spx_session_max_label(spx_session_t* h, int* out)
+} SPX_API_CATCH
+extern "C" int spx_session_max_label(spx_session_t* h, int* out) try
 {
     SES_ENTER(h);
     SPX_REQUIRE(out && s->K > 0, SPX_ERR_BADARG, "max_label: bad argument / no labels");
     *out = s->K - 1;
     return SPX_OK;
-}
+} SPX_API_CATCH
 // per-cell index: boxes[k] = x0, y0, x1, y1 (inclusive; x1 < x0 for an unused id), counts[k] = pixels; rows = capacity
-extern "C" int spx_session_cell_index(spx_session_t* h, int32_t* boxes, int32_t* counts, int rows, int* cells)
+extern "C" int spx_session_cell_index(spx_session_t* h, int32_t* boxes, int32_t* counts, int rows, int* cells) try
 {
     SES_ENTER(h);
     SPX_REQUIRE(s->K > 0, SPX_ERR_BADARG, "cell_index: no labels");
@@ -418,12 +418,12 @@ extern "C" int spx_session_cell_index(spx_session_t* h, int32_t* boxes, int32_t*
         SPX_CUDA(cudaStreamSynchronize(s->st));
     }
     return SPX_OK;
-}
+} SPX_API_CATCH
 // ShowSegmentation (mainwindow.cpp:1936-1969): the viewport composed in one pass; blend values are the sliders' 0..100.
 // dst: vh rows of vw BGR pixels.  holes (optional): countNonZero over the whole mask of pure-black pixels.
 extern "C" int spx_session_compose(spx_session_t* h, int vx, int vy, int vw, int vh, int show_image, int blend_image, int show_mask,
                                    int blend_mask, int show_grid, int blend_grid, int show_selection, int dilation, int show_holes,
-                                   uint8_t* dst, size_t stride, int* holes)
+                                   uint8_t* dst, size_t stride, int* holes) try
 {
     using namespace spx;
     SES_ENTER(h);
@@ -448,4 +448,4 @@ extern "C" int spx_session_compose(spx_session_t* h, int vx, int vy, int vw, int
     SPX_CUDA(cudaStreamSynchronize(s->st));
     if (show_holes && holes) *holes = s->h_flag[2];
     return SPX_OK;
-}
+} SPX_API_CATCH

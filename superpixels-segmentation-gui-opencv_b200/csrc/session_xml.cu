@@ -131,7 +131,7 @@ static void write_matrix(FILE* f, const char* name, const int32_t* m, size_t str
 }  // namespace
 
 extern "C" int spx_session_xml_write(const char* path, int grid_colour, const spx_label_t* list, int n_labels, const int32_t* labels,
-                                     size_t labels_stride, const int32_t* labels_mask, size_t mask_stride, int width, int height)
+                                     size_t labels_stride, const int32_t* labels_mask, size_t mask_stride, int width, int height) try
 {
     using namespace spx;
     SPX_REQUIRE(path && labels && labels_mask && width > 0 && height > 0 && n_labels >= 0 && (n_labels == 0 || list) &&
@@ -151,11 +151,11 @@ extern "C" int spx_session_xml_write(const char* path, int grid_colour, const sp
     const bool ok = fclose(f) == 0;
     SPX_REQUIRE(ok, SPX_ERR_INTERNAL, "session_xml_write: write to %s failed", path);
     return SPX_OK;
-}
+} SPX_API_CATCH
 
 // Reads what the reference reads (mainwindow.cpp:775-820).  First call with labels == NULL to learn rows / cols / n_labels.
 extern "C" int spx_session_xml_read(const char* path, int* grid_colour, spx_label_t* list, int list_capacity, int* n_labels, int32_t* labels,
-                                    size_t labels_stride, int32_t* labels_mask, size_t mask_stride, int* rows, int* cols)
+                                    size_t labels_stride, int32_t* labels_mask, size_t mask_stride, int* rows, int* cols) try
 {
     using namespace spx;
     SPX_REQUIRE(path, SPX_ERR_BADARG, "session_xml_read: path is NULL");
@@ -230,4 +230,4 @@ extern "C" int spx_session_xml_read(const char* path, int* grid_colour, spx_labe
     if (rows) *rows = R;
     if (cols) *cols = Cc;
     return SPX_OK;
-}
+} SPX_API_CATCH

@@ -485,18 +485,32 @@ __global__ void __launch_bounds__(256) strip_push_kernel(const __grid_constant__
         }
     }
 }
-__global__ void __launch_bounds__(256) strip_wait_sum_kernel(const __grid_constant__ StripPeers P, unsigned long long* __restrict__ acc, int iter)
+// The wait is bounded: a peer that died or skipped the exchange must not hang this rank in a kernel nobody can cancel.  After
+// ~4 s (STRIP_SPIN_BUDGET sleeps of 200 ns, generous against any real skew between ranks) the kernel gives up, raises *err and
+// adds nothing; the host reports SPX_ERR_GPU at its next synchronising call (spx_slic_get_label_rows / strip_exchanged_bytes).
+constexpr unsigned STRIP_SPIN_BUDGET = 20u * 1000u * 1000u;
+__global__ void __launch_bounds__(256) strip_wait_sum_kernel(const __grid_constant__ StripPeers P, unsigned long long* __restrict__ acc, int iter,
+                                                              int* __restrict__ err)
 {
     __shared__ int2 rg[STRIP_MAX_WORLD];
+    __shared__ int s_fail;
     const int par = iter & 1;
+    if (threadIdx.x == 0) s_fail = 0;
+    __syncthreads();
     if (threadIdx.x < P.world && threadIdx.x != P.rank) {
         const volatile int* f = strip_flags(P.base[P.rank], P) + threadIdx.x;
-        while (*f < iter) __nanosleep(200);
+        unsigned spins = 0;
+        while (*f < iter && *(volatile int*)err == 0) {
+            __nanosleep(200);
+            if (++spins > STRIP_SPIN_BUDGET) { atomicExch(err, 1 + (int)threadIdx.x); break; }
+        }
+        if (*f < iter) s_fail = 1;
         __threadfence_system();
         const volatile int2* r = strip_range(P.base[P.rank], P, par, threadIdx.x);
         rg[threadIdx.x] = make_int2(r->x, r->y);
     }
     __syncthreads();
+    if (s_fail) return;
     for (int p = 0; p < P.world; p++) {
         if (p == P.rank) continue;
         const int lo = rg[p].x, len = rg[p].y - rg[p].x;
@@ -542,6 +556,7 @@ struct SlicEngine {
     unsigned* d_push_done = nullptr;
     int* d_range = nullptr;
     unsigned long long* d_bytes_sent = nullptr;
+    int* d_strip_err = nullptr;      // raised by strip_wait_sum_kernel when a peer never delivered (1 + its rank)
     int xchg_iter = 0;
     bool peers_open = false;
 
@@ -589,6 +604,8 @@ struct SlicEngine {
         SPX_CUDA(cudaMemcpyAsync(d_range, r0, sizeof(r0), cudaMemcpyHostToDevice, st));
         SPX_CHECK(dalloc(&d_bytes_sent, 1));
         SPX_CUDA(cudaMemsetAsync(d_bytes_sent, 0, sizeof(unsigned long long), st));
+        SPX_CHECK(dalloc(&d_strip_err, 1));
+        SPX_CUDA(cudaMemsetAsync(d_strip_err, 0, sizeof(int), st));
         SPX_CUDA(cudaStreamSynchronize(st));                      // zeroed before any peer can map and write it
         cudaIpcMemHandle_t hd;
         SPX_CUDA(cudaIpcGetMemHandle(&hd, xchg));
@@ -597,6 +614,15 @@ struct SlicEngine {
         if (bytes_out) *bytes_out = xchg_bytes;
         peers.base[rank] = (unsigned long long*)xchg;
         xchg_iter = 0;
+        return SPX_OK;
+    }
+    // after a stream synchronisation: did an exchange give up waiting for a peer?
+    int strip_check_err()
+    {
+        if (!d_strip_err) return SPX_OK;
+        SPX_CUDA(cudaMemcpyAsync(h_pinned + 1, d_strip_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SPX_CUDA(cudaStreamSynchronize(st));
+        SPX_REQUIRE(h_pinned[1] == 0, SPX_ERR_GPU, "strip exchange: rank %d never delivered its sums (peer gone or exchange skipped)", h_pinned[1] - 1);
         return SPX_OK;
     }
     int strip_peer_open(const void* handles)
@@ -622,7 +648,7 @@ struct SlicEngine {
         const int nb = (int)std::min<size_t>((peers.n6 + 255) / 256, 4 * 148);
         strip_range_kernel<<<std::min(cdiv(g.Kcap, 256), 148), 256, 0, st>>>(a.acc + (size_t)(g.C + 2) * g.Kcap, g.Kcap, d_range);
         strip_push_kernel<<<nb, 256, 0, st>>>(peers, a.acc, xchg_iter, d_range, d_push_done, d_bytes_sent);
-        strip_wait_sum_kernel<<<nb, 256, 0, st>>>(peers, a.acc, xchg_iter);
+        strip_wait_sum_kernel<<<nb, 256, 0, st>>>(peers, a.acc, xchg_iter, d_strip_err);
         launches += 3;
         SPX_CUDA(cudaGetLastError());
         return SPX_OK;
@@ -654,7 +680,8 @@ struct SlicEngine {
 
     int init(int w, int h, int C, int alg, int S, float ruler_)
     {
-        SPX_REQUIRE(w > 0 && h > 0 && (long long)w * h < (1ll << 31), SPX_ERR_BADARG, "createSuperpixelSLIC: bad image size %dx%d", w, h);
+        SPX_REQUIRE(w > 0 && h > 0 && h <= SPX_MAX_HEIGHT && (long long)w * h < (1ll << 31), SPX_ERR_BADARG,
+                    "createSuperpixelSLIC: bad image size %dx%d (need w*h < 2^31 and h <= 65535)", w, h);
         SPX_REQUIRE(C >= 1 && C <= SPX_MAXC, SPX_ERR_BADARG, "createSuperpixelSLIC: 1..4 channels supported, got %d", C);
         SPX_REQUIRE(alg == SPX_SLIC || alg == SPX_SLICO || alg == SPX_MSLIC, SPX_ERR_INTERNAL, "No such algorithm");
         SPX_REQUIRE(S >= 1, SPX_ERR_BADARG, "createSuperpixelSLIC: region_size must be >= 1");
@@ -1012,30 +1039,30 @@ static int slic_create_common(const void* image, size_t stride, int w, int h, in
 }
 
 extern "C" int spx_slic_create(const uint8_t* image, size_t stride, int w, int h, int C, int alg, int S, float ruler,
-                               int device, spx_slic_t** out)
+                               int device, spx_slic_t** out) try
 {
     SPX_CHECK(spx::require_device(device));
     return slic_create_common(image, stride, w, h, C, alg, S, ruler, nullptr, false, out);
-}
+} SPX_API_CATCH
 extern "C" int spx_slic_create_bgr(const uint8_t* bgr, size_t stride, int w, int h, int colour_code, int alg, int S, float ruler,
-                                   int device, spx_slic_t** out)
+                                   int device, spx_slic_t** out) try
 {
     SPX_REQUIRE(colour_code == 44 || colour_code == 40, SPX_ERR_BADARG, "createSuperpixelSLIC: colour code must be COLOR_BGR2Lab (44) or COLOR_BGR2HSV (40)");
     SPX_CHECK(spx::require_device(device));
     SPX_CUDA(cudaSetDevice(device));
     return slic_create_common(bgr, stride, w, h, 3, alg, S, ruler, nullptr, false, out, colour_code == 44 ? 0 : 1);
-}
+} SPX_API_CATCH
 extern "C" int spx_slic_create_dev(const void* d_image, size_t stride, int w, int h, int C, int alg, int S, float ruler,
-                                   void* stream, spx_slic_t** out)
+                                   void* stream, spx_slic_t** out) try
 {
     int dev = 0;
     SPX_CUDA(cudaGetDevice(&dev));
     SPX_CHECK(spx::require_device(dev));
     return slic_create_common(d_image, stride, w, h, C, alg, S, ruler, (cudaStream_t)stream, true, out);
-}
+} SPX_API_CATCH
 // ---- row-strip mode ------------------------------------------------------------------------------------------
 extern "C" int spx_slic_create_strip(const uint8_t* rows, size_t stride, int w, int h, int C, int alg, int S, float ruler,
-                                     int row0, int row1, int own_row0, int own_row1, void* stream, spx_slic_t** out)
+                                     int row0, int row1, int own_row0, int own_row1, void* stream, spx_slic_t** out) try
 {
     using namespace spx;
     SPX_REQUIRE(out, SPX_ERR_BADARG, "create_strip: out is NULL");
@@ -1066,8 +1093,8 @@ extern "C" int spx_slic_create_strip(const uint8_t* rows, size_t stride, int w, 
     if (rc != SPX_OK) { delete e; return rc; }
     *out = new spx_slic{e};
     return SPX_OK;
-}
-extern "C" int spx_slic_device_state(spx_slic_t* h, spx_slic_state_t* out)
+} SPX_API_CATCH
+extern "C" int spx_slic_device_state(spx_slic_t* h, spx_slic_state_t* out) try
 {
     SLIC_ENTER(h);
     SPX_REQUIRE(out, SPX_ERR_BADARG, "device_state: out is NULL");
@@ -1075,39 +1102,39 @@ extern "C" int spx_slic_device_state(spx_slic_t* h, spx_slic_state_t* out)
     out->K = e->g.K; out->Kcap = e->g.Kcap; out->channels = e->g.C;
     out->labels = e->d_labels; out->label_pitch = e->g.lp;
     return SPX_OK;
-}
-extern "C" int spx_slic_strip_rebin(spx_slic_t* h)
+} SPX_API_CATCH
+extern "C" int spx_slic_strip_rebin(spx_slic_t* h) try
 {
     SLIC_ENTER(h);
     return e->strip_rebin();
-}
-extern "C" int spx_slic_strip_assign(spx_slic_t* h)
+} SPX_API_CATCH
+extern "C" int spx_slic_strip_assign(spx_slic_t* h) try
 {
     SLIC_ENTER(h);
     e->launches++;
     return e->enqueue_assign();
-}
-extern "C" int spx_slic_strip_update(spx_slic_t* h)
+} SPX_API_CATCH
+extern "C" int spx_slic_strip_update(spx_slic_t* h) try
 {
     SLIC_ENTER(h);
     return e->strip_update();
-}
-extern "C" int spx_slic_strip_peer_alloc(spx_slic_t* h, int world, int rank, void* ipc_handle_out, size_t* bytes_out)
+} SPX_API_CATCH
+extern "C" int spx_slic_strip_peer_alloc(spx_slic_t* h, int world, int rank, void* ipc_handle_out, size_t* bytes_out) try
 {
     SLIC_ENTER(h);
     return e->strip_peer_alloc(world, rank, ipc_handle_out, bytes_out);
-}
-extern "C" int spx_slic_strip_peer_open(spx_slic_t* h, const void* ipc_handles)
+} SPX_API_CATCH
+extern "C" int spx_slic_strip_peer_open(spx_slic_t* h, const void* ipc_handles) try
 {
     SLIC_ENTER(h);
     return e->strip_peer_open(ipc_handles);
-}
-extern "C" int spx_slic_strip_exchange(spx_slic_t* h)
+} SPX_API_CATCH
+extern "C" int spx_slic_strip_exchange(spx_slic_t* h) try
 {
     SLIC_ENTER(h);
     return e->strip_exchange();
-}
-extern "C" int spx_slic_strip_exchanged_bytes(spx_slic_t* h, unsigned long long* out)
+} SPX_API_CATCH
+extern "C" int spx_slic_strip_exchanged_bytes(spx_slic_t* h, unsigned long long* out) try
 {
     SLIC_ENTER(h);
     SPX_REQUIRE(out, SPX_ERR_BADARG, "strip_exchanged_bytes: out is NULL");
@@ -1115,9 +1142,9 @@ extern "C" int spx_slic_strip_exchanged_bytes(spx_slic_t* h, unsigned long long*
     if (!e->d_bytes_sent) return SPX_OK;
     SPX_CUDA(cudaMemcpyAsync(out, e->d_bytes_sent, sizeof(*out), cudaMemcpyDeviceToHost, e->st));
     SPX_CUDA(cudaStreamSynchronize(e->st));
-    return SPX_OK;
-}
-extern "C" int spx_slic_get_label_rows(spx_slic_t* h, int32_t* dst, size_t dst_stride, int row0, int row1)
+    return e->strip_check_err();
+} SPX_API_CATCH
+extern "C" int spx_slic_get_label_rows(spx_slic_t* h, int32_t* dst, size_t dst_stride, int row0, int row1) try
 {
     SLIC_ENTER(h);
     SPX_REQUIRE(dst && dst_stride >= (size_t)e->g.w * 4 && 0 <= row0 && row0 <= row1 && row1 <= e->g.h, SPX_ERR_BADARG, "getLabelRows: bad argument");
@@ -1125,55 +1152,55 @@ extern "C" int spx_slic_get_label_rows(spx_slic_t* h, int32_t* dst, size_t dst_s
         SPX_CUDA(cudaMemcpy2DAsync(dst, dst_stride, e->d_labels + (size_t)row0 * e->g.lp, (size_t)e->g.lp * 4, (size_t)e->g.w * 4, row1 - row0,
                                    cudaMemcpyDeviceToHost, e->st));
     SPX_CUDA(cudaStreamSynchronize(e->st));
-    return SPX_OK;
-}
+    return e->strip_check_err();
+} SPX_API_CATCH
 
-extern "C" int spx_slic_reset(spx_slic_t* h, const uint8_t* image, size_t stride)
+extern "C" int spx_slic_reset(spx_slic_t* h, const uint8_t* image, size_t stride) try
 {
     SLIC_ENTER(h);
     SPX_CHECK(e->upload(image, stride, false));
     return e->seed();
-}
-extern "C" int spx_slic_reset_dev(spx_slic_t* h, const void* d_image, size_t stride)
+} SPX_API_CATCH
+extern "C" int spx_slic_reset_dev(spx_slic_t* h, const void* d_image, size_t stride) try
 {
     SLIC_ENTER(h);
     SPX_CHECK(e->upload((const uint8_t*)d_image, stride, true));
     return e->seed();
-}
-extern "C" int spx_slic_iterate(spx_slic_t* h, int n)
+} SPX_API_CATCH
+extern "C" int spx_slic_iterate(spx_slic_t* h, int n) try
 {
     SLIC_ENTER(h);
     return e->iterate(n);
-}
-extern "C" int spx_slic_enforce_label_connectivity(spx_slic_t* h, int min_element_size)
+} SPX_API_CATCH
+extern "C" int spx_slic_enforce_label_connectivity(spx_slic_t* h, int min_element_size) try
 {
     SLIC_ENTER(h);
     return e->enforce(min_element_size);
-}
-extern "C" int spx_slic_get_number_of_superpixels(spx_slic_t* h, int* out)
+} SPX_API_CATCH
+extern "C" int spx_slic_get_number_of_superpixels(spx_slic_t* h, int* out) try
 {
     SLIC_ENTER(h);
     SPX_REQUIRE(out, SPX_ERR_BADARG, "getNumberOfSuperpixels: out is NULL");
     SPX_CUDA(cudaStreamSynchronize(e->st));
     *out = e->numlabels;
     return SPX_OK;
-}
-extern "C" int spx_slic_get_labels(spx_slic_t* h, int32_t* dst, size_t dst_stride)
+} SPX_API_CATCH
+extern "C" int spx_slic_get_labels(spx_slic_t* h, int32_t* dst, size_t dst_stride) try
 {
     SLIC_ENTER(h);
     SPX_REQUIRE(dst && dst_stride >= (size_t)e->g.w * 4, SPX_ERR_BADARG, "getLabels: bad destination");
     SPX_CUDA(cudaMemcpy2DAsync(dst, dst_stride, e->d_labels, (size_t)e->g.lp * 4, (size_t)e->g.w * 4, e->g.h, cudaMemcpyDeviceToHost, e->st));
     SPX_CUDA(cudaStreamSynchronize(e->st));
     return SPX_OK;
-}
-extern "C" int spx_slic_get_labels_dev(spx_slic_t* h, void* d_dst, size_t dst_stride)
+} SPX_API_CATCH
+extern "C" int spx_slic_get_labels_dev(spx_slic_t* h, void* d_dst, size_t dst_stride) try
 {
     SLIC_ENTER(h);
     SPX_REQUIRE(d_dst && dst_stride >= (size_t)e->g.w * 4, SPX_ERR_BADARG, "getLabels: bad destination");
     SPX_CUDA(cudaMemcpy2DAsync(d_dst, dst_stride, e->d_labels, (size_t)e->g.lp * 4, (size_t)e->g.w * 4, e->g.h, cudaMemcpyDeviceToDevice, e->st));
     return SPX_OK;
-}
-extern "C" int spx_slic_get_label_contour_mask(spx_slic_t* h, uint8_t* dst, size_t dst_stride, int thick_line)
+} SPX_API_CATCH
+extern "C" int spx_slic_get_label_contour_mask(spx_slic_t* h, uint8_t* dst, size_t dst_stride, int thick_line) try
 {
     SLIC_ENTER(h);
     SPX_REQUIRE(dst && dst_stride >= (size_t)e->g.w, SPX_ERR_BADARG, "getLabelContourMask: bad destination");
@@ -1181,14 +1208,14 @@ extern "C" int spx_slic_get_label_contour_mask(spx_slic_t* h, uint8_t* dst, size
     SPX_CUDA(cudaMemcpy2DAsync(dst, dst_stride, e->d_mask, e->g.w, e->g.w, e->g.h, cudaMemcpyDeviceToHost, e->st));
     SPX_CUDA(cudaStreamSynchronize(e->st));
     return SPX_OK;
-}
-extern "C" int spx_slic_get_label_contour_mask_dev(spx_slic_t* h, void* d_dst, size_t dst_stride, int thick_line)
+} SPX_API_CATCH
+extern "C" int spx_slic_get_label_contour_mask_dev(spx_slic_t* h, void* d_dst, size_t dst_stride, int thick_line) try
 {
     SLIC_ENTER(h);
     SPX_REQUIRE(d_dst && dst_stride >= (size_t)e->g.w, SPX_ERR_BADARG, "getLabelContourMask: bad destination");
     return e->contour((unsigned char*)d_dst, dst_stride, thick_line);
-}
-extern "C" int spx_slic_set_labels(spx_slic_t* h, const int32_t* src, size_t src_stride, int numlabels)
+} SPX_API_CATCH
+extern "C" int spx_slic_set_labels(spx_slic_t* h, const int32_t* src, size_t src_stride, int numlabels) try
 {
     SLIC_ENTER(h);
     SPX_REQUIRE(src && src_stride >= (size_t)e->g.w * 4, SPX_ERR_BADARG, "setLabels: bad source");
@@ -1196,8 +1223,8 @@ extern "C" int spx_slic_set_labels(spx_slic_t* h, const int32_t* src, size_t src
     SPX_CUDA(cudaStreamSynchronize(e->st));
     if (numlabels > 0) e->numlabels = numlabels;
     return SPX_OK;
-}
-extern "C" int spx_slic_get_centres(spx_slic_t* h, float* dst, int rows)
+} SPX_API_CATCH
+extern "C" int spx_slic_get_centres(spx_slic_t* h, float* dst, int rows) try
 {
     SLIC_ENTER(h);
     const int K = e->g.K, C = e->g.C, Kcap = e->g.Kcap;
@@ -1210,36 +1237,36 @@ extern "C" int spx_slic_get_centres(spx_slic_t* h, float* dst, int rows)
     for (int k = 0; k < K; k++)
         for (int f = 0; f < C + 2; f++) dst[(size_t)k * (C + 2) + f] = tmp[(size_t)f * Kcap + k];
     return SPX_OK;
-}
-extern "C" int spx_slic_synchronize(spx_slic_t* h)
+} SPX_API_CATCH
+extern "C" int spx_slic_synchronize(spx_slic_t* h) try
 {
     SLIC_ENTER(h);
     SPX_CUDA(cudaStreamSynchronize(e->st));
     return SPX_OK;
-}
-extern "C" int spx_slic_launch_count(spx_slic_t* h, long long* out)
+} SPX_API_CATCH
+extern "C" int spx_slic_launch_count(spx_slic_t* h, long long* out) try
 {
     SPX_REQUIRE(h && h->e && out, SPX_ERR_BADARG, "launch_count: bad argument");
     *out = h->e->launches;
     return SPX_OK;
-}
-extern "C" int spx_slic_time_assign(spx_slic_t* h, int reps, int flush_l2, float* avg_ms)
+} SPX_API_CATCH
+extern "C" int spx_slic_time_assign(spx_slic_t* h, int reps, int flush_l2, float* avg_ms) try
 {
     SLIC_ENTER(h);
     SPX_REQUIRE(avg_ms && reps >= 1, SPX_ERR_BADARG, "time_assign: bad argument");
     return e->time_assign(reps, flush_l2, avg_ms);
-}
-extern "C" int spx_slic_time_iterations(spx_slic_t* h, int iters, int reps, int flush_l2, float* assign_ms)
+} SPX_API_CATCH
+extern "C" int spx_slic_time_iterations(spx_slic_t* h, int iters, int reps, int flush_l2, float* assign_ms) try
 {
     SLIC_ENTER(h);
     SPX_REQUIRE(assign_ms && reps >= 1 && iters >= 1, SPX_ERR_BADARG, "time_iterations: bad argument");
     SPX_REQUIRE(e->g.ty_lo == 0 && e->g.ty_hi == e->g.tiles_y, SPX_ERR_BADARG, "time_iterations: not for strip objects");
     return e->time_iterations(iters, reps, flush_l2, assign_ms);
-}
-extern "C" int spx_slic_destroy(spx_slic_t* h)
+} SPX_API_CATCH
+extern "C" int spx_slic_destroy(spx_slic_t* h) try
 {
     if (!h) return SPX_OK;
     delete h->e;
     delete h;
     return SPX_OK;
-}
+} SPX_API_CATCH

@@ -573,7 +573,7 @@ __global__ void div_selftest_kernel(float w, float r, unsigned seed, int n, int*
 
 }  // namespace spx
 
-extern "C" int spx_selftest_division(float w, int n, int device, int* mismatches)
+extern "C" int spx_selftest_division(float w, int n, int device, int* mismatches) try
 {
     using namespace spx;
     SPX_REQUIRE(mismatches && n > 0, SPX_ERR_BADARG, "selftest_division: bad argument");
@@ -585,4 +585,4 @@ extern "C" int spx_selftest_division(float w, int n, int device, int* mismatches
     SPX_CUDA(cudaMemcpy(mismatches, d, sizeof(int), cudaMemcpyDeviceToHost));
     cudaFree(d);
     return SPX_OK;
-}
+} SPX_API_CATCH

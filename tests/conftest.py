@@ -32,7 +32,7 @@ def O():
     """the CPU oracle (test infrastructure)"""
     from oracle import oracle
     oracle.lib()
-    oracle.set_threads(min(8, os.cpu_count() or 1))
+    oracle.set_threads(min(16, os.cpu_count() or 1))
     return oracle
 
 

@@ -170,6 +170,18 @@ def test_slico_cfg2_4k_equals_oracle(spx, O, synthmod):
     assert (a.getLabelContourMask(False) == b.getLabelContourMask(False)).all()
 
 
+def test_mslic_cfg3_8k_equals_oracle(spx, O, synthmod):
+    """BASELINE.json configs[2], MSLIC half, at config size: 7680x4320, region_size=30, ruler=10, 10 iterations -- K (the
+    adaptive splits grow it), labels and centres against the oracle"""
+    img, _ = synthmod.synth(7680, 4320, 0)
+    lab = spx.cvtColor(img, spx.COLOR_BGR2Lab)
+    a, b = _run_pair(spx, O, lab, spx.MSLIC, 30, 10.0, 10)
+    assert a.getNumberOfSuperpixels() == b.getNumberOfSuperpixels() > 256 * 144
+    la, lb = a.getLabels(), b.getLabels()
+    assert float((la == lb).mean()) == 1.0
+    assert (a.getCentres() == b.getCentres()).all()
+
+
 def test_slic_iterate_twice_equals_oracle(spx, O, synthmod):
     img, _ = synthmod.synth(160, 120, 3)
     a = O.SuperpixelSLIC(img, O.SLIC, 10, 10.0); b = spx.createSuperpixelSLIC(img, spx.SLIC, 10, 10.0)
@@ -296,10 +308,26 @@ def test_lsc_tiled_equals_per_pixel_kernel_8k(spx, synthmod):
     assert (a.getCentres() == b.getCentres()).all()
 
 
+def test_lsc_cfg3_8k_equals_oracle(spx, O, synthmod):
+    """BASELINE.json configs[2], LSC half, at config size: 7680x4320, region_size=30, ratio=0.075, 10 iterations, then
+    enforceLabelConnectivity(25) in the default (= the authors') merge order and the contour mask, all against the oracle"""
+    img, _ = synthmod.synth(7680, 4320, 0)
+    lab = spx.cvtColor(img, spx.COLOR_BGR2Lab)
+    a, b = _lsc_pair(spx, O, lab, 30, 0.075)
+    a.iterate(10); b.iterate(10)
+    la, lb = a.getLabels(), b.getLabels()
+    assert float((la == lb).mean()) == 1.0
+    assert (a.getCentres() == b.getCentres()).all()
+    a.enforceLabelConnectivity(25); b.enforceLabelConnectivity(25)
+    assert a.getNumberOfSuperpixels() == b.getNumberOfSuperpixels()
+    assert (a.getLabels() == b.getLabels()).all()
+    assert (a.getLabelContourMask(False) == b.getLabelContourMask(False)).all()
+
+
 @pytest.mark.parametrize("order", [1, 0])
 @pytest.mark.parametrize("p", [25, 5, 60])
 def test_lsc_full_pipeline_exact(spx, O, example_lab, p, order):
-    """order 1 = hashed visiting order of the small regions (CUDA default), order 0 = the authors' raster order;
+    """order 0 = the authors' raster order of the small regions (default), order 1 = hashed visiting order (opt-in);
     either way the CUDA path must reproduce the oracle running the same order bit for bit"""
     img = np.ascontiguousarray(example_lab[300:780, 420:1060])
     a, b = _lsc_pair(spx, O, img, 20, 0.075)
@@ -369,6 +397,20 @@ def test_seeds_equals_phase_parallel_oracle(spx, O, synthmod, w, h, num, levels,
     assert (a.getLabels() == b.getLabels()).all()
 
 
+def test_seeds_cfg4_1080p_equals_phase_parallel_oracle(spx, O, synthmod):
+    """BASELINE.json configs[3] at config size (1920x1080, 2000 superpixels, 4 levels, 5 bins, prior 2, 10 iterations):
+    labels and both contour flavours bit-exact against the oracle running the GPU's phase-parallel order"""
+    bgr, _ = synthmod.synth(1920, 1080, 0)
+    lab = spx.cvtColor(bgr, spx.COLOR_BGR2Lab)
+    a = O.SuperpixelSEEDS(1920, 1080, 3, 2000, 4, 2, 5, False); a.setOrder(1)
+    b = spx.createSuperpixelSEEDS(1920, 1080, 3, 2000, 4, 2, 5, False)
+    a.iterate(lab, 10); b.iterate(lab, 10)
+    assert a.getNumberOfSuperpixels() == b.getNumberOfSuperpixels() == 1296
+    assert (a.getLabels() == b.getLabels()).all()
+    for thick in (False, True):
+        assert (a.getLabelContourMask(thick) == b.getLabelContourMask(thick)).all()
+
+
 def test_seeds_cfg4_vs_sequential_order(spx, O, synthmod):
     """BASELINE.json configs[3]: 1080p, 2000 superpixels, 4 levels, 5 bins, 10 iterations.  Quality of the GPU's
     phase-parallel order against upstream's sequential order on the same image (statistical, not label parity)."""
@@ -385,8 +427,14 @@ def test_seeds_cfg4_vs_sequential_order(spx, O, synthmod):
     br_g, br_s = synthmod.boundary_recall(Lg, gt), synthmod.boundary_recall(Ls, gt)
     ue_g, ue_s = synthmod.undersegmentation_error(Lg, gt), synthmod.undersegmentation_error(Ls, gt)
     e_g, e_s = s.energy(Lg), s.energy(Ls)
-    # the parallel order must not be worse than the sequential one by more than a small margin
-    assert br_g >= br_s - 0.02 and ue_g <= ue_s + 0.02 and e_g >= e_s - 0.01, (br_g, br_s, ue_g, ue_s, e_g, e_s)
+    # Two-sided: the phase-parallel order is a DIFFERENT optimiser order from upstream's Gauss-Seidel sweep, so the labels
+    # differ and so do the quality figures -- measured: boundary recall +0.016, undersegmentation error
+    # -0.014, energy +0.007.  That is OUTSIDE the north-star's 0.1 % band (on the better side); it is a documented
+    # deviation, and the bands below pin it from both sides so that a drift in either direction is caught.
+    d_br, d_ue, d_e = br_g - br_s, ue_g - ue_s, e_g - e_s
+    print("SEEDS cfg4 phase-parallel minus sequential: dBR %+.4f dUE %+.4f dE %+.4f (BR %.4f/%.4f UE %.4f/%.4f E %.4f/%.4f)"
+          % (d_br, d_ue, d_e, br_g, br_s, ue_g, ue_s, e_g, e_s))
+    assert -0.005 <= d_br <= 0.03 and -0.03 <= d_ue <= 0.005 and -0.002 <= d_e <= 0.02, (br_g, br_s, ue_g, ue_s, e_g, e_s)
     assert g.launchCount() > 0
 
 

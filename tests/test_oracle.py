@@ -152,7 +152,7 @@ def test_seeds_orders_agree_statistically(O, synthmod):
 
 
 def test_lsc_merge_orders_agree_statistically(O, synthmod):
-    """post-pass merge of small regions: the hashed visiting order (CUDA default) vs the authors' raster order --
+    """post-pass merge of small regions: the hashed visiting order (CUDA opt-in, spx_lsc_set_merge_order(h, 1)) vs the authors' raster order (default) --
     same rule, different order; the partitions must be close and both fully connected"""
     bgr, gt = synthmod.synth(480, 360, 6)
     lab = O.bgr2lab8(bgr)

@@ -33,7 +33,6 @@ for i in range(n):
         print("FAIL", name, str(e)[:100]); bad += 1; continue
     try:
         o = O.SuperpixelLSC(img, S, ratio)
-        o.setMergeOrder(1)
         assert g.getNumberOfSuperpixels() == o.getNumberOfSuperpixels(), "K differs"
         g.iterate(it); o.iterate(it)
         assert (g.getLabels() == o.getLabels()).all(), "labels differ (%d px)" % int((g.getLabels() != o.getLabels()).sum())

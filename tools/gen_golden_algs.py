@@ -38,7 +38,6 @@ def compute(lab, slic, lsc, seeds):
         _post(s, o, False)
         out[name] = o
     s = lsc(lab, 30, 0.075)
-    s.setMergeOrder(1)                                 # the hashed visiting order (the CUDA default)
     o = {"K_seeds": int(s.getNumberOfSuperpixels())}
     s.iterate(10)
     o["labels_10it"] = sha(s.getLabels().astype(np.int32))

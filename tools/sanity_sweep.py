@@ -47,7 +47,7 @@ def run(sizes=SIZES, verbose=False):
         for S in (2, 8, 30):
             def f():
                 l = spx.createSuperpixelLSC(img, S, 0.075); l.iterate(2); l.enforceLabelConnectivity(25); L = l.getLabels(); l.getLabelContourMask(True)
-                o = O.SuperpixelLSC(img, S, 0.075); o.setMergeOrder(1); o.iterate(2); o.enforceLabelConnectivity(25)
+                o = O.SuperpixelLSC(img, S, 0.075); o.iterate(2); o.enforceLabelConnectivity(25)
                 assert (o.getLabels() == L).all(), "labels differ"
             chk("lsc %dx%d S %d" % (w, h, S), f)
         for (num, lev) in ((4, 1), (16, 2), (100, 4), (2000, 6)):
