@@ -61,6 +61,9 @@ def lib():
             L.spxo_lsc_set_labels.argtypes = [vp, vp, i32]
             L.spxo_lsc_get_centres.argtypes = [vp, vp]
             L.spxo_lsc_set_merge_order.argtypes = [vp, i32]
+            L.spxo_lsc_set_merge_algo.argtypes = [vp, i32]
+            L.spxo_lsc_merge_iterations.argtypes = [vp]
+            L.spxo_lsc_merge_iterations.restype = i32
             L.spxo_lsc_get_label_contour_mask.argtypes = [vp, vp, i32]
         if hasattr(L, "spxo_seeds_create"):
             L.spxo_seeds_create.restype = vp
@@ -194,8 +197,15 @@ class SuperpixelLSC(_Base):
         lib().spxo_lsc_set_labels(self._h, _p(lab), int(numlabels))
 
     def setMergeOrder(self, order):
-        """0 (default) = the authors' raster order of small regions, 1 = hashed order (what the CUDA path runs by default)"""
+        """0 (default, here and in the CUDA path) = the authors' raster order of small regions, 1 = hashed order (opt-in)"""
         lib().spxo_lsc_set_merge_order(self._h, int(order))
+
+    def setMergeAlgo(self, algo):
+        """0 = the sequential loop (normative); 1 = fixed-point evaluation of the same rule (the CUDA path's form; same output)"""
+        lib().spxo_lsc_set_merge_algo(self._h, int(algo))
+
+    def mergeIterations(self):
+        return lib().spxo_lsc_merge_iterations(self._h)
 
     def getCentres(self):
         """K rows of (2C+4 feature means, seed x, seed y)"""

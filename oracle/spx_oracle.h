@@ -66,6 +66,8 @@ void spxo_lsc_set_labels(spxo_lsc*, const int32_t* src, int numlabels);
 void spxo_lsc_get_centres(const spxo_lsc*, float* dst);
 /* post-pass visiting order: 0 (default) = ascending region index (authors' order), 1 = hashed index (CUDA default) */
 void spxo_lsc_set_merge_order(spxo_lsc*, int order);
+void spxo_lsc_set_merge_algo(spxo_lsc*, int algo);      /* 1: fixed-point evaluation of the sequential rule (same output) */
+int  spxo_lsc_merge_iterations(const spxo_lsc*);
 void spxo_lsc_get_label_contour_mask(const spxo_lsc*, uint8_t* dst, int thick_line);
 
 /* ---- SuperpixelSEEDS, mainwindow.cpp:2123-2127 (PARITY UNPINNED; sizing pinned by screenshot) ---- */

@@ -32,6 +32,7 @@
 #include <float.h>
 #include <math.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
 
 #define LSC_MAXC 4
@@ -42,6 +43,9 @@ struct spxo_lsc {
     int w, h, C, D, S;
     float ratio;
     int K, ColNum, RowNum, stepx, stepy;
+    int merge_algo;          /* 0 = the sequential loop (normative); 1 = fixed-point evaluation of the SAME sequential rule (the form the
+                                CUDA path runs; must give identical output -- tests/test_oracle.py) */
+    int merge_iters;         /* merge_algo 1: iterations the last call needed */
     int merge_order;         /* post-pass visiting order: 0 = ascending region index (authors; default here and in the CUDA path), 1 = hashed index (CUDA opt-in) */
     uint8_t* img;            /* dense interleaved copy */
     int32_t* labels;
@@ -301,6 +305,125 @@ static int cmp_prio(const void* a, const void* b)
     return pa < pb ? -1 : (pa > pb ? 1 : 0);
 }
 void spxo_lsc_set_merge_order(spxo_lsc* s, int order) { s->merge_order = order ? 1 : 0; }
+void spxo_lsc_set_merge_algo(spxo_lsc* s, int algo) { s->merge_algo = algo ? 1 : 0; }
+int spxo_lsc_merge_iterations(const spxo_lsc* s) { return s->merge_iters; }
+
+/* ---- fixed-point evaluation of the sequential merge (visiting order 0 only) ------------------------------------------
+ * The sequential loop visits region i at "time" i.  Its decision (merge or not, and into whom) is a function of the
+ * decisions of the regions j < i only.  So: take ANY table of tentative decisions mg[]/tg[], derive from it -- for every
+ * region and every time -- representative, centre, weight and size, re-take every decision against that state, and
+ * repeat until no decision changes.  After k rounds the first k regions (at least) hold their sequential decision, and a
+ * table that reproduces itself IS the sequential result (induction over i).  Every step of a round is data parallel.
+ *   children of x  = { c : mg[c] && tg[c] == x }, ascending c; c hops into x at time c
+ *   T_x(t)         = orig_x folded with M_c for the children c < t in ascending order (the sequential float update)
+ *   M_x            = T_x(x), the state x has when it is visited (depends on indices < x only: well founded)
+ *   rep_t(p)       = follow p -> tg[p] while the node was visited (index < t), merged, and AFTER it was entered
+ *                    (index > arrival time; in a consistent table that always holds, in a tentative one it cuts cycles)
+ *   decision of x  = small at time x (M_x.size < threshold) and argmin over edges (p,q), rep_x(p) == x, y = rep_x(q) != x
+ *                    of (|M_x.cen - T_y(x).cen|^2, y)
+ */
+typedef struct { float c[LSC_MAXD]; float W; long long size; } lsc_rstate;
+static void lsc_fold(lsc_rstate* a, const lsc_rstate* b, int D)
+{
+    for (int j = 0; j < D; j++) { const float u = a->c[j] * a->W, v = b->c[j] * b->W; a->c[j] = (u + v) / (a->W + b->W); }
+    a->W = a->W + b->W;
+    a->size += b->size;
+}
+static int cmp_u64(const void* a, const void* b)
+{
+    const unsigned long long x = *(const unsigned long long*)a, y = *(const unsigned long long*)b;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+/* returns the number of rounds; fills cur[] (final owner) and alive[] */
+static int lsc_merge_fixedpoint(int R, int D, const float* cen0, const float* W0, const long long* size0, int threshold,
+                                const unsigned long long* edges, size_t E, int* cur, uint8_t* alive)
+{
+    uint8_t* mg = (uint8_t*)calloc(R > 0 ? R : 1, 1);
+    int* tg = (int*)malloc(sizeof(int) * (R > 0 ? R : 1));
+    int* off = (int*)malloc(sizeof(int) * (R + 1));
+    int* ch = (int*)malloc(sizeof(int) * (R > 0 ? R : 1));
+    int* pre = (int*)malloc(sizeof(int) * (R > 0 ? R : 1));
+    lsc_rstate* S = (lsc_rstate*)malloc(sizeof(lsc_rstate) * (R > 0 ? R : 1));     /* S[off[x]+k] = T_x after k+1 children */
+    lsc_rstate* orig = (lsc_rstate*)malloc(sizeof(lsc_rstate) * (R > 0 ? R : 1));
+    unsigned long long* best = (unsigned long long*)malloc(sizeof(unsigned long long) * (R > 0 ? R : 1));
+    for (int r = 0; r < R; r++) {
+        for (int j = 0; j < D; j++) orig[r].c[j] = cen0[(size_t)r * D + j];
+        orig[r].W = W0[r]; orig[r].size = size0[r]; tg[r] = -1;
+    }
+#define T_STATE(y, k) ((k) == 0 ? &orig[y] : &S[off[y] + (k) - 1])
+    int rounds = 0;
+    for (;;) {
+        rounds++;
+        /* children lists (ascending child index by construction) */
+        for (int r = 0; r <= R; r++) off[r] = 0;
+        for (int c = 0; c < R; c++) if (mg[c]) off[tg[c] + 1]++;
+        for (int r = 0; r < R; r++) off[r + 1] += off[r];
+        {
+            int* fillp = (int*)malloc(sizeof(int) * (R > 0 ? R : 1));
+            for (int r = 0; r < R; r++) fillp[r] = off[r];
+            for (int c = 0; c < R; c++) if (mg[c]) ch[fillp[tg[c]]++] = c;
+            free(fillp);
+        }
+        /* trajectories: children < x first (ascending x: M of smaller indices is complete), the rest afterwards */
+        for (int x = 0; x < R; x++) {
+            lsc_rstate st = orig[x];
+            int k = 0;
+            for (int s = off[x]; s < off[x + 1] && ch[s] < x; s++, k++) { const int c = ch[s]; lsc_fold(&st, T_STATE(c, pre[c]), D); S[s] = st; }
+            pre[x] = k;
+        }
+        for (int x = 0; x < R; x++) {
+            if (off[x] + pre[x] == off[x + 1]) continue;
+            lsc_rstate st = *T_STATE(x, pre[x]);
+            for (int s = off[x] + pre[x]; s < off[x + 1]; s++) { const int c = ch[s]; lsc_fold(&st, T_STATE(c, pre[c]), D); S[s] = st; }
+        }
+        /* candidates */
+        for (int r = 0; r < R; r++) best[r] = ~0ull;
+        for (size_t e = 0; e < E; e++)
+            for (int dir = 0; dir < 2; dir++) {
+                const int a = dir ? (int)(edges[e] & 0xffffffffu) : (int)(edges[e] >> 32);
+                const int b = dir ? (int)(edges[e] >> 32) : (int)(edges[e] & 0xffffffffu);
+                int x = a, tarr = -1;
+                for (;;) {
+                    if (x > tarr && size0[x] < threshold) {            /* x is visited at time x with a among its members */
+                        int y = b, ty = -1;
+                        while (y < x && mg[y] && y > ty) { ty = y; y = tg[y]; }
+                        if (y != x) {
+                            /* children of y with index < x */
+                            int lo = off[y], hi = off[y + 1];
+                            while (lo < hi) { const int mid = (lo + hi) >> 1; if (ch[mid] < x) lo = mid + 1; else hi = mid; }
+                            const lsc_rstate* sy = T_STATE(y, lo - off[y]);
+                            const lsc_rstate* sx = T_STATE(x, pre[x]);
+                            float d = 0.f;
+                            for (int j = 0; j < D; j++) { const float t = sx->c[j] - sy->c[j]; d = d + t * t; }
+                            unsigned db; memcpy(&db, &d, 4);
+                            const unsigned long long key = ((unsigned long long)db << 32) | (unsigned)y;
+                            if (key < best[x]) best[x] = key;
+                        }
+                    }
+                    if (mg[x] && x > tarr) { tarr = x; x = tg[x]; } else break;
+                }
+            }
+        /* decisions */
+        int changed = 0;
+        for (int x = 0; x < R; x++) {
+            if (size0[x] >= threshold) continue;
+            const int m = T_STATE(x, pre[x])->size < threshold && best[x] != ~0ull;
+            const int t = m ? (int)(unsigned)(best[x] & 0xffffffffu) : -1;
+            if (m != mg[x] || t != tg[x]) changed++;
+            mg[x] = (uint8_t)m; tg[x] = t;
+        }
+        if (getenv("SPXO_FP_TRACE")) fprintf(stderr, "round %d changed %d\n", rounds, changed);
+        if (!changed) break;
+    }
+#undef T_STATE
+    for (int r = 0; r < R; r++) {
+        int y = r, ty = -1;
+        while (mg[y] && y > ty) { ty = y; y = tg[y]; }
+        cur[r] = y; alive[r] = !mg[r];
+    }
+    free(mg); free(tg); free(off); free(ch); free(pre); free(S); free(orig); free(best);
+    return rounds;
+}
 
 static void lsc_post_enforce(spxo_lsc* s, int threshold)
 {
@@ -353,6 +476,30 @@ static void lsc_post_enforce(spxo_lsc* s, int threshold)
         Wr[r] = (float)((double)sw / 16777216.0);
         size[r] = (long long)(off[r + 1] - off[r]);
         cur[r] = r; next[r] = -1; tail[r] = r; alive[r] = 1;
+    }
+    if (s->merge_algo && !s->merge_order) {
+        /* region adjacency: unique (min, max) pairs of 4-neighbour pixels */
+        size_t ecap = 4 * N + 4, E = 0;
+        unsigned long long* ek = (unsigned long long*)malloc(sizeof(unsigned long long) * ecap);
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) {
+                const int a = reg[(size_t)y * w + x];
+                if (x + 1 < w) { const int b = reg[(size_t)y * w + x + 1]; if (a != b) ek[E++] = ((unsigned long long)(a < b ? a : b) << 32) | (unsigned)(a < b ? b : a); }
+                if (y + 1 < h) { const int b = reg[(size_t)(y + 1) * w + x]; if (a != b) ek[E++] = ((unsigned long long)(a < b ? a : b) << 32) | (unsigned)(a < b ? b : a); }
+            }
+        qsort(ek, E, sizeof(unsigned long long), cmp_u64);
+        size_t U = 0;
+        for (size_t e = 0; e < E; e++) if (e == 0 || ek[e] != ek[e - 1]) ek[U++] = ek[e];
+        s->merge_iters = lsc_merge_fixedpoint(R, D, cen, Wr, size, threshold, ek, U, cur, alive);
+        free(ek);
+        int* newid2 = (int*)malloc(sizeof(int) * R);
+        int K2 = 0;
+        for (int r = 0; r < R; r++) newid2[r] = alive[r] ? K2++ : -1;
+        for (size_t i = 0; i < N; i++) s->labels[i] = newid2[cur[reg[i]]];
+        s->K = K2;
+        free(newid2);
+        free(reg); free(qx); free(qy); free(off); free(cen); free(Wr); free(size); free(cur); free(next); free(tail); free(alive);
+        return;
     }
     /* sequential merge of small regions: in region order (order 0), or in the order of a bijective hash of the region
        index (order 1: same rule, but the dependency chains between merges are short, which is what a GPU needs) */

@@ -641,6 +641,227 @@ __global__ void __launch_bounds__(1024) lsc_rounds_kernel(LscRounds a)
     for (int r = tid; r < a.R; r += nth) a.cur[r] = lsc_cur(a.cur, r);
     if (tid == 0) a.cnt[9] = round;
 }
+// ---- the authors' visiting order (order 0) without its serial dependency chains ------------------------------------
+// In region order every fragment around a superpixel is within graph distance 2 of the next one, so the rounds above
+// degenerate into a wavefront (thousands of rounds, a few dozen merges each).  The sequential loop is evaluated as a
+// FIXED POINT instead (normative CPU form: oracle/spx_oracle_lsc.c, lsc_merge_fixedpoint): region i is visited at
+// "time" i and its decision (merge or not, into whom) depends on the decisions of regions j < i only.  Take any table
+// of tentative decisions tg[], derive from it the state every region has at every time, re-take all decisions against
+// that state, repeat until the table reproduces itself.  After k rounds the first k regions (at least) hold their
+// sequential decision, and a self-consistent table IS the sequential result (induction over i).  Every step is data parallel:
+//   children of x = { c : tg[c] == x }, ascending c (c hops into x at time c): counted, scanned, filled, ranked
+//   T_x(t)  = x's original (centre, weight, size) folded with M_c for its children c < t in ascending order -- the
+//             sequential float update, one thread per region walking its list; prefix states are kept per child slot
+//   M_x     = T_x(x): the state x has when it is visited; depends on smaller indices only, so a few passes settle it
+//   rep_t(p)= follow p -> tg[p] while the node merged at a time < t and AFTER it was entered (in a consistent table
+//             that always holds; in a tentative one it cuts cycles)
+//   decision of x = M_x.size < threshold and arg min over adjacency edges (p,q) with rep_x(p) == x, y = rep_x(q) != x
+//             of (|M_x.centre - T_y(x).centre|^2, y)
+// 8K frame: 1.05 M regions, 1.7 M edges.
+struct LscFix {
+    const unsigned long long* edges; int E; int R; int D; int threshold;
+    const float* cen; const float* Wr; const int* size; const int* smallflag;
+    int* tg;                 // tentative decision: target region, -1 = does not merge
+    int* off;                // [R+1] children lists (CSR)
+    int* nch;                // [R] children count / fill cursor
+    int* tmp; int* ch;       // [R] unsorted / ascending children
+    int* pre;                // [R] number of children with a smaller index than the parent
+    int* prog;               // [R] child slots folded so far in this round
+    float* S;                // [R][D+2] state after each child slot: centre, weight, size (int bits)
+    unsigned long long* best;
+    int* bsum;               // per-CTA partial sums of the scan
+    int* cnt;                // [0..3] "changed" by round & 3, [4..7] "incomplete" by pass & 3, [8] barrier, [9] rounds, [10] passes
+    int* cur; int* alive; int max_rounds;
+};
+struct LscState { float c[LSC_MAXD]; float W; int size; };
+__device__ __forceinline__ LscState lsc_fix_load(const LscFix& a, int y, int k)
+{
+    LscState s;
+    if (k == 0) {
+#pragma unroll
+        for (int j = 0; j < LSC_MAXD; j++) s.c[j] = j < a.D ? a.cen[(size_t)y * a.D + j] : 0.f;
+        s.W = a.Wr[y]; s.size = a.size[y];
+    } else {
+        const float* p = a.S + (size_t)(a.off[y] + k - 1) * (a.D + 2);
+#pragma unroll
+        for (int j = 0; j < LSC_MAXD; j++) s.c[j] = j < a.D ? __ldcg(p + j) : 0.f;
+        s.W = __ldcg(p + a.D); s.size = __float_as_int(__ldcg(p + a.D + 1));
+    }
+    return s;
+}
+__device__ __forceinline__ int lsc_fix_size(const LscFix& a, int y, int k)
+{
+    return k == 0 ? a.size[y] : __float_as_int(__ldcg(a.S + (size_t)(a.off[y] + k - 1) * (a.D + 2) + a.D + 1));
+}
+__global__ void __launch_bounds__(1024) lsc_fixpoint_kernel(LscFix a)
+{
+    __shared__ int s_warp[32];
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned nblk = gridDim.x;
+    unsigned* bar = reinterpret_cast<unsigned*>(a.cnt + 8);
+    unsigned epoch = 0;
+    const int R = a.R, D = a.D;
+    // scan geometry: CTA b owns [b*chunk, (b+1)*chunk), thread t of it a contiguous run of `per` regions
+    const int chunk = (R + (int)nblk - 1) / (int)nblk, per = (chunk + (int)blockDim.x - 1) / (int)blockDim.x;
+    int round = 0, passes = 0;
+    unsigned long long tlast = 0, tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    auto tick = [&](int ph) {
+        if (tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); if (ph >= 0) tacc[ph] += t - tlast; tlast = t; }
+    };
+    tick(-1);
+    for (int x = tid; x < R; x += nth) { a.tg[x] = -1; a.nch[x] = 0; a.prog[x] = 0; a.best[x] = ~0ull; }
+    lsc_grid_barrier(bar, ++epoch * nblk);
+    for (; round < a.max_rounds; round++) {
+        // ---- children lists: count
+        for (int c = tid; c < R; c += nth) { const int p = a.tg[c]; if (p >= 0) atomicAdd(&a.nch[p], 1); }
+        lsc_grid_barrier(bar, ++epoch * nblk);
+        tick(0);
+        // ---- exclusive scan of the counts -> off[]
+        int texcl;
+        {
+            const int lo = min((int)blockIdx.x * chunk + (int)threadIdx.x * per, R), hi = min(min(lo + per, ((int)blockIdx.x + 1) * chunk), R);
+            int sum = 0;
+            for (int x = lo; x < hi; x++) sum += a.nch[x];
+            int incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+            if (lane == 31) s_warp[warp] = incl;
+            __syncthreads();
+            if (warp == 0) {
+                int w = s_warp[lane], wi = w;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += v; }
+                s_warp[lane] = wi - w;
+                if (lane == 31) a.bsum[blockIdx.x] = wi;
+            }
+            __syncthreads();
+            texcl = s_warp[warp] + incl - sum;
+        }
+        lsc_grid_barrier(bar, ++epoch * nblk);
+        {
+            int base = 0;
+            for (int b = lane; b < (int)blockIdx.x; b += 32) base += a.bsum[b];
+#pragma unroll
+            for (int d = 16; d; d >>= 1) base += __shfl_xor_sync(0xffffffffu, base, d);
+            const int lo = min((int)blockIdx.x * chunk + (int)threadIdx.x * per, R), hi = min(min(lo + per, ((int)blockIdx.x + 1) * chunk), R);
+            int run = base + texcl;
+            for (int x = lo; x < hi; x++) { a.off[x] = run; run += a.nch[x]; a.nch[x] = 0; }
+            if (hi == R && lo < R) a.off[R] = run;
+            if (R == 0 && tid == 0) a.off[0] = 0;
+        }
+        lsc_grid_barrier(bar, ++epoch * nblk);
+        tick(1);
+        // ---- fill (any order)
+        for (int c = tid; c < R; c += nth) { const int p = a.tg[c]; if (p >= 0) a.tmp[a.off[p] + atomicAdd(&a.nch[p], 1)] = c; }
+        lsc_grid_barrier(bar, ++epoch * nblk);
+        tick(2);
+        // ---- ascending order by rank counting; pre[x] = children that arrive before x's own visit
+        for (int x = tid; x < R; x += nth) {
+            const int p = a.tg[x];
+            if (p >= 0) {
+                const int lo = a.off[p], hi = a.off[p + 1];
+                int rank = 0;
+                for (int j = lo; j < hi; j++) rank += a.tmp[j] < x ? 1 : 0;
+                a.ch[lo + rank] = x;
+            }
+            const int lo = a.off[x], hi = a.off[x + 1];
+            int pr = 0;
+            for (int j = lo; j < hi; j++) pr += a.tmp[j] < x ? 1 : 0;
+            a.pre[x] = pr;
+        }
+        lsc_grid_barrier(bar, ++epoch * nblk);
+        tick(3);
+        // ---- trajectories: a slot can be folded once the child's own state M_c is complete (prog[c] >= pre[c])
+        for (;;) {
+            int* inc = a.cnt + 4 + (passes & 3);
+            if (tid == 0) a.cnt[4 + ((passes + 2) & 3)] = 0;
+            bool incomplete = false;
+            for (int x = tid; x < R; x += nth) {
+                const int lo = a.off[x], n = a.off[x + 1] - lo;
+                int k = *(volatile int*)&a.prog[x];
+                if (k >= n) continue;
+                LscState st = lsc_fix_load(a, x, k);
+                for (; k < n; k++) {
+                    const int c = a.ch[lo + k];
+                    const int pc = a.pre[c];
+                    if (*(volatile int*)&a.prog[c] < pc) break;
+                    __threadfence();
+                    const LscState sc = lsc_fix_load(a, c, pc);
+                    const float wsum = __fadd_rn(st.W, sc.W);
+#pragma unroll
+                    for (int j = 0; j < LSC_MAXD; j++)
+                        if (j < D) st.c[j] = __fdiv_rn(__fadd_rn(__fmul_rn(st.c[j], st.W), __fmul_rn(sc.c[j], sc.W)), wsum);
+                    st.W = wsum; st.size += sc.size;
+                    float* p = a.S + (size_t)(lo + k) * (D + 2);
+#pragma unroll
+                    for (int j = 0; j < LSC_MAXD; j++) if (j < D) __stcg(p + j, st.c[j]);
+                    __stcg(p + D, st.W); __stcg(p + D + 1, __int_as_float(st.size));
+                    __threadfence();
+                    *(volatile int*)&a.prog[x] = k + 1;
+                }
+                if (k < n) incomplete = true;
+            }
+            if (__syncthreads_or(incomplete) && threadIdx.x == 0) *(volatile int*)inc = 1;
+            lsc_grid_barrier(bar, ++epoch * nblk);
+            passes++;
+            if (!*(volatile int*)inc) break;                                     // uniform
+        }
+        tick(4);
+        // ---- candidates: every adjacency edge, seen from both ends, for every visited small region on the end's chain
+        for (int e = tid; e < 2 * a.E; e += nth) {
+            const unsigned long long key = a.edges[e >> 1];
+            const int ea = (e & 1) ? (int)(key & 0xffffffffull) : (int)(key >> 32);
+            const int eb = (e & 1) ? (int)(key >> 32) : (int)(key & 0xffffffffull);
+            int x = ea, tarr = -1;
+            for (;;) {
+                const int tx = a.tg[x];
+                if (x > tarr && a.smallflag[x]) {
+                    int y = eb, ty = -1;
+                    for (;;) { const int t = y < x ? a.tg[y] : -1; if (t < 0 || y <= ty) break; ty = y; y = t; }
+                    if (y != x) {
+                        int lo = a.off[y], hi = a.off[y + 1];
+                        const int base = lo;
+                        while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.ch[mid] < x) lo = mid + 1; else hi = mid; }
+                        const LscState sy = lsc_fix_load(a, y, lo - base), sx = lsc_fix_load(a, x, a.pre[x]);
+                        float d = 0.f;
+#pragma unroll
+                        for (int j = 0; j < LSC_MAXD; j++) if (j < D) { const float u = __fsub_rn(sx.c[j], sy.c[j]); d = __fadd_rn(d, __fmul_rn(u, u)); }
+                        const unsigned long long k2 = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)y;
+                        if (k2 < a.best[x]) atomicMin(&a.best[x], k2);
+                    }
+                }
+                if (tx >= 0 && x > tarr) { tarr = x; x = tx; } else break;
+            }
+        }
+        lsc_grid_barrier(bar, ++epoch * nblk);
+        tick(5);
+        // ---- decisions (and the reset of the per-round arrays)
+        int* chg = a.cnt + (round & 3);
+        if (tid == 0) a.cnt[(round + 2) & 3] = 0;
+        bool changed = false;
+        for (int x = tid; x < R; x += nth) {
+            if (a.smallflag[x]) {
+                const unsigned long long b = a.best[x];
+                const bool m = b != ~0ull && lsc_fix_size(a, x, a.pre[x]) < a.threshold;
+                const int t = m ? (int)(unsigned)(b & 0xffffffffull) : -1;
+                if (t != a.tg[x]) { changed = true; a.tg[x] = t; }
+                a.best[x] = ~0ull;
+            }
+            a.nch[x] = 0; a.prog[x] = 0;
+        }
+        if (__syncthreads_or(changed) && threadIdx.x == 0) *(volatile int*)chg = 1;
+        lsc_grid_barrier(bar, ++epoch * nblk);
+        tick(6);
+        if (!*(volatile int*)chg) { round++; break; }                            // uniform
+    }
+    // the table is consistent now: owners are plain chains
+    for (int r = tid; r < R; r += nth) {
+        int y = r;
+        for (int t = a.tg[y]; t >= 0; t = a.tg[y]) y = t;
+        a.cur[r] = y; a.alive[r] = a.tg[r] < 0 ? 1 : 0;
+    }
+    if (tid == 0) { a.cnt[9] = round; a.cnt[10] = passes; for (int i = 0; i < 8; i++) a.cnt[16 + i] = (int)(tacc[i] / 1000ull); }
+}
 __global__ void lsc_post_relabel_kernel(const int* __restrict__ reg, const int* __restrict__ cur, const int* __restrict__ newid,
                                         int* __restrict__ lab, int n)
 {
@@ -761,7 +982,7 @@ struct LscEngine {
             SPX_CUDA(cudaMemsetAsync(L.tl_count, 0, (size_t)L.tiles_x * L.tiles_y * sizeof(int), st));
             L.ctab = d_ctab;
         }
-        SPX_CUDA(cudaMallocHost(&h_pinned, 8 * sizeof(int)));
+        SPX_CUDA(cudaMallocHost(&h_pinned, 32 * sizeof(int)));
         L.img = d_img;
         SPX_CUDA(cudaMemcpy2DAsync(d_img, L.ipitch, image, stride, (size_t)w * C, h, cudaMemcpyHostToDevice, st));
         if (cvt_mode >= 0) {                  // cvtColor of mainwindow.cpp:2096-2097 on the uploaded image, in place
@@ -1017,8 +1238,8 @@ struct LscEngine {
                 LSC_TRYCUDA(cudaDeviceGetAttribute(&s_sms, cudaDevAttrMultiProcessorCount, dev));
             }
             int *plist0, *plist1, *rcnt;
-            LSC_TRY(talloc(&plist0, (size_t)R)); LSC_TRY(talloc(&plist1, (size_t)R)); LSC_TRY(talloc(&rcnt, 16));
-            LSC_TRYCUDA(cudaMemsetAsync(rcnt, 0, 16 * sizeof(int), st));
+            LSC_TRY(talloc(&plist0, (size_t)R)); LSC_TRY(talloc(&plist1, (size_t)R)); LSC_TRY(talloc(&rcnt, 32));
+            LSC_TRYCUDA(cudaMemsetAsync(rcnt, 0, 32 * sizeof(int), st));
             LscRounds ra_{};
             ra_.edges[0] = edges; ra_.edges[1] = edges == kbuf0 ? kbuf1 : kbuf0; ra_.E = E;
             ra_.plist[0] = plist0; ra_.plist[1] = plist1;
@@ -1027,12 +1248,28 @@ struct LscEngine {
             ra_.cen = cen; ra_.D = D; ra_.Wr = Wr; ra_.alive = alive; ra_.cur = cur;
             ra_.cnt = rcnt; ra_.max_rounds = R + 2;
             int blocks = std::min(std::max(cdiv(std::max(R, E), 1024), 1), s_sms);   // one CTA per SM at most: all co-resident
-            void* args[] = {(void*)&ra_};
-            LSC_TRYCUDA(cudaLaunchCooperativeKernel((const void*)lsc_rounds_kernel, dim3(blocks), dim3(1024), args, 0, st));
+            if (merge_order == 0 && !getenv("SPX_LSC_ROUNDS")) {
+                // the authors' order: fixed-point evaluation of the sequential rule (see lsc_fixpoint_kernel)
+                LscFix fx{};
+                fx.edges = edges; fx.E = E; fx.R = R; fx.D = D; fx.threshold = threshold;
+                fx.cen = cen; fx.Wr = Wr; fx.size = size; fx.smallflag = smallflag;
+                fx.tg = done; fx.best = best; fx.cur = cur; fx.alive = alive; fx.cnt = rcnt; fx.max_rounds = R + 2;
+                fx.tmp = plist0; fx.ch = plist1;
+                LSC_TRY(talloc(&fx.off, (size_t)R + 1)); LSC_TRY(talloc(&fx.nch, (size_t)R)); LSC_TRY(talloc(&fx.pre, (size_t)R));
+                LSC_TRY(talloc(&fx.prog, (size_t)R)); LSC_TRY(talloc((int**)&fx.S, (size_t)R * (D + 2))); LSC_TRY(talloc(&fx.bsum, (size_t)s_sms + 1));
+                void* args[] = {(void*)&fx};
+                LSC_TRYCUDA(cudaLaunchCooperativeKernel((const void*)lsc_fixpoint_kernel, dim3(blocks), dim3(1024), args, 0, st));
+            } else {
+                void* args[] = {(void*)&ra_};
+                LSC_TRYCUDA(cudaLaunchCooperativeKernel((const void*)lsc_rounds_kernel, dim3(blocks), dim3(1024), args, 0, st));
+            }
             launches++;
-            LSC_TRYCUDA(cudaMemcpyAsync(h_pinned, rcnt + 9, sizeof(int), cudaMemcpyDeviceToHost, st));
+            LSC_TRYCUDA(cudaMemcpyAsync(h_pinned, rcnt + 9, 16 * sizeof(int), cudaMemcpyDeviceToHost, st));
             LSC_TRYCUDA(cudaStreamSynchronize(st));
             rounds = h_pinned[0];
+            if (getenv("SPX_LSC_DEBUG") && merge_order == 0)
+                fprintf(stderr, "[lsc] fixed point: %d rounds, %d trajectory passes; us per phase: count %d scan %d fill %d rank %d trajectories %d edges %d decisions %d\n",
+                        h_pinned[0], h_pinned[1], h_pinned[7], h_pinned[8], h_pinned[9], h_pinned[10], h_pinned[11], h_pinned[12], h_pinned[13]);
         }
         if (getenv("SPX_LSC_DEBUG")) fprintf(stderr, "[lsc] post-pass: %d regions, %d adjacency edges (%llu raw), threshold %d, %d merge rounds, launches %lld\n", R, E, h_ec, threshold, rounds, launches);
         LSC_TRY(exclusive_sum(alive, newid, R + 1));

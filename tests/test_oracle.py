@@ -169,6 +169,21 @@ def test_lsc_merge_orders_agree_statistically(O, synthmod):
     assert float((same0 == same1).mean()) > 0.98
 
 
+@pytest.mark.parametrize("w,h,S,it,p", [(320, 200, 12, 3, 25), (640, 360, 16, 5, 25), (480, 270, 8, 4, 60), (257, 129, 20, 2, 5)])
+def test_lsc_fixed_point_merge_equals_the_sequential_loop(O, synthmod, w, h, S, it, p):
+    """the authors' sequential merge of small regions (visiting order 0) evaluated as a fixed point -- the data-parallel
+    form lsc_fixpoint_kernel runs (oracle/spx_oracle_lsc.c: lsc_merge_fixedpoint) -- gives the sequential loop's output"""
+    bgr, _ = synthmod.synth(w, h, 3)
+    lab = O.bgr2lab8(bgr)
+    out = []
+    for algo in (0, 1):
+        s = O.SuperpixelLSC(lab, S, 0.075); s.setMergeAlgo(algo)
+        s.iterate(it); s.enforceLabelConnectivity(p)
+        out.append((s.getNumberOfSuperpixels(), s.getLabels(), s.mergeIterations()))
+    assert out[0][0] == out[1][0] and (out[0][1] == out[1][1]).all()
+    assert out[1][2] >= 1
+
+
 def test_golden_hashes_reproduce(O, example_bgr):
     """tests/golden/cfg1_hashes.json (tools/gen_golden.py): every stage of configs[0] and of the reference's fixture run"""
     import importlib.util, json, os
