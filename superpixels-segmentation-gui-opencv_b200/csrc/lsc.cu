@@ -646,31 +646,44 @@ __global__ void __launch_bounds__(1024) lsc_rounds_kernel(LscRounds a)
 // degenerate into a wavefront (thousands of rounds, a few dozen merges each).  The sequential loop is evaluated as a
 // FIXED POINT instead (normative CPU form: oracle/spx_oracle_lsc.c, lsc_merge_fixedpoint): region i is visited at
 // "time" i and its decision (merge or not, into whom) depends on the decisions of regions j < i only.  Take any table
-// of tentative decisions tg[], derive from it the state every region has at every time, re-take all decisions against
+// of tentative decisions tg[], derive from it the state every region has at every time, re-take the decisions against
 // that state, repeat until the table reproduces itself.  After k rounds the first k regions (at least) hold their
-// sequential decision, and a self-consistent table IS the sequential result (induction over i).  Every step is data parallel:
+// sequential decision, and a table that a FULL round reproduces IS the sequential result (induction over i).
 //   children of x = { c : tg[c] == x }, ascending c (c hops into x at time c): counted, scanned, filled, ranked
 //   T_x(t)  = x's original (centre, weight, size) folded with M_c for its children c < t in ascending order -- the
-//             sequential float update, one thread per region walking its list; prefix states are kept per child slot
-//   M_x     = T_x(x): the state x has when it is visited; depends on smaller indices only, so a few passes settle it
+//             sequential float update; prefix states are kept per child slot.  A thread walks a region's list and
+//             descends (explicit stack) into children whose own state is not there yet
+//   M_x     = T_x(x): the state x has when it is visited; depends on smaller indices only
 //   rep_t(p)= follow p -> tg[p] while the node merged at a time < t and AFTER it was entered (in a consistent table
 //             that always holds; in a tentative one it cuts cycles)
 //   decision of x = M_x.size < threshold and arg min over adjacency edges (p,q) with rep_x(p) == x, y = rep_x(q) != x
 //             of (|M_x.centre - T_y(x).centre|^2, y)
-// 8K frame: 1.05 M regions, 1.7 M edges.
+// Rounds after the first are INCREMENTAL: a changed decision of c (old target o, new target t) moves the trajectories
+// of o and t from time c on, and of their owners from the time the changed state is folded in (eff[] = earliest
+// affected time, pushed up the chains).  A region whose chain meets such a node is a dirty member; the small regions
+// x > that time which own a neighbour of a dirty member are re-decided, everybody else keeps its decision.  The
+// marking is a heuristic for speed only: the loop ends when a FULL round changes nothing.
+// 8K frame: 1.05 M regions, 1.7 M edges, 87 rounds.
 struct LscFix {
     const unsigned long long* edges; int E; int R; int D; int threshold;
     const float* cen; const float* Wr; const int* size; const int* smallflag;
     int* tg;                 // tentative decision: target region, -1 = does not merge
     int* off;                // [R+1] children lists (CSR)
-    int* nch;                // [R] children count / fill cursor
-    int* tmp; int* ch;       // [R] unsorted / ascending children
+    int* nch;                // [R] counts / fill cursors
+    int* tmp; int* ch;       // [R] unsorted / ascending children (tmp doubles as "previous target" between rounds)
     int* pre;                // [R] number of children with a smaller index than the parent
     int* prog;               // [R] child slots folded so far in this round
-    float* S;                // [R][D+2] state after each child slot: centre, weight, size (int bits)
+    float* S;                // [R][D+2] S[c] = state of c's owner right after c is folded in: centre, weight, size (int bits).
+                             // Indexed by the child, so a slot keeps its place from round to round and an incremental round
+                             // refolds a list from the first child >= eff[owner] only
     unsigned long long* best;
+    int* inc_off; int* inc;  // [R+1], [2E] static incidence lists of the region adjacency graph
+    int* eff;                // [R] earliest time from which the region's trajectory / decision differs from the last round
+    int* need;               // [R] re-decide in this round
+    int* dq; int* dtau;      // [R] dirty members and their times (between rounds dtau[x] = 1: x changed its decision)
     int* bsum;               // per-CTA partial sums of the scan
-    int* cnt;                // [0..3] "changed" by round & 3, [4..7] "incomplete" by pass & 3, [8] barrier, [9] rounds, [10] passes
+    int* cnt;                // [0..3] changed decisions by round & 3, [4..7] "incomplete" by pass & 3, [8] barrier, [9] rounds,
+                             // [10] passes, [11] full rounds, [12..15] dirty members by round & 3, [16..] us per phase
     int* cur; int* alive; int max_rounds;
 };
 struct LscState { float c[LSC_MAXD]; float W; int size; };
@@ -682,7 +695,7 @@ __device__ __forceinline__ LscState lsc_fix_load(const LscFix& a, int y, int k)
         for (int j = 0; j < LSC_MAXD; j++) s.c[j] = j < a.D ? a.cen[(size_t)y * a.D + j] : 0.f;
         s.W = a.Wr[y]; s.size = a.size[y];
     } else {
-        const float* p = a.S + (size_t)(a.off[y] + k - 1) * (a.D + 2);
+        const float* p = a.S + (size_t)a.ch[a.off[y] + k - 1] * (a.D + 2);
 #pragma unroll
         for (int j = 0; j < LSC_MAXD; j++) s.c[j] = j < a.D ? __ldcg(p + j) : 0.f;
         s.W = __ldcg(p + a.D); s.size = __float_as_int(__ldcg(p + a.D + 1));
@@ -691,68 +704,123 @@ __device__ __forceinline__ LscState lsc_fix_load(const LscFix& a, int y, int k)
 }
 __device__ __forceinline__ int lsc_fix_size(const LscFix& a, int y, int k)
 {
-    return k == 0 ? a.size[y] : __float_as_int(__ldcg(a.S + (size_t)(a.off[y] + k - 1) * (a.D + 2) + a.D + 1));
+    return k == 0 ? a.size[y] : __float_as_int(__ldcg(a.S + (size_t)a.ch[a.off[y] + k - 1] * (a.D + 2) + a.D + 1));
 }
+// grid-wide exclusive scan of cntv[0..R) into offv[0..R] (cntv is zeroed); CTA b owns a contiguous chunk, thread t of it a run
+__device__ __forceinline__ void lsc_grid_scan(int* cntv, int* offv, int R, int* bsum, int* s_warp, unsigned* bar, unsigned& epoch)
+{
+    const unsigned nblk = gridDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunk = (R + (int)nblk - 1) / (int)nblk, per = (chunk + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int lo = min((int)blockIdx.x * chunk + (int)threadIdx.x * per, R), hi = min(min(lo + per, ((int)blockIdx.x + 1) * chunk), R);
+    int sum = 0;
+    for (int x = lo; x < hi; x++) sum += cntv[x];
+    int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int w = s_warp[lane];
+        int wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += v; }
+        s_warp[lane] = wi - w;
+        if (lane == 31) bsum[blockIdx.x] = wi;
+    }
+    __syncthreads();
+    const int texcl = s_warp[warp] + incl - sum;
+    lsc_grid_barrier(bar, ++epoch * nblk);
+    int base = 0;
+    for (int b = lane; b < (int)blockIdx.x; b += 32) base += bsum[b];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) base += __shfl_xor_sync(0xffffffffu, base, d);
+    int run = base + texcl;
+    for (int x = lo; x < hi; x++) { offv[x] = run; run += cntv[x]; cntv[x] = 0; }
+    if (hi == R && lo < R) offv[R] = run;
+    if (R == 0 && blockIdx.x == 0 && threadIdx.x == 0) offv[0] = 0;
+    lsc_grid_barrier(bar, ++epoch * nblk);
+}
+constexpr int LSC_FIX_STACK = 24;
+constexpr int LSC_INF = 0x7fffffff;
 __global__ void __launch_bounds__(1024) lsc_fixpoint_kernel(LscFix a)
 {
     __shared__ int s_warp[32];
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x, lane = threadIdx.x & 31;
+    const int gwarp = tid >> 5, nwarps = nth >> 5;
     const unsigned nblk = gridDim.x;
     unsigned* bar = reinterpret_cast<unsigned*>(a.cnt + 8);
     unsigned epoch = 0;
     const int R = a.R, D = a.D;
-    // scan geometry: CTA b owns [b*chunk, (b+1)*chunk), thread t of it a contiguous run of `per` regions
-    const int chunk = (R + (int)nblk - 1) / (int)nblk, per = (chunk + (int)blockDim.x - 1) / (int)blockDim.x;
-    int round = 0, passes = 0;
+    int round = 0, passes = 0, fullrounds = 0;
     unsigned long long tlast = 0, tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     auto tick = [&](int ph) {
         if (tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); if (ph >= 0) tacc[ph] += t - tlast; tlast = t; }
     };
     tick(-1);
-    for (int x = tid; x < R; x += nth) { a.tg[x] = -1; a.nch[x] = 0; a.prog[x] = 0; a.best[x] = ~0ull; }
+    // ---- once: incidence lists of the adjacency graph; initial table = nobody merges
+    for (int x = tid; x < R; x += nth) { a.tg[x] = -1; a.nch[x] = 0; a.prog[x] = 0; a.best[x] = ~0ull; a.eff[x] = LSC_INF; a.need[x] = 0; }
     lsc_grid_barrier(bar, ++epoch * nblk);
+    for (int e = tid; e < a.E; e += nth) {
+        const unsigned long long key = a.edges[e];
+        atomicAdd(&a.nch[(int)(key >> 32)], 1); atomicAdd(&a.nch[(int)(key & 0xffffffffull)], 1);
+    }
+    lsc_grid_barrier(bar, ++epoch * nblk);
+    lsc_grid_scan(a.nch, a.inc_off, R, a.bsum, s_warp, bar, epoch);
+    for (int e = tid; e < a.E; e += nth) {
+        const unsigned long long key = a.edges[e];
+        const int p = (int)(key >> 32), q = (int)(key & 0xffffffffull);
+        a.inc[a.inc_off[p] + atomicAdd(&a.nch[p], 1)] = q; a.inc[a.inc_off[q] + atomicAdd(&a.nch[q], 1)] = p;
+    }
+    lsc_grid_barrier(bar, ++epoch * nblk);
+    for (int x = tid; x < R; x += nth) a.nch[x] = 0;
+    lsc_grid_barrier(bar, ++epoch * nblk);
+    tick(7);
+    bool full = true;
     for (; round < a.max_rounds; round++) {
-        // ---- children lists: count
-        for (int c = tid; c < R; c += nth) { const int p = a.tg[c]; if (p >= 0) atomicAdd(&a.nch[p], 1); }
+        int* ndq = a.cnt + 12 + (round & 3);
+        if (tid == 0) a.cnt[12 + ((round + 2) & 3)] = 0;
+        // ---- children lists: count.  Incremental round: push the times of the changed decisions up the chains
+        for (int c = tid; c < R; c += nth) {
+            const int p = a.tg[c];
+            if (p >= 0) atomicAdd(&a.nch[p], 1);
+            if (!full && a.dtau[c]) {                                            // c changed its decision in the last round
+                for (int side = 0; side < 2; side++) {
+                    int n = side ? p : a.tmp[c], tm = c;
+                    while (n >= 0) {
+                        if (tm < a.eff[n]) atomicMin(&a.eff[n], tm);
+                        if (tm >= n) break;                                      // folded in after n's own visit: n's owner never sees it
+                        tm = n; n = a.tg[n];
+                    }
+                }
+            }
+        }
         lsc_grid_barrier(bar, ++epoch * nblk);
         tick(0);
         // ---- exclusive scan of the counts -> off[]
-        int texcl;
-        {
-            const int lo = min((int)blockIdx.x * chunk + (int)threadIdx.x * per, R), hi = min(min(lo + per, ((int)blockIdx.x + 1) * chunk), R);
-            int sum = 0;
-            for (int x = lo; x < hi; x++) sum += a.nch[x];
-            int incl = sum;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
-            if (lane == 31) s_warp[warp] = incl;
-            __syncthreads();
-            if (warp == 0) {
-                int w = s_warp[lane], wi = w;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += v; }
-                s_warp[lane] = wi - w;
-                if (lane == 31) a.bsum[blockIdx.x] = wi;
-            }
-            __syncthreads();
-            texcl = s_warp[warp] + incl - sum;
-        }
-        lsc_grid_barrier(bar, ++epoch * nblk);
-        {
-            int base = 0;
-            for (int b = lane; b < (int)blockIdx.x; b += 32) base += a.bsum[b];
-#pragma unroll
-            for (int d = 16; d; d >>= 1) base += __shfl_xor_sync(0xffffffffu, base, d);
-            const int lo = min((int)blockIdx.x * chunk + (int)threadIdx.x * per, R), hi = min(min(lo + per, ((int)blockIdx.x + 1) * chunk), R);
-            int run = base + texcl;
-            for (int x = lo; x < hi; x++) { a.off[x] = run; run += a.nch[x]; a.nch[x] = 0; }
-            if (hi == R && lo < R) a.off[R] = run;
-            if (R == 0 && tid == 0) a.off[0] = 0;
-        }
-        lsc_grid_barrier(bar, ++epoch * nblk);
+        lsc_grid_scan(a.nch, a.off, R, a.bsum, s_warp, bar, epoch);
         tick(1);
-        // ---- fill (any order)
-        for (int c = tid; c < R; c += nth) { const int p = a.tg[c]; if (p >= 0) a.tmp[a.off[p] + atomicAdd(&a.nch[p], 1)] = c; }
+        // ---- fill (any order).  Dirty members: regions whose chain meets a moved trajectory / changed decision
+        for (int c0 = tid - lane; c0 < R; c0 += nth) {
+            const int c = c0 + lane;
+            bool dirty = false;
+            int tau = LSC_INF;
+            if (c < R) {
+                const int p = a.tg[c];
+                if (p >= 0) a.tmp[a.off[p] + atomicAdd(&a.nch[p], 1)] = c;
+                if (full) { if (a.smallflag[c]) a.need[c] = 1; }
+                else {
+                    int n = c, tl = -1;
+                    for (;;) { tau = min(tau, a.eff[n]); const int t = a.tg[n]; if (t < 0 || n <= tl) break; tl = n; n = t; }
+                    dirty = tau != LSC_INF;
+                    if (dirty && a.smallflag[c] && tau < c) a.need[c] = 1;
+                }
+            }
+            if (!full) {
+                const int slot = lsc_warp_append(dirty, ndq, lane);
+                if (dirty) { a.dq[slot] = c; a.dtau[slot] = tau; }
+            }
+        }
         lsc_grid_barrier(bar, ++epoch * nblk);
         tick(2);
         // ---- ascending order by rank counting; pre[x] = children that arrive before x's own visit
@@ -765,41 +833,78 @@ __global__ void __launch_bounds__(1024) lsc_fixpoint_kernel(LscFix a)
                 a.ch[lo + rank] = x;
             }
             const int lo = a.off[x], hi = a.off[x + 1];
-            int pr = 0;
-            for (int j = lo; j < hi; j++) pr += a.tmp[j] < x ? 1 : 0;
-            a.pre[x] = pr;
+            const int ex = full ? -1 : a.eff[x];                                 // slots of children < eff[x] are still valid
+            int pr = 0, k0 = 0;
+            for (int j = lo; j < hi; j++) { const int c = a.tmp[j]; pr += c < x ? 1 : 0; k0 += c < ex ? 1 : 0; }
+            a.pre[x] = pr; a.prog[x] = k0;
+        }
+        // ---- (incremental) a warp per dirty member: the small regions that own one of its neighbours later than tau
+        if (!full) {
+            const int n = *(volatile int*)ndq;
+            for (int i = gwarp; i < n; i += nwarps) {
+                const int q = a.dq[i], tau = a.dtau[i];
+                for (int j = a.inc_off[q] + lane; j < a.inc_off[q + 1]; j += 32) {
+                    int x = a.inc[j], tl = -1;
+                    for (;;) {
+                        if (x > tau && a.smallflag[x]) a.need[x] = 1;
+                        const int t = a.tg[x];
+                        if (t < 0 || x <= tl) break;
+                        tl = x; x = t;
+                    }
+                }
+            }
         }
         lsc_grid_barrier(bar, ++epoch * nblk);
         tick(3);
-        // ---- trajectories: a slot can be folded once the child's own state M_c is complete (prog[c] >= pre[c])
+        // ---- trajectories: a slot can be folded once the child's own state M_c is complete (prog[c] >= pre[c]);
+        //      a thread descends into children that are not, to a bounded depth (then another pass)
         for (;;) {
             int* inc = a.cnt + 4 + (passes & 3);
             if (tid == 0) a.cnt[4 + ((passes + 2) & 3)] = 0;
             bool incomplete = false;
             for (int x = tid; x < R; x += nth) {
-                const int lo = a.off[x], n = a.off[x + 1] - lo;
-                int k = *(volatile int*)&a.prog[x];
-                if (k >= n) continue;
-                LscState st = lsc_fix_load(a, x, k);
-                for (; k < n; k++) {
-                    const int c = a.ch[lo + k];
-                    const int pc = a.pre[c];
-                    if (*(volatile int*)&a.prog[c] < pc) break;
+                if (*(volatile int*)&a.prog[x] >= a.off[x + 1] - a.off[x]) continue;
+                int stack[LSC_FIX_STACK];
+                int sp = 1;
+                stack[0] = x;
+                while (sp > 0) {
+                    const int n = stack[sp - 1];
+                    const int lo = a.off[n], limit = sp == 1 ? a.off[n + 1] - lo : a.pre[n];
+                    int k = *(volatile int*)&a.prog[n];
+                    if (k >= limit) { sp--; continue; }
                     __threadfence();
-                    const LscState sc = lsc_fix_load(a, c, pc);
-                    const float wsum = __fadd_rn(st.W, sc.W);
+                    LscState st = lsc_fix_load(a, n, k);
+                    bool descend = false;
+                    const int pn = a.pre[n];
+                    const bool owned = a.tg[n] >= 0;
+                    for (; k < limit; k++) {
+                        const int c = a.ch[lo + k];
+                        const int pc = a.pre[c];
+                        if (pc > 0) {                                             // (a child without earlier children brings its original state)
+                            if (*(volatile int*)&a.prog[c] < pc) {
+                                if (sp == LSC_FIX_STACK) { incomplete = true; sp = 0; }
+                                else stack[sp++] = c;
+                                descend = true;
+                                break;
+                            }
+                            __threadfence();
+                        }
+                        const LscState sc = lsc_fix_load(a, c, pc);
+                        const float wsum = __fadd_rn(st.W, sc.W);
 #pragma unroll
-                    for (int j = 0; j < LSC_MAXD; j++)
-                        if (j < D) st.c[j] = __fdiv_rn(__fadd_rn(__fmul_rn(st.c[j], st.W), __fmul_rn(sc.c[j], sc.W)), wsum);
-                    st.W = wsum; st.size += sc.size;
-                    float* p = a.S + (size_t)(lo + k) * (D + 2);
+                        for (int j = 0; j < LSC_MAXD; j++)
+                            if (j < D) st.c[j] = __fdiv_rn(__fadd_rn(__fmul_rn(st.c[j], st.W), __fmul_rn(sc.c[j], sc.W)), wsum);
+                        st.W = wsum; st.size += sc.size;
+                        float* p = a.S + (size_t)c * (D + 2);
 #pragma unroll
-                    for (int j = 0; j < LSC_MAXD; j++) if (j < D) __stcg(p + j, st.c[j]);
-                    __stcg(p + D, st.W); __stcg(p + D + 1, __int_as_float(st.size));
+                        for (int j = 0; j < LSC_MAXD; j++) if (j < D) __stcg(p + j, st.c[j]);
+                        __stcg(p + D, st.W); __stcg(p + D + 1, __int_as_float(st.size));
+                        if (owned && k + 1 == pn) { __threadfence(); atomicMax(&a.prog[n], k + 1); }      // M_n is complete: its owner may be waiting
+                    }
                     __threadfence();
-                    *(volatile int*)&a.prog[x] = k + 1;
+                    atomicMax(&a.prog[n], k);
+                    if (!descend) sp--;
                 }
-                if (k < n) incomplete = true;
             }
             if (__syncthreads_or(incomplete) && threadIdx.x == 0) *(volatile int*)inc = 1;
             lsc_grid_barrier(bar, ++epoch * nblk);
@@ -807,25 +912,24 @@ __global__ void __launch_bounds__(1024) lsc_fixpoint_kernel(LscFix a)
             if (!*(volatile int*)inc) break;                                     // uniform
         }
         tick(4);
-        // ---- candidates: every adjacency edge, seen from both ends, for every visited small region on the end's chain
-        for (int e = tid; e < 2 * a.E; e += nth) {
-            const unsigned long long key = a.edges[e >> 1];
-            const int ea = (e & 1) ? (int)(key & 0xffffffffull) : (int)(key >> 32);
-            const int eb = (e & 1) ? (int)(key >> 32) : (int)(key & 0xffffffffull);
-            int x = ea, tarr = -1;
+        // ---- candidates: member p of a small region x that is re-decided, every neighbour q of p, seen at time x
+        for (int p = tid; p < R; p += nth) {
+            int x = p, tarr = -1;
             for (;;) {
                 const int tx = a.tg[x];
-                if (x > tarr && a.smallflag[x]) {
-                    int y = eb, ty = -1;
-                    for (;;) { const int t = y < x ? a.tg[y] : -1; if (t < 0 || y <= ty) break; ty = y; y = t; }
-                    if (y != x) {
+                if (x > tarr && a.need[x]) {
+                    const LscState sx = lsc_fix_load(a, x, a.pre[x]);
+                    for (int j = a.inc_off[p]; j < a.inc_off[p + 1]; j++) {
+                        int y = a.inc[j], ty = -1;
+                        for (;;) { const int t = y < x ? a.tg[y] : -1; if (t < 0 || y <= ty) break; ty = y; y = t; }
+                        if (y == x) continue;
                         int lo = a.off[y], hi = a.off[y + 1];
                         const int base = lo;
                         while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.ch[mid] < x) lo = mid + 1; else hi = mid; }
-                        const LscState sy = lsc_fix_load(a, y, lo - base), sx = lsc_fix_load(a, x, a.pre[x]);
+                        const LscState sy = lsc_fix_load(a, y, lo - base);
                         float d = 0.f;
 #pragma unroll
-                        for (int j = 0; j < LSC_MAXD; j++) if (j < D) { const float u = __fsub_rn(sx.c[j], sy.c[j]); d = __fadd_rn(d, __fmul_rn(u, u)); }
+                        for (int jj = 0; jj < LSC_MAXD; jj++) if (jj < D) { const float u = __fsub_rn(sx.c[jj], sy.c[jj]); d = __fadd_rn(d, __fmul_rn(u, u)); }
                         const unsigned long long k2 = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)y;
                         if (k2 < a.best[x]) atomicMin(&a.best[x], k2);
                     }
@@ -838,21 +942,29 @@ __global__ void __launch_bounds__(1024) lsc_fixpoint_kernel(LscFix a)
         // ---- decisions (and the reset of the per-round arrays)
         int* chg = a.cnt + (round & 3);
         if (tid == 0) a.cnt[(round + 2) & 3] = 0;
-        bool changed = false;
+        int nchanged = 0;
         for (int x = tid; x < R; x += nth) {
-            if (a.smallflag[x]) {
+            int e = LSC_INF;
+            bool ch = false;
+            if (a.need[x]) {
                 const unsigned long long b = a.best[x];
                 const bool m = b != ~0ull && lsc_fix_size(a, x, a.pre[x]) < a.threshold;
                 const int t = m ? (int)(unsigned)(b & 0xffffffffull) : -1;
-                if (t != a.tg[x]) { changed = true; a.tg[x] = t; }
-                a.best[x] = ~0ull;
+                const int old = a.tg[x];
+                if (t != old) { nchanged++; a.tg[x] = t; a.tmp[x] = old; e = x; ch = true; }
+                a.best[x] = ~0ull; a.need[x] = 0;
             }
-            a.nch[x] = 0; a.prog[x] = 0;
+            a.eff[x] = e; a.dtau[x] = ch ? 1 : 0; a.nch[x] = 0;
         }
-        if (__syncthreads_or(changed) && threadIdx.x == 0) *(volatile int*)chg = 1;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) nchanged += __shfl_xor_sync(0xffffffffu, nchanged, d);
+        if (lane == 0 && nchanged) atomicAdd(chg, nchanged);
         lsc_grid_barrier(bar, ++epoch * nblk);
         tick(6);
-        if (!*(volatile int*)chg) { round++; break; }                            // uniform
+        const int nc = *(volatile int*)chg;                                      // uniform
+        if (full) fullrounds++;
+        if (nc == 0) { if (full) { round++; break; } full = true; }              // a full round must confirm the table
+        else full = nc > (R >> 4);
     }
     // the table is consistent now: owners are plain chains
     for (int r = tid; r < R; r += nth) {
@@ -860,7 +972,7 @@ __global__ void __launch_bounds__(1024) lsc_fixpoint_kernel(LscFix a)
         for (int t = a.tg[y]; t >= 0; t = a.tg[y]) y = t;
         a.cur[r] = y; a.alive[r] = a.tg[r] < 0 ? 1 : 0;
     }
-    if (tid == 0) { a.cnt[9] = round; a.cnt[10] = passes; for (int i = 0; i < 8; i++) a.cnt[16 + i] = (int)(tacc[i] / 1000ull); }
+    if (tid == 0) { a.cnt[9] = round; a.cnt[10] = passes; a.cnt[11] = fullrounds; for (int i = 0; i < 8; i++) a.cnt[16 + i] = (int)(tacc[i] / 1000ull); }
 }
 __global__ void lsc_post_relabel_kernel(const int* __restrict__ reg, const int* __restrict__ cur, const int* __restrict__ newid,
                                         int* __restrict__ lab, int n)
@@ -1257,6 +1369,8 @@ struct LscEngine {
                 fx.tmp = plist0; fx.ch = plist1;
                 LSC_TRY(talloc(&fx.off, (size_t)R + 1)); LSC_TRY(talloc(&fx.nch, (size_t)R)); LSC_TRY(talloc(&fx.pre, (size_t)R));
                 LSC_TRY(talloc(&fx.prog, (size_t)R)); LSC_TRY(talloc((int**)&fx.S, (size_t)R * (D + 2))); LSC_TRY(talloc(&fx.bsum, (size_t)s_sms + 1));
+                LSC_TRY(talloc(&fx.inc_off, (size_t)R + 1)); LSC_TRY(talloc(&fx.inc, (size_t)2 * E + 1)); LSC_TRY(talloc(&fx.eff, (size_t)R));
+                LSC_TRY(talloc(&fx.need, (size_t)R)); LSC_TRY(talloc(&fx.dq, (size_t)R)); LSC_TRY(talloc(&fx.dtau, (size_t)R));
                 void* args[] = {(void*)&fx};
                 LSC_TRYCUDA(cudaLaunchCooperativeKernel((const void*)lsc_fixpoint_kernel, dim3(blocks), dim3(1024), args, 0, st));
             } else {
@@ -1268,8 +1382,8 @@ struct LscEngine {
             LSC_TRYCUDA(cudaStreamSynchronize(st));
             rounds = h_pinned[0];
             if (getenv("SPX_LSC_DEBUG") && merge_order == 0)
-                fprintf(stderr, "[lsc] fixed point: %d rounds, %d trajectory passes; us per phase: count %d scan %d fill %d rank %d trajectories %d edges %d decisions %d\n",
-                        h_pinned[0], h_pinned[1], h_pinned[7], h_pinned[8], h_pinned[9], h_pinned[10], h_pinned[11], h_pinned[12], h_pinned[13]);
+                fprintf(stderr, "[lsc] fixed point: %d rounds (%d full), %d trajectory passes; us per phase: setup %d count+push %d scan %d fill+dirty %d rank+mark %d trajectories %d candidates %d decisions %d\n",
+                        h_pinned[0], h_pinned[2], h_pinned[1], h_pinned[14], h_pinned[7], h_pinned[8], h_pinned[9], h_pinned[10], h_pinned[11], h_pinned[12], h_pinned[13]);
         }
         if (getenv("SPX_LSC_DEBUG")) fprintf(stderr, "[lsc] post-pass: %d regions, %d adjacency edges (%llu raw), threshold %d, %d merge rounds, launches %lld\n", R, E, h_ec, threshold, rounds, launches);
         LSC_TRY(exclusive_sum(alive, newid, R + 1));
