@@ -1,16 +1,18 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200 superpixel engine (see the contract in DESIGN.md "Measurement").
 
-Workload (BASELINE.json metric "SLIC megapixels/sec (10 iters, 4K)"; configs[4] frame shape):
-  per GPU a batch of B distinct synthetic 3840x2160 frames (already Lab, 8UC3, resident in HBM, B*24.9 MB > L2);
-  a STEP runs, for every frame of the batch, createSuperpixelSLIC(frame, SLIC, 20, 10) [seeds + perturbation],
+Workload (BASELINE.json metric "SLIC megapixels/sec (10 iters, 4K)"; configs[4]: 1024 synthetic 4K frames sharded at 1/2/4/8):
+  a job of F = 1024 frames drawn from 16 synthetic seeds is dealt to the ranks by shard.frames_for_rank (frame i -> rank
+  i mod N, no data-path collective; STRONG scaling: the job is fixed, a rank holds F/N frame buffers, already Lab, 8UC3,
+  resident in HBM, every one its own buffer >> L2);
+  a STEP runs, for every frame of the rank's share, createSuperpixelSLIC(frame, SLIC, 20, 10) [seeds + perturbation],
   iterate(10) and getLabels into a device buffer, through the C-ABI batch entry point.
   value  = megapixels/s over all GPUs with inputs resident (device timing, max over ranks);
   e2e    = same metric through the host-buffer C-ABI calls (pinned host frames in, labels out: H2D + D2H inside);
   roofline = dominant kernel (slic assignment) : 7 B/px algorithmic / measured launch time vs measured HBM peak;
   cpu_baseline = the oracle restatement on the box's host cores, bounded sample.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--frames B]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--frames F]
 """
 import argparse
 import ctypes as C
@@ -30,6 +32,14 @@ PKG = "superpixels-segmentation-gui-opencv_b200"
 
 W4K, H4K, REGION, RULER, ITERS = 3840, 2160, 20, 10.0, 10
 METRIC = "slic_megapixels_per_sec_10iters_4k"
+JOB_FRAMES, JOB_SEEDS = 1024, 16
+WORKLOAD = ("SLIC region_size=20 ruler=10, 10 iterations, 3840x2160 synthetic frames (createSuperpixelSLIC + iterate + getLabels "
+            "per frame); job = 1024 frames from 16 seeds (BASELINE.json configs[4])")
+
+
+def job_config(frames):
+    """identical in both arms (the driver compares the two lines' config)"""
+    return {"workload": WORKLOAD, "frames": frames, "seeds": JOB_SEEDS, "l2": "every frame is its own 24.9 MB buffer: inputs larger than L2"}
 
 
 def ncu_traffic():
@@ -50,6 +60,22 @@ def ncu_traffic():
         except Exception:
             continue
     return best
+
+
+def ncu_issue():
+    """issue utilisation and executed warp-instructions of the dominant kernel from the newest committed ncu summary"""
+    import glob
+    import re
+    out = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_slic_tile_v*.txt"))):
+        txt = open(f).read()
+        a = re.search(r"smsp__issue_active.avg.pct_of_peak_sustained_active\s+([0-9.]+)", txt)
+        b = re.search(r"smsp__inst_executed.sum\s+([0-9.]+)", txt)
+        c = re.search(r"smsp__thread_inst_executed_per_inst_executed.ratio\s+([0-9.]+)", txt)
+        if a and b:
+            out = {"issue_frac": float(a.group(1)) / 100.0, "warp_inst": float(b.group(1)),
+                   "threads_per_inst": float(c.group(1)) if c else 32.0, "source": os.path.relpath(f, ROOT)}
+    return out
 
 
 def peaks():
@@ -136,20 +162,25 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     mps = W4K * H4K / 1e6 / dt
     out = {"impl": "reference", "metric": METRIC, "value": mps, "unit": "MP/s", "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+           "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "SLIC region_size=20 ruler=10, 10 iterations, 3840x2160 synthetic frame "
-                                  "(createSuperpixelSLIC + iterate + getLabels), 1 frame per step"},
+           "config": job_config(args.frames),
            "cpu_baseline": {"value": mps, "unit": "MP/s", "cores": cores, "kind": "port",
-                            "sample": "%d x one 4K frame, oracle restatement of ximgproc SLIC with OpenMP row bands" % args.steps},
+                            "sample": "bounded sample of the job: %d steps x ONE 4K frame (seed 0) each, oracle restatement of ximgproc "
+                                      "SLIC (NOT ximgproc itself: OpenCV-contrib is not installable here) with OpenMP row bands" % args.steps},
            "e2e": {"value": mps, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(out)
 
 
-def other_configs(spx, synth, L):
+def other_configs(spx, synth, L, cpu=True):
     """BASELINE.json's remaining configs on rank 0 (not bench lines: device time of iterate() with the image resident,
-    wall clock around the synchronous C-ABI calls, best of 3).  MP/s = pixels / iterate time."""
+    wall clock around the synchronous C-ABI calls, best of 3).  MP/s = pixels / iterate time.  With `cpu`, the CPU oracle
+    (kind "port": the restatement, not ximgproc) runs the same call sequence ONCE on all host threads beside it."""
     out = {}
+    O = None
+    if cpu:
+        from oracle import oracle as O
+        O.set_threads(os.cpu_count() or 1)
 
     def best(f, n=3):
         t = 1e30
@@ -157,7 +188,43 @@ def other_configs(spx, synth, L):
             t0 = time.perf_counter(); f(); t = min(t, time.perf_counter() - t0)
         return t
 
-    def slic_family(name, alg, W, H, S):
+    def once(f):
+        t0 = time.perf_counter(); r = f(); return time.perf_counter() - t0, r
+
+    # ---- configs[0]: the whole COMPUTE click (mainwindow.cpp:2096-2111) on the reference's example image, host buffers in and out
+    try:
+        import cv2
+        ex = cv2.imread(os.path.join(ROOT, "tests", "golden", "logo-absurdephoton-segmentation-image.png"), cv2.IMREAD_COLOR)
+    except Exception:
+        ex = None
+    if ex is not None:
+        def click():
+            lab = spx.cvtColor(ex, spx.COLOR_BGR2Lab)
+            s = spx.createSuperpixelSLIC(lab, spx.SLIC, 20, 10.0)
+            s.iterate(ITERS); s.enforceLabelConnectivity(25)
+            k = s.getNumberOfSuperpixels(); lab_ = s.getLabels(); m = s.getLabelContourMask(True)
+            s.release()
+            return k, lab_, m
+        click()
+        t = best(click)
+        k, gl, gm = click()
+        e = {"image": "example/logo-absurdephoton-segmentation-image.png %dx%d" % (ex.shape[1], ex.shape[0]),
+             "calls": "cvtColor(BGR2Lab) + createSuperpixelSLIC(SLIC,20,10) + iterate(10) + enforceLabelConnectivity(25) + "
+                      "getNumberOfSuperpixels + getLabels + getLabelContourMask, host buffers",
+             "click_ms": t * 1e3, "MP_s": ex.shape[0] * ex.shape[1] / 1e6 / t, "superpixels": k}
+        if O is not None:
+            def cclick():
+                lab = O.bgr2lab8(ex)
+                s = O.SuperpixelSLIC(lab, O.SLIC, 20, 10.0)
+                s.iterate(ITERS); s.enforceLabelConnectivity(25)
+                return s.getNumberOfSuperpixels(), s.getLabels(), s.getLabelContourMask(True)
+            cclick()
+            ct, (ck, cl, cm) = once(cclick)
+            e.update({"cpu_oracle_click_ms": ct * 1e3, "cpu_cores": os.cpu_count(), "cpu_kind": "port",
+                      "identical_to_cpu_oracle": bool(ck == k and (cl == gl).all() and (cm == gm).all())})
+        out["cfg1_example_S20"] = e
+
+    def slic_family(name, alg, W, H, S, cpu_alg=None):
         bgr = synth.synth(W, H, 0)[0]
         lab = spx.cvtColor(bgr, spx.COLOR_BGR2Lab)
         s = spx.createSuperpixelSLIC(lab, alg, S, RULER)
@@ -171,18 +238,40 @@ def other_configs(spx, synth, L):
         tm = best(lambda: s.getLabelContourMask(False))
         out[name] = {"iterate10_ms": t * 1e3, "MP_s": W * H / 1e6 / t, "frac_of_hbm_roofline_7B_px_iter": 70.0 * W * H / t / 1e9 / peaks()[0],
                      "contour_mask_ms_incl_d2h": tm * 1e3}
+        if O is not None and cpu_alg is not None:
+            c = O.SuperpixelSLIC(lab, cpu_alg, S, RULER)
+            ct, _ = once(lambda: c.iterate(ITERS))
+            out[name].update({"cpu_oracle_iterate10_ms": ct * 1e3, "cpu_MP_s": W * H / 1e6 / ct, "cpu_cores": os.cpu_count(), "cpu_kind": "port",
+                              "labels_identical_to_cpu_oracle": bool((c.getLabels() == s.getLabels()).all())})
         s.release()
 
     slic_family("SLIC_1080p_S20", spx.SLIC, 1920, 1080, 20)          # north-star: 1080p / 4K / 8K at one GPU
     slic_family("SLIC_4K_S20", spx.SLIC, W4K, H4K, 20)
     slic_family("SLIC_8K_S20", spx.SLIC, 7680, 4320, 20)
-    slic_family("cfg2_SLICO_4K_S25", spx.SLICO, W4K, H4K, 25)
-    slic_family("cfg3_MSLIC_8K_S30", spx.MSLIC, 7680, 4320, 30)
+    slic_family("cfg2_SLICO_4K_S25", spx.SLICO, W4K, H4K, 25, O.SLICO if O else None)
+    slic_family("cfg3_MSLIC_8K_S30", spx.MSLIC, 7680, 4320, 30, O.MSLIC if O else None)
     bgr = synth.synth(7680, 4320, 0)[0]
     lab = spx.cvtColor(bgr, spx.COLOR_BGR2Lab)
     l = spx.createSuperpixelLSC(lab, 30, 0.075)
+    t1, _ = once(lambda: (l.iterate(ITERS), l.getNumberOfSuperpixels()))
     t = best(lambda: (l.iterate(ITERS), l.getNumberOfSuperpixels()), 2)       # further iterations on the same object
-    out["cfg3_LSC_8K_S30_ratio0.075"] = {"iterate10_ms": t * 1e3, "MP_s": 7680 * 4320 / 1e6 / t}
+    e = {"iterate10_ms": t * 1e3, "first_iterate10_ms": t1 * 1e3, "MP_s": 7680 * 4320 / 1e6 / t}
+    l.release()
+    tc = []
+    for _ in range(2):                                     # the first call also grows the stream-ordered memory pool
+        l = spx.createSuperpixelLSC(lab, 30, 0.075); l.iterate(ITERS); l.getNumberOfSuperpixels()
+        tc.append(once(lambda: l.enforceLabelConnectivity(25))[0])
+        if len(tc) < 2:
+            l.release()
+    e.update({"enforce_connectivity25_ms": tc[1] * 1e3, "enforce_connectivity25_first_call_ms": tc[0] * 1e3,
+              "merge_order": "upstream raster order (default)", "superpixels": l.getNumberOfSuperpixels()})
+    if O is not None:
+        c = O.SuperpixelLSC(lab, 30, 0.075)
+        ct, _ = once(lambda: c.iterate(ITERS))
+        cc, _ = once(lambda: c.enforceLabelConnectivity(25))
+        e.update({"cpu_oracle_iterate10_ms": ct * 1e3, "cpu_oracle_enforce_connectivity25_ms": cc * 1e3, "cpu_MP_s": 7680 * 4320 / 1e6 / ct,
+                  "cpu_cores": os.cpu_count(), "cpu_kind": "port", "labels_identical_to_cpu_oracle": bool((c.getLabels() == l.getLabels()).all())})
+    out["cfg3_LSC_8K_S30_ratio0.075"] = e
     l.release()
     bgr = synth.synth(1920, 1080, 0)[0]
     lab = spx.cvtColor(bgr, spx.COLOR_BGR2Lab)
@@ -190,8 +279,57 @@ def other_configs(spx, synth, L):
     sd.iterate(lab, ITERS)
     t = best(lambda: sd.iterate(lab, ITERS))
     out["cfg4_SEEDS_1080p_2000sp_4lv_5bins"] = {"iterate10_ms_incl_h2d": t * 1e3, "MP_s": 1920 * 1080 / 1e6 / t}
+    if O is not None:
+        c = O.SuperpixelSEEDS(1920, 1080, 3, 2000, 4, 2, 5, False)       # upstream's sequential visiting order
+        ct, _ = once(lambda: c.iterate(lab, ITERS))
+        out["cfg4_SEEDS_1080p_2000sp_4lv_5bins"].update({"cpu_oracle_iterate10_ms": ct * 1e3, "cpu_MP_s": 1920 * 1080 / 1e6 / ct,
+                                                          "cpu_cores": os.cpu_count(), "cpu_kind": "port (sequential order, one thread)"})
     sd.release()
     return out
+
+
+def strip_leg(spx, dist, rank, world, local):
+    """row-strip mode (one image over all ranks of the job) on a 16384 x 16384 frame: every rank builds only its
+    band (+2 halo rows); rank 0 also runs the single-GPU object on the whole frame for the comparison.  All ranks call this."""
+    import torch
+    strips = importlib.import_module(PKG + ".strips")
+    W = H = 16384
+
+    def rows(a, b):
+        """rows [a, b) of the frame: 64 x 64 blocks of random colour xor per-row noise, the same on every rank"""
+        out = np.empty((b - a, W, 3), np.uint8)
+        for y0 in range(a - a % 64, b, 64):
+            base = np.random.default_rng(7000 + y0 // 64).integers(0, 256, (1, (W + 63) // 64, 3), dtype=np.uint8)
+            blk = np.kron(base, np.ones((64, 64, 1), np.uint8))[:, :W] ^ np.random.default_rng(9000 + y0 // 64).integers(0, 8, (64, W, 3), dtype=np.uint8)
+            lo, hi = max(a, y0), min(b, y0 + 64)
+            out[lo - a:hi - a] = blk[lo - y0:hi - y0]
+        return out
+
+    res = {}
+    for it in range(2):                                    # the first object warms kernels, peer mappings and NCCL up
+        s = strips.StripSLIC(rows, 20, 10.0, dist, local, width=W, height=H, exchange="peer")
+        if it == 0:
+            s.iterate(1); s.release(); continue
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter(); s.iterate(ITERS); torch.cuda.synchronize(); dist.barrier(); t = time.perf_counter() - t0
+        tt = torch.tensor([t], dtype=torch.float64, device=torch.device("cuda", local))
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        labels = s.getLabels()                             # assembled on rank 0
+        res = {"image": "16384x16384 synthetic (64x64 colour blocks xor noise), SLIC S=20 ruler=10, 10 iterations", "n_gpus": world,
+               "strip_iterate10_ms": float(tt.item()) * 1e3, "MP_s": W * H / 1e6 / float(tt.item()),
+               "sent_bytes_per_rank_per_iteration": s.exchangedBytes() / ITERS, "exchange": "NVLink peer stores + flags (library kernels)",
+               "superpixels": s.getNumberOfSuperpixels()}
+        s.release()
+    if rank == 0:
+        img = rows(0, H)
+        g = spx.createSuperpixelSLIC(img, spx.SLIC, 20, 10.0, device=local)
+        spx.lib().spx_slic_synchronize(g._h)
+        t0 = time.perf_counter(); g.iterate(ITERS); spx.lib().spx_slic_synchronize(g._h); t1 = time.perf_counter() - t0
+        res.update({"single_gpu_iterate10_ms": t1 * 1e3, "speedup_vs_one_gpu": t1 * 1e3 / res["strip_iterate10_ms"],
+                    "labels_identical": bool((g.getLabels() == labels).all())})
+        g.release()
+    dist.barrier()
+    return res
 
 
 def bind_to_gpu_numa_node(index):
@@ -243,20 +381,22 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    B = args.frames
+    shard = importlib.import_module(PKG + ".shard")
+    F = args.frames
+    mine = shard.frames_for_rank(F, rank, world)          # frame i -> rank i mod world; no data-path collective
+    B = len(mine)
     npx = W4K * H4K
 
-    # ---- inputs: B distinct device-resident Lab frames (distinct buffers: B * 24.9 MB >> 126 MB L2)
-    distinct = make_frames(synth, args.distinct)
-    frames_host = []
-    frames_dev = []
-    for i in range(B):
-        bgr = distinct[(i + rank) % len(distinct)]
-        t = torch.from_numpy(bgr).to(dev)
+    # ---- inputs: the rank's share of the job, every frame in its own device buffer (B * 24.9 MB >> 126 MB L2), already Lab
+    seeds_dev = {}
+    for sd in sorted({i % JOB_SEEDS for i in mine}):
+        t = torch.from_numpy(synth.synth(W4K, H4K, sd)[0]).to(dev)
         rc = L.spx_bgr2lab8_dev(t.data_ptr(), W4K * 3, t.data_ptr(), W4K * 3, W4K, H4K, None)
         assert rc == 0, L.spx_last_error()
-        frames_dev.append(t)
+        seeds_dev[sd] = t
     torch.cuda.synchronize()
+    frames_dev = [seeds_dev[i % JOB_SEEDS].clone() for i in mine]
+    frames_host = []
     n_host = min(B, args.e2e_frames)
     for i in range(n_host):
         frames_host.append(frames_dev[i].cpu().pin_memory())
@@ -269,39 +409,46 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    launches = [0]
+    def timed_batch(fp, lp, steps, warmup, sample_clocks):
+        """`steps` passes over the given frames through the C-ABI batch call: (seconds = max over ranks, launches of all ranks, wall, clocks)"""
+        n_l = [0]
 
-    def step():
-        launches[0] += spx.slic_batch_dev(fptr, W4K, H4K, 3, spx.SLIC, REGION, RULER, ITERS, 0, lptr, None, False,
-                                          args.streams)
+        def step():
+            n_l[0] += spx.slic_batch_dev(fp, W4K, H4K, 3, spx.SLIC, REGION, RULER, ITERS, 0, lp, None, False, args.streams)
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    launches[0] = 0
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()          # blocks until the batch is done on the library's streams
-    e1.record()
-    barrier()
-    wall = time.perf_counter() - t0
-    ev_ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    el = torch.tensor([max(ev_ms / 1e3, 0.0)], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(el, op=dist.ReduceOp.MAX)
-    elapsed = float(el.item())
-    value = world * B * args.steps * npx / 1e6 / elapsed
-    nl = torch.tensor([float(launches[0])], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(nl, op=dist.ReduceOp.SUM)          # kernels launched by all ranks inside the timed region
-    total_launches = int(nl.item())
+        for _ in range(warmup):
+            step()
+        barrier()
+        sampler = ClockSampler(local)
+        if sample_clocks and rank == 0:
+            sampler.start()
+        n_l[0] = 0
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()          # blocks until the batch is done on the library's streams
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ev_ms = e0.elapsed_time(e1)
+        clk = sampler.stop() if sample_clocks and rank == 0 else None
+        el = torch.tensor([max(ev_ms / 1e3, 0.0)], device=dev, dtype=torch.float64)
+        nl = torch.tensor([float(n_l[0])], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(el, op=dist.ReduceOp.MAX)
+            dist.all_reduce(nl, op=dist.ReduceOp.SUM)      # kernels launched by all ranks inside the timed region
+        return float(el.item()), int(nl.item()), wall, clk
+
+    elapsed, total_launches, wall, clocks = timed_batch(fptr, lptr, args.steps, args.warmup, True)
+    value = F * args.steps * npx / 1e6 / elapsed
+    # the round-1 line for comparison: fixed work per GPU (weak scaling), 32 frames per GPU and step
+    weak = None
+    if B >= 32 and not args.no_other_configs:
+        w_el, _, _, _ = timed_batch(fptr[:32], lptr[:32], 10, 3, False)
+        weak = {"value": world * 32 * 10 * npx / 1e6 / w_el, "unit": "MP/s", "frames_per_gpu_per_step": 32, "ms_per_step": w_el / 10 * 1e3,
+                "scaling": "weak"}
 
     # ---- e2e: host buffers in, host labels out, through the reference-facing calls (H2D + D2H timed)
     n_thr = min(args.e2e_threads, n_host)
@@ -375,7 +522,11 @@ def run_ours(args):
         L.spx_slic_destroy(h)
         alg_bytes = 7.0 * npx                      # per assignment launch: 3 B Lab read + 4 B label write per pixel
         achieved = alg_bytes / (kms.value * 1e-3) / 1e9
+        iss = ncu_issue() or {}
         roof = {"bound": "hbm", "kernel": "slic_assign (fused assignment + centre accumulation)",
+                # the real limiter (instruction issue), from the committed ncu --set full capture of this kernel
+                "issue_frac": iss.get("issue_frac"), "issue_source": iss.get("source"),
+                "inst_per_px": (iss["warp_inst"] * iss["threads_per_inst"] / npx) if iss else None,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (ncu_traffic() or {}).get("bytes"), "traffic_source": (ncu_traffic() or {}).get("source"),
                 "peak_source": peak_src, "kernel_ms": kms.value, "kernel_ms_l2_warm": kms_warm.value,
@@ -387,7 +538,8 @@ def run_ours(args):
         from oracle import oracle as O
         cores = os.cpu_count() or 1
         O.set_threads(cores)
-        lab0 = frames_host[0].numpy()
+        i_last = max(i for i in range(0, n_host, n_thr))          # the frame whose labels thread 0 left in host_labels[0]
+        lab0 = frames_host[i_last].numpy()
         t0 = time.perf_counter()
         nb = 2
         for _ in range(nb):
@@ -398,17 +550,23 @@ def run_ours(args):
                "label_agreement_vs_gpu": float((ol == e2e_ref_labels).mean())}
 
     other = None
+    strip = None
+    if world > 1 and not args.no_other_configs and not args.no_strip:
+        strip = strip_leg(spx, dist, rank, world, local)                    # all ranks: one 16384^2 frame in row strips
     if rank == 0 and not args.no_other_configs:
-        other = other_configs(spx, synth, L)
+        other = other_configs(spx, synth, L, cpu=not args.no_cpu_other)
+        if strip:
+            other["strip_16k"] = strip
 
     if rank == 0:
+        if other is not None and weak is not None:
+            other["weak_32_frames_per_gpu"] = weak
         out = {"metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic",
-               "config": {"workload": "SLIC region_size=20 ruler=10, 10 iterations, 3840x2160 synthetic frames "
-                                      "(createSuperpixelSLIC + iterate + getLabels per frame)",
-                          "frames_per_gpu_per_step": B, "streams": args.streams,
-                          "l2": "inputs larger than L2: %d distinct frame buffers = %.0f MB per GPU" % (B, B * npx * 3 / 1e6)},
+               "config": job_config(F),
+               "run": {"frames_per_step": F, "frames_per_gpu_per_step": shard.shard_sizes(F, world), "sharding": "shard.frames_for_rank: frame i -> rank i mod N",
+                       "streams": args.streams, "device_frame_bytes_per_gpu": B * npx * 3},
                "frames_per_sec": value * 1e6 / npx,
                "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": n_host * npx * 3,
                        "d2h_bytes_per_step": n_host * npx * 4, "frames": n_host, "threads": n_thr,
@@ -444,8 +602,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=32, help="frames per GPU per step")
-    ap.add_argument("--distinct", type=int, default=4, help="distinct synthetic frames generated (cycled)")
+    ap.add_argument("--frames", type=int, default=JOB_FRAMES, help="frames of the whole job per step (dealt to the ranks)")
     ap.add_argument("--streams", type=int, default=8, help="pooled engines (streams) per GPU: 2: 12.9, 4: 14.5, 8: 15.0, 16: 15.0 GP/s")
     ap.add_argument("--e2e-frames", type=int, default=16)
     ap.add_argument("--e2e-reps", type=int, default=4)
@@ -453,6 +610,8 @@ def main():
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to the CPUs of its GPU's NUMA node")
     ap.add_argument("--blocking-sync", action="store_true", help="host threads sleep while waiting for the device (spx_set_blocking_sync)")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the extra (non-headline) configs on rank 0")
+    ap.add_argument("--no-cpu-other", action="store_true", help="other configs without their CPU-oracle timings")
+    ap.add_argument("--no-strip", action="store_true", help="N > 1: skip the row-strip leg (one 16384^2 frame over all ranks)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -33,9 +33,9 @@ int PostWorkspace::alloc(int w_, int h_, cudaStream_t st)
     SPX_CHECK(pool_alloc((void**)&newid, N * sizeof(int), st));
     SPX_CHECK(pool_alloc((void**)&link, N * sizeof(int), st));
     SPX_CHECK(pool_alloc((void**)&blocksum, (N / 1024 + 2) * sizeof(int), st));
-    SPX_CHECK(pool_alloc((void**)&flag, 8 * sizeof(int), st));
+    SPX_CHECK(pool_alloc((void**)&flag, 16 * sizeof(int), st));
     SPX_CHECK(pool_alloc((void**)&diff, N, st));
-    SPX_CUDA(cudaMallocHost(&h_flag, 8 * sizeof(int)));
+    SPX_CUDA(cudaMallocHost(&h_flag, 16 * sizeof(int)));
     return SPX_OK;
 }
 void PostWorkspace::release()
@@ -434,6 +434,252 @@ __global__ void __launch_bounds__(1024) contour_sweeps_kernel(const unsigned cha
     }
 }
 
+// ---- the same recurrence, row by row, as a PREFIX COMPOSITION (the shipped form for widths up to 8192) ----------------
+// Step 1, fully parallel (contour_pre_kernel): per pixel one byte = popc(diff) << 4 | causal difference bits (W, NW, N, NE).
+// Step 2 (contour_band_kernel): once the row above is known, pixel x of a row is one of three functions of its west flag:
+//     c = popc(diff) - #{NW, N, NE differ and are taken};   no west difference: t = [c > lw]   (constant)
+//     west differs: c > lw+1 -> 1, c <= lw -> 0 (constants), c == lw+1 -> t = NOT t(x-1)
+// Functions {0, 1, NOT, ID} are closed under composition (2 bits: f(0) | f(1) << 1), and a composition is "the last constant,
+// flipped once per NOT after it": a thread composes its P pixels, a warp resolves its 32 threads with three ballots, the CTA
+// its warps the same way from one word per warp in shared memory (total function and the function of the warp's first
+// pixel) -- ONE barrier per row: the flag left of a thread is its carry-in, the flag right of a warp follows from the
+// neighbour's first-pixel function and the warp's own carry-out.  The pre bytes arrive through a private cp.async ring.
+// Rows stay sequential, so the image is cut into horizontal BANDS, one CTA each, all co-resident (cooperative launch).  A
+// band needs the flags of the row above it: round 0 starts `warm` rows early from all-zero flags (errors of the guess die
+// out within a few rows) and remembers which flags of the row above it used; after a grid-wide barrier every band compares
+// them with what the band above really produced and, if they differ, recomputes from the true row -- repeated until a round
+// recomputes nothing.  The recurrence only looks backwards, so that fixed point is unique: the result is upstream's
+// sequential scan, bit for bit.
+constexpr int CB_THREADS = 1024;
+constexpr int CB_WARM = 8;
+constexpr int CB_MAXW = 8192;
+constexpr int CB_AHEAD = 4;                 // rows of pre bytes in flight (cp.async); ring of CB_AHEAD + 1 rows in shared memory
+constexpr int CB_RING = CB_AHEAD + 1;
+struct ContourBand {
+    const unsigned char* pre; size_t pp;    // packed per-pixel byte, pitch pp (multiple of 16)
+    int w, h, lw;
+    unsigned char* mask; size_t mp;
+    unsigned char* halo;          // [bands][w] flags of the row above each band that its current rows were computed from
+    int rows; int bands; int warm;
+    unsigned* bar; int* cnt;      // cnt[0..2]: bands recomputed in round r, by r % 3; cnt[3..4]: diagnostics
+};
+// 4 pixels per thread: three label rows (one 16-byte load each where aligned, the two outer neighbours as scalar loads that
+// hit L1) -> 4 packed bytes.  Measured alternatives: outer neighbours by shuffle 29 us, 4 rows per thread rolling 29 us, this 23 us.
+__global__ void __launch_bounds__(256) contour_pre_kernel(const int* __restrict__ lab, int lp, int w, int h, unsigned char* __restrict__ pre, size_t pp, int vec)
+{
+    const int x0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x), y = blockIdx.y;
+    if (x0 >= w) return;
+    int R[3][6];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        const int yy = min(max(y - 1 + r, 0), h - 1);
+        const int* row = lab + (size_t)yy * lp;
+        if (vec && x0 + 4 <= w) {
+            const int4 v = __ldg(reinterpret_cast<const int4*>(row + x0));
+            R[r][1] = v.x; R[r][2] = v.y; R[r][3] = v.z; R[r][4] = v.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) R[r][1 + j] = __ldg(row + min(x0 + j, w - 1));
+        }
+        R[r][0] = __ldg(row + max(x0 - 1, 0));
+        R[r][5] = __ldg(row + min(x0 + 4, w - 1));
+    }
+    unsigned rowmask = 0xffu;
+    if (y == 0) rowmask &= ~(2u | 4u | 8u);
+    if (y == h - 1) rowmask &= ~(32u | 64u | 128u);
+    unsigned out = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int x = x0 + j;
+        const int me = R[1][j + 1];
+        unsigned d = (R[1][j] != me ? 1u : 0u) | (R[0][j] != me ? 2u : 0u) | (R[0][j + 1] != me ? 4u : 0u) | (R[0][j + 2] != me ? 8u : 0u) |
+                     (R[1][j + 2] != me ? 16u : 0u) | (R[2][j + 2] != me ? 32u : 0u) | (R[2][j + 1] != me ? 64u : 0u) | (R[2][j] != me ? 128u : 0u);
+        unsigned vm = rowmask;
+        if (x == 0) vm &= ~(1u | 2u | 128u);
+        if (x == w - 1) vm &= ~(8u | 16u | 32u);
+        d &= vm;
+        if (x >= w) d = 0;
+        out |= (((unsigned)__popc(d) << 4) | (d & 15u)) << (8 * j);
+    }
+    *reinterpret_cast<unsigned*>(pre + (size_t)y * pp + x0) = out;
+}
+__device__ __forceinline__ unsigned cb_compose(unsigned later, unsigned earlier)
+{
+    // table over (later << 2 | earlier): constants absorb, ID passes, NOT swaps the two bits of `earlier`
+    //   later 0 -> 0, 3 -> 3, 2 (ID) -> earlier, 1 (NOT) -> {0->3, 1->2, 2->1, 3->0}
+    return (0xFFE41B00u >> (2u * ((later << 2) | earlier))) & 3u;
+}
+__device__ __forceinline__ void cb_cp4(void* smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cb_cp8(void* smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cb_cp16(void* smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cb_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cb_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// "the last constant, flipped once per NOT after it" over the entries strictly below position `pos`; none: cin flipped
+__device__ __forceinline__ unsigned cb_resolve(unsigned mc, unsigned mv, unsigned mn, int pos, unsigned cin)
+{
+    const unsigned below = pos >= 32 ? 0xffffffffu : (1u << pos) - 1u;
+    const unsigned lc = mc & below;
+    if (lc) { const int p = 31 - __clz(lc); return ((mv >> p) & 1u) ^ (__popc(mn & below & ~((2u << p) - 1u)) & 1u); }
+    return cin ^ (__popc(mn & below) & 1u);
+}
+// rows [ya, yb) of the band; rows < ystore are warm-up (computed, not stored).  On entry sflag (w + 2 bytes, x shifted by
+// one, zero at both ends) holds the flags of row ya-1.  All threads of the CTA call; warps without pixels leave at once.
+template <int P, int T>
+__device__ void cb_rows(const ContourBand& a, int ya, int yb, int ystore, int yhalo, unsigned char* halo_out,
+                        const unsigned char* sflag, unsigned* ring, unsigned* pub)
+{
+    constexpr int WPT = P / 4;                                      // words per thread and row
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = tid * P;
+    const int nw = (a.w + 32 * P - 1) / (32 * P);                   // warps that own pixels
+    if (warp >= nw) return;
+    const int nthr = nw * 32;
+    const bool active = x0 < a.w;
+    auto fetch = [&](int y) {
+        if (active && y < a.h) {
+            unsigned* dst = ring + ((size_t)(y % CB_RING) * T + tid) * WPT;
+            const unsigned char* src = a.pre + (size_t)y * a.pp + x0;
+            if (WPT == 1) cb_cp4(dst, src); else if (WPT == 2) cb_cp8(dst, src); else cb_cp16(dst, src);
+        }
+        cb_commit();
+    };
+#pragma unroll
+    for (int k = 0; k < CB_AHEAD; k++) fetch(ya + k);
+    // flags of row ya-1 at x0-1 .. x0+P
+    unsigned fl = 0;
+#pragma unroll
+    for (int j = 0; j < P + 2; j++) fl |= (x0 + j < a.w + 2 && sflag[x0 + j] ? 1u : 0u) << j;
+    for (int y = ya; y < yb; y++) {
+        fetch(y + CB_AHEAD);                                        // into the slot of row y-1
+        cb_wait<CB_AHEAD>();                                        // row y has landed
+        unsigned pw[WPT];
+        {
+            const unsigned* src = ring + ((size_t)(y % CB_RING) * T + tid) * WPT;
+#pragma unroll
+            for (int q = 0; q < WPT; q++) pw[q] = active ? src[q] : 0u;
+        }
+        unsigned codes = 0, tot = 2u;                               // ID
+#pragma unroll
+        for (int j = 0; j < P; j++) {
+            const unsigned byte = (pw[j >> 2] >> (8 * (j & 3))) & 0xffu;
+            // k = clamp(c - lw, 0, 2) with c = popc(diff) - taken causal-above neighbours; (k, west bit) -> function:
+            // k = 0 -> 0; k = 1 -> west ? NOT : 1; k = 2 -> 1   (popc(diff) <= lw implies k = 0)
+            const int k = min(max((int)(byte >> 4) - a.lw - __popc((byte >> 1) & (fl >> j) & 7u), 0), 2);
+            unsigned f = (0xF70u >> (2u * (2u * (unsigned)k + (byte & 1u)))) & 3u;
+            if (x0 + j >= a.w) f = 2u;                              // beyond the row: transparent
+            codes |= f << (2 * j);
+            tot = cb_compose(f, tot);
+        }
+        const unsigned mc = __ballot_sync(0xffffffffu, tot == 0u || tot == 3u);
+        const unsigned mv = __ballot_sync(0xffffffffu, tot == 3u);
+        const unsigned mn = __ballot_sync(0xffffffffu, tot == 1u);
+        unsigned* prow = pub + (y & 1) * 32;
+        if (lane == 0) {
+            unsigned wt;                                            // the warp's total function
+            if (mc) { const int p = 31 - __clz(mc); wt = (((mv >> p) & 1u) ^ (__popc(mn & ~((2u << p) - 1u)) & 1u)) ? 3u : 0u; }
+            else wt = (__popc(mn) & 1) ? 1u : 2u;
+            prow[warp] = wt | ((codes & 3u) << 2);
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+        const unsigned rec = lane < nw ? prow[lane] : 2u;
+        const unsigned wt_ = rec & 3u;
+        const unsigned wc = __ballot_sync(0xffffffffu, wt_ == 0u || wt_ == 3u);
+        const unsigned wvv = __ballot_sync(0xffffffffu, wt_ == 3u);
+        const unsigned wn = __ballot_sync(0xffffffffu, wt_ == 1u);
+        const unsigned cw = cb_resolve(wc, wvv, wn, warp, 0u);      // carry into this warp = flag left of its first pixel
+        unsigned t = cb_resolve(mc, mv, mn, lane, cw);              // carry into this thread = flag of pixel x0-1
+        const unsigned left = t;
+        unsigned bits = 0;
+#pragma unroll
+        for (int j = 0; j < P; j++) { t = (codes >> (2 * j + t)) & 1u; bits |= t << j; }
+        if (!active) bits = 0;
+        else if (a.w - x0 < P) bits &= (1u << (a.w - x0)) - 1u;
+        if (active) {
+            const int n = min(P, a.w - x0);
+            if (y >= ystore) {
+                unsigned char* mo = a.mask + (size_t)y * a.mp + x0;
+                if (n == P && (((uintptr_t)mo) & 3u) == 0) {
+#pragma unroll
+                    for (int q = 0; q < WPT; q++) {
+                        const unsigned b4 = bits >> (4 * q);
+                        reinterpret_cast<unsigned*>(mo)[q] = ((b4 & 1u) ? 0xffu : 0u) | ((b4 & 2u) ? 0xff00u : 0u) | ((b4 & 4u) ? 0xff0000u : 0u) | ((b4 & 8u) ? 0xff000000u : 0u);
+                    }
+                } else {
+                    for (int j = 0; j < n; j++) mo[j] = (bits >> j) & 1u ? 255 : 0;
+                }
+            }
+            if (y == yhalo) for (int j = 0; j < n; j++) halo_out[x0 + j] = (unsigned char)((bits >> j) & 1u);
+        }
+        // flags of this row at x0-1 .. x0+P for the next one
+        unsigned right = __shfl_down_sync(0xffffffffu, bits & 1u, 1);
+        const unsigned recn = __shfl_sync(0xffffffffu, rec, (warp + 1) & 31);
+        if (lane == 31) {
+            const unsigned cnext = cb_resolve(wc, wvv, wn, warp + 1, 0u);                  // carry out of this warp
+            right = warp + 1 < nw ? ((recn >> 2) >> cnext) & 1u : 0u;
+        }
+        fl = left | (bits << 1) | (right << (P + 1));
+    }
+    cb_wait<0>();
+}
+template <int P, int T>
+__global__ void __launch_bounds__(T, T == 512 ? 2 : 1) contour_band_kernel(ContourBand a)
+{
+    extern __shared__ unsigned char cb_smem[];
+    __shared__ unsigned pub[2 * 32];
+    __shared__ int s_diff;
+    unsigned char* sflag = cb_smem;
+    const int fw = a.w + 2;
+    unsigned* ring = reinterpret_cast<unsigned*>(cb_smem + ((fw + 15) & ~15));
+    const int b = blockIdx.x;
+    const int y0 = b * a.rows, y1 = min(y0 + a.rows, a.h);
+    const unsigned nblk = gridDim.x;
+    unsigned char* myhalo = a.halo + (size_t)b * a.w;
+    // ---- round 0: start `warm` rows early from all-zero flags
+    {
+        const int ya = max(y0 - a.warm, 0);
+        for (int i = threadIdx.x; i < fw; i += T) sflag[i] = 0;
+        __syncthreads();
+        cb_rows<P, T>(a, ya, y1, y0, y0 - 1, myhalo, sflag, ring, pub);
+    }
+    contour_grid_barrier(a.bar, nblk);
+    for (unsigned round = 1;; round++) {
+        int* cnt = a.cnt + round % 3;
+        if (b == 0 && threadIdx.x == 0) a.cnt[(round + 1) % 3] = 0;
+        if (b > 0) {
+            // the flags this band's rows were computed from against the row above as it stands now (one snapshot, through L2)
+            if (threadIdx.x == 0) { s_diff = 0; sflag[0] = 0; sflag[fw - 1] = 0; }
+            __syncthreads();
+            const unsigned char* trow = a.mask + (size_t)(y0 - 1) * a.mp;
+            bool differ = false;
+            for (int x = threadIdx.x; x < a.w; x += T) {
+                const unsigned char v = __ldcg(trow + x) ? 1 : 0;
+                sflag[x + 1] = v;
+                differ |= v != __ldcg(myhalo + x);
+            }
+            if (differ) s_diff = 1;
+            __syncthreads();
+            if (s_diff) {                                           // uniform
+                for (int x = threadIdx.x; x < a.w; x += T) myhalo[x] = sflag[x + 1];
+                if (threadIdx.x == 0) atomicAdd(cnt, 1);
+                cb_rows<P, T>(a, y0, y1, y0, -2, myhalo, sflag, ring, pub);
+            }
+        }
+        contour_grid_barrier(a.bar, (round + 1) * nblk);
+        const int redone = *(volatile int*)cnt;
+        if (b == 0 && threadIdx.x == 0) { a.cnt[3] = (int)round; a.cnt[4] += redone; }     // diagnostics: rounds, bands recomputed
+        if (redone == 0) break;
+    }
+}
+
 int contour_mask_dev(PostWorkspace& ws, const int* d_labels, int lp, int thick_line, int flavour,
                      unsigned char* d_mask, size_t mp, cudaStream_t st)
 {
@@ -446,15 +692,51 @@ int contour_mask_dev(PostWorkspace& ws, const int* d_labels, int lp, int thick_l
         return SPX_OK;
     }
     int lw = flavour == 1 ? 1 : (thick_line ? 2 : 1);
-    contour_diff_kernel<0><<<g2, b2, 0, st>>>(d_labels, lp, w, h, ws.diff, d_mask, mp, 0);
-    SPX_CUDA(cudaMemsetAsync(ws.flag + 4, 0, 4 * sizeof(int), st));        // barrier counter + 3 change flags
-    // persistent grid: one CTA of 1024 threads per SM (the in-kernel barrier needs all of them running: cooperative launch)
     static int s_sms = 0;
     if (!s_sms) {
         int dev = 0;
         SPX_CUDA(cudaGetDevice(&dev));
         SPX_CUDA(cudaDeviceGetAttribute(&s_sms, cudaDevAttrMultiProcessorCount, dev));
     }
+    if (w <= CB_MAXW && (((size_t)w + 15) & ~(size_t)15) * (size_t)h <= (size_t)w * h * sizeof(int) && !getenv("SPX_CONTOUR_SWEEPS")) {
+        // row recurrence by prefix composition, one CTA per band of rows (see contour_band_kernel)
+        ContourBand cb{};
+        const size_t pp = ((size_t)w + 15) & ~(size_t)15;
+        unsigned char* pre = reinterpret_cast<unsigned char*>(ws.newid);          // pp * h bytes <= 4 N (scratch of the connectivity pass)
+        const int vecl = (lp % 4 == 0 && ((uintptr_t)d_labels & 15u) == 0) ? 1 : 0;
+        contour_pre_kernel<<<dim3(cdiv(cdiv(w, 4), 256), h), 256, 0, st>>>(d_labels, lp, w, h, pre, pp, vecl);
+        cb.pre = pre; cb.pp = pp; cb.w = w; cb.h = h; cb.lw = lw; cb.mask = d_mask; cb.mp = mp;
+        cb.halo = ws.diff;                                   // bands * w bytes <= N
+        cb.warm = lw >= 2 ? 12 : CB_WARM;
+        int T = 512;                                         // two CTAs per SM: their row phases interleave
+        if (getenv("SPX_CB_T")) T = atoi(getenv("SPX_CB_T")) == 1024 ? 1024 : 512;
+        const int ctas = s_sms * (T == 512 ? 2 : 1);
+        cb.rows = std::max(16, cdiv(h, ctas));                // (8 rows + 8 warm-up rows per band measured slower: 48 vs 41 us at 4K)
+        if (getenv("SPX_CB_WARM")) cb.warm = atoi(getenv("SPX_CB_WARM"));
+        if (getenv("SPX_CB_ROWS")) cb.rows = std::max(cdiv(h, ctas), atoi(getenv("SPX_CB_ROWS")));
+        cb.bands = cdiv(h, cb.rows);
+        SPX_CUDA(cudaMemsetAsync(ws.flag + 4, 0, 6 * sizeof(int), st));    // barrier counter + 3 round counters + 2 diagnostics
+        cb.bar = reinterpret_cast<unsigned*>(ws.flag + 4); cb.cnt = ws.flag + 5;
+        const int P = w > 8 * T ? 16 : (w > 4 * T ? 8 : 4);
+        const void* fn = T == 1024 ? (P == 8 ? (const void*)contour_band_kernel<8, 1024> : (const void*)contour_band_kernel<4, 1024>)
+                                   : (P == 16 ? (const void*)contour_band_kernel<16, 512> : P == 8 ? (const void*)contour_band_kernel<8, 512>
+                                                                                                     : (const void*)contour_band_kernel<4, 512>);
+        void* args[] = {(void*)&cb};
+        const size_t smem = (((size_t)(w + 2) + 15) & ~(size_t)15) + (size_t)CB_RING * T * P;
+        if (smem > 48 * 1024) SPX_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SPX_CUDA(cudaLaunchCooperativeKernel(fn, dim3(cb.bands), dim3(T), args, smem, st));
+        ws.launches += 2;
+        SPX_CUDA(cudaGetLastError());
+        if (getenv("SPX_CONTOUR_DEBUG")) {
+            SPX_CUDA(cudaMemcpyAsync(ws.h_flag + 8, ws.flag + 8, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            SPX_CUDA(cudaStreamSynchronize(st));
+            fprintf(stderr, "[contour] %dx%d lw %d: %d bands of %d rows, %d rounds, %d bands recomputed\n", w, h, lw, cb.bands, cb.rows, ws.h_flag[8], ws.h_flag[9]);
+        }
+        return SPX_OK;
+    }
+    contour_diff_kernel<0><<<g2, b2, 0, st>>>(d_labels, lp, w, h, ws.diff, d_mask, mp, 0);
+    SPX_CUDA(cudaMemsetAsync(ws.flag + 4, 0, 4 * sizeof(int), st));        // barrier counter + 3 change flags
+    // persistent grid: one CTA of 1024 threads per SM (the in-kernel barrier needs all of them running: cooperative launch)
     const int runs = cdiv(w, CT_RUN) * h;
     int blocks = std::min(cdiv(runs, 1024), s_sms);
     if (blocks < 1) blocks = 1;
