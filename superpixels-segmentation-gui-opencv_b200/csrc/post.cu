@@ -34,7 +34,7 @@ int PostWorkspace::alloc(int w_, int h_, cudaStream_t st)
     SPX_CHECK(pool_alloc((void**)&link, N * sizeof(int), st));
     SPX_CHECK(pool_alloc((void**)&blocksum, (N / 1024 + 2) * sizeof(int), st));
     SPX_CHECK(pool_alloc((void**)&flag, 16 * sizeof(int), st));
-    SPX_CHECK(pool_alloc((void**)&diff, N, st));
+    SPX_CHECK(pool_alloc((void**)&diff, N + 64, st));       // (+64: the bitmap and prefix words of a tiny image)
     SPX_CUDA(cudaMallocHost(&h_flag, 16 * sizeof(int)));
     return SPX_OK;
 }
@@ -69,12 +69,20 @@ __device__ __forceinline__ void uf_unite(int* P, int a, int b)
     } while (!done);
 }
 
-// Block-local union-find first (shared memory), global unions only along tile borders:
-//   ccl_local_kernel   32x32 tile per CTA of 256 threads (a warp = one tile row at a time, 4 rows per thread): parent = head of the horizontal run
-//                      (one ballot), vertical unions inside the tile with shared-memory atomicMin (skipped when the left
-//                      neighbour already carries the same union), flatten, P[i] = global index of the local root.  The local
-//                      root is the tile's smallest raster index of the component, so global roots stay "smallest raster index".
+// Block-local union-find first (shared memory), global unions only along tile borders, and after that everything works on the
+// (few) LOCAL ROOTS instead of on pixels:
+//   ccl_local_kernel   32x32 tile per CTA of 256 threads (a warp = one tile row at a time, 4 rows per thread): parent = head of the
+//                      horizontal run (one ballot), vertical unions inside the tile with shared-memory atomicMin (skipped when the
+//                      left neighbour already carries the same union), pointer jumping until every pixel points at its local root
+//                      (= the tile's smallest raster index of the component, so global roots stay "smallest raster index"),
+//                      pixel counts per local root (warp-aggregated), P[i] = global index of the local root; the local roots go
+//                      to a compact list with their counts.
 //   ccl_border_kernel  unions across tile borders (top row with the row above, left column with the column to the left).
+//   ccl_roots_kernel   list: local root -> global root (flattened), its count added to the global root's size.
+//   ccl_keep_kernel    list: global roots: kept (size > min) -> one bit in a raster-order bitmap; small -> its link.
+//   bitmap scan        new id of a kept root = number of kept roots before it in raster order = prefix popcount (a 1 MB scan at 4K
+//                      instead of two passes over the 33 MB parent array).
+//   ccl_relabel_kernel pixel -> local root -> global root -> (links while small) -> prefix popcount.
 constexpr int CT = 32;
 __device__ __forceinline__ int sm_find(const int* P, int a)
 {
@@ -82,11 +90,17 @@ __device__ __forceinline__ int sm_find(const int* P, int a)
     while (p != a) { a = p; p = P[a]; }
     return a;
 }
+// The pixel counts come from the runs of equal local root along a tile row (the head of a run adds the run's length: one shared
+// atomic per run, not per pixel); root pixels append themselves to the list, one global atomic per warp row that holds any.
 __global__ void __launch_bounds__(256) ccl_local_kernel(const int* __restrict__ lab, int lp, int w, int h, int* __restrict__ P,
-                                                        int* __restrict__ csize)
+                                                        int* __restrict__ csize, int* __restrict__ roots, int* __restrict__ nroots)
 {
     __shared__ int sl[CT][CT + 1];
     __shared__ int sp[CT * CT];
+    __shared__ int sc[CT * CT];
+    __shared__ int s_roots[CT * CT];
+    __shared__ int s_n, s_base;
+    if (threadIdx.x == 0) s_n = 0;
     const int lx = threadIdx.x & 31, ly0 = threadIdx.x >> 5;             // 8 warps; warp q owns tile rows q, q+8, q+16, q+24
     const int x = blockIdx.x * CT + lx;
     int me[4];
@@ -100,6 +114,7 @@ __global__ void __launch_bounds__(256) ccl_local_kernel(const int* __restrict__ 
     for (int k = 0; k < 4; k++) {
         const int ly = ly0 + 8 * k;
         sl[ly][lx] = me[k];
+        sc[ly * CT + lx] = 0;
         prev[k] = __shfl_up_sync(0xffffffffu, me[k], 1);
         const unsigned heads = __ballot_sync(0xffffffffu, lx == 0 || prev[k] != me[k]) & (0xffffffffu >> (31 - lx));
         sp[ly * CT + lx] = ly * CT + lx - (lx - (31 - __clz(heads)));
@@ -120,14 +135,48 @@ __global__ void __launch_bounds__(256) ccl_local_kernel(const int* __restrict__ 
         }
     }
     __syncthreads();
+    // local roots of the tile -> a shared list (typically 3-6 entries)
+    int r[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int ly = ly0 + 8 * k, y = blockIdx.y * CT + ly;
-        if (x < w && y < h) {
-            const int r = sm_find(sp, ly * CT + lx);
-            P[y * w + x] = (blockIdx.y * CT + (r >> 5)) * w + blockIdx.x * CT + (r & 31);
-            csize[y * w + x] = 0;
+        r[k] = sm_find(sp, ly * CT + lx);
+        if (x < w && y < h && r[k] == ly * CT + lx) s_roots[atomicAdd(&s_n, 1)] = r[k];
+    }
+    __syncthreads();
+    const int nr = s_n;
+    if (nr <= 16) {
+        // few roots: every warp counts its pixels of root j (one REDUX), one shared atomic per warp and root
+        for (int j = 0; j < nr; j++) {
+            const int rj = s_roots[j];
+            int c = (r[0] == rj) + (r[1] == rj) + (r[2] == rj) + (r[3] == rj);
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (lx == 0 && c) atomicAdd(&sc[rj], c);
         }
+    } else {
+        // many roots (noise): the head of every run of equal root along a row adds the run's length
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int prevr = __shfl_up_sync(0xffffffffu, r[k], 1);
+            const unsigned hb = __ballot_sync(0xffffffffu, lx == 0 || prevr != r[k]);
+            if ((hb >> lx) & 1u) {
+                const unsigned above = lx == 31 ? 0u : hb >> (lx + 1);
+                atomicAdd(&sc[r[k]], above ? __ffs(above) : 32 - lx);    // (pixels outside the image are their own roots, never listed)
+            }
+        }
+    }
+    if (threadIdx.x == 0 && nr) s_base = atomicAdd(nroots, nr);          // one global atomic per tile
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int y = blockIdx.y * CT + ly0 + 8 * k;
+        if (x < w && y < h) P[y * w + x] = (blockIdx.y * CT + (r[k] >> 5)) * w + blockIdx.x * CT + (r[k] & 31);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < nr; j += 256) {
+        const int rj = s_roots[j];
+        const int gi = (blockIdx.y * CT + (rj >> 5)) * w + blockIdx.x * CT + (rj & 31);
+        csize[gi] = sc[rj];
+        roots[s_base + j] = gi;
     }
 }
 // one thread per pixel of a tile's top row / left column
@@ -151,52 +200,49 @@ __global__ void ccl_border_kernel(const int* __restrict__ lab, int lp, int w, in
     const int* row = lab + (size_t)y * lp;
     if (row[x] == row[x - 1]) uf_unite(P, y * w + x, y * w + x - 1);
 }
-// flatten + component sizes: warp-aggregated atomics (a warp covers 32 consecutive pixels, i.e. 1-3 roots; the ballot against
-// lane 0's root settles the common single-root case without MATCH)
-__global__ void ccl_flatten_kernel(int* __restrict__ P, int* __restrict__ csize, int n)
+// local root -> global root; its pixels are added to the global root's size
+__global__ void ccl_roots_kernel(int* __restrict__ P, int* __restrict__ csize, const int* __restrict__ roots, const int* __restrict__ nroots)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool act = i < n;
-    int r = -1 - (int)(threadIdx.x & 31);
-    if (act) { r = uf_find(P, i); P[i] = r; }
-    const int r0 = __shfl_sync(0xffffffffu, r, 0);
-    unsigned m = __ballot_sync(0xffffffffu, r == r0);
-    if (m != 0xffffffffu) m = __match_any_sync(0xffffffffu, r);
-    if (act && (int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&csize[r], __popc(m));
+    const int n = *nroots;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {      // (the host does not know n)
+        const int lr = roots[j];
+        const int g = uf_find(P, lr);
+        if (g != lr) { P[lr] = g; atomicAdd(&csize[g], csize[lr]); }
+    }
 }
+// global root of the pixel next to a root pixel: pixel -> local root -> global root (the list pass flattened the local roots)
+__device__ __forceinline__ int root2(const int* __restrict__ P, int i) { return P[P[i]]; }
 // a small root's link: the component supplying upstream's `adjlabel` = last of the L,U,R,D neighbours of the root pixel whose
 // component starts earlier (left and up always do); -1: no neighbour labelled yet (pixel 0)
 __device__ __forceinline__ int small_root_link(const int* __restrict__ P, int i, int w, int h)
 {
     const int x = i % w, y = i / w;
     int adj = -1;
-    if (x > 0) adj = P[i - 1];
-    if (y > 0) adj = P[i - w];
-    if (x < w - 1) { int r = P[i + 1]; if (r < i) adj = r; }
-    if (y < h - 1) { int r = P[i + w]; if (r < i) adj = r; }
+    if (x > 0) adj = root2(P, i - 1);
+    if (y > 0) adj = root2(P, i - w);
+    if (x < w - 1) { int r = root2(P, i + 1); if (r < i) adj = r; }
+    if (y < h - 1) { int r = root2(P, i + w); if (r < i) adj = r; }
     return adj;
 }
-
-// exclusive scan of kept-root flags over raster order: block counts -> block offsets -> ids
-#define SCAN_CHUNK 2048
-__device__ __forceinline__ int kept_flag(const int* P, const int* csize, int i, int n, int min_sp)
+__global__ void ccl_keep_kernel(const int* __restrict__ P, const int* __restrict__ csize, const int* __restrict__ roots, const int* __restrict__ nroots,
+                                int min_sp, unsigned* __restrict__ bitmap, int* __restrict__ link, int w, int h)
 {
-    return (i < n && P[i] == i && csize[i] > min_sp) ? 1 : 0;
+    const int n = *nroots;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int r = roots[j];
+        if (P[r] != r) continue;
+        if (csize[r] > min_sp) atomicOr(&bitmap[r >> 5], 1u << (r & 31));
+        else link[r] = small_root_link(P, r, w, h);
+    }
 }
-// block counts of kept roots; the small roots met on the way get their link (one pass over P serves both)
-__global__ void __launch_bounds__(256) scan_count_kernel(const int* __restrict__ P, const int* __restrict__ csize, int n,
-                                                          int min_sp, int* __restrict__ blocksum, int* __restrict__ link, int w, int h)
+// exclusive prefix popcount of the bitmap words: block sums -> block offsets (scan_blocks_kernel) -> per-word prefix
+#define SCANW_CHUNK 1024
+__global__ void __launch_bounds__(256) scanw_count_kernel(const unsigned* __restrict__ bitmap, int nwords, int* __restrict__ blocksum)
 {
     __shared__ int s[8];
-    int base = blockIdx.x * SCAN_CHUNK;
+    const int base = blockIdx.x * SCANW_CHUNK;
     int c = 0;
-    for (int k = threadIdx.x; k < SCAN_CHUNK; k += 256) {
-        const int i = base + k;
-        if (i < n && P[i] == i) {
-            if (csize[i] > min_sp) c++;
-            else link[i] = small_root_link(P, i, w, h);
-        }
-    }
+    for (int k = threadIdx.x; k < SCANW_CHUNK; k += 256) { const int i = base + k; if (i < nwords) c += __popc(bitmap[i]); }
     c = __reduce_add_sync(0xffffffffu, c);
     if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
     __syncthreads();
@@ -229,25 +275,26 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(int* __restrict__ blo
     }
     if (threadIdx.x == 0) *total = s_carry;
 }
-__global__ void __launch_bounds__(256) scan_apply_kernel(const int* __restrict__ P, const int* __restrict__ csize, int n,
-                                                          int min_sp, const int* __restrict__ blocksum, int* __restrict__ newid)
+__global__ void __launch_bounds__(256) scanw_apply_kernel(const unsigned* __restrict__ bitmap, int nwords, const int* __restrict__ blocksum,
+                                                           int* __restrict__ prefix)
 {
     __shared__ int s_w[8];
     __shared__ int s_carry;
     if (threadIdx.x == 0) s_carry = blocksum[blockIdx.x];
     __syncthreads();
-    int base = blockIdx.x * SCAN_CHUNK;
-    for (int k = 0; k < SCAN_CHUNK; k += 256) {
-        int i = base + k + threadIdx.x;
-        int f = kept_flag(P, csize, i, n, min_sp);
-        unsigned b = __ballot_sync(0xffffffffu, f);
-        int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        int pre = __popc(b & ((1u << lane) - 1));
-        if (lane == 0) s_w[wid] = __popc(b);
+    const int base = blockIdx.x * SCANW_CHUNK;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int k = 0; k < SCANW_CHUNK; k += 256) {
+        const int i = base + k + threadIdx.x;
+        const int v = i < nwords ? __popc(bitmap[i]) : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_w[wid] = inc;
         __syncthreads();
         int off = s_carry;
         for (int q = 0; q < wid; q++) off += s_w[q];
-        if (f) newid[i] = off + pre;
+        if (i < nwords) prefix[i] = off + inc - v;
         __syncthreads();
         if (threadIdx.x == 0) { int t = 0; for (int q = 0; q < 8; q++) t += s_w[q]; s_carry += t; }
         __syncthreads();
@@ -255,14 +302,34 @@ __global__ void __launch_bounds__(256) scan_apply_kernel(const int* __restrict__
 }
 // new label of a pixel = id of its component's root if kept, otherwise of the kept root its chain of links ends at (links
 // strictly decrease, so the walk terminates; a chain that ends at a small component holding pixel 0 keeps upstream's adjlabel 0)
-__global__ void ccl_relabel_kernel(const int* __restrict__ P, const int* __restrict__ csize, const int* __restrict__ link,
-                                   const int* __restrict__ newid, int* __restrict__ lab, int lp, int w, int h, int min_sp)
+__device__ __forceinline__ int ccl_new_id(const int* __restrict__ P, const int* __restrict__ csize, const int* __restrict__ link,
+                                          const unsigned* __restrict__ bitmap, const int* __restrict__ prefix, int lr, int min_sp)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= w) return;
-    int r = P[y * w + x];
+    int r = P[lr];
     while (r >= 0 && csize[r] <= min_sp) r = link[r];
-    lab[(size_t)y * lp + x] = r >= 0 ? newid[r] : 0;
+    return r >= 0 ? prefix[r >> 5] + __popc(bitmap[r >> 5] & ((1u << (r & 31)) - 1u)) : 0;
+}
+// 4 pixels per thread; neighbours mostly share their local root, so the chain of gathers runs once per run of pixels
+__global__ void __launch_bounds__(256) ccl_relabel_kernel(const int* __restrict__ P, const int* __restrict__ csize, const int* __restrict__ link,
+                                                          const unsigned* __restrict__ bitmap, const int* __restrict__ prefix, int* __restrict__ lab,
+                                                          int lp, int w, int h, int min_sp, int vec)
+{
+    const int x0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x), y = blockIdx.y;
+    if (x0 >= w) return;
+    const int* prow = P + (size_t)y * w + x0;
+    int* lrow = lab + (size_t)y * lp + x0;
+    if (vec && x0 + 4 <= w) {
+        const int4 q = *reinterpret_cast<const int4*>(prow);
+        int4 o;
+        o.x = ccl_new_id(P, csize, link, bitmap, prefix, q.x, min_sp);
+        o.y = q.y == q.x ? o.x : ccl_new_id(P, csize, link, bitmap, prefix, q.y, min_sp);
+        o.z = q.z == q.y ? o.y : ccl_new_id(P, csize, link, bitmap, prefix, q.z, min_sp);
+        o.w = q.w == q.z ? o.z : ccl_new_id(P, csize, link, bitmap, prefix, q.w, min_sp);
+        *reinterpret_cast<int4*>(lrow) = o;
+    } else {
+        const int n = min(4, w - x0);
+        for (int j = 0; j < n; j++) lrow[j] = ccl_new_id(P, csize, link, bitmap, prefix, prow[j], min_sp);
+    }
 }
 
 int enforce_connectivity_dev(PostWorkspace& ws, int* d_labels, int lp, int numlabels, int min_element_size,
@@ -278,18 +345,29 @@ int enforce_connectivity_dev(PostWorkspace& ws, int* d_labels, int lp, int numla
     int min_sp = supsz / div;
     if (min_sp < 3) min_sp = 3;
     int* d_link = ws.link;
-    dim3 b2(256), g2(cdiv(w, 256), h);
-    int g1 = cdiv(n, 256);
-    ccl_local_kernel<<<dim3(cdiv(w, CT), cdiv(h, CT)), 256, 0, st>>>(d_labels, lp, w, h, ws.parent, ws.csize);
+    dim3 b2(256), g4(cdiv(cdiv(w, 4), 256), h);
+    const int vec4 = (w % 4 == 0 && lp % 4 == 0 && ((uintptr_t)d_labels & 15u) == 0 && ((uintptr_t)ws.parent & 15u) == 0) ? 1 : 0;
+    // scratch: the list of local roots in newid [N ints]; bitmap + per-word prefix in diff [N bytes >= 2 * (N/32 + 1) ints]
+    int* roots = ws.newid;
+    const int nwords = cdiv(n, 32);
+    unsigned* bitmap = reinterpret_cast<unsigned*>(ws.diff);
+    int* prefix = reinterpret_cast<int*>(ws.diff) + nwords;
+    int* nroots = ws.flag + 1;
+    SPX_CUDA(cudaMemsetAsync(nroots, 0, sizeof(int), st));
+    SPX_CUDA(cudaMemsetAsync(bitmap, 0, (size_t)nwords * sizeof(unsigned), st));
+    ccl_local_kernel<<<dim3(cdiv(w, CT), cdiv(h, CT)), 256, 0, st>>>(d_labels, lp, w, h, ws.parent, ws.csize, roots, nroots);
     const int nborder = (cdiv(h, CT) - 1) * w + (cdiv(w, CT) - 1) * h;
     if (nborder > 0) ccl_border_kernel<<<cdiv(nborder, 256), 256, 0, st>>>(d_labels, lp, w, h, ws.parent);
-    ccl_flatten_kernel<<<g1, 256, 0, st>>>(ws.parent, ws.csize, n);
-    int nb = cdiv(n, SCAN_CHUNK);
-    scan_count_kernel<<<nb, 256, 0, st>>>(ws.parent, ws.csize, n, min_sp, ws.blocksum, d_link, w, h);
+    // the list kernels walk *nroots entries with a fixed grid (typical: 3-5 roots per tile; the host never learns the count)
+    const int lb = std::max(1, std::min(cdiv(4 * cdiv(w, CT) * cdiv(h, CT), 256), 148 * 4));
+    ccl_roots_kernel<<<lb, 256, 0, st>>>(ws.parent, ws.csize, roots, nroots);
+    ccl_keep_kernel<<<lb, 256, 0, st>>>(ws.parent, ws.csize, roots, nroots, min_sp, bitmap, d_link, w, h);
+    const int nb = cdiv(nwords, SCANW_CHUNK);
+    scanw_count_kernel<<<nb, 256, 0, st>>>(bitmap, nwords, ws.blocksum);
     scan_blocks_kernel<<<1, 1024, 0, st>>>(ws.blocksum, nb, ws.flag);
-    scan_apply_kernel<<<nb, 256, 0, st>>>(ws.parent, ws.csize, n, min_sp, ws.blocksum, ws.newid);
-    ccl_relabel_kernel<<<g2, b2, 0, st>>>(ws.parent, ws.csize, d_link, ws.newid, d_labels, lp, w, h, min_sp);
-    ws.launches += nborder > 0 ? 7 : 6;
+    scanw_apply_kernel<<<nb, 256, 0, st>>>(bitmap, nwords, ws.blocksum, prefix);
+    ccl_relabel_kernel<<<g4, b2, 0, st>>>(ws.parent, ws.csize, d_link, bitmap, prefix, d_labels, lp, w, h, min_sp, vec4);
+    ws.launches += nborder > 0 ? 8 : 7;
     SPX_CUDA(cudaGetLastError());
     SPX_CUDA(cudaMemcpyAsync(ws.h_flag, ws.flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     SPX_CUDA(cudaStreamSynchronize(st));
