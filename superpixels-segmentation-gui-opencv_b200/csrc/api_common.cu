@@ -1,5 +1,6 @@
 // api_common.cu -- version / error reporting / device probing of libspx_b200.so
 #include "common.cuh"
+#include <cstdlib>
 
 namespace spx {
 static thread_local char g_err[512] = "";
@@ -9,6 +10,11 @@ void set_error(const char* fmt, ...)
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+bool pdl_enabled()
+{
+    static const bool on = !getenv("SPX_NO_PDL");
+    return on;
 }
 int require_device(int device)
 {

@@ -48,6 +48,24 @@ void set_error(const char* fmt, ...);
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
+// Programmatic dependent launch: the kernel may become resident while its predecessor in the stream drains; it must execute
+// pdl_wait() before touching anything the predecessor writes.  pdl_trigger() in the predecessor lets the dependent in early.
+// Both are no-ops in launches without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // fails loudly when there is no usable CUDA device (no CPU fallback anywhere in this library)
 int require_device(int device);
 

@@ -200,6 +200,8 @@ __global__ void __launch_bounds__(BIN_CTA) slic_finalize_kernel(SlicGeom g, Slic
     __shared__ BinStage sh;
     int t = blockIdx.x * BIN_CTA + threadIdx.x;
     const int nb = g.nbx * g.nby;
+    pdl_trigger();
+    pdl_wait();
     if (t < nb) (parity ? a.head[1] : a.head[0])[t] = -1;
     if (g.tile_on && t < g.tiles_x * g.tiles_y) (parity ? a.tl_count[1] : a.tl_count[0])[t] = 0;
     //              // the lists just consumed; reused two iterations later
@@ -227,6 +229,60 @@ __global__ void __launch_bounds__(BIN_CTA) slic_finalize_kernel(SlicGeom g, Slic
     bin_stage(g, a, parity ^ 1, sh, threadIdx.x, t, t < K);
     __syncthreads();
     bin_scatter(g, a, parity ^ 1, sh);
+}
+
+// The same update for SLIC / SLICO with the scatter spread over threads: 16 threads per centre.  All 16 read the six sums (one
+// broadcast load each) and compute the means redundantly; thread j = 0 writes the centre, empties its sums and re-bins it; thread
+// j takes tile (j & 3, j >> 2) of the centre's span (larger spans: strided repeats).  No shared staging, no barrier: two dependent
+// memory round trips (sums, list position) instead of five.
+constexpr int FIN16_CTA = 128;
+__global__ void __launch_bounds__(FIN16_CTA) slic_finalize16_kernel(SlicGeom g, SlicArrays a, int parity)
+{
+    const int t = blockIdx.x * FIN16_CTA + threadIdx.x;
+    pdl_trigger();                                        // the next assignment may start loading its pixels
+    pdl_wait();                                           // the assignment's sums
+    const int nb = g.nbx * g.nby;
+    if (t < nb) (parity ? a.head[1] : a.head[0])[t] = -1;                            // the lists just consumed; reused two iterations later
+    if (g.tile_on && t < g.tiles_x * g.tiles_y) (parity ? a.tl_count[1] : a.tl_count[0])[t] = 0;
+    const int n = t >> 4, j = t & 15;
+    if (n >= g.K) return;
+    constexpr int C = 3;                                  // (launched for 3-channel images only)
+    unsigned long long sum[C + 3];
+    #pragma unroll
+    for (int f = 0; f < C + 3; f++) sum[f] = a.acc[(size_t)f * g.Kcap + n];
+    const int off = a.ioff[n];
+    const float m = (float)(sum[C + 2] == 0 ? 1ull : sum[C + 2]);
+    float kc[C];
+    for (int c = 0; c < C; c++) kc[c] = __fdiv_rn((float)sum[c], m);
+    const float kx = __fdiv_rn((float)sum[C], m), ky = __fdiv_rn((float)sum[C + 1], m);
+    const int ix = (int)kx, iy = (int)ky;
+    const int par = parity ^ 1;
+    if (j == 0) {
+        for (int f = 0; f < C + 3; f++) a.acc[(size_t)f * g.Kcap + n] = 0;          // (the group's loads are the same instruction, one step earlier)
+        for (int c = 0; c < C; c++) a.kc[(size_t)c * g.Kcap + n] = kc[c];
+        a.kx[n] = kx; a.ky[n] = ky; a.ikx[n] = ix; a.iky[n] = iy;
+        if (g.alg == 101) a.maxc[n] = __uint_as_float(a.maxc_acc[n]);                 // maxchans[k] <- accumulated maximum; seeds the next one
+        int* head = par ? a.head[1] : a.head[0];
+        const int bx = min(max(ix, 0) / g.S, g.nbx - 1), by = min(max(iy, 0) / g.S, g.nby - 1);
+        a.next[n] = atomicExch(&head[by * g.nbx + bx], n);
+    }
+    if (!g.tile_on) return;
+    const int tx0 = max(ix - off, 0) / TILE_W, tx1 = min(ix + off - 1, g.w - 1) / TILE_W;
+    const int ty0 = max(max(iy - off, 0) / TILE_H, g.ty_lo), ty1 = min(min(iy + off - 1, g.h - 1) / TILE_H, g.ty_hi - 1);
+    int* cnt = par ? a.tl_count[1] : a.tl_count[0];
+    TileRec* recs = par ? a.tl_rec[1] : a.tl_rec[0];
+    const float4 ra = make_float4(kx, ky, kc[0], kc[1]);
+    const float4 rb = make_float4(kc[2], __int_as_float(n), __int_as_float(ix), __int_as_float(iy));
+    for (int ty = ty0 + (j >> 2); ty <= ty1; ty += 4)
+        for (int tx = tx0 + (j & 3); tx <= tx1; tx += 4) {
+            const int tile = ty * g.tiles_x + tx;
+            const int pos = atomicAdd(&cnt[tile], 1);
+            if (pos < TILE_CAP) {
+                float4* dst = reinterpret_cast<float4*>(&recs[(size_t)tile * TILE_CAP + pos]);
+                dst[0] = ra;
+                dst[1] = rb;
+            }
+        }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -815,7 +871,11 @@ struct SlicEngine {
         launches++;
         if (e1) SPX_CUDA(cudaEventRecord(e1, st));
         const int do_bin = g.alg == SPX_MSLIC ? 0 : 1;
-        slic_finalize_kernel<<<cdiv(threads_fin, BIN_CTA), BIN_CTA, 0, st>>>(g, a, d_K, parity, do_bin);
+        if (do_bin && g.C == 3) {
+            const int th16 = max(max(16 * g.K, g.nbx * g.nby), g.tiles_x * g.tiles_y);
+            SPX_CUDA(launch_pdl(slic_finalize16_kernel, dim3(cdiv(th16, FIN16_CTA)), dim3(FIN16_CTA), st, g, a, parity));
+        } else
+            SPX_CUDA(launch_pdl(slic_finalize_kernel, dim3(cdiv(threads_fin, BIN_CTA)), dim3(BIN_CTA), st, g, a, (const int*)d_K, parity, do_bin));
         launches++;
         if (g.alg == SPX_MSLIC) {
             // the tiled assignment kernel already summed the manifold areas per cluster; the generic path does it here

@@ -234,6 +234,7 @@ __global__ void __launch_bounds__(NT, ALG == SPX_SLIC ? 9 : 8) slic_tile_kernel(
 
     // ---- candidates: the centre-update kernel appended every cluster whose window touches this tile
     // (the record loads do not wait for the count: slots beyond it hold stale records that are never used)
+    pdl_wait();                                                   // the centre update that wrote the lists (the pixel loads above are already in flight)
     float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
     if (tid < CAP) {
         const float4* src = reinterpret_cast<const float4*>(&t.tl_rec[(size_t)tile * CAP + tid]);
@@ -442,6 +443,7 @@ __global__ void __launch_bounds__(NT, ALG == SPX_SLIC ? 9 : 8) slic_tile_kernel(
         lrow += 16 * t.lp;
     }
 
+    pdl_trigger();                                                // the centre update may become resident while the last tiles flush
     __syncthreads();
     // ---- flush: fold the copies, then one global atomic per field per candidate that received pixels
     for (int i = tid; i < cnt * 4; i += NT) {
@@ -539,14 +541,14 @@ int slic_tile_assign(const SlicGeom& g, const SlicArrays& a, const unsigned char
     t.area_px = d_area_px; t.area = reinterpret_cast<unsigned long long*>(a.area);
     const bool p2 = is_pow2(g.xywt);
     if (g.alg == SPX_SLICO) {
-        if (p2) slic_tile_kernel<true, SPX_SLICO><<<grid, NT, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);
-        else slic_tile_kernel<false, SPX_SLICO><<<grid, NT, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);
+        if (p2) SPX_CUDA(launch_pdl(slic_tile_kernel<true, SPX_SLICO>, grid, dim3(NT), st, t, g, a, d_img, d_labels, parity, d_overflow));
+        else SPX_CUDA(launch_pdl(slic_tile_kernel<false, SPX_SLICO>, grid, dim3(NT), st, t, g, a, d_img, d_labels, parity, d_overflow));
     } else if (g.alg == SPX_MSLIC) {
-        if (p2) slic_tile_kernel<true, SPX_MSLIC><<<grid, NT, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);
-        else slic_tile_kernel<false, SPX_MSLIC><<<grid, NT, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);
+        if (p2) SPX_CUDA(launch_pdl(slic_tile_kernel<true, SPX_MSLIC>, grid, dim3(NT), st, t, g, a, d_img, d_labels, parity, d_overflow));
+        else SPX_CUDA(launch_pdl(slic_tile_kernel<false, SPX_MSLIC>, grid, dim3(NT), st, t, g, a, d_img, d_labels, parity, d_overflow));
     } else {
-        if (p2) slic_tile_kernel<true, SPX_SLIC><<<grid, NT, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);
-        else slic_tile_kernel<false, SPX_SLIC><<<grid, NT, 0, st>>>(t, g, a, d_img, d_labels, parity, d_overflow);
+        if (p2) SPX_CUDA(launch_pdl(slic_tile_kernel<true, SPX_SLIC>, grid, dim3(NT), st, t, g, a, d_img, d_labels, parity, d_overflow));
+        else SPX_CUDA(launch_pdl(slic_tile_kernel<false, SPX_SLIC>, grid, dim3(NT), st, t, g, a, d_img, d_labels, parity, d_overflow));
     }
     SPX_CUDA(cudaGetLastError());
     return SPX_OK;
