@@ -57,7 +57,7 @@ spxo_seeds* spxo_seeds_create(int w, int h, int channels, int num_superpixels, i
     if (w <= 0 || h <= 0 || channels < 1 || channels > 4 || num_superpixels < 1 || num_levels < 1 || histogram_bins < 1) return NULL;
     double hs = 1.0;
     for (int c = 0; c < channels; c++) hs *= histogram_bins;
-    if (hs > 4096.0) return NULL;               /* explicit limit of this engine: bins^channels <= 4096 */
+    if (hs >= 2147483648.0) return NULL;        /* (memory is the only other limit, as upstream) */
     const int nsp_h = (int)sqrtf((float)num_superpixels * (float)h / (float)w);
     if (nsp_h < 1) return NULL;
     const int nsp_w = (int)floorf((float)nsp_h * (float)w / (float)h);

@@ -309,10 +309,21 @@ __device__ __forceinline__ int ccl_new_id(const int* __restrict__ P, const int* 
     while (r >= 0 && csize[r] <= min_sp) r = link[r];
     return r >= 0 ? prefix[r >> 5] + __popc(bitmap[r >> 5] & ((1u << (r & 31)) - 1u)) : 0;
 }
-// 4 pixels per thread; neighbours mostly share their local root, so the chain of gathers runs once per run of pixels
-__global__ void __launch_bounds__(256) ccl_relabel_kernel(const int* __restrict__ P, const int* __restrict__ csize, const int* __restrict__ link,
-                                                          const unsigned* __restrict__ bitmap, const int* __restrict__ prefix, int* __restrict__ lab,
-                                                          int lp, int w, int h, int min_sp, int vec)
+// list: the new id of every local root, written over its own parent entry as -1 - id.  Only that thread reads the entry (the
+// walk to a kept root goes through csize / link, indexed by GLOBAL roots), and only the relabel pass reads P afterwards.
+__global__ void ccl_final_kernel(int* __restrict__ P, const int* __restrict__ csize, const int* __restrict__ link,
+                                 const unsigned* __restrict__ bitmap, const int* __restrict__ prefix, const int* __restrict__ roots,
+                                 const int* __restrict__ nroots, int min_sp)
+{
+    const int n = *nroots;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int lr = roots[j];
+        P[lr] = -1 - ccl_new_id(P, csize, link, bitmap, prefix, lr, min_sp);
+    }
+}
+// 4 pixels per thread: pixel -> local root -> -1 - id (a local root pixel holds its id itself); neighbours mostly share the root
+__device__ __forceinline__ int ccl_id_of(const int* __restrict__ P, int q) { return -1 - (q >= 0 ? P[q] : q); }
+__global__ void __launch_bounds__(256) ccl_relabel_kernel(const int* __restrict__ P, int* __restrict__ lab, int lp, int w, int h, int vec)
 {
     const int x0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x), y = blockIdx.y;
     if (x0 >= w) return;
@@ -321,14 +332,14 @@ __global__ void __launch_bounds__(256) ccl_relabel_kernel(const int* __restrict_
     if (vec && x0 + 4 <= w) {
         const int4 q = *reinterpret_cast<const int4*>(prow);
         int4 o;
-        o.x = ccl_new_id(P, csize, link, bitmap, prefix, q.x, min_sp);
-        o.y = q.y == q.x ? o.x : ccl_new_id(P, csize, link, bitmap, prefix, q.y, min_sp);
-        o.z = q.z == q.y ? o.y : ccl_new_id(P, csize, link, bitmap, prefix, q.z, min_sp);
-        o.w = q.w == q.z ? o.z : ccl_new_id(P, csize, link, bitmap, prefix, q.w, min_sp);
+        o.x = ccl_id_of(P, q.x);
+        o.y = q.y == q.x ? o.x : ccl_id_of(P, q.y);
+        o.z = q.z == q.y ? o.y : ccl_id_of(P, q.z);
+        o.w = q.w == q.z ? o.z : ccl_id_of(P, q.w);
         *reinterpret_cast<int4*>(lrow) = o;
     } else {
         const int n = min(4, w - x0);
-        for (int j = 0; j < n; j++) lrow[j] = ccl_new_id(P, csize, link, bitmap, prefix, prow[j], min_sp);
+        for (int j = 0; j < n; j++) lrow[j] = ccl_id_of(P, prow[j]);
     }
 }
 
@@ -359,15 +370,16 @@ int enforce_connectivity_dev(PostWorkspace& ws, int* d_labels, int lp, int numla
     const int nborder = (cdiv(h, CT) - 1) * w + (cdiv(w, CT) - 1) * h;
     if (nborder > 0) ccl_border_kernel<<<cdiv(nborder, 256), 256, 0, st>>>(d_labels, lp, w, h, ws.parent);
     // the list kernels walk *nroots entries with a fixed grid (typical: 3-5 roots per tile; the host never learns the count)
-    const int lb = std::max(1, std::min(cdiv(4 * cdiv(w, CT) * cdiv(h, CT), 256), 148 * 4));
+    const int lb = std::max(1, std::min(cdiv(16 * cdiv(w, CT) * cdiv(h, CT), 256), 148 * 8));
     ccl_roots_kernel<<<lb, 256, 0, st>>>(ws.parent, ws.csize, roots, nroots);
     ccl_keep_kernel<<<lb, 256, 0, st>>>(ws.parent, ws.csize, roots, nroots, min_sp, bitmap, d_link, w, h);
     const int nb = cdiv(nwords, SCANW_CHUNK);
     scanw_count_kernel<<<nb, 256, 0, st>>>(bitmap, nwords, ws.blocksum);
     scan_blocks_kernel<<<1, 1024, 0, st>>>(ws.blocksum, nb, ws.flag);
     scanw_apply_kernel<<<nb, 256, 0, st>>>(bitmap, nwords, ws.blocksum, prefix);
-    ccl_relabel_kernel<<<g4, b2, 0, st>>>(ws.parent, ws.csize, d_link, bitmap, prefix, d_labels, lp, w, h, min_sp, vec4);
-    ws.launches += nborder > 0 ? 8 : 7;
+    ccl_final_kernel<<<lb, 256, 0, st>>>(ws.parent, ws.csize, d_link, bitmap, prefix, roots, nroots, min_sp);
+    ccl_relabel_kernel<<<g4, b2, 0, st>>>(ws.parent, d_labels, lp, w, h, vec4);
+    ws.launches += nborder > 0 ? 9 : 8;
     SPX_CUDA(cudaGetLastError());
     SPX_CUDA(cudaMemcpyAsync(ws.h_flag, ws.flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     SPX_CUDA(cudaStreamSynchronize(st));

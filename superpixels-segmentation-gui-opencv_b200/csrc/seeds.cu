@@ -27,7 +27,7 @@ constexpr float SEEDS_REQ_CONF = 0.1f;
 struct SeedsDev {
     int w, h, C, bins, prior, nlev, top, sw, sh, hsize, K;
     int nr_w[SEEDS_MAXLEV], nr_h[SEEDS_MAXLEV];
-    unsigned short* bin;
+    unsigned* bin;                   // histogram bin of every pixel (bins^channels can exceed 16 bits: the GUI slider goes to 50)
     int* hist[SEEDS_MAXLEV];
     int* T[SEEDS_MAXLEV];
     int* parent[SEEDS_MAXLEV];
@@ -54,7 +54,7 @@ __global__ void seeds_bins_kernel(SeedsDev S, const unsigned char* __restrict__ 
     const unsigned char* p = img + (size_t)y * ipitch + (size_t)x * S.C;
     unsigned b = 0;
     for (int c = 0; c < S.C; c++) b = b * S.bins + (unsigned)(p[c] * S.bins / 256);
-    S.bin[(size_t)y * S.w + x] = (unsigned short)b;
+    S.bin[(size_t)y * S.w + x] = b;
     const int blk = seeds_blk0(S, x, y);
     atomicAdd(&S.hist[0][(size_t)blk * S.hsize + b], 1);
     atomicAdd(&S.T[0][blk], 1);
@@ -358,7 +358,7 @@ struct SeedsEngine {
         SPX_REQUIRE(num_superpixels >= 1 && num_levels >= 1 && bins >= 1, SPX_ERR_BADARG, "createSuperpixelSEEDS: bad parameter");
         double hs = 1.0;
         for (int c = 0; c < C; c++) hs *= bins;
-        SPX_REQUIRE(hs <= 4096.0, SPX_ERR_BADARG, "createSuperpixelSEEDS: histogram_bins^channels = %.0f exceeds this engine's limit of 4096", hs);
+        SPX_REQUIRE(hs < 2147483648.0, SPX_ERR_BADARG, "createSuperpixelSEEDS: histogram_bins^channels = %.0f does not fit an int", hs);
         const int nsp_h = (int)sqrtf((float)num_superpixels * (float)h / (float)w);
         SPX_REQUIRE(nsp_h >= 1, SPX_ERR_BADARG, "createSuperpixelSEEDS: too few superpixels for this aspect ratio");
         const int nsp_w = (int)floorf((float)nsp_h * (float)w / (float)h);
@@ -381,6 +381,15 @@ struct SeedsEngine {
         S.K = S.nr_w[S.top] * S.nr_h[S.top];
         const size_t N = (size_t)w * h;
         ipitch = round_up((size_t)w * C, 16);
+        {   // upstream allocates one histogram of bins^channels entries per block of every level, too: a request that cannot
+            // fit fails there with cv::Exception (OutOfMemory); here with SPX_ERR_NOMEM before anything is allocated
+            double need = 0;
+            for (int l = 0; l < L; l++) need += (double)S.nr_w[l] * S.nr_h[l] * (hs + 2.0) * sizeof(int);
+            size_t fr = 0, tot = 0;
+            SPX_CUDA(cudaMemGetInfo(&fr, &tot));
+            SPX_REQUIRE(need < 0.9 * (double)fr, SPX_ERR_NOMEM,
+                        "createSuperpixelSEEDS: the histograms of %d levels with %d^%d bins need %.1f GB, %.1f GB are free", L, bins, C, need / 1e9, (double)fr / 1e9);
+        }
         SPX_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         SPX_CHECK(dalloc(&d_img, ipitch * h));
         SPX_CHECK(dalloc(&d_mask, N));

@@ -380,7 +380,9 @@ def test_lsc_errors(spx):
 # order (order 0) is a statistical comparison (tests/test_oracle.py and below)
 @pytest.mark.parametrize("w,h,num,levels,prior,bins,dstep,iters", [
     (320, 240, 200, 3, 2, 5, False, 4), (203, 157, 150, 2, 0, 4, True, 3), (256, 256, 64, 4, 5, 3, False, 5),
-    (160, 120, 300, 1, 1, 5, False, 2), (640, 360, 400, 4, 3, 5, True, 6)])
+    (160, 120, 300, 1, 1, 5, False, 2), (640, 360, 400, 4, 3, 5, True, 6),
+    (128, 96, 40, 2, 2, 50, False, 2),          # the GUI slider's maximum (mainwindow.ui:2490): 50^3 = 125000 bins per histogram
+    (200, 150, 60, 3, 2, 20, True, 3)])
 def test_seeds_equals_phase_parallel_oracle(spx, O, synthmod, w, h, num, levels, prior, bins, dstep, iters):
     bgr, _ = synthmod.synth(w, h, 9)
     lab = O.bgr2lab8(bgr)
@@ -444,8 +446,8 @@ def test_seeds_screenshot_sizing(spx):
 
 
 def test_seeds_errors(spx):
-    with pytest.raises(spx.SpxError):
-        spx.createSuperpixelSEEDS(64, 64, 3, 100, 4, 2, 50, False)       # 50^3 bins: over the engine's limit
+    with pytest.raises(spx.SpxError):                                    # 8K, 50^3 bins, 8 levels: terabytes of histograms --
+        spx.createSuperpixelSEEDS(7680, 4320, 3, 2000, 8, 2, 50, False)  # fails with StsNoMem, as upstream's allocation would
     s = spx.createSuperpixelSEEDS(64, 48, 3, 20, 2)
     with pytest.raises(spx.SpxError):
         s.iterate(np.zeros((48, 60, 3), np.uint8), 2)
