@@ -644,7 +644,7 @@ __global__ void __launch_bounds__(1024) lsc_rounds_kernel(LscRounds a)
 // ---- the authors' visiting order (order 0) without its serial dependency chains ------------------------------------
 // In region order every fragment around a superpixel is within graph distance 2 of the next one, so the rounds above
 // degenerate into a wavefront (thousands of rounds, a few dozen merges each).  The sequential loop is evaluated as a
-// FIXED POINT instead (normative CPU form: oracle/spx_oracle_lsc.c, lsc_merge_fixedpoint): region i is visited at
+// FIXED POINT instead (normative CPU form: the test oracle under oracle/, LSC section, lsc_merge_fixedpoint): region i is visited at
 // "time" i and its decision (merge or not, into whom) depends on the decisions of regions j < i only.  Take any table
 // of tentative decisions tg[], derive from it the state every region has at every time, re-take the decisions against
 // that state, repeat until the table reproduces itself.  After k rounds the first k regions (at least) hold their

@@ -236,7 +236,10 @@ __global__ void __launch_bounds__(BIN_CTA) slic_finalize_kernel(SlicGeom g, Slic
 // j takes tile (j & 3, j >> 2) of the centre's span (larger spans: strided repeats).  No shared staging, no barrier: two dependent
 // memory round trips (sums, list position) instead of five.
 constexpr int FIN16_CTA = 128;
-__global__ void __launch_bounds__(FIN16_CTA) slic_finalize16_kernel(SlicGeom g, SlicArrays a, int parity)
+// Strip partition: a rank updates only the clusters [k_lo, k_hi) it maintains; a cluster whose centre has
+// moved more than 2S - 2 rows away from its seed row could reach a band whose rank does not maintain it: *err = 100.
+struct FinRange { int k_lo, k_hi; int guard, xstrips, yerr_i; int* err; };
+__global__ void __launch_bounds__(FIN16_CTA) slic_finalize16_kernel(SlicGeom g, SlicArrays a, int parity, FinRange fr)
 {
     const int t = blockIdx.x * FIN16_CTA + threadIdx.x;
     pdl_trigger();                                        // the next assignment may start loading its pixels
@@ -244,8 +247,8 @@ __global__ void __launch_bounds__(FIN16_CTA) slic_finalize16_kernel(SlicGeom g, 
     const int nb = g.nbx * g.nby;
     if (t < nb) (parity ? a.head[1] : a.head[0])[t] = -1;                            // the lists just consumed; reused two iterations later
     if (g.tile_on && t < g.tiles_x * g.tiles_y) (parity ? a.tl_count[1] : a.tl_count[0])[t] = 0;
-    const int n = t >> 4, j = t & 15;
-    if (n >= g.K) return;
+    const int n = fr.k_lo + (t >> 4), j = t & 15;
+    if (n >= fr.k_hi) return;
     constexpr int C = 3;                                  // (launched for 3-channel images only)
     unsigned long long sum[C + 3];
     #pragma unroll
@@ -262,6 +265,11 @@ __global__ void __launch_bounds__(FIN16_CTA) slic_finalize16_kernel(SlicGeom g, 
         for (int c = 0; c < C; c++) a.kc[(size_t)c * g.Kcap + n] = kc[c];
         a.kx[n] = kx; a.ky[n] = ky; a.ikx[n] = ix; a.iky[n] = iy;
         if (g.alg == 101) a.maxc[n] = __uint_as_float(a.maxc_acc[n]);                 // maxchans[k] <- accumulated maximum; seeds the next one
+        if (fr.guard) {
+            const int gy = n / fr.xstrips;
+            const int seed_y = min(gy * g.S + g.S / 2 + gy * fr.yerr_i, g.h - 1);
+            if (abs(iy - seed_y) > 2 * g.S - 2) atomicExch(fr.err, 100);
+        }
         int* head = par ? a.head[1] : a.head[0];
         const int bx = min(max(ix, 0) / g.S, g.nbx - 1), by = min(max(iy, 0) / g.S, g.nby - 1);
         a.next[n] = atomicExch(&head[by * g.nbx + bx], n);
@@ -483,6 +491,9 @@ struct StripPeers {
     unsigned long long* base[STRIP_MAX_WORLD];     // exchange buffer of every rank in THIS process's address space
     int world, rank, Kcap, nf;                     // nf = channels + 3 fields of Kcap entries each
     size_t n6;                                     // nf * Kcap
+    // neighbour mode (strip partition): only the two adjacent ranks exchange, and only the index range of the clusters both maintain
+    int mode;                                      // 0: every rank to every rank (replicated cluster state); 1: neighbours only
+    int nbr[2], nlo[2], nhi[2];                    // rank - 1 / rank + 1 (or -1) and the shared cluster range [nlo, nhi) with each
 };
 // layout of an exchange buffer: recv[2][world][n6] u64 | flag[MAX_WORLD] int | range[2][MAX_WORLD] int2
 __device__ __forceinline__ unsigned long long* strip_slot(unsigned long long* base, const StripPeers& P, int par, int src)
@@ -512,6 +523,34 @@ __global__ void __launch_bounds__(256) strip_push_kernel(const __grid_constant__
                                                           unsigned long long* __restrict__ bytes_sent)
 {
     const int par = iter & 1;
+    if (P.mode == 1) {
+        for (int q = 0; q < 2; q++) {
+            const int p = P.nbr[q], lo = P.nlo[q], len = P.nhi[q] - P.nlo[q];
+            if (p < 0 || len <= 0) continue;
+            unsigned long long* slot = strip_slot(P.base[p], P, par, P.rank);
+            for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < (size_t)P.nf * len; i += (size_t)gridDim.x * 256) {
+                const int f = (int)(i / len);
+                const size_t j = (size_t)f * P.Kcap + lo + (i - (size_t)f * len);
+                slot[j] = acc[j];
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(done, 1u) == gridDim.x - 1) {
+            *done = 0;
+            for (int q = 0; q < 2; q++) {
+                const int p = P.nbr[q];
+                if (p < 0) continue;
+                *bytes_sent += (unsigned long long)P.nf * max(P.nhi[q] - P.nlo[q], 0) * 8ull;
+                volatile int* r = reinterpret_cast<volatile int*>(strip_range(P.base[p], P, par, P.rank));
+                r[0] = P.nlo[q]; r[1] = max(P.nhi[q], P.nlo[q]);
+            }
+            __threadfence_system();
+            for (int q = 0; q < 2; q++)
+                if (P.nbr[q] >= 0) *reinterpret_cast<volatile int*>(&strip_flags(P.base[P.nbr[q]], P)[P.rank]) = iter;
+        }
+        return;
+    }
     int lo = range[0], hi = range[1] + 1;
     if (hi <= lo) lo = hi = 0;                     // the band received no pixel at all
     const int len = hi - lo;
@@ -553,7 +592,9 @@ __global__ void __launch_bounds__(256) strip_wait_sum_kernel(const __grid_consta
     const int par = iter & 1;
     if (threadIdx.x == 0) s_fail = 0;
     __syncthreads();
-    if (threadIdx.x < P.world && threadIdx.x != P.rank) {
+    const bool is_src = (int)threadIdx.x < P.world && (int)threadIdx.x != P.rank &&
+                        (P.mode == 0 || (int)threadIdx.x == P.nbr[0] || (int)threadIdx.x == P.nbr[1]);
+    if (is_src) {
         const volatile int* f = strip_flags(P.base[P.rank], P) + threadIdx.x;
         unsigned spins = 0;
         while (*f < iter && *(volatile int*)err == 0) {
@@ -568,7 +609,7 @@ __global__ void __launch_bounds__(256) strip_wait_sum_kernel(const __grid_consta
     __syncthreads();
     if (s_fail) return;
     for (int p = 0; p < P.world; p++) {
-        if (p == P.rank) continue;
+        if (p == P.rank || (P.mode == 1 && p != P.nbr[0] && p != P.nbr[1])) continue;
         const int lo = rg[p].x, len = rg[p].y - rg[p].x;
         const unsigned long long* slot = strip_slot(P.base[P.rank], P, par, p);
         for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < (size_t)P.nf * len; i += (size_t)gridDim.x * 256) {
@@ -615,6 +656,10 @@ struct SlicEngine {
     int* d_strip_err = nullptr;      // raised by strip_wait_sum_kernel when a peer never delivered (1 + its rank)
     int xchg_iter = 0;
     bool peers_open = false;
+    // strip partition (neighbour exchange): the clusters this rank maintains and the ranges it shares with rank - 1 / rank + 1
+    bool part_on = false;
+    int part_k_lo = 0, part_k_hi = 0, part_core_lo = 0, part_core_hi = 0;
+    int part_nbr[2] = {-1, -1}, part_nlo[2] = {0, 0}, part_nhi[2] = {0, 0};
 
     template <typename T> int dalloc(T** p, size_t n)
     {
@@ -642,6 +687,46 @@ struct SlicEngine {
         if (xchg) cudaFree(xchg);
         xchg = nullptr;
     }
+    // Strip partition.  own_rows[2q], own_rows[2q+1] = the rows rank q owns.  Rank q MAINTAINS the clusters whose seed row lies within
+    // M = 3S rows of its band (cluster indices are row-major in the seed grid: a contiguous index range).  A centre may drift up to
+    // 2S rows from its seed row (checked every update), so its window -- and every pixel carrying its label -- stays within 3S rows of
+    // the seed row: exactly the bands of the ranks that maintain it.  Bands taller than 6S + 2 seed pitches make those at most two
+    // ADJACENT ranks, which exchange their partial sums over the shared index range; nobody else needs them.
+    int strip_partition(const int* own_rows, int world, int rank, int* info)
+    {
+        SPX_REQUIRE(own_rows && world >= 2 && world <= STRIP_MAX_WORLD && rank >= 0 && rank < world, SPX_ERR_BADARG, "strip_partition: bad argument");
+        SPX_REQUIRE(g.alg == SPX_SLIC && !xchg, SPX_ERR_BADARG, "strip_partition: SLIC only, before strip_peer_alloc");
+        int K = 0;
+        const SeedParams sp = seed_params(&K);
+        const int ystrips = K / sp.xstrips, S = g.S, M = 3 * S;
+        auto seed_y = [&](int gy) { return std::min(gy * S + S / 2 + gy * sp.yerr_i, g.h - 1); };
+        std::vector<int> lo(world), hi(world), clo(world), chi(world);
+        for (int q = 0; q < world; q++) {
+            const int y0 = own_rows[2 * q], y1 = own_rows[2 * q + 1];
+            SPX_REQUIRE(y1 > y0, SPX_ERR_BADARG, "strip_partition: rank %d owns no rows", q);
+            int a0 = ystrips, a1 = 0, c0 = ystrips, c1 = 0;
+            for (int gy = 0; gy < ystrips; gy++) {
+                const int y = seed_y(gy);
+                if (y >= y0 - M && y < y1 + M) { a0 = std::min(a0, gy); a1 = std::max(a1, gy + 1); }
+                if (y >= y0 && y < y1) { c0 = std::min(c0, gy); c1 = std::max(c1, gy + 1); }
+            }
+            if (a1 < a0) a0 = a1 = 0;
+            if (c1 < c0) c0 = c1 = a0;
+            lo[q] = a0 * sp.xstrips; hi[q] = a1 * sp.xstrips; clo[q] = c0 * sp.xstrips; chi[q] = c1 * sp.xstrips;
+        }
+        for (int q = 0; q + 2 < world; q++)
+            SPX_REQUIRE(hi[q] <= lo[q + 2], SPX_ERR_BADARG, "strip_partition: bands are too thin for the neighbour exchange (need more than %d rows per rank)", 6 * S + 2 * S);
+        part_on = true;
+        part_k_lo = lo[rank]; part_k_hi = hi[rank]; part_core_lo = clo[rank]; part_core_hi = chi[rank];
+        for (int q = 0; q < 2; q++) {
+            const int p = q == 0 ? rank - 1 : rank + 1;
+            part_nbr[q] = (p >= 0 && p < world) ? p : -1;
+            part_nlo[q] = part_nhi[q] = 0;
+            if (part_nbr[q] >= 0) { part_nlo[q] = std::max(lo[rank], lo[p]); part_nhi[q] = std::max(part_nlo[q], std::min(hi[rank], hi[p])); }
+        }
+        if (info) { info[0] = part_k_lo; info[1] = part_k_hi; info[2] = part_core_lo; info[3] = part_core_hi; }
+        return SPX_OK;
+    }
     int strip_peer_alloc(int world, int rank, void* handle_out, size_t* bytes_out)
     {
         SPX_REQUIRE(world >= 1 && world <= STRIP_MAX_WORLD && rank >= 0 && rank < world && handle_out, SPX_ERR_BADARG,
@@ -649,6 +734,8 @@ struct SlicEngine {
         SPX_REQUIRE(!xchg, SPX_ERR_BADARG, "strip_peer_alloc: called twice");
         peers = StripPeers{};
         peers.world = world; peers.rank = rank; peers.Kcap = g.Kcap; peers.nf = g.C + 3; peers.n6 = (size_t)(g.C + 3) * g.Kcap;
+        peers.mode = part_on ? 1 : 0;
+        for (int q = 0; q < 2; q++) { peers.nbr[q] = part_nbr[q]; peers.nlo[q] = part_nlo[q]; peers.nhi[q] = part_nhi[q]; }
         xchg_bytes = (size_t)2 * world * peers.n6 * sizeof(unsigned long long) + (size_t)STRIP_MAX_WORLD * sizeof(int) +
                      (size_t)2 * STRIP_MAX_WORLD * sizeof(int2);
         SPX_CUDA(cudaMalloc(&xchg, xchg_bytes));
@@ -678,6 +765,8 @@ struct SlicEngine {
         if (!d_strip_err) return SPX_OK;
         SPX_CUDA(cudaMemcpyAsync(h_pinned + 1, d_strip_err, sizeof(int), cudaMemcpyDeviceToHost, st));
         SPX_CUDA(cudaStreamSynchronize(st));
+        SPX_REQUIRE(h_pinned[1] != 100, SPX_ERR_ASSERT, "strip partition: a cluster moved more than 2 * region_size rows away from its seed row; "
+                    "the neighbour exchange does not cover that -- rerun with the all-to-all exchange");
         SPX_REQUIRE(h_pinned[1] == 0, SPX_ERR_GPU, "strip exchange: rank %d never delivered its sums (peer gone or exchange skipped)", h_pinned[1] - 1);
         return SPX_OK;
     }
@@ -701,11 +790,20 @@ struct SlicEngine {
         SPX_REQUIRE(peers_open || peers.world == 1, SPX_ERR_BADARG, "strip_exchange: peers are not mapped");
         if (peers.world == 1) return SPX_OK;
         xchg_iter++;
-        const int nb = (int)std::min<size_t>((peers.n6 + 255) / 256, 4 * 148);
-        strip_range_kernel<<<std::min(cdiv(g.Kcap, 256), 148), 256, 0, st>>>(a.acc + (size_t)(g.C + 2) * g.Kcap, g.Kcap, d_range);
-        strip_push_kernel<<<nb, 256, 0, st>>>(peers, a.acc, xchg_iter, d_range, d_push_done, d_bytes_sent);
-        strip_wait_sum_kernel<<<nb, 256, 0, st>>>(peers, a.acc, xchg_iter, d_strip_err);
-        launches += 3;
+        if (peers.mode == 1) {
+            // neighbours only: the shared ranges are a few seed rows of clusters (tens to hundreds of KB)
+            const int len = std::max(std::max(peers.nhi[0] - peers.nlo[0], peers.nhi[1] - peers.nlo[1]), 1);
+            const int nb = (int)std::min<size_t>(((size_t)peers.nf * len + 255) / 256, 148);
+            strip_push_kernel<<<nb, 256, 0, st>>>(peers, a.acc, xchg_iter, d_range, d_push_done, d_bytes_sent);
+            strip_wait_sum_kernel<<<nb, 256, 0, st>>>(peers, a.acc, xchg_iter, d_strip_err);
+            launches += 2;
+        } else {
+            const int nb = (int)std::min<size_t>((peers.n6 + 255) / 256, 4 * 148);
+            strip_range_kernel<<<std::min(cdiv(g.Kcap, 256), 148), 256, 0, st>>>(a.acc + (size_t)(g.C + 2) * g.Kcap, g.Kcap, d_range);
+            strip_push_kernel<<<nb, 256, 0, st>>>(peers, a.acc, xchg_iter, d_range, d_push_done, d_bytes_sent);
+            strip_wait_sum_kernel<<<nb, 256, 0, st>>>(peers, a.acc, xchg_iter, d_strip_err);
+            launches += 3;
+        }
         SPX_CUDA(cudaGetLastError());
         return SPX_OK;
     }
@@ -847,8 +945,14 @@ struct SlicEngine {
     }
     int strip_update()
     {
-        const int threads_fin = max(max(g.Kcap, g.nbx * g.nby), g.tiles_x * g.tiles_y);
-        slic_finalize_kernel<<<cdiv(threads_fin, BIN_CTA), BIN_CTA, 0, st>>>(g, a, d_K, parity, 1);
+        FinRange fr{0, g.K, 0, 1, 0, d_strip_err};
+        if (part_on) {
+            int K = 0;
+            const SeedParams sp = seed_params(&K);
+            fr = FinRange{part_k_lo, part_k_hi, 1, sp.xstrips, sp.yerr_i, d_strip_err};
+        }
+        const int th16 = max(max(16 * (fr.k_hi - fr.k_lo), g.nbx * g.nby), g.tiles_x * g.tiles_y);
+        SPX_CUDA(launch_pdl(slic_finalize16_kernel, dim3(cdiv(th16, FIN16_CTA)), dim3(FIN16_CTA), st, g, a, parity, fr));
         launches++;
         parity ^= 1;
         SPX_CUDA(cudaGetLastError());
@@ -873,7 +977,8 @@ struct SlicEngine {
         const int do_bin = g.alg == SPX_MSLIC ? 0 : 1;
         if (do_bin && g.C == 3) {
             const int th16 = max(max(16 * g.K, g.nbx * g.nby), g.tiles_x * g.tiles_y);
-            SPX_CUDA(launch_pdl(slic_finalize16_kernel, dim3(cdiv(th16, FIN16_CTA)), dim3(FIN16_CTA), st, g, a, parity));
+            SPX_CUDA(launch_pdl(slic_finalize16_kernel, dim3(cdiv(th16, FIN16_CTA)), dim3(FIN16_CTA), st, g, a, parity,
+                                FinRange{0, g.K, 0, 1, 0, nullptr}));
         } else
             SPX_CUDA(launch_pdl(slic_finalize_kernel, dim3(cdiv(threads_fin, BIN_CTA)), dim3(BIN_CTA), st, g, a, (const int*)d_K, parity, do_bin));
         launches++;
@@ -1178,6 +1283,11 @@ extern "C" int spx_slic_strip_update(spx_slic_t* h) try
 {
     SLIC_ENTER(h);
     return e->strip_update();
+} SPX_API_CATCH
+extern "C" int spx_slic_strip_partition(spx_slic_t* h, const int* own_rows, int world, int rank, int* info_out) try
+{
+    SLIC_ENTER(h);
+    return e->strip_partition(own_rows, world, rank, info_out);
 } SPX_API_CATCH
 extern "C" int spx_slic_strip_peer_alloc(spx_slic_t* h, int world, int rank, void* ipc_handle_out, size_t* bytes_out) try
 {

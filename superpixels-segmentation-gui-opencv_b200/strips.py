@@ -5,11 +5,17 @@ rows) and uploads those rows plus two halo rows.  Cluster state is replicated; p
 integer accumulators (pixel sums per cluster) over the ranks -- only clusters near a cut receive pixels from two ranks,
 the sums are integers, so the result is bit-identical to the single-GPU object.
 
-The exchange step runs over NVLink peer memory by default (``exchange="peer"``): every rank's exchange buffer is mapped
-into its peers through CUDA IPC, the library's own kernels store the partial sums into the peers' buffers, publish a
-flag, wait for the peers' flags and add (``spx_slic_strip_exchange``; csrc/slic.cu).  ``exchange="nccl"`` keeps the
-NCCL all-reduce on the library's device pointers (``__cuda_array_interface__`` views) for comparison.  torch is plumbing:
-the process group carries the 64-byte IPC handles, the one-off assembly of the seeds and the barriers.
+The exchange step runs over NVLink peer memory: every rank's exchange buffer is mapped into its peers through CUDA IPC,
+the library's own kernels store partial sums into the peers' buffers, publish a flag, wait for the peers' flags and add
+(``spx_slic_strip_exchange``; csrc/slic.cu).
+  * ``exchange="neighbour"`` (default): the cluster state is PARTITIONED by band -- a rank maintains the clusters whose seed
+    row lies within 3S rows of its band and exchanges only with rank-1 / rank+1, over the few seed rows of clusters both
+    maintain (``spx_slic_strip_partition``).  Exact while no centre moves more than 2S rows from its seed row; the centre
+    update checks that on the device and iterate() reruns the whole object with the all-to-all exchange if it ever fails
+    (an empty cluster jumping to the origin is the one way to get there).  Thin bands fall back to "peer" at construction.
+  * ``exchange="peer"``: replicated cluster state, every rank stores the index range its band touched into every peer.
+  * ``exchange="nccl"``: replicated state, NCCL all-reduce on the library's device pointers, for comparison.
+torch is plumbing: the process group carries the 64-byte IPC handles, the one-off assembly of the seeds and the barriers.
 """
 import ctypes as C
 
@@ -50,11 +56,13 @@ class StripSLIC:
     """cv::ximgproc::SuperpixelSLIC (algorithm SLIC) over the row band of this rank.  `image` is the whole 8UC3 image
     or a callable rows(row0, row1) -> ndarray, so a rank never needs more than its band in host memory."""
 
-    def __init__(self, image, region_size, ruler, dist, device, width=None, height=None, exchange="peer"):
+    def __init__(self, image, region_size, ruler, dist, device, width=None, height=None, exchange="neighbour"):
         import torch
-        if exchange not in ("peer", "nccl"):
-            raise SpxError(-5, "StripSLIC: exchange must be 'peer' or 'nccl'")
+        if exchange not in ("neighbour", "peer", "nccl"):
+            raise SpxError(-5, "StripSLIC: exchange must be 'neighbour', 'peer' or 'nccl'")
         self.exchange = exchange
+        self._args = (image, region_size, ruler, dist, device, width, height)
+        self._iters_done = 0
         self.torch, self.dist = torch, dist
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         if callable(image):
@@ -99,7 +107,24 @@ class StripSLIC:
                 dist.all_reduce(t, op=dist.ReduceOp.SUM)
         _ck(L.spx_slic_strip_rebin(self._h))
         self.exchanged_bytes = 0
-        if exchange == "peer" and self.world > 1:
+        self._core = (0, self.K)
+        if self.exchange == "neighbour" and self.world > 1:
+            L.spx_slic_strip_partition.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_int)]
+            flat = [v for b in row_bands(self.h, self.world) for v in b]
+            own = (C.c_int * len(flat))(*flat)
+            info = (C.c_int * 4)()
+            rc = L.spx_slic_strip_partition(self._h, own, self.world, self.rank, info)
+            ok = torch.tensor([1 if rc == 0 else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)              # (the geometry is the same on every rank, so is rc; belt and braces)
+            if int(ok.item()) == 1:
+                self._core = (info[2], info[3])
+            else:
+                if rc == 0:
+                    raise SpxError(-5, "StripSLIC: the ranks disagree about the strip partition")
+                self.exchange = "peer"                              # bands too thin: replicated state, all-to-all exchange
+        elif self.exchange == "neighbour":
+            self.exchange = "peer"
+        if self.exchange in ("peer", "neighbour") and self.world > 1:
             L.spx_slic_strip_peer_alloc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_size_t)]
             L.spx_slic_strip_peer_open.argtypes = [C.c_void_p, C.c_void_p]
             L.spx_slic_strip_exchange.argtypes = [C.c_void_p]
@@ -115,7 +140,29 @@ class StripSLIC:
 
     def iterate(self, num_iterations=10):
         L = lib()
-        peer = self.exchange == "peer" and self.world > 1
+        peer = self.exchange in ("peer", "neighbour") and self.world > 1
+        self._iters_done += int(num_iterations)
+        self._iterate(L, peer, num_iterations)
+        bad = 0
+        if self.exchange == "neighbour" and self.world > 1:
+            try:
+                self.exchangedBytes()                              # synchronises and reports the device-side drift check
+            except SpxError as e:
+                if e.code != -215:
+                    raise
+                bad = 1
+            t = self.torch.tensor([bad], device=self._acc.device)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            bad = int(t.item())
+        if bad:
+            # a centre left the rows the partition covers: redo everything so far with replicated state (exact in every case)
+            image, region_size, ruler, dist, device, width, height = self._args
+            n = self._iters_done
+            self.release()
+            self.__init__(image, region_size, ruler, dist, device, width, height, exchange="peer")
+            self.iterate(n)
+
+    def _iterate(self, L, peer, num_iterations):
         for _ in range(int(num_iterations)):
             _ck(L.spx_slic_strip_assign(self._h))
             if peer:
@@ -130,8 +177,8 @@ class StripSLIC:
         return self.K
 
     def exchangedBytes(self):
-        """bytes this rank has sent in exchange steps so far (peer mode: counted on the device by the push kernel)"""
-        if self.exchange == "peer" and self.world > 1:
+        """bytes this rank has sent in exchange steps so far (peer modes: counted on the device by the push kernel)"""
+        if self.exchange in ("peer", "neighbour") and self.world > 1:
             L = lib()
             L.spx_slic_strip_exchanged_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong)]
             v = C.c_ulonglong(0)
@@ -204,16 +251,25 @@ class StripSLIC:
         self.stream.synchronize()
 
     def getCentres(self):
+        """(K, 5) centres c0 c1 c2 x y.  Neighbour mode: every rank contributes the clusters of its own band; collective."""
         t = self.torch
         self.stream.synchronize()
         K, Kcap = self.K, self._seed_f[0].numel()
         kc = self._seed_f[2].view(3, Kcap)[:, :K].t()
-        return t.cat([kc, self._seed_f[0][:K, None], self._seed_f[1][:K, None]], 1).cpu().numpy()
+        mine = t.cat([kc, self._seed_f[0][:K, None], self._seed_f[1][:K, None]], 1).cpu().numpy()
+        if self.exchange != "neighbour" or self.world == 1:
+            return mine
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, (self._core, mine[self._core[0]:self._core[1]]))
+        out = mine.copy()
+        for (lo, hi), v in parts:
+            out[lo:hi] = v
+        return out
 
     def release(self, barrier=True):
-        """collective when exchange == "peer": no rank may free its exchange buffer while a peer can still write to it"""
+        """collective in the peer modes: no rank may free its exchange buffer while a peer can still write to it"""
         if self._h.value:
-            if barrier and self.exchange == "peer" and self.world > 1:
+            if barrier and self.exchange in ("peer", "neighbour") and self.world > 1:
                 self.stream.synchronize()
                 self.dist.barrier()
             lib().spx_slic_destroy(self._h)

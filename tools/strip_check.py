@@ -32,7 +32,8 @@ def run(exchange):
     return out
 
 
-Ls, Cs, t, xb, K, Lc, Mc, Kc, tc = run("peer")                              # NVLink peer stores + flags by the library's own kernels
+Lb, Cb, tb, xbb, _ = run("neighbour")                       # partitioned cluster state, boundary sums to rank-1 / rank+1 only
+Ls, Cs, t, xb, K, Lc, Mc, Kc, tc = run("peer")                              # replicated state, touched range to every peer
 Ln, Cn, tn, xbn, _ = run("nccl")                            # NCCL all-reduce of the accumulators
 if rank == 0:
     g = spx.createSuperpixelSLIC(lab, spx.SLIC, S, RULER, device=local)
@@ -42,12 +43,14 @@ if rank == 0:
     g.enforceLabelConnectivity(25)
     post_ok = bool(Kc == g.getNumberOfSuperpixels() and (Lc == g.getLabels()).all() and (Mc == g.getLabelContourMask(False)).all())
     print(json.dumps({"strip_check": "%dx%d SLIC S=%d %d iterations" % (W, H, S, IT), "n_gpus": world, "bands": strips.row_bands(H, world),
-                      "labels_identical": bool((Ls == Lg).all() and (Ln == Lg).all()),
-                      "centres_identical": bool((Cs == Cg).all() and (Cn == Cg).all()),
+                      "labels_identical": bool((Ls == Lg).all() and (Ln == Lg).all() and (Lb == Lg).all()),
+                      "centres_identical": bool((Cs == Cg).all() and (Cn == Cg).all() and (Cb == Cg).all()),
+                      "strip_iterate_ms_neighbour": tb * 1e3, "sent_MB_per_rank_per_iteration_neighbour": xbb / IT / 1e6,
                       "connectivity_and_contour_identical": post_ok, "gather_plus_connectivity_ms": tc * 1e3, "K_connected": Kc,
                       "strip_iterate_ms": t * 1e3, "strip_iterate_ms_nccl_allreduce": tn * 1e3, "single_gpu_iterate_ms": t1 * 1e3,
                       "exchange": "peer memory (CUDA IPC over NVLink): stores + flags by the library's kernels",
                       "sent_MB_per_rank_per_iteration": xb / IT / 1e6, "allreduce_payload_MB_per_iteration": xbn / IT / 1e6, "K": K}))
     assert (Ls == Lg).all() and (Cs == Cg).all() and (Ln == Lg).all() and (Cn == Cg).all() and post_ok
+    assert (Lb == Lg).all() and (Cb == Cg).all()
 dist.barrier()
 dist.destroy_process_group()
