@@ -306,20 +306,26 @@ def strip_leg(spx, dist, rank, world, local):
         return out
 
     res = {}
-    for it in range(2):                                    # the first object warms kernels, peer mappings and NCCL up
-        s = strips.StripSLIC(rows, 20, 10.0, dist, local, width=W, height=H, exchange="peer")
-        if it == 0:
-            s.iterate(1); s.release(); continue
-        torch.cuda.synchronize(); dist.barrier()
-        t0 = time.perf_counter(); s.iterate(ITERS); torch.cuda.synchronize(); dist.barrier(); t = time.perf_counter() - t0
-        tt = torch.tensor([t], dtype=torch.float64, device=torch.device("cuda", local))
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        labels = s.getLabels()                             # assembled on rank 0
-        res = {"image": "16384x16384 synthetic (64x64 colour blocks xor noise), SLIC S=20 ruler=10, 10 iterations", "n_gpus": world,
-               "strip_iterate10_ms": float(tt.item()) * 1e3, "MP_s": W * H / 1e6 / float(tt.item()),
-               "sent_bytes_per_rank_per_iteration": s.exchangedBytes() / ITERS, "exchange": "NVLink peer stores + flags (library kernels)",
-               "superpixels": s.getNumberOfSuperpixels()}
-        s.release()
+    labels = None
+    for mode in ("peer", "neighbour"):                     # replicated state + all-to-all first (comparison), then the partitioned default
+        for it in range(2):                                # the first object warms kernels, peer mappings and NCCL up
+            s = strips.StripSLIC(rows, 20, 10.0, dist, local, width=W, height=H, exchange=mode)
+            if it == 0:
+                s.iterate(1); s.release(); continue
+            torch.cuda.synchronize(); dist.barrier()
+            t0 = time.perf_counter(); s.iterate(ITERS); torch.cuda.synchronize(); dist.barrier(); t = time.perf_counter() - t0
+            tt = torch.tensor([t], dtype=torch.float64, device=torch.device("cuda", local))
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            if mode == "peer":
+                res.update({"all_to_all_iterate10_ms": float(tt.item()) * 1e3, "all_to_all_sent_bytes_per_rank_per_iteration": s.exchangedBytes() / ITERS})
+            else:
+                labels = s.getLabels()                     # assembled on rank 0
+                res.update({"image": "16384x16384 synthetic (64x64 colour blocks xor noise), SLIC S=20 ruler=10, 10 iterations", "n_gpus": world,
+                            "strip_iterate10_ms": float(tt.item()) * 1e3, "MP_s": W * H / 1e6 / float(tt.item()),
+                            "sent_bytes_per_rank_per_iteration": s.exchangedBytes() / ITERS,
+                            "exchange": "%s: NVLink peer stores + flags (library kernels)" % s.exchange,
+                            "superpixels": s.getNumberOfSuperpixels()})
+            s.release()
     if rank == 0:
         img = rows(0, H)
         g = spx.createSuperpixelSLIC(img, spx.SLIC, 20, 10.0, device=local)
