@@ -1082,7 +1082,8 @@ struct LscEngine {
         SPX_CHECK(dalloc(&d_flag, 8));
         SPX_CHECK(dalloc(&d_tile_overflow, 1));
         SPX_CUDA(cudaMemsetAsync(d_tile_overflow, 0, sizeof(int), st));
-        tiled = C == 3 && L.stepx >= LSC_TILE_MIN_STEP && L.stepy >= LSC_TILE_MIN_STEP && !getenv("SPX_LSC_NO_TILE") &&
+        static const int min_step = getenv("SPX_LSC_TILE_MIN_STEP") ? atoi(getenv("SPX_LSC_TILE_MIN_STEP")) : LSC_TILE_MIN_STEP;   // (experiments)
+        tiled = C == 3 && L.stepx >= min_step && L.stepy >= min_step && !getenv("SPX_LSC_NO_TILE") &&
                 20.0f * ratio_ < 32768.0f;          // (lsc_sadd64's split assumes |feature| * 2^32 * 4 < 2^55)
         L.tiles_x = cdiv(w, 32); L.tiles_y = cdiv(h, LSC_TH);
         L.ctab = nullptr; L.tl_count = nullptr; L.tl_k = nullptr;

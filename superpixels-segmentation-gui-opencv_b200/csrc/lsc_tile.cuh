@@ -19,7 +19,7 @@
 // (no include guard needed: included once, inside namespace spx, by lsc.cu, which includes f32x2.cuh at file scope)
 
 constexpr int LSC_NCOPY = 8;
-constexpr int LSC_TILE_MIN_STEP = 14;
+constexpr int LSC_TILE_MIN_STEP = 10;   // measured at 4K (r2): step 10 tiled 3.2 ms vs per-pixel 4.6 ms per iterate(10), step 12: 2.2 vs 4.3; step 8: 15 vs 4.7 (lists overflow)
 constexpr int LSC_SLOTW = 24;                      // words per slot: 10 feature sums + W as {lo, hi}; x | y << 16; count
 constexpr int LSC_COPYW = LSC_CAP * LSC_SLOTW + 4; // the +4 words rotate the copies over the banks
 

@@ -25,6 +25,7 @@
 #include "slic_generic.cuh"
 #include "f32x2.cuh"
 #include <cfloat>
+#include <cstdlib>
 #include <cmath>
 #include <type_traits>
 
@@ -35,7 +36,8 @@ constexpr int TH = TILE_H;   // 32: two warp rows x 8 rows x two steps
 constexpr int CAP = TILE_CAP;
 constexpr int NT = 128;      // threads per CTA
 constexpr int NCOPY = 8;
-constexpr int MIN_S = 14;    // below this the candidate lists outgrow CAP too often: generic kernel instead
+constexpr int MIN_S = 7;     // measured at 4K (r2): S = 7 tiled 2.1 ms vs generic 5.3 ms per iterate(10) although many tiles overflow into the
+                             // exact per-pixel path; S = 6: 12.1 vs 5.5 ms (every tile overflows CAP = 48); S = 8..13: 4-6x faster tiled
 
 // ---- shared memory layout -----------------------------------------------------------------------
 // one record per candidate, so that a single multiply addresses everything the inner loop reads
@@ -495,7 +497,8 @@ static bool markstein_ok(float w)
 
 bool slic_tile_supported(const SlicGeom& g)
 {
-    return (g.alg == SPX_SLIC || g.alg == SPX_SLICO || g.alg == SPX_MSLIC) && g.C == 3 && g.S >= MIN_S && (is_pow2(g.xywt) || markstein_ok(g.xywt));
+    static const int min_s = getenv("SPX_TILE_MIN_S") ? atoi(getenv("SPX_TILE_MIN_S")) : MIN_S;    // (experiments)
+    return (g.alg == SPX_SLIC || g.alg == SPX_SLICO || g.alg == SPX_MSLIC) && g.C == 3 && g.S >= min_s && (is_pow2(g.xywt) || markstein_ok(g.xywt));
 }
 
 // 8UC3 rows -> Lab1 words (c0 | c1<<8 | c2<<16 | 1<<24); the padding of the tile grid stays zero

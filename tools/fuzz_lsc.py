@@ -12,7 +12,7 @@ rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 bad = 0
 for i in range(n):
     w, h = int(rng.integers(16, 400)), int(rng.integers(16, 260))
-    S = int(rng.choice([6, 10, 14, 15, 16, 20, 23, 30, 32, 40, 47, 64]))
+    S = int(rng.choice([6, 10, 11, 12, 13, 14, 15, 16, 20, 23, 30, 32, 40, 47, 64]))
     ratio = float(rng.choice([0.02, 0.075, 0.2, 0.5]))
     it = int(rng.integers(1, 6))
     kind = int(rng.integers(0, 3))

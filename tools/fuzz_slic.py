@@ -12,7 +12,7 @@ bad = 0
 for i in range(n):
     w, h = int(rng.integers(8, 330)), int(rng.integers(8, 200))
     alg = int(rng.choice([100, 101, 102]))
-    S = int(rng.choice([5, 9, 14, 15, 16, 20, 23, 32, 40, 47, 64, 90]))
+    S = int(rng.choice([5, 7, 8, 9, 11, 13, 14, 15, 16, 20, 23, 32, 40, 47, 64, 90]))
     ruler = float(rng.choice([1.0, 5.0, 8.0, 10.0, 16.0, 30.0, 45.0]))
     it = int(rng.integers(1, 5))
     kind = int(rng.integers(0, 3))
