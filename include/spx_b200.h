@@ -88,6 +88,10 @@ int spx_slic_get_label_contour_mask_dev(spx_slic_t*, void* d_dst, size_t dst_str
 /* test hooks: inject a label map (bit-exact checks of connectivity / contour), read the centres.
  * centres: rows of (c0..c[channels-1], x, y) float32; `rows` = capacity of dst in rows. */
 int spx_slic_set_labels(spx_slic_t*, const int32_t* src, size_t src_stride, int numlabels);
+/* on = 1: the object is one of several working concurrently on the device (other streams): use the centre-update kernel with the
+ * fewest instructions instead of the one with the shortest latency (default, best for a single COMPUTE click).  Results are
+ * identical.  spx_slic_batch_dev sets it for its pooled objects. */
+int spx_slic_set_throughput_mode(spx_slic_t*, int on);
 int spx_slic_get_centres(spx_slic_t*, float* dst, int rows);
 int spx_slic_synchronize(spx_slic_t*);
 /* number of kernels this object has launched so far (bench.py's gpu_launches) */

@@ -47,6 +47,7 @@ extern "C" int spx_slic_batch_dev(const void* const* d_frames, int n_frames, int
             spx_slic_t* e = nullptr;
             rc = spx_slic_create_dev(d_frames[i], (size_t)w * C, w, h, C, alg, S, ruler, nullptr, &e);
             if (rc != SPX_OK) break;
+            spx_slic_set_throughput_mode(e, 1);                    // several frames in flight: the instruction-lean centre update
             eng.push_back(e);
         } else {
             rc = spx_slic_reset_dev(eng[s], d_frames[i], (size_t)w * C);

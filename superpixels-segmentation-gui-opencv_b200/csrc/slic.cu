@@ -642,6 +642,11 @@ struct SlicEngine {
     int parity = 0;
     bool use_tile = false;
     bool use_graph = true;
+    // Centre update: slic_finalize16_kernel (16 threads per centre) has the shortest dependent chain -- best for one frame on an
+    // otherwise idle device (4K iterate(10) 0.575 vs 0.649 ms) -- but executes 3.0 M warp-instructions per launch, 7 % of an
+    // assignment launch; with several frames in flight on other streams (spx_slic_batch_dev) that costs 5 % of the throughput
+    // (14.2 vs 15.0 GP/s), so the batch engines keep slic_finalize_kernel (one thread per centre, shared staging).
+    bool lean_update = false;
     long long launches = 0;
     PostWorkspace post;
     std::map<long long, cudaGraphExec_t> graphs;
@@ -975,7 +980,7 @@ struct SlicEngine {
         launches++;
         if (e1) SPX_CUDA(cudaEventRecord(e1, st));
         const int do_bin = g.alg == SPX_MSLIC ? 0 : 1;
-        if (do_bin && g.C == 3) {
+        if (do_bin && g.C == 3 && !lean_update) {
             const int th16 = max(max(16 * g.K, g.nbx * g.nby), g.tiles_x * g.tiles_y);
             SPX_CUDA(launch_pdl(slic_finalize16_kernel, dim3(cdiv(th16, FIN16_CTA)), dim3(FIN16_CTA), st, g, a, parity,
                                 FinRange{0, g.K, 0, 1, 0, nullptr}));
@@ -1412,6 +1417,18 @@ extern "C" int spx_slic_synchronize(spx_slic_t* h) try
 {
     SLIC_ENTER(h);
     SPX_CUDA(cudaStreamSynchronize(e->st));
+    return SPX_OK;
+} SPX_API_CATCH
+extern "C" int spx_slic_set_throughput_mode(spx_slic_t* h, int on) try
+{
+    SLIC_ENTER(h);
+    if (e->lean_update != (on != 0)) {
+        SPX_CUDA(cudaStreamSynchronize(e->st));
+        for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);   // captured with the other centre-update kernel
+        e->graphs.clear();
+        e->graph_launches.clear();
+        e->lean_update = on != 0;
+    }
     return SPX_OK;
 } SPX_API_CATCH
 extern "C" int spx_slic_launch_count(spx_slic_t* h, long long* out) try
