@@ -212,6 +212,8 @@ int spx_lsc_destroy(spx_lsc_t*);
 
 /* ---- cv::ximgproc::SuperpixelSEEDS (mainwindow.h:172, mainwindow.cpp:2123-2127) ---- */
 typedef struct spx_seeds spx_seeds_t;
+/* histogram_bins: any value >= 1 (the GUI slider goes to 50); one histogram of bins^channels int counters is kept per block of
+ * every level, as upstream does: SPX_ERR_NOMEM when that does not fit the free device memory. */
 int spx_seeds_create(int width, int height, int channels, int num_superpixels, int num_levels,
                      int prior, int histogram_bins, int double_step, int device, spx_seeds_t** out);
 /* SuperpixelSEEDS::iterate(img, num_iterations) -- mainwindow.cpp:2124 */
