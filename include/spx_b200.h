@@ -150,13 +150,15 @@ int spx_slic_strip_update(spx_slic_t*);
  * after all ranks have finished iterating (a barrier on the host side). */
 /* Neighbour exchange (the north-star's "NVLink peer exchange of boundary cluster sums"): call spx_slic_strip_partition() BEFORE
  * spx_slic_strip_peer_alloc().  own_rows = {own_row0, own_row1} of every rank, in rank order.  The cluster state is then
- * PARTITIONED: a rank updates only the clusters whose seed row lies within 3 * region_size rows of its band and exchanges partial
+ * PARTITIONED: a rank updates only the clusters whose seed row lies within 5 * region_size rows of its band and exchanges partial
  * sums only with rank - 1 / rank + 1, over the index range of the clusters both maintain (a few seed rows).  Exact while no
- * centre moves more than 2 * region_size rows from its seed row; the centre update checks that and a violation surfaces as
+ * centre moves more than 4 * region_size rows from its seed row; the centre update checks that and a violation surfaces as
  * SPX_ERR_ASSERT at the next synchronising call (strips.py then reruns with the all-to-all exchange).  Returns SPX_ERR_BADARG
  * when the bands are too thin (three ranks would maintain one cluster).  info_out[4] = the maintained index range [k_lo, k_hi)
  * and the core range [core_lo, core_hi) of clusters whose seed row lies in this rank's own band (for gathering centres). */
 int spx_slic_strip_partition(spx_slic_t*, const int* own_rows /* world x 2 */, int world, int rank, int* info_out /* 4 ints or NULL */);
+/* the same arithmetic without an object or a device (host logic only): plan_out[4q..4q+3] = k_lo, k_hi, core_lo, core_hi of rank q */
+int spx_slic_strip_plan(int width, int height, int region_size, const int* own_rows /* world x 2 */, int world, int* plan_out /* world x 4 */);
 int spx_slic_strip_peer_alloc(spx_slic_t*, int world, int rank, void* ipc_handle_out /* 64 bytes */, size_t* bytes_out);
 int spx_slic_strip_peer_open(spx_slic_t*, const void* ipc_handles /* world x 64 bytes, rank order */);
 int spx_slic_strip_exchange(spx_slic_t*);

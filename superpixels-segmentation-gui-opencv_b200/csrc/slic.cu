@@ -237,8 +237,11 @@ __global__ void __launch_bounds__(BIN_CTA) slic_finalize_kernel(SlicGeom g, Slic
 // memory round trips (sums, list position) instead of five.
 constexpr int FIN16_CTA = 128;
 // Strip partition: a rank updates only the clusters [k_lo, k_hi) it maintains; a cluster whose centre has
-// moved more than 2S - 2 rows away from its seed row could reach a band whose rank does not maintain it: *err = 100.
+// moved more than 4S - 2 rows away from its seed row could reach a band whose rank does not maintain it: *err = 100.
 struct FinRange { int k_lo, k_hi; int guard, xstrips, yerr_i; int* err; };
+// a rank maintains the clusters whose seed row lies within STRIP_MARGIN_S * S rows of its band; centres may then drift
+// (STRIP_MARGIN_S - 1) * S rows from their seed row (measured on the synthetic frames: up to 39 rows = 2 S in 10 iterations)
+constexpr int STRIP_MARGIN_S = 5;
 __global__ void __launch_bounds__(FIN16_CTA) slic_finalize16_kernel(SlicGeom g, SlicArrays a, int parity, FinRange fr)
 {
     const int t = blockIdx.x * FIN16_CTA + threadIdx.x;
@@ -268,7 +271,7 @@ __global__ void __launch_bounds__(FIN16_CTA) slic_finalize16_kernel(SlicGeom g, 
         if (fr.guard) {
             const int gy = n / fr.xstrips;
             const int seed_y = min(gy * g.S + g.S / 2 + gy * fr.yerr_i, g.h - 1);
-            if (abs(iy - seed_y) > 2 * g.S - 2) atomicExch(fr.err, 100);
+            if (abs(iy - seed_y) > (STRIP_MARGIN_S - 1) * g.S - 2 || fr.guard == 2) atomicExch(fr.err, 100);
         }
         int* head = par ? a.head[1] : a.head[0];
         const int bx = min(max(ix, 0) / g.S, g.nbx - 1), by = min(max(iy, 0) / g.S, g.nby - 1);
@@ -621,6 +624,36 @@ __global__ void __launch_bounds__(256) strip_wait_sum_kernel(const __grid_consta
     }
 }
 
+// The strip partition's index ranges (host arithmetic only; also exported as spx_slic_strip_plan for tests without a device).
+// Seeds of the strip grid (GetChSeedsS): row gy sits at y = gy*S + S/2 + gy*yerr_i; cluster index = gy * xstrips + gx.
+static int strip_plan(int w, int h, int S, const int* own_rows, int world, std::vector<int>& lo, std::vector<int>& hi,
+                      std::vector<int>& clo, std::vector<int>& chi)
+{
+    SPX_REQUIRE(w > 0 && h > 0 && S >= 1 && own_rows && world >= 1, SPX_ERR_BADARG, "strip_plan: bad argument");
+    const int xstrips = (int)(0.5f + (float)w / (float)S), ystrips = (int)(0.5f + (float)h / (float)S);
+    SPX_REQUIRE(xstrips >= 1 && ystrips >= 1, SPX_ERR_BADARG, "strip_plan: region_size leaves no seed");
+    const int yerr_i = (int)((float)(h - S * ystrips) / (float)ystrips);
+    const int M = STRIP_MARGIN_S * S;
+    auto seed_y = [&](int gy) { return std::min(gy * S + S / 2 + gy * yerr_i, h - 1); };
+    lo.assign(world, 0); hi.assign(world, 0); clo.assign(world, 0); chi.assign(world, 0);
+    for (int q = 0; q < world; q++) {
+        const int y0 = own_rows[2 * q], y1 = own_rows[2 * q + 1];
+        SPX_REQUIRE(y1 > y0, SPX_ERR_BADARG, "strip_partition: rank %d owns no rows", q);
+        int a0 = ystrips, a1 = 0, c0 = ystrips, c1 = 0;
+        for (int gy = 0; gy < ystrips; gy++) {
+            const int y = seed_y(gy);
+            if (y >= y0 - M && y < y1 + M) { a0 = std::min(a0, gy); a1 = std::max(a1, gy + 1); }
+            if (y >= y0 && y < y1) { c0 = std::min(c0, gy); c1 = std::max(c1, gy + 1); }
+        }
+        if (a1 < a0) a0 = a1 = 0;
+        if (c1 < c0) c0 = c1 = a0;
+        lo[q] = a0 * xstrips; hi[q] = a1 * xstrips; clo[q] = c0 * xstrips; chi[q] = c1 * xstrips;
+    }
+    for (int q = 0; q + 2 < world; q++)
+        SPX_REQUIRE(hi[q] <= lo[q + 2], SPX_ERR_BADARG, "strip_partition: bands are too thin for the neighbour exchange (need more than %d rows per rank)", (2 * STRIP_MARGIN_S + 2) * S);
+    return SPX_OK;
+}
+
 struct SlicEngine {
     int device = 0;
     cudaStream_t st = nullptr;
@@ -693,34 +726,16 @@ struct SlicEngine {
         xchg = nullptr;
     }
     // Strip partition.  own_rows[2q], own_rows[2q+1] = the rows rank q owns.  Rank q MAINTAINS the clusters whose seed row lies within
-    // M = 3S rows of its band (cluster indices are row-major in the seed grid: a contiguous index range).  A centre may drift up to
-    // 2S rows from its seed row (checked every update), so its window -- and every pixel carrying its label -- stays within 3S rows of
-    // the seed row: exactly the bands of the ranks that maintain it.  Bands taller than 6S + 2 seed pitches make those at most two
+    // M = 5S rows of its band (cluster indices are row-major in the seed grid: a contiguous index range).  A centre may drift up to
+    // 4S rows from its seed row (checked every update), so its window -- and every pixel carrying its label -- stays within 5S rows of
+    // the seed row: exactly the bands of the ranks that maintain it.  Bands taller than 10S + 2 seed pitches make those at most two
     // ADJACENT ranks, which exchange their partial sums over the shared index range; nobody else needs them.
     int strip_partition(const int* own_rows, int world, int rank, int* info)
     {
         SPX_REQUIRE(own_rows && world >= 2 && world <= STRIP_MAX_WORLD && rank >= 0 && rank < world, SPX_ERR_BADARG, "strip_partition: bad argument");
         SPX_REQUIRE(g.alg == SPX_SLIC && !xchg, SPX_ERR_BADARG, "strip_partition: SLIC only, before strip_peer_alloc");
-        int K = 0;
-        const SeedParams sp = seed_params(&K);
-        const int ystrips = K / sp.xstrips, S = g.S, M = 3 * S;
-        auto seed_y = [&](int gy) { return std::min(gy * S + S / 2 + gy * sp.yerr_i, g.h - 1); };
-        std::vector<int> lo(world), hi(world), clo(world), chi(world);
-        for (int q = 0; q < world; q++) {
-            const int y0 = own_rows[2 * q], y1 = own_rows[2 * q + 1];
-            SPX_REQUIRE(y1 > y0, SPX_ERR_BADARG, "strip_partition: rank %d owns no rows", q);
-            int a0 = ystrips, a1 = 0, c0 = ystrips, c1 = 0;
-            for (int gy = 0; gy < ystrips; gy++) {
-                const int y = seed_y(gy);
-                if (y >= y0 - M && y < y1 + M) { a0 = std::min(a0, gy); a1 = std::max(a1, gy + 1); }
-                if (y >= y0 && y < y1) { c0 = std::min(c0, gy); c1 = std::max(c1, gy + 1); }
-            }
-            if (a1 < a0) a0 = a1 = 0;
-            if (c1 < c0) c0 = c1 = a0;
-            lo[q] = a0 * sp.xstrips; hi[q] = a1 * sp.xstrips; clo[q] = c0 * sp.xstrips; chi[q] = c1 * sp.xstrips;
-        }
-        for (int q = 0; q + 2 < world; q++)
-            SPX_REQUIRE(hi[q] <= lo[q + 2], SPX_ERR_BADARG, "strip_partition: bands are too thin for the neighbour exchange (need more than %d rows per rank)", 6 * S + 2 * S);
+        std::vector<int> lo, hi, clo, chi;
+        SPX_CHECK(strip_plan(g.w, g.h, g.S, own_rows, world, lo, hi, clo, chi));
         part_on = true;
         part_k_lo = lo[rank]; part_k_hi = hi[rank]; part_core_lo = clo[rank]; part_core_hi = chi[rank];
         for (int q = 0; q < 2; q++) {
@@ -770,7 +785,7 @@ struct SlicEngine {
         if (!d_strip_err) return SPX_OK;
         SPX_CUDA(cudaMemcpyAsync(h_pinned + 1, d_strip_err, sizeof(int), cudaMemcpyDeviceToHost, st));
         SPX_CUDA(cudaStreamSynchronize(st));
-        SPX_REQUIRE(h_pinned[1] != 100, SPX_ERR_ASSERT, "strip partition: a cluster moved more than 2 * region_size rows away from its seed row; "
+        SPX_REQUIRE(h_pinned[1] != 100, SPX_ERR_ASSERT, "strip partition: a cluster moved more than 4 * region_size rows away from its seed row; "
                     "the neighbour exchange does not cover that -- rerun with the all-to-all exchange");
         SPX_REQUIRE(h_pinned[1] == 0, SPX_ERR_GPU, "strip exchange: rank %d never delivered its sums (peer gone or exchange skipped)", h_pinned[1] - 1);
         return SPX_OK;
@@ -954,7 +969,9 @@ struct SlicEngine {
         if (part_on) {
             int K = 0;
             const SeedParams sp = seed_params(&K);
-            fr = FinRange{part_k_lo, part_k_hi, 1, sp.xstrips, sp.yerr_i, d_strip_err};
+            // test hook: SPX_STRIP_FORCE_DRIFT=i raises the drift flag in the i-th update, so that the host's rerun path gets exercised
+            static const int force_at = getenv("SPX_STRIP_FORCE_DRIFT") ? atoi(getenv("SPX_STRIP_FORCE_DRIFT")) : 0;
+            fr = FinRange{part_k_lo, part_k_hi, (force_at > 0 && xchg_iter == force_at) ? 2 : 1, sp.xstrips, sp.yerr_i, d_strip_err};
         }
         const int th16 = max(max(16 * (fr.k_hi - fr.k_lo), g.nbx * g.nby), g.tiles_x * g.tiles_y);
         SPX_CUDA(launch_pdl(slic_finalize16_kernel, dim3(cdiv(th16, FIN16_CTA)), dim3(FIN16_CTA), st, g, a, parity, fr));
@@ -1288,6 +1305,14 @@ extern "C" int spx_slic_strip_update(spx_slic_t* h) try
 {
     SLIC_ENTER(h);
     return e->strip_update();
+} SPX_API_CATCH
+extern "C" int spx_slic_strip_plan(int w, int h, int region_size, const int* own_rows, int world, int* plan_out) try
+{
+    SPX_REQUIRE(plan_out, SPX_ERR_BADARG, "strip_plan: plan_out is NULL");
+    std::vector<int> lo, hi, clo, chi;
+    SPX_CHECK(spx::strip_plan(w, h, region_size, own_rows, world, lo, hi, clo, chi));
+    for (int q = 0; q < world; q++) { plan_out[4 * q] = lo[q]; plan_out[4 * q + 1] = hi[q]; plan_out[4 * q + 2] = clo[q]; plan_out[4 * q + 3] = chi[q]; }
+    return SPX_OK;
 } SPX_API_CATCH
 extern "C" int spx_slic_strip_partition(spx_slic_t* h, const int* own_rows, int world, int rank, int* info_out) try
 {

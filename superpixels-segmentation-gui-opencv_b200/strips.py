@@ -9,8 +9,8 @@ The exchange step runs over NVLink peer memory: every rank's exchange buffer is 
 the library's own kernels store partial sums into the peers' buffers, publish a flag, wait for the peers' flags and add
 (``spx_slic_strip_exchange``; csrc/slic.cu).
   * ``exchange="neighbour"`` (default): the cluster state is PARTITIONED by band -- a rank maintains the clusters whose seed
-    row lies within 3S rows of its band and exchanges only with rank-1 / rank+1, over the few seed rows of clusters both
-    maintain (``spx_slic_strip_partition``).  Exact while no centre moves more than 2S rows from its seed row; the centre
+    row lies within 5S rows of its band and exchanges only with rank-1 / rank+1, over the few seed rows of clusters both
+    maintain (``spx_slic_strip_partition``).  Exact while no centre moves more than 4S rows from its seed row; the centre
     update checks that on the device and iterate() reruns the whole object with the all-to-all exchange if it ever fails
     (an empty cluster jumping to the origin is the one way to get there).  Thin bands fall back to "peer" at construction.
   * ``exchange="peer"``: replicated cluster state, every rank stores the index range its band touched into every peer.

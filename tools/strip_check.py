@@ -16,6 +16,7 @@ W, H = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (4096, 409
 S, RULER, IT = 20, 10.0, 10
 bgr, _ = synth.synth(W, H, 3)                               # every rank builds the same image and slices its band
 lab = spx.cvtColor(bgr, spx.COLOR_BGR2Lab, device=local)
+final_mode = {}
 def run(exchange):
     w = strips.StripSLIC(lab, S, RULER, dist, local, exchange=exchange)
     w.iterate(1)                                            # kernel / NCCL / peer-mapping warm-up
@@ -24,6 +25,7 @@ def run(exchange):
     torch.cuda.synchronize(); dist.barrier()
     t0 = time.perf_counter(); s.iterate(IT); torch.cuda.synchronize(); dist.barrier(); t = time.perf_counter() - t0
     out = [s.getLabels(), s.getCentres(), t, s.exchangedBytes(), s.getNumberOfSuperpixels()]
+    final_mode[exchange] = s.exchange                        # "neighbour" falls back to "peer" when the drift check fires
     if exchange == "peer":                                  # the rest of the COMPUTE click on the strip object (gathered on rank 0's device)
         torch.cuda.synchronize(); dist.barrier()
         t0 = time.perf_counter(); s.enforceLabelConnectivity(25); torch.cuda.synchronize(); dist.barrier(); tc = time.perf_counter() - t0
@@ -45,7 +47,7 @@ if rank == 0:
     print(json.dumps({"strip_check": "%dx%d SLIC S=%d %d iterations" % (W, H, S, IT), "n_gpus": world, "bands": strips.row_bands(H, world),
                       "labels_identical": bool((Ls == Lg).all() and (Ln == Lg).all() and (Lb == Lg).all()),
                       "centres_identical": bool((Cs == Cg).all() and (Cn == Cg).all() and (Cb == Cg).all()),
-                      "strip_iterate_ms_neighbour": tb * 1e3, "sent_MB_per_rank_per_iteration_neighbour": xbb / IT / 1e6,
+                      "neighbour_mode_ran_as": final_mode.get("neighbour"), "strip_iterate_ms_neighbour": tb * 1e3, "sent_MB_per_rank_per_iteration_neighbour": xbb / IT / 1e6,
                       "connectivity_and_contour_identical": post_ok, "gather_plus_connectivity_ms": tc * 1e3, "K_connected": Kc,
                       "strip_iterate_ms": t * 1e3, "strip_iterate_ms_nccl_allreduce": tn * 1e3, "single_gpu_iterate_ms": t1 * 1e3,
                       "exchange": "peer memory (CUDA IPC over NVLink): stores + flags by the library's kernels",
