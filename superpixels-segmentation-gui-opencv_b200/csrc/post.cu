@@ -101,29 +101,61 @@ __global__ void __launch_bounds__(256) ccl_local_kernel(const int* __restrict__ 
     __shared__ int s_roots[CT * CT];
     __shared__ int s_n, s_base;
     if (threadIdx.x == 0) s_n = 0;
-    const int lx = threadIdx.x & 31, ly0 = threadIdx.x >> 5;             // 8 warps; warp q owns tile rows q, q+8, q+16, q+24
+    // 8 warps; warp q owns the SLAB of tile rows 4q .. 4q+3 and sweeps it top-down, lane = column, everything in registers:
+    // a run of equal labels that continues a run of the row above takes that run's root (one ballot + one shuffle), otherwise it
+    // opens a root at its head; only a run that joins two different roots (U shapes, rare) touches the parent table with atomics.
+    // Then the 7 slab borders are united (shared-memory union-find on slab roots: chains at most 8 deep), then one short find per
+    // pixel.  (The form before this one united every row with the row above concurrently: parent chains as deep as a component
+    // is tall, 223 thread-instructions per pixel, 75 us at 4K.)
+    const int lx = threadIdx.x & 31, wq = threadIdx.x >> 5;
     const int x = blockIdx.x * CT + lx;
     int me[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const int y = blockIdx.y * CT + ly0 + 8 * k;
+        const int y = blockIdx.y * CT + 4 * wq + k;
         me[k] = (x < w && y < h) ? lab[(size_t)y * lp + x] : -1 - lx;    // outside: never equal to a neighbour
     }
-    int prev[4];
+    const unsigned le = 0xffffffffu >> (31 - lx);                        // lanes <= lx
+    int above_root = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const int ly = ly0 + 8 * k;
+        const int ly = 4 * wq + k, t = ly * CT + lx;
         sl[ly][lx] = me[k];
-        sc[ly * CT + lx] = 0;
-        prev[k] = __shfl_up_sync(0xffffffffu, me[k], 1);
-        const unsigned heads = __ballot_sync(0xffffffffu, lx == 0 || prev[k] != me[k]) & (0xffffffffu >> (31 - lx));
-        sp[ly * CT + lx] = ly * CT + lx - (lx - (31 - __clz(heads)));
+        sc[t] = 0;
+        const int prevl = __shfl_up_sync(0xffffffffu, me[k], 1);
+        const unsigned hb = __ballot_sync(0xffffffffu, lx == 0 || prevl != me[k]);
+        const int headpos = 31 - __clz(hb & le);
+        const unsigned after = lx == 31 ? 0u : hb >> (lx + 1);           // heads to the right of this lane
+        const int endpos = after ? lx + __ffs(after) : 32;               // the run is lanes [headpos, endpos)
+        const unsigned runmask = (endpos == 32 ? 0xffffffffu : (1u << endpos) - 1u) & ~((1u << headpos) - 1u);
+        const bool conn = k > 0 && me[k] == me[k > 0 ? k - 1 : 0];
+        const unsigned cb = __ballot_sync(0xffffffffu, conn) & runmask;
+        const int src = cb ? __ffs(cb) - 1 : lx;
+        const int taken = __shfl_sync(0xffffffffu, above_root, src);
+        const int root = cb ? taken : ly * CT + headpos;
+        sp[t] = root;                                                    // (a new root's head writes sp[root] = root)
+        if (__any_sync(0xffffffffu, conn && above_root != root)) {       // a run joining two roots: unite them (warp-uniform branch)
+            __syncwarp();
+            if (conn && above_root != root) {
+                int a = root, b = above_root;
+                bool done;
+                do {
+                    a = sm_find(sp, a); b = sm_find(sp, b);
+                    if (a < b) { const int old = atomicMin(&sp[b], a); done = old == b; b = old; }
+                    else if (b < a) { const int old = atomicMin(&sp[a], b); done = old == a; a = old; }
+                    else done = true;
+                } while (!done);
+            }
+            __syncwarp();
+        }
+        above_root = root;
     }
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int ly = ly0 + 8 * k, t = ly * CT + lx;
-        if (me[k] >= 0 && ly > 0 && sl[ly - 1][lx] == me[k] && !(lx > 0 && prev[k] == me[k] && sl[ly - 1][lx - 1] == me[k])) {
+    // slab borders: rows 4, 8, .., 28 with the row above (the left neighbour carries the union when it has the same pair)
+    if (threadIdx.x < 7 * CT) {
+        const int ly = 4 * (1 + (threadIdx.x >> 5)), t = ly * CT + lx;
+        const int m = sl[ly][lx];
+        if (m >= 0 && sl[ly - 1][lx] == m && !(lx > 0 && sl[ly][lx - 1] == m && sl[ly - 1][lx - 1] == m)) {
             int a = t, b = t - CT;
             bool done;
             do {
@@ -139,7 +171,7 @@ __global__ void __launch_bounds__(256) ccl_local_kernel(const int* __restrict__ 
     int r[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const int ly = ly0 + 8 * k, y = blockIdx.y * CT + ly;
+        const int ly = 4 * wq + k, y = blockIdx.y * CT + ly;
         r[k] = sm_find(sp, ly * CT + lx);
         if (x < w && y < h && r[k] == ly * CT + lx) s_roots[atomicAdd(&s_n, 1)] = r[k];
     }
@@ -168,7 +200,7 @@ __global__ void __launch_bounds__(256) ccl_local_kernel(const int* __restrict__ 
     if (threadIdx.x == 0 && nr) s_base = atomicAdd(nroots, nr);          // one global atomic per tile
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const int y = blockIdx.y * CT + ly0 + 8 * k;
+        const int y = blockIdx.y * CT + 4 * wq + k;
         if (x < w && y < h) P[y * w + x] = (blockIdx.y * CT + (r[k] >> 5)) * w + blockIdx.x * CT + (r[k] & 31);
     }
     __syncthreads();
