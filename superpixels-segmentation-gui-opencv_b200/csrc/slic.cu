@@ -296,6 +296,88 @@ __global__ void __launch_bounds__(FIN16_CTA) slic_finalize16_kernel(SlicGeom g, 
         }
 }
 
+// The instruction-lean form of the same update: one WARP per 32 centres.  Phase 1: lane = centre (sums, means, centre arrays, bin
+// list: the arithmetic is done once per centre).  Phase 2: the (centre, tile) pairs of the warp's 32 spans, 16 per centre and 32
+// per step; a lane fetches its centre's record and span from the owning lane with shuffles and appends it to tile (j & 3, j >> 2)
+// of the span (larger spans: strided repeats).  0.44 M warp-instructions per 20 k centres against 3.0 M of the 16-threads-per-
+// centre kernel, at the price of a longer dependent chain (4K single frame: 0.63 vs 0.56 ms per iterate(10)): used where many
+// centres are updated at once (8K frames, row strips of gigapixel images) and for objects in throughput mode.
+__global__ void __launch_bounds__(FIN16_CTA) slic_finalize_warp_kernel(SlicGeom g, SlicArrays a, int parity, FinRange fr)
+{
+    const int t = blockIdx.x * FIN16_CTA + threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
+    const int nb = g.nbx * g.nby;
+    for (int i = t; i < nb; i += gridDim.x * FIN16_CTA) (parity ? a.head[1] : a.head[0])[i] = -1;
+    if (g.tile_on)
+        for (int i = t; i < g.tiles_x * g.tiles_y; i += gridDim.x * FIN16_CTA) (parity ? a.tl_count[1] : a.tl_count[0])[i] = 0;
+    const int lane = threadIdx.x & 31;
+    const int n = fr.k_lo + t;
+    if (n - lane >= fr.k_hi) return;                      // (whole warp)
+    const bool valid = n < fr.k_hi;
+    constexpr int C = 3;                                  // (launched for 3-channel images only)
+    const int par = parity ^ 1;
+    float kc0 = 0.f, kc1 = 0.f, kc2 = 0.f, kx = 0.f, ky = 0.f;
+    int ix = 0, iy = 0, tx0 = 0, ty0 = 0, nx = 0, ny = 0;
+    if (valid) {
+        unsigned long long sum[C + 3];
+#pragma unroll
+        for (int f = 0; f < C + 3; f++) sum[f] = a.acc[(size_t)f * g.Kcap + n];
+        const int off = a.ioff[n];
+        const float m = (float)(sum[C + 2] == 0 ? 1ull : sum[C + 2]);
+        kc0 = __fdiv_rn((float)sum[0], m); kc1 = __fdiv_rn((float)sum[1], m); kc2 = __fdiv_rn((float)sum[2], m);
+        kx = __fdiv_rn((float)sum[C], m); ky = __fdiv_rn((float)sum[C + 1], m);
+        ix = (int)kx; iy = (int)ky;
+#pragma unroll
+        for (int f = 0; f < C + 3; f++) a.acc[(size_t)f * g.Kcap + n] = 0;
+        a.kc[n] = kc0; a.kc[(size_t)g.Kcap + n] = kc1; a.kc[2 * (size_t)g.Kcap + n] = kc2;
+        a.kx[n] = kx; a.ky[n] = ky; a.ikx[n] = ix; a.iky[n] = iy;
+        if (g.alg == 101) a.maxc[n] = __uint_as_float(a.maxc_acc[n]);
+        if (fr.guard) {
+            const int gy = n / fr.xstrips;
+            const int seed_y = min(gy * g.S + g.S / 2 + gy * fr.yerr_i, g.h - 1);
+            if (abs(iy - seed_y) > (STRIP_MARGIN_S - 1) * g.S - 2 || fr.guard == 2) atomicExch(fr.err, 100);
+        }
+        int* head = par ? a.head[1] : a.head[0];
+        const int bx = min(max(ix, 0) / g.S, g.nbx - 1), by = min(max(iy, 0) / g.S, g.nby - 1);
+        a.next[n] = atomicExch(&head[by * g.nbx + bx], n);
+        if (g.tile_on) {
+            tx0 = max(ix - off, 0) / TILE_W;
+            const int tx1 = min(ix + off - 1, g.w - 1) / TILE_W;
+            ty0 = max(max(iy - off, 0) / TILE_H, g.ty_lo);
+            const int ty1 = min(min(iy + off - 1, g.h - 1) / TILE_H, g.ty_hi - 1);
+            nx = max(tx1 - tx0 + 1, 0); ny = max(ty1 - ty0 + 1, 0);
+        }
+    }
+    if (!g.tile_on) return;
+    int* cnt = par ? a.tl_count[1] : a.tl_count[0];
+    TileRec* recs = par ? a.tl_rec[1] : a.tl_rec[0];
+    const int span = tx0 | (ty0 << 16), ext = nx | (ny << 16);
+    const int j = lane & 15;
+#pragma unroll 4
+    for (int i = 0; i < 16; i++) {
+        const int src = 2 * i + (lane >> 4);              // the centre (lane of phase 1) this lane works for in this step
+        const float skx = __shfl_sync(0xffffffffu, kx, src), sky = __shfl_sync(0xffffffffu, ky, src);
+        const float s0 = __shfl_sync(0xffffffffu, kc0, src), s1 = __shfl_sync(0xffffffffu, kc1, src), s2 = __shfl_sync(0xffffffffu, kc2, src);
+        const int six = __shfl_sync(0xffffffffu, ix, src), siy = __shfl_sync(0xffffffffu, iy, src);
+        const int sspan = __shfl_sync(0xffffffffu, span, src), sext = __shfl_sync(0xffffffffu, ext, src);
+        const int sx0 = sspan & 0xffff, sy0 = sspan >> 16, snx = sext & 0xffff, sny = sext >> 16;
+        const int sn = n - lane + src;
+        const float4 ra = make_float4(skx, sky, s0, s1);
+        const float4 rb = make_float4(s2, __int_as_float(sn), __int_as_float(six), __int_as_float(siy));
+        for (int ty = j >> 2; ty < sny; ty += 4)
+            for (int tx = j & 3; tx < snx; tx += 4) {
+                const int tile = (sy0 + ty) * g.tiles_x + sx0 + tx;
+                const int pos = atomicAdd(&cnt[tile], 1);
+                if (pos < TILE_CAP) {
+                    float4* dst = reinterpret_cast<float4*>(&recs[(size_t)tile * TILE_CAP + pos]);
+                    dst[0] = ra;
+                    dst[1] = rb;
+                }
+            }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // MSLIC content-adaptive step (normative statement: DESIGN.md, "MSLIC restatement")
 // ------------------------------------------------------------------------------------------------
@@ -678,7 +760,8 @@ struct SlicEngine {
     // Centre update: slic_finalize16_kernel (16 threads per centre) has the shortest dependent chain -- best for one frame on an
     // otherwise idle device (4K iterate(10) 0.575 vs 0.649 ms) -- but executes 3.0 M warp-instructions per launch, 7 % of an
     // assignment launch; with several frames in flight on other streams (spx_slic_batch_dev) that costs 5 % of the throughput
-    // (14.2 vs 15.0 GP/s), so the batch engines keep slic_finalize_kernel (one thread per centre, shared staging).
+    // (14.2 vs 15.0 GP/s), so the batch engines use slic_finalize_warp_kernel (lane = centre, shuffles for the scatter), as does
+    // any update over more than 32768 centres (8K frames, gigapixel strips).
     bool lean_update = false;
     long long launches = 0;
     PostWorkspace post;
@@ -963,6 +1046,19 @@ struct SlicEngine {
         SPX_CUDA(cudaGetLastError());
         return SPX_OK;
     }
+    // SLIC / SLICO centre update over the clusters [fr.k_lo, fr.k_hi): the latency-lean kernel for a single frame with few
+    // centres, the instruction-lean one for many centres or objects in throughput mode (see the kernels)
+    int launch_centre_update(const FinRange& fr)
+    {
+        const int n = max(fr.k_hi - fr.k_lo, 1);
+        if (lean_update || n > 32768) {
+            SPX_CUDA(launch_pdl(slic_finalize_warp_kernel, dim3(cdiv(n, FIN16_CTA)), dim3(FIN16_CTA), st, g, a, parity, fr));
+        } else {
+            const int th16 = max(max(16 * n, g.nbx * g.nby), g.tiles_x * g.tiles_y);
+            SPX_CUDA(launch_pdl(slic_finalize16_kernel, dim3(cdiv(th16, FIN16_CTA)), dim3(FIN16_CTA), st, g, a, parity, fr));
+        }
+        return SPX_OK;
+    }
     int strip_update()
     {
         FinRange fr{0, g.K, 0, 1, 0, d_strip_err};
@@ -973,8 +1069,7 @@ struct SlicEngine {
             static const int force_at = getenv("SPX_STRIP_FORCE_DRIFT") ? atoi(getenv("SPX_STRIP_FORCE_DRIFT")) : 0;
             fr = FinRange{part_k_lo, part_k_hi, (force_at > 0 && xchg_iter == force_at) ? 2 : 1, sp.xstrips, sp.yerr_i, d_strip_err};
         }
-        const int th16 = max(max(16 * (fr.k_hi - fr.k_lo), g.nbx * g.nby), g.tiles_x * g.tiles_y);
-        SPX_CUDA(launch_pdl(slic_finalize16_kernel, dim3(cdiv(th16, FIN16_CTA)), dim3(FIN16_CTA), st, g, a, parity, fr));
+        SPX_CHECK(launch_centre_update(fr));
         launches++;
         parity ^= 1;
         SPX_CUDA(cudaGetLastError());
@@ -997,10 +1092,8 @@ struct SlicEngine {
         launches++;
         if (e1) SPX_CUDA(cudaEventRecord(e1, st));
         const int do_bin = g.alg == SPX_MSLIC ? 0 : 1;
-        if (do_bin && g.C == 3 && !lean_update) {
-            const int th16 = max(max(16 * g.K, g.nbx * g.nby), g.tiles_x * g.tiles_y);
-            SPX_CUDA(launch_pdl(slic_finalize16_kernel, dim3(cdiv(th16, FIN16_CTA)), dim3(FIN16_CTA), st, g, a, parity,
-                                FinRange{0, g.K, 0, 1, 0, nullptr}));
+        if (do_bin && g.C == 3) {
+            SPX_CHECK(launch_centre_update(FinRange{0, g.K, 0, 1, 0, nullptr}));
         } else
             SPX_CUDA(launch_pdl(slic_finalize_kernel, dim3(cdiv(threads_fin, BIN_CTA)), dim3(BIN_CTA), st, g, a, (const int*)d_K, parity, do_bin));
         launches++;
