@@ -62,7 +62,10 @@ typedef struct spx_slic spx_slic_t;
 int spx_slic_create(const uint8_t* image, size_t stride, int width, int height, int channels,
                     int algorithm, int region_size, float ruler, int device, spx_slic_t** out);
 /* same, image already resident on the current CUDA device; work is enqueued on `cuda_stream`
- * (NULL = a private stream owned by the object). */
+ * (NULL = a private non-blocking stream owned by the object).  ORDERING: the object reads d_image on ITS stream.  With
+ * cuda_stream = NULL nothing orders that read against the stream that produced the image: the caller must have synchronised
+ * the producer (stream / event / device synchronise) before the call; with a caller-supplied stream, stream order does it.
+ * The same holds for spx_slic_reset_dev and for every frame handed to spx_slic_batch_dev. */
 int spx_slic_create_dev(const void* d_image, size_t stride, int width, int height, int channels,
                         int algorithm, int region_size, float ruler, void* cuda_stream, spx_slic_t** out);
 /* re-run the constructor on a new frame of identical geometry/parameters, reusing all device
@@ -170,7 +173,8 @@ int spx_slic_get_label_rows(spx_slic_t*, int32_t* dst, size_t dst_stride, int ro
  * [enforceLabelConnectivity(min_element_size) if > 0] ; getLabels -> d_labels[i]
  * ; [getLabelContourMask(thick_line) -> d_masks[i] if d_masks != NULL].
  * All pointers in the arrays are DEVICE pointers (dense: stride = width*channels, width*4, width).
- * `n_streams` engines work concurrently.  Blocks until the batch is done. */
+ * `n_streams` engines work concurrently on private streams.  The frames must be complete in device memory when the call is
+ * made (see spx_slic_create_dev: ORDERING).  Blocks until the batch is done. */
 int spx_slic_batch_dev(const void* const* d_frames, int n_frames, int width, int height, int channels,
                        int algorithm, int region_size, float ruler, int num_iterations,
                        int min_element_size, void* const* d_labels, void* const* d_masks, int thick_line,
