@@ -888,19 +888,63 @@ struct SlicEngine {
         return SPX_OK;
     }
     // the exchange step: deliver the local partial sums to every peer, wait for theirs, add them up
+    // neighbour mode: the two halves of the exchange (the shared ranges are a few seed rows of clusters: tens to hundreds of KB)
+    int strip_nb_blocks() const
+    {
+        const int len = std::max(std::max(peers.nhi[0] - peers.nlo[0], peers.nhi[1] - peers.nlo[1]), 1);
+        return (int)std::min<size_t>(((size_t)peers.nf * len + 255) / 256, 148);
+    }
+    int strip_push_neighbours()
+    {
+        xchg_iter++;
+        strip_push_kernel<<<strip_nb_blocks(), 256, 0, st>>>(peers, a.acc, xchg_iter, d_range, d_push_done, d_bytes_sent);
+        launches++;
+        return SPX_OK;
+    }
+    int strip_wait_neighbours()
+    {
+        strip_wait_sum_kernel<<<strip_nb_blocks(), 256, 0, st>>>(peers, a.acc, xchg_iter, d_strip_err);
+        launches++;
+        return SPX_OK;
+    }
+    // One whole iteration of a strip object.  Partitioned mode: the tile rows next to the cuts are assigned FIRST -- only they can
+    // hold pixels of the clusters shared with a neighbour (within 2 * 5S rows of the cut) --, their sums go out, and the interior
+    // of the band is assigned while the neighbours' sums travel; the wait then finds the flags set.
+    int strip_iteration()
+    {
+        if (!(peers_open && peers.mode == 1)) {
+            launches++;
+            SPX_CHECK(enqueue_assign());
+            SPX_CHECK(strip_exchange());
+            return strip_update();
+        }
+        const int nbt = cdiv(2 * STRIP_MARGIN_S * g.S, TILE_H);
+        const int top_end = peers.nbr[0] >= 0 ? std::min(g.ty_lo + nbt, g.ty_hi) : g.ty_lo;
+        const int bot_beg = peers.nbr[1] >= 0 ? std::max(g.ty_hi - nbt, top_end) : g.ty_hi;
+        auto assign_rows = [&](int r0, int r1) -> int {
+            if (r1 <= r0) return SPX_OK;
+            SlicGeom g2 = g;
+            g2.ty_lo = r0; g2.ty_hi = r1;
+            launches++;
+            return slic_tile_assign(g2, a, d_img, d_img4, d_labels, d_dcplane, d_area_px, d_K, parity, d_overflow, st);
+        };
+        SPX_CHECK(assign_rows(g.ty_lo, top_end));
+        SPX_CHECK(assign_rows(bot_beg, g.ty_hi));
+        SPX_CHECK(strip_push_neighbours());
+        SPX_CHECK(assign_rows(top_end, bot_beg));
+        SPX_CHECK(strip_wait_neighbours());
+        SPX_CUDA(cudaGetLastError());
+        return strip_update();
+    }
     int strip_exchange()
     {
         SPX_REQUIRE(peers_open || peers.world == 1, SPX_ERR_BADARG, "strip_exchange: peers are not mapped");
         if (peers.world == 1) return SPX_OK;
-        xchg_iter++;
         if (peers.mode == 1) {
-            // neighbours only: the shared ranges are a few seed rows of clusters (tens to hundreds of KB)
-            const int len = std::max(std::max(peers.nhi[0] - peers.nlo[0], peers.nhi[1] - peers.nlo[1]), 1);
-            const int nb = (int)std::min<size_t>(((size_t)peers.nf * len + 255) / 256, 148);
-            strip_push_kernel<<<nb, 256, 0, st>>>(peers, a.acc, xchg_iter, d_range, d_push_done, d_bytes_sent);
-            strip_wait_sum_kernel<<<nb, 256, 0, st>>>(peers, a.acc, xchg_iter, d_strip_err);
-            launches += 2;
+            SPX_CHECK(strip_push_neighbours());
+            SPX_CHECK(strip_wait_neighbours());
         } else {
+            xchg_iter++;
             const int nb = (int)std::min<size_t>((peers.n6 + 255) / 256, 4 * 148);
             strip_range_kernel<<<std::min(cdiv(g.Kcap, 256), 148), 256, 0, st>>>(a.acc + (size_t)(g.C + 2) * g.Kcap, g.Kcap, d_range);
             strip_push_kernel<<<nb, 256, 0, st>>>(peers, a.acc, xchg_iter, d_range, d_push_done, d_bytes_sent);
@@ -1426,6 +1470,11 @@ extern "C" int spx_slic_strip_exchange(spx_slic_t* h) try
 {
     SLIC_ENTER(h);
     return e->strip_exchange();
+} SPX_API_CATCH
+extern "C" int spx_slic_strip_iteration(spx_slic_t* h) try
+{
+    SLIC_ENTER(h);
+    return e->strip_iteration();
 } SPX_API_CATCH
 extern "C" int spx_slic_strip_exchanged_bytes(spx_slic_t* h, unsigned long long* out) try
 {

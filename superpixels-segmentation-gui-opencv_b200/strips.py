@@ -163,6 +163,11 @@ class StripSLIC:
             self.iterate(n)
 
     def _iterate(self, L, peer, num_iterations):
+        if peer:
+            L.spx_slic_strip_iteration.argtypes = [C.c_void_p]
+            for _ in range(int(num_iterations)):
+                _ck(L.spx_slic_strip_iteration(self._h))           # assign (cut rows first) + exchange + update, one call
+            return
         for _ in range(int(num_iterations)):
             _ck(L.spx_slic_strip_assign(self._h))
             if peer:
