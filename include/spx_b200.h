@@ -165,8 +165,7 @@ int spx_slic_strip_plan(int width, int height, int region_size, const int* own_r
 int spx_slic_strip_peer_alloc(spx_slic_t*, int world, int rank, void* ipc_handle_out /* 64 bytes */, size_t* bytes_out);
 int spx_slic_strip_peer_open(spx_slic_t*, const void* ipc_handles /* world x 64 bytes, rank order */);
 int spx_slic_strip_exchange(spx_slic_t*);
-/* assign + exchange + update in one call (peer modes).  With a partition the tile rows next to the cuts are assigned first, their
- * sums are pushed, and the interior of the band is assigned while the neighbours' sums are on their way. */
+/* assign + exchange + update in one call (peer modes). */
 int spx_slic_strip_iteration(spx_slic_t*);
 int spx_slic_strip_exchanged_bytes(spx_slic_t*, unsigned long long* out);   /* bytes this rank has stored into its peers so far */
 int spx_slic_get_label_rows(spx_slic_t*, int32_t* dst, size_t dst_stride, int row0, int row1);

@@ -907,12 +907,14 @@ struct SlicEngine {
         launches++;
         return SPX_OK;
     }
-    // One whole iteration of a strip object.  Partitioned mode: the tile rows next to the cuts are assigned FIRST -- only they can
-    // hold pixels of the clusters shared with a neighbour (within 2 * 5S rows of the cut) --, their sums go out, and the interior
-    // of the band is assigned while the neighbours' sums travel; the wait then finds the flags set.
+    // One whole iteration of a strip object: assign, exchange, update.  SPX_STRIP_SPLIT=1 (partitioned mode) assigns the tile rows
+    // next to the cuts FIRST -- only they can hold pixels of the clusters shared with a neighbour (within 2 * 5S rows of the cut)
+    // --, pushes their sums and assigns the interior of the band while the neighbours' sums travel.  Measured (16384^2, r2): 2 GPUs
+    // 4096^2 1.11 vs 1.19 ms, but 4 GPUs 4.51 vs 4.46 ms and 8 GPUs 2.72 vs 2.59 ms per iterate(10): two more launches per
+    // iteration cost more than the hidden flag latency saves, so it is opt-in.
     int strip_iteration()
     {
-        if (!(peers_open && peers.mode == 1)) {
+        if (!(peers_open && peers.mode == 1) || !getenv("SPX_STRIP_SPLIT")) {
             launches++;
             SPX_CHECK(enqueue_assign());
             SPX_CHECK(strip_exchange());

@@ -166,7 +166,7 @@ class StripSLIC:
         if peer:
             L.spx_slic_strip_iteration.argtypes = [C.c_void_p]
             for _ in range(int(num_iterations)):
-                _ck(L.spx_slic_strip_iteration(self._h))           # assign (cut rows first) + exchange + update, one call
+                _ck(L.spx_slic_strip_iteration(self._h))           # assign + exchange + update, one call
             return
         for _ in range(int(num_iterations)):
             _ck(L.spx_slic_strip_assign(self._h))

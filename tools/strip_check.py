@@ -34,6 +34,9 @@ def run(exchange):
     return out
 
 
+os.environ["SPX_STRIP_SPLIT"] = "1"                         # A/B: the tile rows next to the cuts first, interior during the exchange
+_, _, tb_split, _, _ = run("neighbour")
+del os.environ["SPX_STRIP_SPLIT"]
 Lb, Cb, tb, xbb, _ = run("neighbour")                       # partitioned cluster state, boundary sums to rank-1 / rank+1 only
 Ls, Cs, t, xb, K, Lc, Mc, Kc, tc = run("peer")                              # replicated state, touched range to every peer
 Ln, Cn, tn, xbn, _ = run("nccl")                            # NCCL all-reduce of the accumulators
@@ -47,7 +50,7 @@ if rank == 0:
     print(json.dumps({"strip_check": "%dx%d SLIC S=%d %d iterations" % (W, H, S, IT), "n_gpus": world, "bands": strips.row_bands(H, world),
                       "labels_identical": bool((Ls == Lg).all() and (Ln == Lg).all() and (Lb == Lg).all()),
                       "centres_identical": bool((Cs == Cg).all() and (Cn == Cg).all() and (Cb == Cg).all()),
-                      "neighbour_mode_ran_as": final_mode.get("neighbour"), "strip_iterate_ms_neighbour": tb * 1e3, "sent_MB_per_rank_per_iteration_neighbour": xbb / IT / 1e6,
+                      "neighbour_mode_ran_as": final_mode.get("neighbour"), "strip_iterate_ms_neighbour": tb * 1e3, "strip_iterate_ms_neighbour_cut_rows_first": tb_split * 1e3, "sent_MB_per_rank_per_iteration_neighbour": xbb / IT / 1e6,
                       "connectivity_and_contour_identical": post_ok, "gather_plus_connectivity_ms": tc * 1e3, "K_connected": Kc,
                       "strip_iterate_ms": t * 1e3, "strip_iterate_ms_nccl_allreduce": tn * 1e3, "single_gpu_iterate_ms": t1 * 1e3,
                       "exchange": "peer memory (CUDA IPC over NVLink): stores + flags by the library's kernels",
