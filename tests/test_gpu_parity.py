@@ -3,6 +3,8 @@ Integer / index stages must be bit-exact; SLIC labels and centres are compared e
 (north-star tolerance: >= 99.9 % label agreement, centres within 1e-3)."""
 import os
 
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -236,6 +238,43 @@ def test_slic_4k_equals_oracle(spx, O, synthmod):
     a, b = _run_pair(spx, O, lab, spx.SLIC, 20, 10.0, 10)
     la, lb = a.getLabels(), b.getLabels()
     assert float((la == lb).mean()) == 1.0
+    assert (a.getCentres() == b.getCentres()).all()
+
+
+@pytest.mark.parametrize("alg", ["SLIC", "SLICO"])
+def test_throughput_mode_gives_identical_results(spx, O, synthmod, alg):
+    """spx_slic_set_throughput_mode: the instruction-lean centre update (what spx_slic_batch_dev's pooled objects run) against the
+    oracle and against the default latency-lean kernel"""
+    img, _ = synthmod.synth(640, 480, 5)
+    lab = O.bgr2lab8(img)
+    A = getattr(spx, alg)
+    a = O.SuperpixelSLIC(lab, getattr(O, alg), 16, 10.0); a.iterate(6)
+    b = spx.createSuperpixelSLIC(lab, A, 16, 10.0)
+    L = spx.lib()
+    L.spx_slic_set_throughput_mode.argtypes = [C.c_void_p, C.c_int]
+    assert L.spx_slic_set_throughput_mode(b._h, 1) == 0, L.spx_last_error()
+    b.iterate(6)
+    c = spx.createSuperpixelSLIC(lab, A, 16, 10.0); c.iterate(6)
+    assert (a.getLabels() == b.getLabels()).all() and (b.getLabels() == c.getLabels()).all()
+    assert (a.getCentres() == b.getCentres()).all() and (b.getCentres() == c.getCentres()).all()
+
+
+def test_slic_many_centres_8k_equals_oracle(spx, O, synthmod):
+    """7680x4320, S = 20: 82 944 centres -- above the 32 768 from which the warp-cooperative centre update takes over"""
+    img, _ = synthmod.synth(7680, 4320, 2)
+    lab = spx.cvtColor(img, spx.COLOR_BGR2Lab)
+    a, b = _run_pair(spx, O, lab, spx.SLIC, 20, 10.0, 3)
+    assert (a.getLabels() == b.getLabels()).all()
+    assert (a.getCentres() == b.getCentres()).all()
+
+
+@pytest.mark.parametrize("alg,S", [("SLIC", 7), ("SLIC", 9), ("SLICO", 8), ("MSLIC", 11), ("SLIC", 13)])
+def test_small_region_sizes_on_the_tiled_path(spx, O, synthmod, alg, S):
+    """region sizes 7..13 run on the tiled kernel since round 2 (tiles whose candidate list overflows take the exact per-pixel path)"""
+    img, _ = synthmod.synth(600, 400, 11)
+    lab = O.bgr2lab8(img)
+    a, b = _run_pair(spx, O, lab, getattr(spx, alg), S, 10.0, 5)
+    assert (a.getLabels() == b.getLabels()).all()
     assert (a.getCentres() == b.getCentres()).all()
 
 
