@@ -125,7 +125,7 @@ int spx_set_blocking_sync(int device, int on);
  *             [sum acc over ranks]          exact: integer sums (only clusters near a cut receive pixels from two ranks)
  *             spx_slic_strip_update()       centre update (identical on every rank) + re-binning
  *     spx_slic_get_label_rows()             the owned rows of the label map
- * The result is bit-identical to the single-GPU object.  SLIC (algorithm 100), 3 channels, region_size >= 14. */
+ * The result is bit-identical to the single-GPU object.  SLIC (algorithm 100), 3 channels, region_size >= 7. */
 typedef struct {
     void* kx; void* ky;      /* float[Kcap]            */
     void* kc;                /* float[channels][Kcap]  */

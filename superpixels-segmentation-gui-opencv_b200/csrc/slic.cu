@@ -1406,7 +1406,7 @@ extern "C" int spx_slic_create_strip(const uint8_t* rows, size_t stride, int w, 
     SlicEngine* e = nullptr;
     SPX_CHECK(make_engine(w, h, C, alg, S, ruler, (cudaStream_t)stream, &e));
     int rc = SPX_OK;
-    if (!e->use_tile) { set_error("create_strip: configuration outside the tiled path (region_size >= 14 required)"); rc = SPX_ERR_BADARG; }
+    if (!e->use_tile) { set_error("create_strip: configuration outside the tiled path (region_size >= 7 required)"); rc = SPX_ERR_BADARG; }
     if (rc == SPX_OK) {
         e->g.ty_lo = own_row0 / TILE_H; e->g.ty_hi = cdiv(own_row1, TILE_H);
         e->g.own_y0 = own_row0; e->g.own_y1 = own_row1;
