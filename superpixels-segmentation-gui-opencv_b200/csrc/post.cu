@@ -470,6 +470,10 @@ __global__ void __launch_bounds__(1024) contour_sweeps_kernel(const unsigned cha
     const int rpr = (w + CT_RUN - 1) / CT_RUN;
     const int total = rpr * h;
     const unsigned nblk = gridDim.x;
+    // `full`: this sweep visits every run (the first one, and the VERIFICATION sweep after the lists have run dry: the kernel ends
+    // only when a full sweep changes nothing, i.e. at the fixed point whatever the list bookkeeping missed -- at 16384 x 16384 the
+    // list-only form left a handful of pixels unsettled in most runs)
+    bool full = true;
     for (unsigned sweep = 0;; sweep++) {
         // a run is re-evaluated only if one of its inputs (the run to its left, the three runs above) changed in the
         // previous sweep: a changed run appends its dependents to the next sweep's work list (once: `dirty` flag).
@@ -478,9 +482,9 @@ __global__ void __launch_bounds__(1024) contour_sweeps_kernel(const unsigned cha
         int* nxt = (sweep & 1) ? list0 : list1;
         int* ncount = &count[(sweep + 1) % 3];
         if (blockIdx.x == 0 && threadIdx.x == 0) count[(sweep + 2) % 3] = 0;
-        const int nwork = sweep == 0 ? total : *(volatile int*)&count[sweep % 3];
+        const int nwork = full ? total : *(volatile int*)&count[sweep % 3];
         for (int wi = blockIdx.x * blockDim.x + threadIdx.x; wi < nwork; wi += nblk * blockDim.x) {
-            const int run = sweep == 0 ? wi : __ldcg(cur + wi);
+            const int run = full ? wi : __ldcg(cur + wi);
             if (sweep > 0) dirty[run] = 0;
             bool touched = false;
             const int y = run / rpr, rx = run - y * rpr, x0 = rx * CT_RUN;
@@ -552,11 +556,14 @@ __global__ void __launch_bounds__(1024) contour_sweeps_kernel(const unsigned cha
             }
         }
         contour_grid_barrier(bar, (sweep + 1) * nblk);
-        if (*(volatile int*)ncount == 0) break;
+        if (*(volatile int*)ncount == 0) {
+            if (full) break;
+            full = true;
+        } else full = false;
     }
 }
 
-// ---- the same recurrence, row by row, as a PREFIX COMPOSITION (the shipped form for widths up to 8192) ----------------
+// ---- the same recurrence, row by row, as a PREFIX COMPOSITION (the shipped form for widths up to 16384) ----------------
 // Step 1, fully parallel (contour_pre_kernel): per pixel one byte = popc(diff) << 4 | causal difference bits (W, NW, N, NE).
 // Step 2 (contour_band_kernel): once the row above is known, pixel x of a row is one of three functions of its west flag:
 //     c = popc(diff) - #{NW, N, NE differ and are taken};   no west difference: t = [c > lw]   (constant)
@@ -574,7 +581,7 @@ __global__ void __launch_bounds__(1024) contour_sweeps_kernel(const unsigned cha
 // sequential scan, bit for bit.
 constexpr int CB_THREADS = 1024;
 constexpr int CB_WARM = 8;
-constexpr int CB_MAXW = 8192;
+constexpr int CB_MAXW = 16384;             // one CTA walks whole rows: 1024 threads x 16 pixels
 constexpr int CB_AHEAD = 4;                 // rows of pre bytes in flight (cp.async); ring of CB_AHEAD + 1 rows in shared memory
 constexpr int CB_RING = CB_AHEAD + 1;
 struct ContourBand {
@@ -830,8 +837,8 @@ int contour_mask_dev(PostWorkspace& ws, const int* d_labels, int lp, int thick_l
         cb.pre = pre; cb.pp = pp; cb.w = w; cb.h = h; cb.lw = lw; cb.mask = d_mask; cb.mp = mp;
         cb.halo = ws.diff;                                   // bands * w bytes <= N
         cb.warm = lw >= 2 ? 12 : CB_WARM;
-        int T = 512;                                         // two CTAs per SM: their row phases interleave
-        if (getenv("SPX_CB_T")) T = atoi(getenv("SPX_CB_T")) == 1024 ? 1024 : 512;
+        int T = w > 8192 ? 1024 : 512;                       // 512: two CTAs per SM, their row phases interleave
+        if (getenv("SPX_CB_T") && w <= 8192) T = atoi(getenv("SPX_CB_T")) == 1024 ? 1024 : 512;
         const int ctas = s_sms * (T == 512 ? 2 : 1);
         cb.rows = std::max(16, cdiv(h, ctas));                // (8 rows + 8 warm-up rows per band measured slower: 48 vs 41 us at 4K)
         if (getenv("SPX_CB_WARM")) cb.warm = atoi(getenv("SPX_CB_WARM"));
@@ -840,7 +847,7 @@ int contour_mask_dev(PostWorkspace& ws, const int* d_labels, int lp, int thick_l
         SPX_CUDA(cudaMemsetAsync(ws.flag + 4, 0, 6 * sizeof(int), st));    // barrier counter + 3 round counters + 2 diagnostics
         cb.bar = reinterpret_cast<unsigned*>(ws.flag + 4); cb.cnt = ws.flag + 5;
         const int P = w > 8 * T ? 16 : (w > 4 * T ? 8 : 4);
-        const void* fn = T == 1024 ? (P == 8 ? (const void*)contour_band_kernel<8, 1024> : (const void*)contour_band_kernel<4, 1024>)
+        const void* fn = T == 1024 ? (P == 16 ? (const void*)contour_band_kernel<16, 1024> : P == 8 ? (const void*)contour_band_kernel<8, 1024> : (const void*)contour_band_kernel<4, 1024>)
                                    : (P == 16 ? (const void*)contour_band_kernel<16, 512> : P == 8 ? (const void*)contour_band_kernel<8, 512>
                                                                                                      : (const void*)contour_band_kernel<4, 512>);
         void* args[] = {(void*)&cb};

@@ -58,6 +58,18 @@ def test_contour_bit_exact(spx, O, thick, seeds, w, h, cell, noise):
     assert (out == ref).all()
 
 
+@pytest.mark.parametrize("thick", [False, True])
+@pytest.mark.parametrize("w,h,cell,noise", [(9001, 160, 9, 0.05), (16384, 96, 20, 0.02), (16500, 70, 14, 0.1)])
+def test_contour_wide_images(spx, O, thick, w, h, cell, noise, monkeypatch):
+    """widths above 8192: the 1024-thread band kernel (up to 16384), the persistent sweep kernel beyond; and the sweep kernel
+    forced at every width -- it must end on a full verification sweep (a list-only version left pixels unsettled at 16384^2)"""
+    lab = random_label_map(np.random.default_rng(w + h), h, w, cell, noise)
+    ref = O.label_contour_mask(lab, thick)
+    assert (spx.label_contour_mask(lab, thick) == ref).all()
+    monkeypatch.setenv("SPX_CONTOUR_SWEEPS", "1")
+    assert (spx.label_contour_mask(lab, thick) == ref).all()
+
+
 def test_contour_single_label(spx):
     assert spx.label_contour_mask(np.zeros((40, 50), np.int32), True).sum() == 0
 

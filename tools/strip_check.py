@@ -17,6 +17,7 @@ S, RULER, IT = 20, 10.0, 10
 bgr, _ = synth.synth(W, H, 3)                               # every rank builds the same image and slices its band
 lab = spx.cvtColor(bgr, spx.COLOR_BGR2Lab, device=local)
 final_mode = {}
+post_times = {}
 def run(exchange):
     w = strips.StripSLIC(lab, S, RULER, dist, local, exchange=exchange)
     w.iterate(1)                                            # kernel / NCCL / peer-mapping warm-up
@@ -28,8 +29,13 @@ def run(exchange):
     final_mode[exchange] = s.exchange                        # "neighbour" falls back to "peer" when the drift check fires
     if exchange == "peer":                                  # the rest of the COMPUTE click on the strip object (gathered on rank 0's device)
         torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter(); s.gatherLabels(); torch.cuda.synchronize(); dist.barrier(); tg = time.perf_counter() - t0
+        t0 = time.perf_counter(); s._gathered = False; s.gatherLabels(); torch.cuda.synchronize(); dist.barrier(); tg2 = time.perf_counter() - t0
         t0 = time.perf_counter(); s.enforceLabelConnectivity(25); torch.cuda.synchronize(); dist.barrier(); tc = time.perf_counter() - t0
+        post_times.update({"gather_first_ms": tg * 1e3, "gather_again_ms": tg2 * 1e3, "connectivity_first_call_ms": tc * 1e3})
         out += [s.getLabels(), s.getLabelContourMask(False), s.getNumberOfSuperpixels(), tc]
+        t0 = time.perf_counter(); s.enforceLabelConnectivity(25); torch.cuda.synchronize(); dist.barrier()
+        post_times["connectivity_second_call_ms"] = (time.perf_counter() - t0) * 1e3
     s.release()
     return out
 
@@ -46,12 +52,13 @@ if rank == 0:
     t1 = time.perf_counter(); g.iterate(IT); spx.lib().spx_slic_synchronize(g._h); t1 = time.perf_counter() - t1
     Lg, Cg = g.getLabels(), g.getCentres()
     g.enforceLabelConnectivity(25)
-    post_ok = bool(Kc == g.getNumberOfSuperpixels() and (Lc == g.getLabels()).all() and (Mc == g.getLabelContourMask(False)).all())
+    post_detail = {"K": bool(Kc == g.getNumberOfSuperpixels()), "labels": float((Lc == g.getLabels()).mean()), "mask": float((Mc == g.getLabelContourMask(False)).mean())}
+    post_ok = bool(post_detail["K"] and post_detail["labels"] == 1.0 and post_detail["mask"] == 1.0)
     print(json.dumps({"strip_check": "%dx%d SLIC S=%d %d iterations" % (W, H, S, IT), "n_gpus": world, "bands": strips.row_bands(H, world),
                       "labels_identical": bool((Ls == Lg).all() and (Ln == Lg).all() and (Lb == Lg).all()),
                       "centres_identical": bool((Cs == Cg).all() and (Cn == Cg).all() and (Cb == Cg).all()),
                       "neighbour_mode_ran_as": final_mode.get("neighbour"), "strip_iterate_ms_neighbour": tb * 1e3, "strip_iterate_ms_neighbour_cut_rows_first": tb_split * 1e3, "sent_MB_per_rank_per_iteration_neighbour": xbb / IT / 1e6,
-                      "connectivity_and_contour_identical": post_ok, "gather_plus_connectivity_ms": tc * 1e3, "K_connected": Kc,
+                      "connectivity_and_contour_identical": post_ok, "post_on_rank0": post_times, "post_detail": post_detail, "K_connected": Kc,
                       "strip_iterate_ms": t * 1e3, "strip_iterate_ms_nccl_allreduce": tn * 1e3, "single_gpu_iterate_ms": t1 * 1e3,
                       "exchange": "peer memory (CUDA IPC over NVLink): stores + flags by the library's kernels",
                       "sent_MB_per_rank_per_iteration": xb / IT / 1e6, "allreduce_payload_MB_per_iteration": xbn / IT / 1e6, "K": K}))
