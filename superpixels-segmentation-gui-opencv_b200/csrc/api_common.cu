@@ -1,6 +1,8 @@
 // api_common.cu -- version / error reporting / device probing of libspx_b200.so
 #include "common.cuh"
 #include <cstdlib>
+#include <mutex>
+#include <vector>
 
 namespace spx {
 static thread_local char g_err[512] = "";
@@ -10,6 +12,29 @@ void set_error(const char* fmt, ...)
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+namespace {
+std::mutex g_pin_mu;
+std::vector<void*> g_pin_free;
+constexpr size_t PIN_BLOCK = 256;
+}
+int pinned_scratch_alloc(void** p, size_t bytes)
+{
+    SPX_REQUIRE(p && bytes <= PIN_BLOCK, SPX_ERR_INTERNAL, "pinned_scratch_alloc: at most %zu bytes", PIN_BLOCK);
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        if (!g_pin_free.empty()) { *p = g_pin_free.back(); g_pin_free.pop_back(); memset(*p, 0, PIN_BLOCK); return SPX_OK; }
+    }
+    SPX_CUDA(cudaMallocHost(p, PIN_BLOCK));
+    memset(*p, 0, PIN_BLOCK);
+    return SPX_OK;
+}
+void pinned_scratch_free(void* p)
+{
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    if (g_pin_free.size() < 256) g_pin_free.push_back(p);      // (portable pinned memory: usable from any device of the process)
+    else cudaFreeHost(p);
 }
 bool pdl_enabled()
 {

@@ -74,6 +74,11 @@ int require_device(int device);
 // instead of paying cudaMalloc/cudaFree (milliseconds for the 100+ MB buffers of a 4K frame) each time.
 int pool_alloc(void** p, size_t bytes, cudaStream_t st);
 void pool_free(void* p, cudaStream_t st);
+// Small pinned host scratch (a few flags / counters per object).  cudaMallocHost / cudaFreeHost cost a good fraction of a
+// millisecond each -- per COMPUTE click, since the GUI makes a new Superpixel object every time -- so freed blocks of 256 bytes
+// are kept and handed out again.
+int pinned_scratch_alloc(void** p, size_t bytes);
+void pinned_scratch_free(void* p);
 
 // 8-bit BGR -> Lab (mode 0) / HSV (mode 1) on device buffers, in place allowed (color.cu)
 int cvt8_dev(int mode, const void* d_src, size_t sstride, void* d_dst, size_t dstride, int w, int h, cudaStream_t st);

@@ -1020,7 +1020,7 @@ struct LscEngine {
         for (void* p : allocs) pool_free(p, st);
         if (d_scan_tmp) pool_free(d_scan_tmp, st);
         post.release();
-        if (h_pinned) cudaFreeHost(h_pinned);
+        pinned_scratch_free(h_pinned);
         if (st) cudaStreamDestroy(st);
     }
     int scan_tmp(size_t bytes)
@@ -1095,7 +1095,7 @@ struct LscEngine {
             SPX_CUDA(cudaMemsetAsync(L.tl_count, 0, (size_t)L.tiles_x * L.tiles_y * sizeof(int), st));
             L.ctab = d_ctab;
         }
-        SPX_CUDA(cudaMallocHost(&h_pinned, 32 * sizeof(int)));
+        SPX_CHECK(pinned_scratch_alloc((void**)&h_pinned, 32 * sizeof(int)));
         L.img = d_img;
         SPX_CUDA(cudaMemcpy2DAsync(d_img, L.ipitch, image, stride, (size_t)w * C, h, cudaMemcpyHostToDevice, st));
         if (cvt_mode >= 0) {                  // cvtColor of mainwindow.cpp:2096-2097 on the uploaded image, in place

@@ -35,14 +35,14 @@ int PostWorkspace::alloc(int w_, int h_, cudaStream_t st)
     SPX_CHECK(pool_alloc((void**)&blocksum, (N / 1024 + 2) * sizeof(int), st));
     SPX_CHECK(pool_alloc((void**)&flag, 16 * sizeof(int), st));
     SPX_CHECK(pool_alloc((void**)&diff, N + 64, st));       // (+64: the bitmap and prefix words of a tiny image)
-    SPX_CUDA(cudaMallocHost(&h_flag, 16 * sizeof(int)));
+    SPX_CHECK(pinned_scratch_alloc((void**)&h_flag, 16 * sizeof(int)));
     return SPX_OK;
 }
 void PostWorkspace::release()
 {
     pool_free(parent, st_alloc); pool_free(csize, st_alloc); pool_free(newid, st_alloc); pool_free(link, st_alloc);
     pool_free(blocksum, st_alloc); pool_free(flag, st_alloc); pool_free(diff, st_alloc);
-    if (h_flag) cudaFreeHost(h_flag);
+    pinned_scratch_free(h_flag);
     parent = csize = newid = link = blocksum = flag = nullptr;
     diff = nullptr; h_flag = nullptr;
     w = h = 0;

@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <map>
+#include <set>
 #include <vector>
 
 namespace spx {
@@ -449,12 +450,16 @@ struct SeedsEngine {
     // iteration count into a CUDA graph and replayed
     std::map<int, cudaGraphExec_t> graphs;
     std::map<int, long long> graph_launches;
+    std::set<int> seen_n;
     int iterate(const uint8_t* img, size_t stride, int n)
     {
         SPX_REQUIRE(img && stride >= (size_t)S.w * S.C, SPX_ERR_BADARG, "SuperpixelSEEDS::iterate: bad image pointer/stride");
         SPX_REQUIRE(n >= 0, SPX_ERR_BADARG, "SuperpixelSEEDS::iterate: num_iterations must be >= 0");
         SPX_CUDA(cudaMemcpy2DAsync(d_img, ipitch, img, stride, (size_t)S.w * S.C, S.h, cudaMemcpyHostToDevice, st));
-        if (getenv("SPX_NO_GRAPH")) { SPX_CHECK(enqueue(n)); }
+        // (as for SLIC: a graph only from the second iterate(n) of an object on; the GUI's one-shot objects launch directly)
+        const bool first_use = graphs.find(n) == graphs.end() && !seen_n.count(n);
+        if (first_use) seen_n.insert(n);
+        if (getenv("SPX_NO_GRAPH") || first_use) { SPX_CHECK(enqueue(n)); }
         else {
             auto it = graphs.find(n);
             if (it == graphs.end()) {

@@ -16,6 +16,7 @@
 #include "slic_generic.cuh"
 #include <cfloat>
 #include <map>
+#include <set>
 #include <vector>
 #include <cstdlib>
 
@@ -795,7 +796,7 @@ struct SlicEngine {
         for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
         for (void* p : allocs) pool_free(p, st);
         post.release();
-        if (h_pinned) cudaFreeHost(h_pinned);
+        pinned_scratch_free(h_pinned);
         strip_peer_close();
         if (own_stream && st) cudaStreamDestroy(st);
     }
@@ -1025,7 +1026,7 @@ struct SlicEngine {
             SPX_CHECK(dalloc(&d_area_px, (size_t)g.lp * g.tiles_y * TILE_H));
             SPX_CUDA(cudaMemsetAsync(d_area_px, 0, (size_t)g.lp * g.tiles_y * TILE_H * sizeof(float), st));   // last row / column and padding stay 0
         }
-        SPX_CUDA(cudaMallocHost(&h_pinned, 4 * sizeof(int)));
+        SPX_CHECK(pinned_scratch_alloc((void**)&h_pinned, 4 * sizeof(int)));
         SPX_CUDA(cudaMemsetAsync(d_img, 0, g.ipitch * (size_t)(h + 1), st));
         use_tile = slic_tile_supported(g) && !getenv("SPX_SLIC_GENERIC");
         g.tile_on = use_tile ? 1 : 0;
@@ -1257,9 +1258,13 @@ struct SlicEngine {
     {
         SPX_REQUIRE(n >= 0, SPX_ERR_BADARG, "iterate: num_iterations must be >= 0");
         if (n == 0) return SPX_OK;
-        if (!use_graph) { SPX_CHECK(enqueue_iterations(n)); }
+        long long key = ((long long)n << 1) | parity;
+        // A graph pays off from the second use on: capturing + instantiating it costs more than launching the ~20 kernels once,
+        // and the GUI makes a new object for every COMPUTE click.  The first iterate() with a given (n, parity) launches directly.
+        const bool first_use = use_graph && graphs.find(key) == graphs.end() && !seen_keys.count(key);
+        if (first_use) seen_keys.insert(key);
+        if (!use_graph || first_use) { SPX_CHECK(enqueue_iterations(n)); }
         else {
-            long long key = ((long long)n << 1) | parity;
             auto it = graphs.find(key);
             if (it == graphs.end()) {
                 cudaGraph_t graph = nullptr;
@@ -1291,6 +1296,7 @@ struct SlicEngine {
         return SPX_OK;
     }
     std::map<long long, long long> graph_launches;
+    std::set<long long> seen_keys;
 
     int ensure_post()
     {
