@@ -149,11 +149,10 @@ static int cvt8_host(int mode, const uint8_t* src, size_t sstride, uint8_t* dst,
     unsigned char* d = nullptr;
     SPX_CHECK(pool_alloc((void**)&d, pitch * h, 0));
     int rc = SPX_OK;
-    cudaError_t e = cudaMemcpy2D(d, pitch, src, sstride, (size_t)w * 3, h, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) rc = cvt8_dev(mode, d, pitch, d, pitch, w, h, 0);
-    if (e == cudaSuccess && rc == SPX_OK) e = cudaMemcpy2D(dst, dstride, d, pitch, (size_t)w * 3, h, cudaMemcpyDeviceToHost);
+    rc = upload_2d(d, pitch, src, sstride, (size_t)w * 3, h, 0);
+    if (rc == SPX_OK) rc = cvt8_dev(mode, d, pitch, d, pitch, w, h, 0);
+    if (rc == SPX_OK) rc = download_2d(dst, dstride, d, pitch, (size_t)w * 3, h, 0);
     pool_free(d, 0);
-    if (e != cudaSuccess) { set_error("cvtColor: %s", cudaGetErrorString(e)); return SPX_ERR_GPU; }
     return rc;
 }
 }  // namespace spx

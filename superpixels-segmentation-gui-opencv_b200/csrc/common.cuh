@@ -79,6 +79,16 @@ void pool_free(void* p, cudaStream_t st);
 // are kept and handed out again.
 int pinned_scratch_alloc(void** p, size_t bytes);
 void pinned_scratch_free(void* p);
+// Host <-> device copies of whole images for the host-buffer entry points.  The GUI's cv::Mat buffers are PAGEABLE: a plain
+// cudaMemcpy2D of a 4K frame from pageable memory runs at ~11 GB/s (the driver stages it on one thread) and such copies are 70 %
+// of a COMPUTE click.  These helpers check the pointer: pinned / registered memory goes straight to cudaMemcpy2DAsync; pageable
+// memory of 2 MB or more is cut into row ranges, one per lane (up to 4 host threads), each lane staging through its own pair of
+// pinned buffers on its own stream, so the host-side memcpy of one chunk overlaps the DMA of the previous one and the lanes
+// overlap each other.  For pageable memory both return only when the host buffer is free / filled (like the pageable cudaMemcpy2D
+// they replace) and `st` is synchronised first, so the copy is ordered after everything enqueued on it; a PINNED source is
+// uploaded asynchronously on `st` exactly as before (download_2d always returns with the data in place).
+int upload_2d(void* d_dst, size_t dpitch, const void* h_src, size_t hpitch, size_t width_bytes, size_t rows, cudaStream_t st);
+int download_2d(void* h_dst, size_t hpitch, const void* d_src, size_t dpitch, size_t width_bytes, size_t rows, cudaStream_t st);
 
 // 8-bit BGR -> Lab (mode 0) / HSV (mode 1) on device buffers, in place allowed (color.cu)
 int cvt8_dev(int mode, const void* d_src, size_t sstride, void* d_dst, size_t dstride, int w, int h, cudaStream_t st);

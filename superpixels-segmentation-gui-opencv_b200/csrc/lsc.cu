@@ -1097,7 +1097,7 @@ struct LscEngine {
         }
         SPX_CHECK(pinned_scratch_alloc((void**)&h_pinned, 32 * sizeof(int)));
         L.img = d_img;
-        SPX_CUDA(cudaMemcpy2DAsync(d_img, L.ipitch, image, stride, (size_t)w * C, h, cudaMemcpyHostToDevice, st));
+        SPX_CHECK(upload_2d(d_img, L.ipitch, image, stride, (size_t)w * C, h, st));
         if (cvt_mode >= 0) {                  // cvtColor of mainwindow.cpp:2096-2097 on the uploaded image, in place
             SPX_REQUIRE(C == 3, SPX_ERR_BADARG, "createSuperpixelLSC: the fused colour conversion needs a 3-channel BGR image");
             SPX_CHECK(cvt8_dev(cvt_mode, d_img, L.ipitch, d_img, L.ipitch, w, h, st));
@@ -1463,7 +1463,7 @@ extern "C" int spx_lsc_get_labels(spx_lsc_t* h, int32_t* dst, size_t dst_stride)
 {
     LSC_ENTER(h);
     SPX_REQUIRE(dst && dst_stride >= (size_t)e->L.w * 4, SPX_ERR_BADARG, "getLabels: bad destination");
-    SPX_CUDA(cudaMemcpy2DAsync(dst, dst_stride, e->d_labels, (size_t)e->L.w * 4, (size_t)e->L.w * 4, e->L.h, cudaMemcpyDeviceToHost, e->st));
+    SPX_CHECK(spx::download_2d(dst, dst_stride, e->d_labels, (size_t)e->L.w * 4, (size_t)e->L.w * 4, e->L.h, e->st));
     SPX_CUDA(cudaStreamSynchronize(e->st));
     return SPX_OK;
 } SPX_API_CATCH
@@ -1475,7 +1475,7 @@ extern "C" int spx_lsc_get_label_contour_mask(spx_lsc_t* h, uint8_t* dst, size_t
     long long l0 = e->post.launches;
     SPX_CHECK(spx::contour_mask_dev(e->post, e->d_labels, e->L.w, thick_line, 0, e->d_mask, e->L.w, e->st));
     e->launches += e->post.launches - l0;
-    SPX_CUDA(cudaMemcpy2DAsync(dst, dst_stride, e->d_mask, e->L.w, e->L.w, e->L.h, cudaMemcpyDeviceToHost, e->st));
+    SPX_CHECK(spx::download_2d(dst, dst_stride, e->d_mask, e->L.w, e->L.w, e->L.h, e->st));
     SPX_CUDA(cudaStreamSynchronize(e->st));
     return SPX_OK;
 } SPX_API_CATCH

@@ -455,7 +455,7 @@ struct SeedsEngine {
     {
         SPX_REQUIRE(img && stride >= (size_t)S.w * S.C, SPX_ERR_BADARG, "SuperpixelSEEDS::iterate: bad image pointer/stride");
         SPX_REQUIRE(n >= 0, SPX_ERR_BADARG, "SuperpixelSEEDS::iterate: num_iterations must be >= 0");
-        SPX_CUDA(cudaMemcpy2DAsync(d_img, ipitch, img, stride, (size_t)S.w * S.C, S.h, cudaMemcpyHostToDevice, st));
+        SPX_CHECK(upload_2d(d_img, ipitch, img, stride, (size_t)S.w * S.C, S.h, st));
         // (as for SLIC: a graph only from the second iterate(n) of an object on; the GUI's one-shot objects launch directly)
         const bool first_use = graphs.find(n) == graphs.end() && !seen_n.count(n);
         if (first_use) seen_n.insert(n);
@@ -567,7 +567,7 @@ extern "C" int spx_seeds_get_labels(spx_seeds_t* h, int32_t* dst, size_t dst_str
 {
     SEEDS_ENTER(h);
     SPX_REQUIRE(dst && dst_stride >= (size_t)e->S.w * 4, SPX_ERR_BADARG, "getLabels: bad destination");
-    SPX_CUDA(cudaMemcpy2DAsync(dst, dst_stride, e->S.labels, (size_t)e->S.w * 4, (size_t)e->S.w * 4, e->S.h, cudaMemcpyDeviceToHost, e->st));
+    SPX_CHECK(spx::download_2d(dst, dst_stride, e->S.labels, (size_t)e->S.w * 4, (size_t)e->S.w * 4, e->S.h, e->st));
     SPX_CUDA(cudaStreamSynchronize(e->st));
     return SPX_OK;
 } SPX_API_CATCH
@@ -579,7 +579,7 @@ extern "C" int spx_seeds_get_label_contour_mask(spx_seeds_t* h, uint8_t* dst, si
     long long l0 = e->post.launches;
     SPX_CHECK(spx::contour_mask_dev(e->post, e->S.labels, e->S.w, thick_line, 1, e->d_mask, e->S.w, e->st));
     e->launches += e->post.launches - l0;
-    SPX_CUDA(cudaMemcpy2DAsync(dst, dst_stride, e->d_mask, e->S.w, e->S.w, e->S.h, cudaMemcpyDeviceToHost, e->st));
+    SPX_CHECK(spx::download_2d(dst, dst_stride, e->d_mask, e->S.w, e->S.w, e->S.h, e->st));
     SPX_CUDA(cudaStreamSynchronize(e->st));
     return SPX_OK;
 } SPX_API_CATCH

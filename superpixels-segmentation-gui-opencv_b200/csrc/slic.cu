@@ -15,6 +15,7 @@
 #include "slic.cuh"
 #include "slic_generic.cuh"
 #include <cfloat>
+#include <chrono>
 #include <map>
 #include <set>
 #include <vector>
@@ -1077,8 +1078,8 @@ struct SlicEngine {
     int upload(const uint8_t* img, size_t stride, bool from_device)
     {
         SPX_REQUIRE(img && stride >= (size_t)g.w * g.C, SPX_ERR_BADARG, "createSuperpixelSLIC: bad image pointer/stride");
-        SPX_CUDA(cudaMemcpy2DAsync(d_img, g.ipitch, img, stride, (size_t)g.w * g.C, g.h,
-                                   from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        if (from_device) SPX_CUDA(cudaMemcpy2DAsync(d_img, g.ipitch, img, stride, (size_t)g.w * g.C, g.h, cudaMemcpyDeviceToDevice, st));
+        else SPX_CHECK(upload_2d(d_img, g.ipitch, img, stride, (size_t)g.w * g.C, g.h, st));      // (pageable cv::Mat: staged on several lanes)
         return SPX_OK;
     }
 
@@ -1360,11 +1361,18 @@ static int slic_create_common(const void* image, size_t stride, int w, int h, in
     SPX_REQUIRE(image, SPX_ERR_BADARG, "createSuperpixelSLIC: image is NULL");
     SPX_REQUIRE(cvt_mode < 0 || C == 3, SPX_ERR_BADARG, "createSuperpixelSLIC: the fused colour conversion needs a 3-channel BGR image");
     SlicEngine* e = nullptr;
+    static const bool trace = getenv("SPX_TRACE") != nullptr;          // host-side phases of the constructor, for tools/click_stages.py
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = trace ? now() : 0;
     SPX_CHECK(make_engine(w, h, C, alg, S, ruler, stream, &e));
+    const double t1 = trace ? now() : 0;
     int rc = e->upload((const uint8_t*)image, stride, from_device);
+    const double t2 = trace ? now() : 0;
     // cvtColor(BGR2Lab / BGR2HSV) of mainwindow.cpp:2096-2097 on the freshly uploaded image, in place: no extra host round trip
     if (rc == SPX_OK && cvt_mode >= 0) { rc = cvt8_dev(cvt_mode, e->d_img, e->g.ipitch, e->d_img, e->g.ipitch, w, h, e->st); e->launches++; }
     if (rc == SPX_OK) rc = e->seed();
+    if (trace) fprintf(stderr, "[spx] create %dx%d: engine (stream, allocations, memsets) %.3f ms, upload %.3f ms, seeding enqueued %.3f ms\n", w, h,
+                       t1 - t0, t2 - t1, now() - t2);
     if (rc != SPX_OK) { delete e; return rc; }
     *out = new spx_slic{e};
     return SPX_OK;
@@ -1539,7 +1547,7 @@ extern "C" int spx_slic_get_labels(spx_slic_t* h, int32_t* dst, size_t dst_strid
 {
     SLIC_ENTER(h);
     SPX_REQUIRE(dst && dst_stride >= (size_t)e->g.w * 4, SPX_ERR_BADARG, "getLabels: bad destination");
-    SPX_CUDA(cudaMemcpy2DAsync(dst, dst_stride, e->d_labels, (size_t)e->g.lp * 4, (size_t)e->g.w * 4, e->g.h, cudaMemcpyDeviceToHost, e->st));
+    SPX_CHECK(spx::download_2d(dst, dst_stride, e->d_labels, (size_t)e->g.lp * 4, (size_t)e->g.w * 4, e->g.h, e->st));
     SPX_CUDA(cudaStreamSynchronize(e->st));
     return SPX_OK;
 } SPX_API_CATCH
@@ -1555,7 +1563,7 @@ extern "C" int spx_slic_get_label_contour_mask(spx_slic_t* h, uint8_t* dst, size
     SLIC_ENTER(h);
     SPX_REQUIRE(dst && dst_stride >= (size_t)e->g.w, SPX_ERR_BADARG, "getLabelContourMask: bad destination");
     SPX_CHECK(e->contour(e->d_mask, e->g.w, thick_line));
-    SPX_CUDA(cudaMemcpy2DAsync(dst, dst_stride, e->d_mask, e->g.w, e->g.w, e->g.h, cudaMemcpyDeviceToHost, e->st));
+    SPX_CHECK(spx::download_2d(dst, dst_stride, e->d_mask, e->g.w, e->g.w, e->g.h, e->st));
     SPX_CUDA(cudaStreamSynchronize(e->st));
     return SPX_OK;
 } SPX_API_CATCH
