@@ -154,9 +154,14 @@ int staged_copy(bool up, void* dev, size_t dpitch, void* host, size_t hpitch, si
     std::vector<int> rc((size_t)n, 0);
     std::vector<std::thread> th;
     auto part = [&](int i) { return rows * (size_t)i / (size_t)n; };
-    for (int i = 1; i < n; i++)
-        th.emplace_back([&, i] { rc[i] = stage_lane_run(L[i], up, (unsigned char*)dev, dpitch, (unsigned char*)host, hpitch, wb, part(i), part(i + 1)); });
-    rc[0] = stage_lane_run(L[0], up, (unsigned char*)dev, dpitch, (unsigned char*)host, hpitch, wb, part(0), part(1));
+    auto run = [&](int i) { rc[i] = stage_lane_run(L[i], up, (unsigned char*)dev, dpitch, (unsigned char*)host, hpitch, wb, part(i), part(i + 1)); };
+    th.reserve((size_t)n);
+    int started = 1;                                               // lanes 1 .. started-1 have a thread; a failed thread creation
+    for (; started < n; started++) {                               // (resource limits) leaves the rest to this thread
+        try { th.emplace_back(run, started); } catch (...) { break; }
+    }
+    run(0);
+    for (int i = started; i < n; i++) run(i);
     for (auto& t : th) t.join();
     for (StageLane* l : L) stage_release(l);
     for (int i = 0; i < n; i++)
