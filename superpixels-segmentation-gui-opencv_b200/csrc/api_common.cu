@@ -41,7 +41,7 @@ void pinned_scratch_free(void* p)
 // ---- staged copies between pageable host memory and the device (see common.cuh) -----------------------------------------
 namespace {
 constexpr size_t STAGE_BYTES = 2u << 20;             // per pinned buffer
-constexpr int STAGE_MAX_LANES = 4;
+constexpr int STAGE_MAX_LANES = 8;
 struct StageLane {
     int device = -1;
     cudaStream_t st = nullptr;
@@ -87,7 +87,7 @@ int stage_lanes(size_t bytes)
     static const int hw = (int)std::thread::hardware_concurrency();
     static const int forced = getenv("SPX_STAGE_LANES") ? atoi(getenv("SPX_STAGE_LANES")) : -1;     // 0 = never stage
     if (forced == 0 || bytes < STAGE_BYTES) return 0;
-    int n = forced > 0 ? forced : std::max(1, std::min(STAGE_MAX_LANES, hw / 4));
+    int n = forced > 0 ? forced : std::max(1, std::min(4, hw / 4));          // measured on a 16-core host: 3 / 4 / 6 / 8 lanes -> 6.97 / 5.71 / 5.93 / 6.24 ms per 4K click
     static const size_t per_lane = getenv("SPX_STAGE_PER_LANE_MB") ? (size_t)atoi(getenv("SPX_STAGE_PER_LANE_MB")) << 20 : STAGE_BYTES;
     n = (int)std::min<size_t>((size_t)n, std::max<size_t>(1, bytes / per_lane));
     return std::min(n, STAGE_MAX_LANES);
