@@ -194,6 +194,78 @@ int download_2d(void* h_dst, size_t hpitch, const void* d_src, size_t dpitch, si
     SPX_CUDA(cudaStreamSynchronize(st));
     return staged_copy(false, const_cast<void*>(d_src), dpitch, h_dst, hpitch, width_bytes, rows, lanes);
 }
+namespace {
+int stage_lane_transform(StageLane* L, unsigned char* dev, size_t dpitch, const unsigned char* src, size_t spitch, unsigned char* dst, size_t hdpitch,
+                         size_t wb, size_t r0, size_t r1, staged_kernel_fn kernel, void* ctx, int* krc)
+{
+    if (cudaSetDevice(L->device) != cudaSuccess) return (int)cudaGetLastError();
+    const size_t lane_bytes = (r1 - r0) * wb;
+    const size_t chunk = std::min(STAGE_BYTES, std::max<size_t>(512u << 10, lane_bytes / 4));
+    const size_t rows_per = std::max<size_t>(1, chunk / wb);
+    cudaError_t e = cudaSuccess;
+    int k = 0, pend_k = -1;
+    size_t r = r0, pend_r = 0, pend_n = 0;
+    while ((r < r1 || pend_k >= 0) && e == cudaSuccess && *krc == SPX_OK) {
+        int cur_k = -1;
+        size_t cur_r = 0, cur_n = 0;
+        if (r < r1) {
+            cur_k = k; cur_r = r; cur_n = std::min(rows_per, r1 - r);
+            // buf[k] was drained two steps ago (the pending chunk sits in the other buffer)
+            for (size_t i = 0; i < cur_n; i++) memcpy(L->buf[k] + i * wb, src + (r + i) * spitch, wb);
+            e = cudaMemcpy2DAsync(dev + r * dpitch, dpitch, L->buf[k], wb, wb, cur_n, cudaMemcpyHostToDevice, L->st);
+            if (e == cudaSuccess) { const int rc = kernel(ctx, dev + r * dpitch, cur_n, L->st); if (rc != SPX_OK) *krc = rc; }
+            if (e == cudaSuccess) e = cudaMemcpy2DAsync(L->buf[k], wb, dev + r * dpitch, dpitch, wb, cur_n, cudaMemcpyDeviceToHost, L->st);
+            if (e == cudaSuccess) e = cudaEventRecord(L->ev[k], L->st);
+            r += cur_n; k ^= 1;
+        }
+        if (pend_k >= 0 && e == cudaSuccess) {
+            e = cudaEventSynchronize(L->ev[pend_k]);
+            if (e == cudaSuccess)
+                for (size_t i = 0; i < pend_n; i++) memcpy(dst + (pend_r + i) * hdpitch, L->buf[pend_k] + i * wb, wb);
+        }
+        pend_k = cur_k; pend_r = cur_r; pend_n = cur_n;
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(L->st);
+    return (int)e;
+}
+}  // namespace
+int staged_transform_2d(void* h_dst, size_t hdpitch, const void* h_src, size_t hspitch, unsigned char* d_scratch, size_t dpitch,
+                        size_t width_bytes, size_t rows, staged_kernel_fn kernel, void* ctx)
+{
+    const int lanes = (width_bytes <= STAGE_BYTES && is_pageable(h_src) && is_pageable(h_dst)) ? stage_lanes(width_bytes * rows) : 0;
+    if (lanes == 0) return SPX_NOT_STAGED;
+    int device = 0;
+    SPX_CUDA(cudaGetDevice(&device));
+    std::vector<StageLane*> L;
+    for (int i = 0; i < lanes; i++) {
+        StageLane* l = stage_acquire(device);
+        if (!l) break;
+        L.push_back(l);
+    }
+    if (L.empty()) return SPX_NOT_STAGED;
+    const int n = (int)L.size();
+    std::vector<int> rc((size_t)n, 0), krc((size_t)n, SPX_OK);
+    std::vector<std::thread> th;
+    auto part = [&](int i) { return rows * (size_t)i / (size_t)n; };
+    auto run = [&](int i) {
+        rc[i] = stage_lane_transform(L[i], d_scratch, dpitch, (const unsigned char*)h_src, hspitch, (unsigned char*)h_dst, hdpitch, width_bytes,
+                                     part(i), part(i + 1), kernel, ctx, &krc[i]);
+    };
+    th.reserve((size_t)n);
+    int started = 1;
+    for (; started < n; started++) {
+        try { th.emplace_back(run, started); } catch (...) { break; }
+    }
+    run(0);
+    for (int i = started; i < n; i++) run(i);
+    for (auto& t : th) t.join();
+    for (StageLane* l : L) stage_release(l);
+    for (int i = 0; i < n; i++) {
+        SPX_REQUIRE(rc[i] == 0, SPX_ERR_GPU, "staged transform: %s", cudaGetErrorString((cudaError_t)rc[i]));
+        if (krc[i] != SPX_OK) return krc[i];
+    }
+    return SPX_OK;
+}
 bool pdl_enabled()
 {
     static const bool on = !getenv("SPX_NO_PDL");

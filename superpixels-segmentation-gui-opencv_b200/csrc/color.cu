@@ -148,10 +148,22 @@ static int cvt8_host(int mode, const uint8_t* src, size_t sstride, uint8_t* dst,
     size_t pitch = round_up((size_t)w * 3, 16);
     unsigned char* d = nullptr;
     SPX_CHECK(pool_alloc((void**)&d, pitch * h, 0));
-    int rc = SPX_OK;
-    rc = upload_2d(d, pitch, src, sstride, (size_t)w * 3, h, 0);
-    if (rc == SPX_OK) rc = cvt8_dev(mode, d, pitch, d, pitch, w, h, 0);
-    if (rc == SPX_OK) rc = download_2d(dst, dstride, d, pitch, (size_t)w * 3, h, 0);
+    int rc = load_tables();
+    if (rc == SPX_OK) rc = (cudaStreamSynchronize(0) == cudaSuccess) ? SPX_OK : SPX_ERR_GPU;      // (the allocation above is stream-0 ordered)
+    // pageable images: upload, conversion and download pipelined chunk by chunk on the staging lanes
+    struct Ctx { int mode; size_t pitch; int w; } ctx{mode, pitch, w};
+    if (rc == SPX_OK) {
+        rc = staged_transform_2d(dst, dstride, src, sstride, d, pitch, (size_t)w * 3, h,
+                                 [](void* c, unsigned char* rows, size_t n, cudaStream_t st) -> int {
+                                     const Ctx* x = static_cast<const Ctx*>(c);
+                                     return cvt8_dev(x->mode, rows, x->pitch, rows, x->pitch, x->w, (int)n, st);
+                                 }, &ctx);
+        if (rc == SPX_NOT_STAGED) {
+            rc = upload_2d(d, pitch, src, sstride, (size_t)w * 3, h, 0);
+            if (rc == SPX_OK) rc = cvt8_dev(mode, d, pitch, d, pitch, w, h, 0);
+            if (rc == SPX_OK) rc = download_2d(dst, dstride, d, pitch, (size_t)w * 3, h, 0);
+        }
+    }
     pool_free(d, 0);
     return rc;
 }

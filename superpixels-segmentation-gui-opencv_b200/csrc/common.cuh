@@ -88,6 +88,14 @@ void pinned_scratch_free(void* p);
 // they replace) and `st` is synchronised first, so the copy is ordered after everything enqueued on it; a PINNED source is
 // uploaded asynchronously on `st` exactly as before (download_2d always returns with the data in place).
 int upload_2d(void* d_dst, size_t dpitch, const void* h_src, size_t hpitch, size_t width_bytes, size_t rows, cudaStream_t st);
+// host image -> device -> per-row-range kernel -> host image, pipelined on the same lanes (cvtColor on host buffers): a lane
+// uploads a chunk of rows, runs `kernel(ctx, d_rows, n_rows, lane_stream)` on it and downloads it while it fills the next chunk,
+// so the whole call takes about max(upload, download) instead of their sum.  d_scratch: device image of `rows` rows, pitch
+// dpitch.  Returns SPX_ERR_INTERNAL + 1000 when the buffers are not pageable / too small to stage (the caller then copies whole).
+typedef int (*staged_kernel_fn)(void* ctx, unsigned char* d_rows, size_t n_rows, cudaStream_t st);
+constexpr int SPX_NOT_STAGED = 1000;
+int staged_transform_2d(void* h_dst, size_t hdpitch, const void* h_src, size_t hspitch, unsigned char* d_scratch, size_t dpitch,
+                        size_t width_bytes, size_t rows, staged_kernel_fn kernel, void* ctx);
 int download_2d(void* h_dst, size_t hpitch, const void* d_src, size_t dpitch, size_t width_bytes, size_t rows, cudaStream_t st);
 
 // 8-bit BGR -> Lab (mode 0) / HSV (mode 1) on device buffers, in place allowed (color.cu)
