@@ -386,8 +386,8 @@ struct SeedsEngine {
             // fit fails there with cv::Exception (OutOfMemory); here with SPX_ERR_NOMEM before anything is allocated
             double need = 0;
             for (int l = 0; l < L; l++) need += (double)S.nr_w[l] * S.nr_h[l] * (hs + 2.0) * sizeof(int);
-            size_t fr = 0, tot = 0;
-            SPX_CUDA(cudaMemGetInfo(&fr, &tot));
+            size_t fr = ~(size_t)0, tot = 0;
+            if (need > 1e9) SPX_CUDA(cudaMemGetInfo(&fr, &tot));   // (the query itself costs a good part of a millisecond: only when it can matter)
             SPX_REQUIRE(need < 0.9 * (double)fr, SPX_ERR_NOMEM,
                         "createSuperpixelSEEDS: the histograms of %d levels with %d^%d bins need %.1f GB, %.1f GB are free", L, bins, C, need / 1e9, (double)fr / 1e9);
         }
