@@ -54,3 +54,47 @@ def test_plan_refuses_thin_bands():
     assert rc != 0
     rc, _ = _plan(spx, 2048, 1536, 20, [(0, 512), (512, 512), (512, 1536)])   # a rank without rows
     assert rc != 0
+
+
+def _gloo_worker(rank, world, port, q):
+    import os
+    import sys
+    import torch.distributed as dist
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    spx = importlib.import_module(PKG)
+    strips = importlib.import_module(PKG + ".strips")
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    W, H, S = 8192, 8192, 20
+    bands = strips.row_bands(H, world)
+    rc, plan = _plan(spx, W, H, S, bands)
+    got = [None] * world
+    dist.all_gather_object(got, (rc, plan))
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, got))
+
+
+def test_two_ranks_agree_on_the_partition_gloo():
+    """world_size 2 over gloo (no GPU): every rank derives the same partition from the image geometry alone -- what
+    StripSLIC relies on when each rank calls spx_slic_strip_partition on its own -- and the ranges the two ranks share
+    are the same seen from either side"""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    out = dict(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(60)
+    assert out[0] == out[1]
+    (rc0, plan0), (rc1, plan1) = out[0]
+    assert rc0 == 0 and rc1 == 0 and plan0 == plan1
+    (lo0, hi0, _, _), (lo1, hi1, _, _) = plan0
+    assert max(lo0, lo1) < min(hi0, hi1)                 # the two ranks share the clusters around the cut ...
+    assert lo0 == 0 and hi1 == plan0[1][3]                # ... and together cover every cluster
